@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the intrinsic-reward hot path (BASELINE.json metric): samples/s of
+bonus + update on an RND [T,B] rollout batch, T=128, B=1024 per GPU, 4x84x84 uint8 frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--B 1024] [--T 128]
+
+One "step" = RndStep.__call__: compute_bonus -> reward += r_int -> GAE/valid -> compute_loss
+forward+backward over all T*B samples -> (all-reduce) -> clip -> Adam.  Prints ONE JSON line on
+rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops on
+all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+# algorithmic FLOPs per sample, RND bonus + one-epoch update: 2*fwd + bwd
+FWD_MAC_TARGET = 64 * 32 * 400 + 512 * 64 * 81 + 576 * 64 * 49 + 3136 * 512
+FWD_MAC_PRED = FWD_MAC_TARGET + 2 * 512 * 512
+FLOP_PER_SAMPLE = 2 * (2 * (FWD_MAC_TARGET + FWD_MAC_PRED)                       # bonus fwd + loss fwd
+                       + 2 * FWD_MAC_PRED - 64 * 32 * 400)                       # bwd: wgrad all + dgrad (no conv1 dgrad)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_reference(T, B, steps, warmup, seconds_cap=120.0):
+    """The reference's CPU path for the same unit of work, restated in oracle/ (torch CPU fp32,
+    all host threads): bonus -> reward/GAE -> loss.backward -> clip_grad_norm_ -> Adam.step."""
+    import recipes as R
+    from oracle import curiosity_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    params = R.make_params(R.rnd_shapes(), 1, gain=1.4)
+    p = {k: v.clone().requires_grad_(k.startswith("forward")) for k, v in params.items()}
+    train = [v for k, v in p.items() if k.startswith("forward")]
+    opt = torch.optim.Adam(train, lr=1e-4)
+    m = O.RndOracle(drop_probability=0.25)
+    frames = R.make_frames(2, T, B)
+    done = R.make_suffix_done(3, T, B, frac=0.01)
+    value, boot = R.make_normal(4, T, B), R.make_normal(5, B)
+    mask = R.make_mask(6, (T, B), 0.25)
+
+    def step():
+        r_int = m.compute_bonus(p, frames, done)
+        adv, ret = O.generalized_advantage_estimation(r_int.clone(), value, done, boot, 0.99, 0.95)
+        valid = O.valid_from_done(done)
+        opt.zero_grad()
+        loss = m.compute_loss(p, frames, valid, mask)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(train, 1.0)
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done_steps = 0
+    for _ in range(steps):
+        step()
+        done_steps += 1
+        if time.perf_counter() - t0 > seconds_cap:
+            break
+    dt = (time.perf_counter() - t0) / done_steps
+    return T * B / dt, dt * 1e3, done_steps
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--T", type=int, default=128)
+    ap.add_argument("--B", type=int, default=1024, help="env columns per GPU (weak scaling)")
+    ap.add_argument("--engine", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-B", type=int, default=8)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    T, B = args.T, args.B
+    workload = f"RND bonus+update, T={T}, B={B}/GPU, 4x84x84 uint8 (BASELINE configs[1])"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, ms, k = cpu_reference(T, args.cpu_B, args.steps, args.warmup)
+        sample = f"T={T}, B={args.cpu_B} ({T * args.cpu_B} samples/step) of the same workload, {k} steps"
+        print(json.dumps({
+            "impl": "reference", "metric": "intrinsic-reward samples/sec (bonus+update)", "value": v,
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    from curiosity_baselines_b200 import _lib as L
+    from curiosity_baselines_b200 import layers as LY
+    from curiosity_baselines_b200.curiosity.rnd import RND
+    from curiosity_baselines_b200.trainer import RndStep
+    from curiosity_baselines_b200.agents.hooks import newest_frame_to_device
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    LY.set_engine(args.engine)
+
+    torch.manual_seed(0)                       # identical weights on every rank
+    model = RND(image_shape=(4, 84, 84), prediction_beta=1.0, drop_probability=0.25, gamma=0.99).to(dev)
+    step = RndStep(model, lr=1e-4)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    # synthetic rollout, device resident (3.7 GB of frames at the default size: larger than L2)
+    frames = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    first = torch.randint(1, T + 1, (B,), device=dev, generator=g)
+    has = torch.rand(B, device=dev, generator=g) < 0.01
+    first = torch.where(has, first, torch.full_like(first, T))
+    done = (torch.arange(T, device=dev).unsqueeze(1) >= first.unsqueeze(0)).float()
+    value = torch.randn(T, B, device=dev, generator=g)
+    boot = torch.randn(B, device=dev, generator=g)
+    mask = (torch.rand(T, B, device=dev, generator=g) > 0.25).float()
+    reward0 = torch.zeros(T, B, device=dev)     # no_extrinsic
+
+    def one_step():
+        return step(frames, done, reward0.clone(), value, boot, mask)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss, r_int, adv, ret = one_step()
+    ev1.record()
+    barrier()
+    launches = L.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value_sps = world * T * B / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-facing call: pinned host buffers in, results out
+    h_frames = torch.empty((T, B, 4, 84, 84), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(frames)
+    h_small = [t.cpu().pin_memory() for t in (done, value, boot, mask)]
+    h_out = [torch.empty(T, B).pin_memory() for _ in range(3)]
+    h_loss = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        d_frames = newest_frame_to_device(h_frames, dev)            # only the newest frame is read by RND
+        d_done, d_value, d_boot, d_mask = (t.to(dev, non_blocking=True) for t in h_small)
+        loss, r_int, adv, ret = step(d_frames, d_done, torch.zeros(T, B, device=dev), d_value, d_boot, d_mask)
+        h_out[0].copy_(r_int, non_blocking=True); h_out[1].copy_(adv, non_blocking=True)
+        h_out[2].copy_(ret, non_blocking=True); h_loss.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    h2d = T * B * 84 * 84 + sum(t.numel() * 4 for t in h_small)
+    d2h = 3 * T * B * 4 + 4
+
+    # ---- roofline of the dominant kernel: predictor conv2 forward (implicit GEMM 512x64 per position)
+    hbm, tf_burst, tf_sust, src = peaks()
+    layer = model._chains[0].layers[1]
+    n = T * B
+    a1 = torch.randn(n * 400, 32, device=dev).to(torch.bfloat16)
+    for _ in range(3):
+        layer.forward(a1, n)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    k0.record()
+    for _ in range(reps):
+        layer.forward(a1, n)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / reps
+    kern_tflops = 2.0 * 512 * 64 * 81 * n / (kern_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv2 forward (32->64, k4 s2) implicit GEMM",
+                "achieved": kern_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": kern_tflops / tf_burst,
+                "traffic": None, "peak_source": f"{src} bf16 burst", "kernel_ms": kern_ms,
+                "step_tflops": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12,
+                "step_frac_of_sustained": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12 / tf_sust}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, ms_cpu, k = cpu_reference(T, args.cpu_B, 6, 1, seconds_cap=25.0)
+        cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"T={T}, B={args.cpu_B} ({T * args.cpu_B} samples/step), {k} steps, {ms_cpu:.0f} ms/step"}
+    print(json.dumps({
+        "metric": "intrinsic-reward samples/sec (bonus+update)", "value": value_sps, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "global_B": B * world, "l2": "inputs (3.7 GB frames/GPU) larger than L2",
+                   "engine": args.engine, "parallelism": f"dp{world} over B"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": world * T * B / (float(e2e_ms) * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_ms)},
+        "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""Agent hooks: drop-in for ``RecurrentCategoricalPgAgentBase.curiosity_step`` /
+``curiosity_loss`` (rlpyt/agents/pg/categorical.py:83-130).  They can be bound onto the
+reference agent class; they need ``self.model.curiosity_model``, ``self.device`` and the
+number of actions (from ``self.distribution.dim`` or the model).
+
+Host-to-device staging differs from the reference on purpose: uint8 frame stacks are copied
+once per call with ``non_blocking`` from (ideally pinned) sampler buffers, and RND uploads only
+the newest frame of each stack (7056 of 28224 bytes per sample) since nothing else is read
+(rnd.py:130-131).
+"""
+from collections import namedtuple
+
+import torch
+
+AgentCuriosityStep = namedtuple("AgentCuriosityStep", ["r_int", "agent_curiosity_info"])
+IcmInfo = namedtuple("IcmInfo", [])
+NdigoInfo = namedtuple("NdigoInfo", ["prev_gru_state"])
+RndInfo = namedtuple("RndInfo", [])
+
+
+def _device(agent):
+    dev = torch.device(getattr(agent, "device", "cuda"))
+    if dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _onehot(agent, idx, dev):
+    n = agent.distribution.dim if hasattr(agent, "distribution") else agent.model.curiosity_model.action_size
+    idx = idx.to(dev).long()
+    return torch.zeros(idx.shape + (n,), dtype=torch.float32, device=dev).scatter_(-1, idx.unsqueeze(-1), 1)
+
+
+def newest_frame_to_device(frames, dev):
+    """[T,B,C,H,W] uint8 (host or device) -> device [T,B,1,H,W] holding only the newest frame."""
+    if frames.is_cuda:
+        return frames
+    from .. import _lib as L
+    T, B, C, H, W = frames.shape
+    if frames.dtype != torch.uint8 or not frames.is_contiguous():
+        return frames[:, :, -1:].contiguous().to(dev, non_blocking=True)
+    out = torch.empty((T, B, 1, H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.call("cb_h2d_2d", out.data_ptr(), H * W, frames.data_ptr() + (C - 1) * H * W, C * H * W,
+               H * W, T * B, L.stream())
+    return out
+
+
+@torch.no_grad()
+def curiosity_step(self, curiosity_type, *args):
+    dev = _device(self)
+    cm = self.model.curiosity_model
+    if curiosity_type in ("icm", "disagreement"):
+        observation, next_observation, actions = args
+        r_int = cm.compute_bonus(observation.to(dev, non_blocking=True),
+                                 next_observation.to(dev, non_blocking=True), _onehot(self, actions, dev))
+        info = IcmInfo()
+    elif curiosity_type == "ndigo":
+        observation, prev_actions, actions = args
+        r_int = cm.compute_bonus(observation.to(dev, non_blocking=True), _onehot(self, prev_actions, dev),
+                                 _onehot(self, actions, dev))
+        info = NdigoInfo(prev_gru_state=None)
+    elif curiosity_type == "rnd":
+        next_observation, done = args
+        r_int = cm.compute_bonus(newest_frame_to_device(next_observation, dev), done.to(dev))
+        info = RndInfo()
+    else:
+        raise ValueError(curiosity_type)
+    return AgentCuriosityStep(r_int=r_int.to("cpu"), agent_curiosity_info=info)
+
+
+def curiosity_loss(self, curiosity_type, *args):
+    dev = _device(self)
+    cm = self.model.curiosity_model
+    if curiosity_type in ("icm", "disagreement"):
+        observation, next_observation, actions, valid = args
+        inv, fwd = cm.compute_loss(observation.to(dev, non_blocking=True),
+                                   next_observation.to(dev, non_blocking=True),
+                                   _onehot(self, actions, dev), valid.to(dev))
+        return inv.to("cpu"), fwd.to("cpu")
+    if curiosity_type == "ndigo":
+        observations, prev_actions, actions, valid = args
+        loss = cm.compute_loss(observations.to(dev, non_blocking=True), _onehot(self, prev_actions, dev),
+                               _onehot(self, actions, dev), valid.to(dev))
+        return loss.to("cpu")
+    if curiosity_type == "rnd":
+        next_observation, valid = args
+        loss = cm.compute_loss(newest_frame_to_device(next_observation, dev), valid.to(dev))
+        return loss.to("cpu")
+    raise ValueError(curiosity_type)

@@ -1,0 +1,227 @@
+"""Random Network Distillation on B200 -- drop-in for rlpyt/models/curiosity/rnd.py:15-212.
+
+Same constructor, ``state_dict`` keys (forward_model.{0,2,4,7,9,11}.*, target_model.{0,2,4,7}.*),
+initialisation (orthogonal, gain sqrt 2, zero bias) and method signatures as the reference.
+The ``torch.nn`` modules below are parameter holders only; every forward / backward runs in
+libcuriosity_b200.so.  Differences from the reference, by design:
+  * running statistics stay on the GPU in float64 (no .cpu().numpy() round trips);
+  * ``compute_loss`` takes an optional ``mask`` replaying rnd.py:208-209 for parity tests.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import dist
+from ..layers import Chain, conv_layer, linear_layer
+from ..utils.averages import RunningMeanStd, RewardForwardFilter
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise L.CuriosityLibError(f"{what} must be on a CUDA device (no CPU fallback)")
+
+
+class _RndLoss(torch.autograd.Function):
+    """loss = valid_mean(err * mask); gradients of the predictor are produced by the library
+    during forward (upstream 1) and scaled by the incoming gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, model, observations, valid, mask, *params):
+        loss, grads = model._loss_and_grads(observations, valid, mask,
+                                            need_grad=any(p.requires_grad for p in params))
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.grads
+        out = tuple(None if gr is None else gr * g for gr in grads)
+        return (None, None, None, None) + out
+
+
+class RND(nn.Module):
+    """rnd.py:15-124."""
+
+    def __init__(self, image_shape, prediction_beta=1.0, drop_probability=1.0, gamma=0.99,
+                 device="cpu"):
+        super().__init__()
+        self.prediction_beta = prediction_beta
+        self.drop_probability = drop_probability
+        self.gamma = gamma
+        c, h, w = 1, image_shape[1], image_shape[2]
+        self.image_hw = (h, w)
+        self.feature_size = 512
+        self.conv_feature_size = 7 * 7 * 64
+
+        def trunk():
+            return [nn.Conv2d(1, 32, kernel_size=8, stride=4), nn.LeakyReLU(),
+                    nn.Conv2d(32, 64, kernel_size=4, stride=2), nn.LeakyReLU(),
+                    nn.Conv2d(64, 64, kernel_size=3, stride=1), nn.LeakyReLU(),
+                    nn.Flatten(), nn.Linear(self.conv_feature_size, self.feature_size)]
+
+        self.forward_model = nn.Sequential(*trunk(), nn.ReLU(),
+                                           nn.Linear(self.feature_size, self.feature_size), nn.ReLU(),
+                                           nn.Linear(self.feature_size, self.feature_size))
+        self.target_model = nn.Sequential(*trunk())
+        for net in (self.forward_model, self.target_model):
+            for m in net:
+                if isinstance(m, (nn.Conv2d, nn.Linear)):
+                    nn.init.orthogonal_(m.weight, np.sqrt(2))
+                    m.bias.data.zero_()
+        for p in self.target_model.parameters():
+            p.requires_grad = False
+
+        # running state (rnd.py:34-36), allocated on first use on the parameters' device
+        self.obs_rms = RunningMeanStd(shape=(1, c, h, w))
+        self.rew_rms = RunningMeanStd()
+        self.rew_rff = RewardForwardFilter(gamma)
+        self._chains = None
+        self._norm = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _build(self):
+        dev = self.forward_model[0].weight.device
+        if dev.type != "cuda":
+            raise L.CuriosityLibError("RND parameters must be on a CUDA device (no CPU fallback)")
+        if self._chains is not None and self._dev == dev:
+            return
+        h, w = self.image_hw
+        fm, tm = self.forward_model, self.target_model
+
+        def trunk(net, trainable, fc_act):
+            l1 = conv_layer(net[0], (h, w, 1), "lrelu", trainable)
+            l2 = conv_layer(net[2], (l1.out_h, l1.out_w, 32), "lrelu", trainable)
+            l3 = conv_layer(net[4], (l2.out_h, l2.out_w, 64), "lrelu", trainable)
+            assert l3.out_h == l3.out_w and l3.out_h * l3.out_w * 64 == self.conv_feature_size
+            fc = linear_layer(net[7], fc_act, spatial=(l3.out_h, 64), trainable=trainable)
+            return [l1, l2, l3, fc]
+
+        pred = trunk(fm, True, "relu") + [linear_layer(fm[9], "relu"), linear_layer(fm[11], "none")]
+        self._chains = (Chain(pred), Chain(trunk(tm, False, "none")))
+        self._dev = dev
+        self.obs_rms.to(dev); self.rew_rms.to(dev)
+        px = h * w
+        self._sum = torch.zeros(2, px, dtype=torch.int64, device=dev)
+        self._n_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._mean_len = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._norm = (torch.zeros(px, dtype=torch.float32, device=dev),
+                      torch.ones(px, dtype=torch.float32, device=dev))
+        self._refresh_norm()
+
+    def _refresh_norm(self):
+        """fp32 mean and 1/sqrt(var) of the current obs_rms (rnd.py:162-169)."""
+        self._norm[0].copy_(self.obs_rms._mean)
+        self._norm[1].copy_(self.obs_rms._var.rsqrt())
+
+    def _frame_view(self, obs):
+        """Address the newest frame of each stack in place (rnd.py:130-131): base pointer and
+        element strides (n, h, w, c) of the uint8 [T,B,C,H,W] tensor."""
+        _require_cuda(obs, "observations")
+        if obs.dtype != torch.uint8:
+            raise L.CuriosityLibError("RND expects uint8 frame stacks")
+        if obs.dim() != 5:
+            raise ValueError("RND expects [T,B,C,H,W] observations")
+        obs = obs.contiguous()
+        T, B, Cs, H, W = obs.shape
+        base = obs.data_ptr() + (Cs - 1) * H * W
+        return obs, T, B, base, (Cs * H * W, W, 1, H * W)
+
+    def _forward_nets(self, obs, keep_acts):
+        obs, T, B, base, strides = self._frame_view(obs)
+        n = T * B
+        pred, targ = self._chains
+        _, phi = targ.forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm)
+        acts, phi_hat = pred.forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm)
+        return obs, T, B, base, strides, phi, phi_hat, (acts if keep_acts else None)
+
+    # ------------------------------------------------------------------ bonus
+    @torch.no_grad()
+    def compute_bonus(self, next_observation, done):
+        """rnd.py:181-203 -> fp32 [T,B] on the device."""
+        self._build()
+        obs, T, B, base, strides = self._frame_view(next_observation)
+        done = done.to(self._dev, torch.float32).reshape(T, B).contiguous()
+        st = L.stream()
+        px = self.image_hw[0] * self.image_hw[1]
+        # observation statistics over the first n_valid[b] frames of each env (rnd.py:150-160)
+        n_valid = torch.empty(B, dtype=torch.int32, device=self._dev)
+        L.call("cb_valid_lengths", L.ptr(done), L.ptr(n_valid), L.ptr(self._n_total), T, B, st)
+        self._sum.zero_()
+        L.call("cb_obs_moments_u8", base, strides[0], px, L.ptr(n_valid), T, B,
+               L.ptr(self._sum[0]), L.ptr(self._sum[1]), st)
+        dist.all_reduce_sum_(self._sum)          # exact integer sums: sharded == single process
+        dist.all_reduce_sum_(self._n_total)
+        rms = self.obs_rms
+        L.call("cb_rms_merge_from_sums", L.ptr(self._sum[0]), L.ptr(self._sum[1]),
+               L.ptr(self._n_total), L.ptr(rms._mean), L.ptr(rms._var), L.ptr(rms._count),
+               L.ptr(self._norm[0]), L.ptr(self._norm[1]), px, st)
+        # target / predictor features and per-sample error (rnd.py:174-183)
+        _, _, _, _, _, phi, phi_hat, _ = self._forward_nets(obs, False)
+        err = torch.empty(T, B, dtype=torch.float32, device=self._dev)
+        L.call("cb_rowwise_sqerr", L.ptr(phi_hat), L.ptr(phi), 1.0 / self.feature_size, L.ptr(err),
+               T * B, self.feature_size, st)
+        # reward normalisation (rnd.py:184-203)
+        total = self.rew_rff.update_sequence(err, done)
+        L.call("cb_valid_count", L.ptr(done), L.ptr(self._mean_len), T * B, st)
+        dist.all_reduce_sum_(self._mean_len)
+        self.rew_rms.update_from_values(total, self._mean_len, float(B * dist.world_size()))
+        out = torch.empty_like(err)
+        L.call("cb_rnd_scale_bonus", L.ptr(err), L.ptr(done), L.ptr(self.rew_rms._var),
+               float(self.prediction_beta), L.ptr(out), T * B, st)
+        return out
+
+    # ------------------------------------------------------------------ loss
+    def _loss_and_grads(self, observations, valid, mask, need_grad, inplace=False):
+        self._build()
+        obs, T, B, base, strides, phi, phi_hat, acts = self._forward_nets(observations, need_grad)
+        n, F = T * B, self.feature_size
+        st = L.stream()
+        valid = valid.to(self._dev, torch.float32).reshape(n).contiguous()
+        if mask is None:   # rnd.py:208-209
+            mask = (torch.rand(T, B, device=self._dev) > self.drop_probability).float()
+        mask = mask.to(self._dev, torch.float32).reshape(n).contiguous()
+        err = torch.empty(n, dtype=torch.float32, device=self._dev)
+        L.call("cb_rowwise_sqerr", L.ptr(phi_hat), L.ptr(phi), 1.0 / F, L.ptr(err), n, F, st)
+        coef = torch.empty(n, dtype=torch.float32, device=self._dev)
+        denom = None
+        if dist.world_size() > 1:     # global sum(valid): every rank divides by the same count
+            denom = dist.all_reduce_sum_(valid.sum().reshape(1))
+        L.call("cb_loss_coef", L.ptr(valid), L.ptr(mask), 1.0, L.ptr(denom), L.ptr(coef), n, st)
+        loss = torch.empty(1, dtype=torch.float32, device=self._dev)
+        L.call("cb_dot", L.ptr(err), L.ptr(coef), L.ptr(loss), n, st)
+        params = [p for p in self.forward_model.parameters()]
+        if not need_grad:
+            return loss[0], [None] * len(params)
+        dphi = torch.empty(n, F, dtype=torch.bfloat16, device=self._dev)
+        L.call("cb_sqerr_grad", L.ptr(phi_hat), L.ptr(phi), L.ptr(coef), 1.0 / F, None, 1.0,
+               L.ptr(dphi), n, F, st)
+        if inplace:     # overwrite the existing .grad buffers (views of a flat buffer)
+            self._chains[0].backward(base, acts, dphi, n, in_dtype=L.U8, strides=strides,
+                                     norm=self._norm)
+            return loss[0], None
+        saved = [p.grad for p in params]
+        for p in params:
+            p.grad = None
+        self._chains[0].backward(base, acts, dphi, n, in_dtype=L.U8, strides=strides, norm=self._norm)
+        grads = [p.grad for p in params]
+        for p, g in zip(params, saved):
+            p.grad = g
+        return loss[0], grads
+
+    def compute_loss(self, observations, valid, mask=None):
+        """rnd.py:205-212 -> scalar (autograd-connected to the predictor's parameters)."""
+        params = list(self.forward_model.parameters())
+        return _RndLoss.apply(self, observations, valid, mask, *params)
+
+    def invalidate_weights(self):
+        """Call after the fp32 master weights were updated outside torch's version tracking."""
+        if self._chains is not None:
+            for layer in self._chains[0].layers:
+                layer._version = None
+
+    def loss_and_grads_(self, observations, valid, mask=None):
+        """Fused training entry used by the B200 step driver: computes the loss and leaves the
+        predictor gradients directly in ``.grad`` (no autograd graph, no extra copies)."""
+        loss, _ = self._loss_and_grads(observations, valid, mask, need_grad=True, inplace=True)
+        return loss

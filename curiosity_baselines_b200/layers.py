@@ -1,0 +1,236 @@
+"""Host-side driver for the GEMM-shaped layers of the curiosity models.
+
+A ``GemmLayer`` binds one ``torch.nn.Conv2d`` / ``torch.nn.Linear`` parameter holder (kept only
+so that ``state_dict`` keys match the reference) to the library's conv entry points:
+prepared bf16 weights in the kernel layout, forward, dgrad and wgrad.  ``torch`` is used for
+allocation and for copying gradients into ``param.grad`` -- no arithmetic of the path runs in
+torch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+ACT = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "elu": L.ACT_ELU}
+
+_engine = L.ENGINE_AUTO
+
+
+def set_engine(engine):
+    """Force the engine of every subsequent GEMM-shaped call: 'auto' | 'simt' | 'umma'."""
+    global _engine
+    _engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "umma": L.ENGINE_UMMA}[engine]
+
+
+def get_engine():
+    return _engine
+
+
+class GemmLayer:
+    """One conv / linear layer.
+
+    in_shape  (h, w, c) of the NHWC input (linear: (1, 1, K))
+    k, stride, pad, out_c, act
+    side_dim  extra fp32 input columns concatenated after the c channels (one-hot action,
+              icm.py:19-21); only for linear layers.
+    """
+
+    def __init__(self, module, in_shape, k, stride, pad, out_c, act="none", side_dim=0,
+                 trainable=True):
+        self.module = module
+        self.in_h, self.in_w, self.in_c = in_shape
+        self.k, self.stride, self.pad, self.out_c = k, stride, pad, out_c
+        self.out_h = (self.in_h + 2 * pad - k) // stride + 1
+        self.out_w = (self.in_w + 2 * pad - k) // stride + 1
+        self.act = ACT[act]
+        self.side_dim = side_dim
+        self.trainable = trainable
+        self.K = k * k * self.in_c
+        self.w_fwd = self.w_t = self.bias = self.side_w = None
+        self._version = None
+
+    # ---------------------------------------------------------------- weights
+    def _torch_weight_4d(self):
+        """View of the holder's weight as [out_c, in_c, k, k] (+ the side columns)."""
+        w = self.module.weight
+        if w.dim() == 4:
+            return w, None
+        main = w[:, : self.K] if self.side_dim else w
+        side = w[:, self.K:] if self.side_dim else None
+        # a Linear after a CHW flatten is a kxk conv over the (k,k,c) NHWC map: [o, c*k*k]
+        return main.reshape(self.out_c, self.in_c, self.k, self.k), side
+
+    def prepare(self, force=False):
+        """(Re)build the bf16 kernel-layout copies when the fp32 master weights changed."""
+        w = self.module.weight
+        ver = (w._version, w.data_ptr(), self.module.bias._version)
+        if not force and ver == self._version:
+            return
+        dev = w.device
+        w4, side = self._torch_weight_4d()
+        w4 = w4.detach().contiguous()
+        if self.w_fwd is None:
+            self.w_fwd = torch.empty(self.out_c, self.K, dtype=torch.bfloat16, device=dev)
+            self.w_t = torch.empty(self.in_c, self.k * self.k * self.out_c, dtype=torch.bfloat16,
+                                   device=dev)
+        L.call("cb_prepare_conv_weight", L.ptr(w4), L.ptr(self.w_fwd), L.ptr(self.w_t),
+               self.out_c, self.in_c, self.k, self.k, L.stream())
+        self.bias = self.module.bias.detach()
+        self.side_w = side.detach().contiguous() if side is not None else None
+        self._version = ver
+
+    # ---------------------------------------------------------------- descriptors
+    def desc(self, n, in_dtype=L.BF16, strides=None, act=None):
+        d = L.ConvDesc()
+        d.n = n
+        d.in_h, d.in_w, d.in_c = self.in_h, self.in_w, self.in_c
+        d.k_h = d.k_w = self.k
+        d.stride, d.pad = self.stride, self.pad
+        d.out_h, d.out_w, d.out_c = self.out_h, self.out_w, self.out_c
+        d.in_dtype = in_dtype
+        if strides is None:   # dense NHWC
+            strides = (self.in_h * self.in_w * self.in_c, self.in_w * self.in_c, self.in_c, 1)
+        d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = strides
+        d.act = self.act if act is None else act
+        d.engine = _engine
+        return d
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x, n, in_dtype=L.BF16, strides=None, side=None, residual=None, norm=None,
+                out_bf16=True, out_f32=False):
+        """Returns (bf16 NHWC output or None, fp32 output or None), each [n*out_h*out_w, out_c]."""
+        self.prepare()
+        m = n * self.out_h * self.out_w
+        dev = self.w_fwd.device
+        yb = torch.empty(m, self.out_c, dtype=torch.bfloat16, device=dev) if out_bf16 else None
+        yf = torch.empty(m, self.out_c, dtype=torch.float32, device=dev) if out_f32 else None
+        e = L.Epilogue()
+        e.bias = L.ptr(self.bias)
+        e.residual = L.ptr(residual)
+        if self.side_dim:
+            assert side is not None and side.shape[-1] == self.side_dim
+            e.side, e.side_w, e.side_dim = L.ptr(side), L.ptr(self.side_w), self.side_dim
+        if norm is not None:
+            e.norm_mean, e.norm_rstd = L.ptr(norm[0]), L.ptr(norm[1])
+        e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
+        d = self.desc(n, in_dtype, strides)
+        xp = x if isinstance(x, int) else L.ptr(x)
+        L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(self.w_fwd), C.byref(e), L.stream())
+        return yb, yf
+
+    # ---------------------------------------------------------------- backward
+    def dgrad(self, dy, n, x_saved=None, x_act="none", dx_add=None):
+        """dx (bf16 NHWC [n*in_h*in_w, in_c]) = (dy (*) w + dx_add) .* act'(x_saved)."""
+        self.prepare()
+        dx = torch.empty(n * self.in_h * self.in_w, self.in_c, dtype=torch.bfloat16,
+                         device=dy.device)
+        d = self.desc(n)
+        L.call("cb_conv_dgrad", C.byref(d), L.ptr(dy), L.ptr(self.w_t), L.ptr(x_saved), ACT[x_act],
+               L.ptr(dx_add), L.ptr(dx), L.stream())
+        return dx
+
+    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+        """Weight / bias gradients written (or accumulated) into the holder's ``.grad`` in the
+        torch layout."""
+        if not self.trainable:
+            return
+        dev = dy.device
+        w, b = self.module.weight, self.module.bias
+        if w.grad is None:
+            w.grad = torch.zeros_like(w)
+        if b.grad is None:
+            b.grad = torch.zeros_like(b)
+        beta = 1.0 if accumulate else 0.0
+        direct = self.k == 1 and not self.side_dim and w.dim() == 2
+        dw = w.grad if direct else torch.empty(self.out_c, self.K, dtype=torch.float32, device=dev)
+        d = self.desc(n, in_dtype, strides)
+        xp = x if isinstance(x, int) else L.ptr(x)
+        mean, rstd = (L.ptr(norm[0]), L.ptr(norm[1])) if norm is not None else (None, None)
+        if direct or not accumulate:
+            L.call("cb_conv_wgrad", C.byref(d), xp, L.ptr(dy), mean, rstd, L.ptr(dw),
+                   L.ptr(b.grad), beta if direct else 0.0, L.stream())
+        else:   # dw is scratch (beta 0); the bias gradient must still accumulate
+            db = torch.empty_like(b.grad)
+            L.call("cb_conv_wgrad", C.byref(d), xp, L.ptr(dy), mean, rstd, L.ptr(dw), L.ptr(db),
+                   0.0, L.stream())
+            b.grad.add_(db)
+        if direct:
+            return
+        if not self.side_dim:      # conv, or Linear over a flattened [c,k,k] map
+            g4 = w.grad.view(self.out_c, self.in_c, self.k, self.k)
+            L.call("cb_unprepare_conv_grad", L.ptr(dw), L.ptr(g4), self.out_c, self.in_c, self.k,
+                   self.k, beta, L.stream())
+            return
+        m = n * self.out_h * self.out_w
+        dsw = torch.empty(self.out_c, self.side_dim, dtype=torch.float32, device=dev)
+        L.call("cb_side_wgrad", L.ptr(dy), L.ptr(side), L.ptr(dsw), m, self.out_c, self.side_dim,
+               0.0, L.stream())
+        if accumulate:
+            w.grad[:, : self.K].add_(dw)
+            w.grad[:, self.K:].add_(dsw)
+        else:
+            w.grad[:, : self.K].copy_(dw)
+            w.grad[:, self.K:].copy_(dsw)
+
+def conv_layer(module, in_shape, act, trainable=True):
+    k, s, p = module.kernel_size[0], module.stride[0], module.padding[0]
+    return GemmLayer(module, in_shape, k, s, p, module.out_channels, act, 0, trainable)
+
+
+def linear_layer(module, act="none", side_dim=0, spatial=None, trainable=True):
+    """``spatial=(k, c)``: the Linear consumes a flattened [c,k,k] map (Burda / Maze heads) and is
+    run as a kxk convolution over the NHWC map; otherwise a plain [*, K] GEMM."""
+    if spatial is not None:
+        k, c = spatial
+        return GemmLayer(module, (k, k, c), k, 1, 0, module.out_features, act, 0, trainable)
+    K = module.in_features - side_dim
+    return GemmLayer(module, (1, 1, K), 1, 1, 0, module.out_features, act, side_dim, trainable)
+
+
+class Chain:
+    """A feed-forward stack of GemmLayers (conv encoder + MLP head).
+
+    ``forward`` keeps every layer's bf16 output (needed by wgrad / act' in ``backward``); the
+    last layer can additionally emit fp32 (features entering a loss stay in fp32 so the
+    squared-error / variance epilogues do not see bf16 cancellation).
+    """
+
+    ACT_NAME = {v: k for k, v in ACT.items()}
+
+    def __init__(self, layers):
+        self.layers = layers
+
+    def forward(self, x, n, in_dtype=L.BF16, strides=None, norm=None, last_f32=True,
+                last_bf16=False):
+        acts = []
+        cur = x
+        last = len(self.layers) - 1
+        out_f32 = None
+        for i, layer in enumerate(self.layers):
+            kw = dict(in_dtype=in_dtype, strides=strides, norm=norm) if i == 0 else {}
+            want_f32 = last_f32 and i == last
+            want_bf16 = (i != last) or last_bf16 or not last_f32
+            yb, yf = layer.forward(cur, n, out_bf16=want_bf16, out_f32=want_f32, **kw)
+            acts.append(yb)
+            cur = yb
+            if i == last:
+                out_f32 = yf
+        return acts, out_f32
+
+    def backward(self, x, acts, dy, n, in_dtype=L.BF16, strides=None, norm=None, accumulate=False,
+                 need_dx=False, x_saved=None, x_act="none"):
+        """dy: bf16 gradient w.r.t. the last layer's (pre-loss) output.  Fills ``.grad`` of all
+        trainable holders; returns the gradient w.r.t. the chain input when ``need_dx``."""
+        for i in range(len(self.layers) - 1, -1, -1):
+            layer = self.layers[i]
+            if i == 0:
+                layer.wgrad(x, dy, n, in_dtype=in_dtype, strides=strides, norm=norm,
+                            accumulate=accumulate)
+                if need_dx:
+                    return layer.dgrad(dy, n, x_saved=x_saved, x_act=x_act)
+                return None
+            prev = self.layers[i - 1]
+            layer.wgrad(acts[i - 1], dy, n, accumulate=accumulate)
+            dy = layer.dgrad(dy, n, x_saved=acts[i - 1], x_act=self.ACT_NAME[prev.act])
+        return None

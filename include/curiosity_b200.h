@@ -1,0 +1,229 @@
+/*
+ * curiosity_b200.h -- C ABI of libcuriosity_b200.so: the B200 (sm_100a) implementation of
+ * the intrinsic-reward hot path of Improbable-AI/curiosity_baselines.
+ *
+ * The reference has no native ABI for this path: it is a Python object protocol
+ * (`curiosity_model.compute_bonus/compute_loss`, the free functions in
+ * rlpyt/algos/utils.py).  Each entry point below names the reference lines whose
+ * arithmetic it replaces; the Python host in curiosity_baselines_b200/ sequences them
+ * behind the reference's own class/function signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - plain pointers and sizes only, no framework types; `stream` is a cudaStream_t
+ *     passed as void* (NULL = default stream);
+ *   - the library never allocates or frees caller memory; scratch space is passed in
+ *     (`ws`, sized by the matching *_workspace_bytes query);
+ *   - returns 0 on success, <0 on error (CB_E_*); cb_last_error() gives the message of
+ *     the last failing call on the calling thread;
+ *   - launches are asynchronous on `stream`; no global mutable state, re-entrant per
+ *     stream; one CUDA context (the primary context) per process;
+ *   - layouts: rollout tensors are time-major [T,B,...]; frames are uint8 NCHW exactly as
+ *     the sampler writes them; activations between layers are bf16 NHWC; "prepared"
+ *     weights are bf16 [C_out][k_h][k_w][C_in] (see cb_prepare_* in the Python host).
+ */
+#ifndef CURIOSITY_B200_H
+#define CURIOSITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK            0
+#define CB_E_ARG        -1   /* bad shape / null pointer / unsupported combination */
+#define CB_E_ALIGN      -2   /* pointer or stride not aligned as the kernel requires */
+#define CB_E_CUDA       -3   /* a CUDA runtime / driver call failed */
+#define CB_E_ARCH       -4   /* device is not sm_100 (tcgen05 kernels) */
+#define CB_E_WORKSPACE  -5   /* workspace too small */
+
+/* element types of gathered inputs */
+#define CB_U8    0
+#define CB_BF16  1
+#define CB_F32   2
+
+/* activations (encoders.py / icm.py / rnd.py) */
+#define CB_ACT_NONE   0
+#define CB_ACT_RELU   1
+#define CB_ACT_LRELU  2      /* negative slope 0.01, torch default */
+#define CB_ACT_ELU    3      /* alpha 1 */
+
+/* execution engine for the GEMM-shaped ops */
+#define CB_ENGINE_AUTO  0    /* tcgen05 where a specialisation exists, else SIMT */
+#define CB_ENGINE_SIMT  1    /* generic CUDA-core implicit GEMM (any shape) */
+#define CB_ENGINE_UMMA  2    /* tcgen05/TMEM/TMA; CB_E_ARG if shape unsupported */
+
+const char* cb_last_error(void);
+int         cb_version(void);
+/* 1 if the current device can run the tcgen05 kernels (compute capability 10.x) */
+int         cb_device_supports_umma(void);
+
+/* ------------------------------------------------------------------------------------
+ * Returns / advantages over T, parallel over B.     rlpyt/algos/utils.py
+ * All tensors fp32 [T,B] row-major (b contiguous); bootstrap [B]; done is 0/1 float.
+ * Bit-exact with the reference's fp32 operation order (no FMA contraction).
+ * ---------------------------------------------------------------------------------- */
+/* algos/utils.py:8-21 */
+int cb_discount_return(const float* reward, const float* done, const float* bootstrap,
+                       float discount, float* return_, int T, int B, void* stream);
+/* algos/utils.py:24-40 */
+int cb_gae(const float* reward, const float* value, const float* done, const float* bootstrap,
+           float discount, float gae_lambda, float* advantage, float* return_,
+           int T, int B, void* stream);
+/* algos/utils.py:104-112 */
+int cb_valid_from_done(const float* done, float* valid, int T, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Running statistics.     rlpyt/utils/averages.py:41-89, models/curiosity/rnd.py:150-203
+ * A RunningMeanStd state is three device arrays: mean[n] f64, var[n] f64, count[1] f64.
+ * ---------------------------------------------------------------------------------- */
+/* rnd.py:150-152: n_valid[b] = sum_t |done[t,b]-1| (int32 [B]); also total -> *n_total */
+int cb_valid_lengths(const float* done, int32_t* n_valid, int64_t* n_total, int T, int B,
+                     void* stream);
+/* rnd.py:153-160 + averages.py:48-52: exact integer per-pixel sums over the frames
+ * (t,b) with t < n_valid[b].  frames: uint8, frame (t,b) starts at
+ * frames + (t*B+b)*frame_stride bytes and has `pixels` bytes (pixels % 16 == 0,
+ * frame_stride % 16 == 0).  sum/sumsq: uint64 [pixels], must be zeroed by the caller. */
+int cb_obs_moments_u8(const uint8_t* frames, int64_t frame_stride, int pixels,
+                      const int32_t* n_valid, int T, int B,
+                      unsigned long long* sum, unsigned long long* sumsq, void* stream);
+/* averages.py:54-68 (Chan merge) from the integer sums; also emits fp32 mean and
+ * 1/sqrt(var) (rnd.py:162-169) for the conv-1 loader. */
+int cb_rms_merge_from_sums(const unsigned long long* sum, const unsigned long long* sumsq,
+                           const int64_t* n_total, double* mean, double* var, double* count,
+                           float* mean_f32, float* rstd_f32, int pixels, void* stream);
+/* averages.py:75-89 driven as rnd.py:186-189: per-env discounted running sum over T with
+ * the not-done mask |done-1|; rewems[B] persists across calls; *initialized is 0 before the first
+ * call (first row seeds all envs unmasked) and set to 1.  total[T,B] receives the copy
+ * returned at each step. */
+int cb_reward_filter(const float* rews, const float* done, float gamma, float* rewems,
+                     int32_t* initialized, float* total, int T, int B, void* stream);
+/* rnd.py:190-193 / algos/pg/base.py:77-81, stage 1: sums = {sum x, sum x^2, n} in f64
+ * (deterministic; ws >= 2048 f64).  A data-parallel host all-reduces `sums` before stage 2. */
+int cb_moments_partial(const float* x, int64_t n, double* sums, double* ws, void* stream);
+/* stage 2, averages.py:54-68: merge mean/var from `sums` into the scalar running state with
+ * batch_count = *count_num / count_den (rnd.py:190-193: mean valid length), or n when
+ * count_num is NULL (algos/pg/base.py:81). */
+int cb_rms_merge_moments(const double* sums, const double* count_num, double count_den,
+                         double* mean, double* var, double* count, void* stream);
+/* out[0] = sum |done-1| over n elements (numerator of the mean valid length, rnd.py:190) */
+int cb_valid_count(const float* done, double* out, int64_t n, void* stream);
+/* algos/pg/base.py:95-103: out = (x - mean_m) / max(std_m, floor) with mean/unbiased std over
+ * the elements where mask > 0 (all when mask is NULL) */
+int cb_masked_normalize(const float* x, const float* mask, float floor_std, float* out,
+                        int64_t n, void* stream);
+/* rnd.py:198-203: r = beta * err / sqrt(var) * |done-1| */
+int cb_rnd_scale_bonus(const float* err, const float* done, const double* rew_var,
+                       float beta, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GEMM-shaped layers (convolution as implicit GEMM; Linear is the 1x1 case).
+ * encoders.py:7-119, icm.py:9-43,88-92, rnd.py:54-117.
+ * ---------------------------------------------------------------------------------- */
+typedef struct cb_conv_desc {
+    int32_t n;                       /* samples (T*B) */
+    int32_t in_h, in_w, in_c;        /* input extent */
+    int32_t k_h, k_w, stride, pad;   /* filter */
+    int32_t out_h, out_w, out_c;     /* output extent (NHWC bf16) */
+    int32_t in_dtype;                /* CB_U8 or CB_BF16 */
+    int64_t in_stride_n, in_stride_h, in_stride_w, in_stride_c;  /* in elements */
+    int32_t act;                     /* activation applied to the output */
+    int32_t engine;                  /* CB_ENGINE_* */
+} cb_conv_desc;
+
+typedef struct cb_epilogue {
+    const float*   bias;             /* [out_c] or NULL */
+    const void*    residual;         /* bf16 [M,out_c] added after the activation, or NULL */
+    const float*   side;             /* fp32 [M,side_dim]: extra input columns (one-hot action) */
+    const float*   side_w;           /* fp32 [out_c,side_dim]: their weights (icm.py:19-21) */
+    int32_t        side_dim;
+    const float*   norm_mean;        /* CB_U8 input only: per-pixel mean  [in_h*in_w] (rnd.py:169) */
+    const float*   norm_rstd;        /* per-pixel 1/sqrt(var); input clamped to [-5,5] */
+    void*          out_bf16;         /* bf16 [M,out_c] or NULL */
+    float*         out_f32;          /* fp32 [M,out_c] or NULL */
+} cb_epilogue;
+
+/* y = act(conv(x, w) + bias + side*side_w) + residual.   w: bf16 [out_c][k_h][k_w][in_c] */
+int cb_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e,
+                void* stream);
+/* dx = (dy (*) w + dx_add) .* act'(x_saved).  dy: bf16 [n,out_h,out_w,out_c];
+ * w_t: bf16 [in_c][k_h][k_w][out_c]; x_saved: the bf16 NHWC *output* of the layer that
+ * produced x (its activation x_act decides act'), or NULL; dx_add: bf16 gradient arriving
+ * at x over a skip connection (icm.py:22), or NULL; dx: bf16 NHWC [n,in_h,in_w,in_c] */
+int cb_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved,
+                  int32_t x_act, const void* dx_add, void* dx, void* stream);
+/* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise
+ * (NULL to skip).  x addressed as in cb_conv_fwd (norm_* honoured for CB_U8). */
+int cb_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
+                  const float* norm_rstd, float* dw, float* dbias, float beta, void* stream);
+/* side-input weight gradient: dsw[out_c,side_dim] = beta*dsw + dy^T side */
+int cb_side_wgrad(const void* dy, const float* side, float* dsw, int64_t m, int32_t out_c,
+                  int32_t side_dim, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Per-sample losses / bonuses (row-wise reductions).
+ * ---------------------------------------------------------------------------------- */
+/* icm.py:133, rnd.py:183: out[m] = scale * sum_f (pred[m,f]-target[m,f])^2  (fp32 in) */
+int cb_rowwise_sqerr(const float* pred, const float* target, float scale, float* out,
+                     int64_t m, int32_t f, void* stream);
+/* d/dpred of sum_m coef[m]*out[m]: dpred[m,f] (bf16) = 2*scale*coef[m]*(pred-target);
+ * optional elementwise keep-mask/(1-p) (disagreement.py:155) */
+int cb_sqerr_grad(const float* pred, const float* target, const float* coef, float scale,
+                  const float* elem_mask, float elem_scale, void* dpred_bf16,
+                  int64_t m, int32_t f, void* stream);
+/* disagreement.py:155-164: out[m] = scale*sum_f mask[m,f]*elem_scale*(pred-target)^2 */
+int cb_rowwise_sqerr_masked(const float* pred, const float* target, const float* elem_mask,
+                            float elem_scale, float scale, float* out, int64_t m, int32_t f,
+                            void* stream);
+/* disagreement.py:136-140: out[m] = beta * mean_f var_e(pred[e][m,f]) (unbiased, two-pass);
+ * preds: E pointers to fp32 [m,f] packed in a device array of pointers */
+int cb_ensemble_variance(const float* const* preds, int32_t e, float beta, float* out,
+                         int64_t m, int32_t f, void* stream);
+/* icm.py:141: per-row cross entropy of logits[m,a] against argmax(onehot[m,:]);
+ * dlogits (fp32, may be NULL) = coef[m]*(softmax-onehot_of_argmax) */
+int cb_cross_entropy(const float* logits, const float* onehot, const float* coef, float* loss,
+                     float* dlogits, int64_t m, int32_t a, void* stream);
+/* utils/tensor.py:39-46: out[0] = sum(x*w)/sum(w) (w NULL -> mean); deterministic order.
+ * Also writes out[1] = sum(w). */
+int cb_weighted_mean(const float* x, const float* w, float* out, int64_t n, void* stream);
+/* out[0] = sum_i x[i]*w[i] (f64 accumulation, fixed order) */
+int cb_dot(const float* x, const float* w, float* out, int64_t n, void* stream);
+/* coef[m] = upstream * mask[m]*valid[m]/D with D = *denom when given (the all-reduced
+ * sum(valid) of a sharded batch) else the local sum(valid); mask may be NULL */
+int cb_loss_coef(const float* valid, const float* mask, float upstream, const float* denom,
+                 float* coef, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser.   ppo.py:147-150 (clip_grad_norm_ over all params, then Adam.step)
+ * ---------------------------------------------------------------------------------- */
+/* out[0] += sum g^2 over n elements (caller zeroes out; call once per flat buffer) */
+int cb_sumsq(const float* g, int64_t n, double* out, void* stream);
+/* scale = min(1, max_norm/(sqrt(*sumsq)+1e-6)); Adam (torch defaults: no amsgrad, L2 wd=0)
+ * p,m,v,g fp32 flat; step is the 1-based step count for bias correction. */
+int cb_adam_clip_step(float* p, float* m, float* v, const float* g, int64_t n,
+                      const double* sumsq, float max_norm, float lr, float beta1, float beta2,
+                      float eps, int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Layout helpers for prepared weights.
+ * ---------------------------------------------------------------------------------- */
+/* torch conv weight fp32 [o][i][kh][kw] -> bf16 [o][kh][kw][i] and bf16 [i][kh][kw][o] */
+int cb_prepare_conv_weight(const float* w, void* w_fwd, void* w_t, int32_t o, int32_t i,
+                           int32_t kh, int32_t kw, void* stream);
+/* inverse for gradients: fp32 [o][kh][kw][i] -> fp32 [o][i][kh][kw] (dst = beta*dst + src) */
+int cb_unprepare_conv_grad(const float* g, float* dst, int32_t o, int32_t i, int32_t kh,
+                           int32_t kw, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Staging.  agents/pg/categorical.py:89-99 (buffer_to(device)) for the uint8 frame stacks.
+ * ---------------------------------------------------------------------------------- */
+/* rows x width_bytes from (pinned) host memory with pitch src_pitch to device memory with
+ * pitch dst_pitch, asynchronously on `stream`. */
+int cb_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch,
+              int64_t width_bytes, int64_t rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURIOSITY_B200_H */

@@ -1,0 +1,107 @@
+"""RND on the GPU vs the reference's golden vectors and vs the oracle on larger seeded batches.
+Tolerance (north_star): per-sample bonus and loss within 1e-2 relative (bf16 operands, fp32
+accumulation); running statistics within 1e-5 relative of the float64 reference."""
+import numpy as np
+import pytest
+import torch
+
+import recipes as R
+from helpers import golden, rel_err, check_grads
+from oracle import curiosity_oracle as O
+from curiosity_baselines_b200.curiosity.rnd import RND
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_model(params, **kw):
+    m = RND(image_shape=(4, 84, 84), **kw).to(DEV)
+    missing = m.load_state_dict(params)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m
+
+
+def test_state_dict_keys_match_reference():
+    m = RND(image_shape=(4, 84, 84))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(R.rnd_shapes())
+    assert all(not p.requires_grad for p in m.target_model.parameters())
+
+
+def test_golden_three_batches_then_loss():
+    g = golden("rnd")
+    T, B, seed = int(g["T"]), int(g["B"]), int(g["seed"])
+    m = make_model(R.make_params(R.rnd_shapes(), seed, gain=1.4), prediction_beta=1.0,
+                   drop_probability=0.25, gamma=0.99)
+    for it in range(3):
+        frames = R.make_frames(seed + 10 * it, T, B).to(DEV)
+        done = R.make_suffix_done(seed + 10 * it + 1, T, B, frac=0.6).to(DEV)
+        bonus = m.compute_bonus(frames, done)
+        assert rel_err(bonus.cpu(), g[f"bonus{it}"]) < 1e-2, it
+        np.testing.assert_allclose(m.obs_rms.mean, g[f"obs_mean{it}"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(m.obs_rms.var, g[f"obs_var{it}"], rtol=1e-9)
+        assert np.isclose(m.obs_rms.count, g[f"obs_count{it}"], rtol=1e-12)
+        assert np.isclose(m.rew_rms.count, g[f"rew_count{it}"], rtol=1e-6)
+        assert np.isclose(m.rew_rms.var, g[f"rew_var{it}"], rtol=2e-2)     # inherits the bf16 error of err
+        np.testing.assert_allclose(m.rew_rff.rewems, g[f"rewems{it}"], rtol=1e-2)
+    frames = R.make_frames(seed + 20, T, B).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 22, T, B, frac=0.5)).to(DEV)
+    mask = R.make_mask(seed + 23, (T, B), 0.25).to(DEV)
+    loss = m.compute_loss(frames, valid, mask)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-2
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert len(grads) == 12
+    bad = check_grads(grads, g, cos_min=0.999, norm_tol=1e-2)
+    assert not bad, bad
+    assert all(p.grad is None for p in m.target_model.parameters())
+
+
+@pytest.mark.parametrize("T,B,frac", [(16, 8, 0.5), (3, 1, 0.0), (32, 6, 1.0)])
+def test_oracle_parity_larger_batches(T, B, frac):
+    seed = 900 + T
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    m = make_model(params, prediction_beta=0.5, drop_probability=0.0, gamma=0.99)
+    o = O.RndOracle(prediction_beta=0.5, drop_probability=0.0, gamma=0.99)
+    for it in range(2):
+        frames = R.make_frames(seed + it, T, B)
+        done = R.make_suffix_done(seed + 50 + it, T, B, frac=frac)
+        if frac == 1.0:
+            done[0] = 0            # keep at least one valid frame per env
+        b_ref = o.compute_bonus(params, frames, done)
+        b = m.compute_bonus(frames.to(DEV), done.to(DEV)).cpu()
+        nz = b_ref.abs() > 0
+        assert torch.equal(b == 0, ~nz)
+        assert float(((b - b_ref).abs()[nz] / b_ref.abs()[nz]).max()) < 1e-2
+    valid = O.valid_from_done(done)
+    p = {k: v.clone().requires_grad_(k.startswith("forward")) for k, v in params.items()}
+    l_ref = o.compute_loss(p, frames, valid, torch.ones(T, B))
+    l_ref.backward()
+    loss = m.compute_loss(frames.to(DEV), valid.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(l_ref)) / float(l_ref) < 1e-2
+    for k, prm in m.named_parameters():
+        if not k.startswith("forward"):
+            continue
+        gref = p[k].grad
+        g = prm.grad.cpu()
+        cos = float((g.flatten() @ gref.flatten()) / (g.norm() * gref.norm()))
+        assert cos > 0.999 and abs(float(g.norm() / gref.norm()) - 1) < 1e-2, (k, cos)
+
+
+def test_loss_is_zero_with_reference_default_drop_probability():
+    """arguments.py:100 default drop_probability=1.0 zeroes the loss."""
+    m = RND(image_shape=(4, 84, 84)).to(DEV)
+    frames = R.make_frames(5, 4, 2).to(DEV)
+    loss = m.compute_loss(frames, torch.ones(4, 2, device=DEV))
+    assert float(loss) == 0.0
+
+
+def test_upstream_gradient_scaling():
+    m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    frames = R.make_frames(6, 4, 3).to(DEV)
+    valid = torch.ones(4, 3, device=DEV)
+    m.compute_loss(frames, valid).backward()
+    g1 = m.forward_model[11].weight.grad.clone()
+    m.zero_grad()
+    (3.0 * m.compute_loss(frames, valid)).backward()
+    assert torch.allclose(m.forward_model[11].weight.grad, 3 * g1, rtol=1e-5, atol=1e-8)

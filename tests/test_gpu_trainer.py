@@ -1,0 +1,78 @@
+"""The fused step driver (bonus -> returns -> loss/grad -> clip -> Adam) vs the same sequence
+on the CPU oracle with torch.optim.Adam + clip_grad_norm_ (ppo.py:147-150)."""
+import pytest
+import torch
+
+import recipes as R
+from oracle import curiosity_oracle as O
+from curiosity_baselines_b200.curiosity.rnd import RND
+from curiosity_baselines_b200.trainer import RndStep, FlatAdam
+from curiosity_baselines_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_flat_adam_matches_torch():
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in [(5, 7), (33,), (4, 3, 2, 2)]]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt_ref = torch.optim.Adam(ref, lr=1e-2)
+    opt = FlatAdam(ps, lr=1e-2, max_norm=0.5)
+    for it in range(4):
+        for p, q in zip(ps, ref):
+            g = torch.randn_like(q) * (it + 1)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        opt_ref.step()
+        opt.step()
+        for p, q in zip(ps, ref):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), it
+
+
+def test_rnd_step_against_oracle_two_iterations():
+    T, B, seed = 12, 6, 77
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    model = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    model.load_state_dict(params)
+    step = RndStep(model, lr=1e-3)
+    o = O.RndOracle(drop_probability=0.0)
+    p = {k: v.clone().requires_grad_(k.startswith("forward")) for k, v in params.items()}
+    train = [v for k, v in p.items() if k.startswith("forward")]
+    opt = torch.optim.Adam(train, lr=1e-3)
+    for it in range(2):
+        frames = R.make_frames(seed + it, T, B)
+        done = R.make_suffix_done(seed + 10 + it, T, B, frac=0.4)
+        value, boot = R.make_normal(seed + 20 + it, T, B), R.make_normal(seed + 30 + it, B)
+        loss, r_int, adv, ret = step(frames.to(DEV), done.to(DEV), torch.zeros(T, B, device=DEV),
+                                     value.to(DEV), boot.to(DEV), torch.ones(T, B, device=DEV))
+        r_ref = o.compute_bonus(p, frames, done)
+        a_ref, ret_ref = O.generalized_advantage_estimation(r_ref.clone(), value, done, boot, 0.99, 0.95)
+        valid = O.valid_from_done(done)
+        opt.zero_grad()
+        l_ref = o.compute_loss(p, frames, valid, torch.ones(T, B))
+        l_ref.backward()
+        gn_ref = float(torch.nn.utils.clip_grad_norm_(train, 1.0))
+        opt.step()
+        assert abs(float(loss) - float(l_ref)) / float(l_ref) < 1e-2, it
+        assert abs(step.opt.grad_norm() - gn_ref) / gn_ref < 1e-2, it
+        assert float((adv.cpu() - a_ref).abs().max() / a_ref.abs().max()) < 1e-2
+        assert float((ret.cpu() - ret_ref).abs().max() / ret_ref.abs().max()) < 1e-2
+    # parameter updates point the same way
+    for k, prm in model.named_parameters():
+        if not k.startswith("forward"):
+            assert torch.equal(prm.cpu(), params[k])          # target stays frozen
+            continue
+        d = (prm.detach().cpu() - params[k]).flatten()
+        d_ref = (p[k].detach() - params[k]).flatten()
+        cos = float(d @ d_ref / (d.norm() * d_ref.norm()))
+        assert cos > 0.97, (k, cos)
+
+
+def test_host_staging_of_newest_frame():
+    from curiosity_baselines_b200.agents.hooks import newest_frame_to_device
+    frames = R.make_frames(3, 5, 4).pin_memory()
+    out = newest_frame_to_device(frames, torch.device(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), frames[:, :, -1:])
