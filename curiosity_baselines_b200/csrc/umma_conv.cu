@@ -1,18 +1,313 @@
-// tcgen05 engine entry points (placeholder until the kernels land: reports "unsupported" so
-// CB_ENGINE_AUTO falls through to the SIMT engine and CB_ENGINE_UMMA fails loudly).
-#include "common.cuh"
+// tcgen05 engine: host side.  Maps a cb_conv_desc onto the TMA-gather GEMM of umma_gemm.cuh by
+// choosing a tensor-map *view* of the activation tensor under which every 64-wide k-block of the
+// implicit GEMM is one TMA box:
+//
+//   linear / flatten-linear   [rows, K]                        rank 2, box {64, rows}
+//   stride-1 conv, C%64==0    NHWC as (c, w, h, n)             rank 4, box {64, out_w, out_h, S}
+//                             start (c0, kw-pad, kh-pad, n0): out-of-range pixels are zero-filled
+//                             by TMA, which is exactly the zero padding (and the "full" correlation
+//                             of a stride-1 dgrad, run as a pad = k-1 forward over dy)
+//   stride-2 conv, C==32      NHWC [n][h][w][32] re-read as [n][h/2][2][w/2][64]: two horizontally
+//                             adjacent pixels form one 128-byte k-block row (rank 5, box
+//                             {64, out_w, 1, out_h, S})
+//
+// S = samples per tile so that S*out_h*out_w <= 256 rows (two M=128 UMMA sub-tiles).
+#include "umma_gemm.cuh"
+#include <mutex>
+
 namespace cb {
-bool umma_supports_fwd(const cb_conv_desc*, const cb_epilogue*) { return false; }
-bool umma_supports_dgrad(const cb_conv_desc*) { return false; }
+
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor map; dims[0] is the contiguous dimension; strides_bytes has rank-1 entries
+int encode_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
+    EncodeFn enc = get_encode();
+    CB_REQUIRE(enc, CB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    CB_REQUIRE(((uintptr_t)base & 15) == 0, CB_E_ALIGN, "TMA base address not 16-byte aligned");
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        CB_REQUIRE(strides_bytes[i] % 16 == 0, CB_E_ALIGN, "TMA stride %d (%llu B) not a multiple of 16", i,
+                   (unsigned long long)strides_bytes[i]);
+        gs[i] = strides_bytes[i];
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CB_REQUIRE(r == CUDA_SUCCESS, CB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CB_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+bool device_ok() {
+    static int ok = -1;
+    if (ok < 0) ok = cb_device_supports_umma();
+    return ok == 1;
+}
+
+void identity_map(umma::CoordMap& m) {
+    for (int i = 0; i < 5; ++i) { m.div[i] = 1; m.mod[i] = 1; m.mul[i] = 0; }   // (idx/1 % 1)*0 == 0
+}
+
+struct Plan {
+    CUtensorMap tmA, tmB;
+    umma::GemmParams p;
+    int bn, mt;
+};
+
+template <int BN, int MT>
+int launch(const Plan& pl, cudaStream_t s) {
+    using Cfg = umma::GemmConfig<BN, MT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CB_CUDA(cudaFuncSetAttribute(umma::umma_gemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int tiles = pl.p.m_tiles * pl.p.n_tiles;
+    int grid = tiles < sm_count() ? tiles : sm_count();
+    umma::umma_gemm_kernel<BN, MT><<<grid, 192, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int dispatch(const Plan& pl, cudaStream_t s) {
+    switch (pl.bn * 10 + pl.mt) {
+        case 2561: return launch<256, 1>(pl, s);
+        case 2241: return launch<224, 1>(pl, s);
+        case 1282: return launch<128, 2>(pl, s);
+        case 642:  return launch<64, 2>(pl, s);
+        case 322:  return launch<32, 2>(pl, s);
+        default:   return fail(CB_E_ARG, "umma: no kernel for BN=%d MT=%d", pl.bn, pl.mt);
+    }
+}
+
+int pick_bn(int n_total, int* mt) {
+    if (n_total % 256 == 0) { *mt = 1; return 256; }
+    if (n_total % 128 == 0) { *mt = 2; return 128; }
+    if (n_total % 224 == 0) { *mt = 1; return 224; }
+    if (n_total % 64 == 0)  { *mt = 2; return 64; }
+    if (n_total % 32 == 0)  { *mt = 2; return 32; }
+    return 0;
+}
+
+// ---- the three A views ---------------------------------------------------------------------
+enum View { VIEW_NONE = 0, VIEW_ROWS, VIEW_CONV_S1, VIEW_CONV_S2 };
+
+// geometry of an implicit GEMM whose A operand is a bf16 NHWC tensor [n, h, w, c]
+struct Geo {
+    int n, h, w, c;            // tensor read by TMA
+    int kh, kw, stride, pad;   // filter walk
+    int oh, ow;                // rows per sample = oh*ow
+};
+
+View classify(const Geo& g) {
+    if (g.kh == g.h && g.kw == g.w && g.pad == 0 && g.oh == 1 && g.ow == 1 && (g.h * g.w * g.c) % 8 == 0)
+        return VIEW_ROWS;                                   // linear, or Linear over a flattened map
+    if (g.stride == 1 && g.c % 64 == 0 && g.oh * g.ow <= 256 && g.ow <= 256 && g.oh <= 256) return VIEW_CONV_S1;
+    if (g.stride == 2 && g.c == 32 && g.pad == 0 && g.kw % 2 == 0 && g.w % 2 == 0 && g.h % 2 == 0 &&
+        g.oh * g.ow <= 256)
+        return VIEW_CONV_S2;
+    return VIEW_NONE;
+}
+
+// fills tmA and the A-related params; `x` is the bf16 NHWC tensor
+int plan_a(Plan& pl, const Geo& g, const void* x, int mt) {
+    umma::GemmParams& p = pl.p;
+    identity_map(p.a_tile);
+    identity_map(p.a_kb);
+    View v = classify(g);
+    const int max_rows = mt * 128;
+    if (v == VIEW_ROWS) {
+        const uint64_t K = (uint64_t)g.h * g.w * g.c;
+        uint64_t dims[2] = {K, (uint64_t)g.n};
+        uint64_t strides[1] = {K * 2};
+        uint32_t box[2] = {64, (uint32_t)max_rows};
+        int rc = encode_bf16(&pl.tmA, x, 2, dims, strides, box); if (rc) return rc;
+        p.a_rank = 2;
+        p.a_kb.div[0] = 1; p.a_kb.mod[0] = 0; p.a_kb.mul[0] = 64;
+        p.a_tile.div[1] = 1; p.a_tile.mod[1] = 0; p.a_tile.mul[1] = max_rows;
+        p.kb_count = (int)((K + 63) / 64);
+        p.rows_per_tile = max_rows;
+        p.a_box_bytes = max_rows * 128;
+        p.m_total = g.n;
+        p.m_tiles = (g.n + max_rows - 1) / max_rows;
+        return CB_OK;
+    }
+    const int P = g.oh * g.ow;
+    int S = max_rows / P; if (S < 1) return fail(CB_E_ARG, "umma: %d rows per sample exceed the tile", P);
+    if (S > 256) S = 256;
+    p.rows_per_tile = S * P;
+    p.a_box_bytes = S * P * 128;
+    p.m_total = (long long)g.n * P;
+    p.m_tiles = (g.n + S - 1) / S;
+    if (v == VIEW_CONV_S1) {
+        const int cb = g.c / 64;
+        uint64_t dims[4] = {(uint64_t)g.c, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+        uint64_t strides[3] = {(uint64_t)g.c * 2, (uint64_t)g.w * g.c * 2, (uint64_t)g.h * g.w * g.c * 2};
+        uint32_t box[4] = {64, (uint32_t)g.ow, (uint32_t)g.oh, (uint32_t)S};
+        int rc = encode_bf16(&pl.tmA, x, 4, dims, strides, box); if (rc) return rc;
+        p.a_rank = 4;
+        // k-block kb = ((kh*KW)+kw)*cb + c64   ->  (c64*64, kw-pad, kh-pad)
+        p.a_kb.div[0] = 1;            p.a_kb.mod[0] = cb;   p.a_kb.mul[0] = 64;
+        p.a_kb.div[1] = cb;           p.a_kb.mod[1] = g.kw; p.a_kb.mul[1] = 1;
+        p.a_kb.div[2] = cb * g.kw;    p.a_kb.mod[2] = 0;    p.a_kb.mul[2] = 1;
+        p.a_tile.div[3] = 1; p.a_tile.mod[3] = 0; p.a_tile.mul[3] = S;
+        p.kb_count = g.kh * g.kw * cb;
+        p.a_off[1] = -g.pad; p.a_off[2] = -g.pad;
+        return CB_OK;
+    }
+    if (v == VIEW_CONV_S2) {
+        // [n][h][w][32] == [n][h/2][2][w/2][64]
+        uint64_t dims[5] = {64, (uint64_t)g.w / 2, 2, (uint64_t)g.h / 2, (uint64_t)g.n};
+        uint64_t strides[4] = {128, (uint64_t)g.w * 64, (uint64_t)g.w * 128, (uint64_t)g.h * g.w * 64};
+        uint32_t box[5] = {64, (uint32_t)g.ow, 1, (uint32_t)g.oh, (uint32_t)S};
+        int rc = encode_bf16(&pl.tmA, x, 5, dims, strides, box); if (rc) return rc;
+        p.a_rank = 5;
+        const int kw2 = g.kw / 2;
+        // k-block kb = kh*kw2 + j  (j = kw pair)  ->  (0, j, kh%2, kh/2)
+        p.a_kb.div[1] = 1;        p.a_kb.mod[1] = kw2; p.a_kb.mul[1] = 1;
+        p.a_kb.div[2] = kw2;      p.a_kb.mod[2] = 2;   p.a_kb.mul[2] = 1;
+        p.a_kb.div[3] = kw2 * 2;  p.a_kb.mod[3] = 0;   p.a_kb.mul[3] = 1;
+        p.a_tile.div[4] = 1; p.a_tile.mod[4] = 0; p.a_tile.mul[4] = S;
+        p.kb_count = g.kh * kw2;
+        return CB_OK;
+    }
+    return fail(CB_E_ARG, "umma: unsupported A view");
+}
+
+int plan_b(Plan& pl, const void* w, int n_total, long long k_total) {
+    uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)n_total};
+    uint64_t strides[1] = {(uint64_t)k_total * 2};
+    uint32_t box[2] = {64, (uint32_t)pl.bn};
+    return encode_bf16(&pl.tmB, w, 2, dims, strides, box);
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+Geo fwd_geo(const cb_conv_desc* d) {
+    return Geo{d->n, d->in_h, d->in_w, d->in_c, d->k_h, d->k_w, d->stride, d->pad, d->out_h, d->out_w};
+}
+
+bool dense_nhwc(const cb_conv_desc* d) {
+    return d->in_dtype == CB_BF16 && d->in_stride_c == 1 && d->in_stride_w == d->in_c &&
+           d->in_stride_h == (int64_t)d->in_w * d->in_c && d->in_stride_n == (int64_t)d->in_h * d->in_w * d->in_c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ forward
+bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
+    if (!device_ok() || !dense_nhwc(d) || e->norm_mean) return false;
+    int mt;
+    if (!pick_bn(d->out_c, &mt)) return false;
+    if (e->side_dim > 16) return false;
+    Geo g = fwd_geo(d);
+    View v = classify(g);
+    if (v == VIEW_NONE) return false;
+    if (v != VIEW_ROWS && g.oh * g.ow > mt * 128) return false;
+    return true;
+}
+
+int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
+    CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
+    Plan pl{};
+    pl.bn = pick_bn(d->out_c, &pl.mt);
+    Geo g = fwd_geo(d);
+    int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
+    const long long K = (long long)d->k_h * d->k_w * d->in_c;
+    rc = plan_b(pl, w, d->out_c, K); if (rc) return rc;
+    umma::GemmParams& p = pl.p;
+    p.n_total = d->out_c;
+    p.n_tiles = d->out_c / pl.bn;
+    p.bias = e->bias;
+    p.side = e->side; p.side_w = e->side_w; p.side_dim = e->side_dim;
+    p.act = d->act;
+    p.residual = (const __nv_bfloat16*)e->residual;
+    p.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.out_f32 = e->out_f32;
+    CB_REQUIRE(aligned16(p.out_bf16) && aligned16(p.out_f32) && aligned16(p.residual), CB_E_ALIGN,
+               "cb_conv_fwd: outputs must be 16-byte aligned");
+    return dispatch(pl, s);
+}
+
+// ------------------------------------------------------------------------------ dgrad
+// dx[rows=(n,ih,iw), ci] = sum_{kh,kw,co} dy[n, ih+pad-kh, iw+pad-kw, co] * w_t[ci][kh][kw][co]   (stride 1)
+// which is a stride-1 forward over dy with the filter walked backwards; linear layers are the 1x1 case.
+bool umma_supports_dgrad(const cb_conv_desc* d) {
+    if (!device_ok()) return false;
+    int mt;
+    if (!pick_bn(d->in_c, &mt)) return false;
+    if (d->k_h == 1 && d->k_w == 1 && d->in_h == 1 && d->in_w == 1 && d->out_c % 8 == 0) return true;
+    if (d->stride == 1 && d->out_c % 64 == 0 && d->in_h * d->in_w <= mt * 128 &&
+        !(d->k_h == d->in_h && d->k_w == d->in_w))
+        return true;
+    return false;
+}
+
+int umma_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved, int x_act,
+                    const void* dx_add, void* dx, cudaStream_t s) {
+    CB_REQUIRE(dy && w_t && dx, CB_E_ARG, "cb_conv_dgrad: null pointer");
+    Plan pl{};
+    pl.bn = pick_bn(d->in_c, &pl.mt);
+    umma::GemmParams& p = pl.p;
+    int rc;
+    if (d->k_h == 1 && d->k_w == 1 && d->in_h == 1 && d->in_w == 1) {
+        Geo g{d->n, 1, 1, d->out_c, 1, 1, 1, 0, 1, 1};
+        rc = plan_a(pl, g, dy, pl.mt); if (rc) return rc;
+    } else {
+        // rows are input pixels (ih, iw); tap (kh, kw) reads dy at (ih + pad - kh, iw + pad - kw)
+        Geo g{d->n, d->out_h, d->out_w, d->out_c, d->k_h, d->k_w, 1, 0, d->in_h, d->in_w};
+        rc = plan_a(pl, g, dy, pl.mt); if (rc) return rc;
+        // coordinate = pad - k: walk the filter backwards from a constant offset
+        p.a_kb.mul[1] = -1; p.a_kb.mul[2] = -1;
+        p.a_off[1] = d->pad; p.a_off[2] = d->pad;
+    }
+    const long long K = (long long)d->k_h * d->k_w * d->out_c;
+    rc = plan_b(pl, w_t, d->in_c, K); if (rc) return rc;
+    p.n_total = d->in_c;
+    p.n_tiles = d->in_c / pl.bn;
+    p.add_pre = (const __nv_bfloat16*)dx_add;
+    p.act = CB_ACT_NONE;
+    p.actgrad_src = (const __nv_bfloat16*)x_saved; p.actgrad_act = x_act;
+    p.out_bf16 = (__nv_bfloat16*)dx;
+    CB_REQUIRE(aligned16(dx) && aligned16(dx_add) && aligned16(x_saved), CB_E_ALIGN,
+               "cb_conv_dgrad: operands must be 16-byte aligned");
+    return dispatch(pl, s);
+}
+
+// ------------------------------------------------------------------------------ wgrad (not yet on tcgen05)
 bool umma_supports_wgrad(const cb_conv_desc*) { return false; }
-int umma_conv_fwd(const cb_conv_desc*, const void*, const void*, const cb_epilogue*, cudaStream_t) {
-    return fail(CB_E_ARG, "umma_conv_fwd: not built");
-}
-int umma_conv_dgrad(const cb_conv_desc*, const void*, const void*, const void*, int, const void*, void*, cudaStream_t) {
-    return fail(CB_E_ARG, "umma_conv_dgrad: not built");
-}
 int umma_conv_wgrad(const cb_conv_desc*, const void*, const void*, const float*, const float*, float*, float*,
                     float, cudaStream_t) {
     return fail(CB_E_ARG, "umma_conv_wgrad: not built");
 }
+
 }  // namespace cb

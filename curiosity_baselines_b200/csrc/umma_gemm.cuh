@@ -1,0 +1,287 @@
+// Persistent, warp-specialised tcgen05 GEMM with TMA-fed K-major operands (sm_100a).
+//
+//   D[rows, n] = epilogue( sum_k A[rows, k] * B[n, k] )
+//
+// A rows are *gathered by TMA*: the A tensor map is a rank-2..5 view of the activation tensor
+// and every k-block is one box of <=256 rows x 64 bf16 (128 B, SWIZZLE_128B), so an implicit-GEMM
+// convolution is the same kernel as a Linear layer with a different view (see umma_conv.cu for
+// the views).  B is the [N, K] bf16 weight matrix.  fp32 accumulators live in TMEM, double
+// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> bias/side/activation/residual -> global).
+#pragma once
+#include "common.cuh"
+#include "umma_common.cuh"
+
+namespace umma {
+
+struct CoordMap {          // coordinate = ((index / div) % mod) * mul   (mod == 0: no modulo)
+    int div[5], mod[5], mul[5];
+};
+
+struct GemmParams {
+    // operand A view
+    int a_rank;
+    CoordMap a_tile;       // from the m-tile index
+    CoordMap a_kb;         // from the k-block index
+    int a_off[5];          // constant coordinate offset (e.g. -pad)
+    int a_box_bytes;       // bytes one A box deposits in shared memory
+    int kb_count;          // K / 64
+    // tiling
+    int m_tiles, n_tiles;
+    int rows_per_tile;     // valid rows of each tile (<= MT*128)
+    long long m_total;     // total output rows
+    int n_total;           // total output columns (row stride of all row-major operands below)
+    // epilogue
+    const float* bias;
+    const float* side; const float* side_w; int side_dim;
+    const __nv_bfloat16* add_pre;      // added before the activation (dgrad skip gradient)
+    int act;                           // activation on the result
+    const __nv_bfloat16* actgrad_src;  // multiply by act'(this), derivative from the saved output
+    int actgrad_act;
+    const __nv_bfloat16* residual;     // added after the activation
+    __nv_bfloat16* out_bf16; float* out_f32;
+    // optional pixel-shuffle of the output rows (stride-2 dgrad): 0 = rows are contiguous
+    int shuffle; int sh_a, sh_b, sh_c;       // see store_row_offset
+};
+
+template <int BN, int MT>
+struct GemmConfig {
+    static constexpr int A_BYTES = MT * 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int ACC_COLS = MT * BN;                       // one accumulator stage
+    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
+                                     : 2 * ACC_COLS <= 256 ? 256 : 512;   // allocation: power of two
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+};
+
+__device__ __forceinline__ int map_coord(const CoordMap& m, int i, int idx) {
+    int v = idx / m.div[i];
+    if (m.mod[i]) v %= m.mod[i];
+    return v * m.mul[i];
+}
+
+// element offset of output row `grow` (global row index) in a row-major [*, n_total] tensor
+__device__ __forceinline__ long long store_row_offset(const GemmParams& p, long long grow) {
+    return grow * (long long)p.n_total;
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+    using Cfg = GemmConfig<BN, MT>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int kb_count = p.kb_count;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
+                int tc[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) tc[i] = p.a_off[i] + map_coord(p.a_tile, i, tm);
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
+                    int c[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) c[i] = tc[i] + map_coord(p.a_kb, i, kb);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    tma_load(p.a_rank, sa, &tmA, full_bar(stage), c);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * 64, tn * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                fence_after_thread_sync();
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    fence_after_thread_sync();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {           // 4 x UMMA_K(16) = 64
+                            const uint64_t da = make_smem_desc(sa + mt * 16384 + k * 32, 16, 1024);
+                            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
+                            mma_f16_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(empty_bar(stage));             // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                mma_commit(tfull_bar(acc));                   // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            fence_after_thread_sync();
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = mt * 128 + quarter * 32 + lane;           // row inside the tile
+                const long long grow = (long long)tm * p.rows_per_tile + r;
+                const bool valid = r < p.rows_per_tile && grow < p.m_total;
+                const long long ro = store_row_offset(p, grow);
+                float sv[16];
+                if (p.side_dim) {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        sv[s] = (valid && s < p.side_dim) ? __ldg(p.side + grow * p.side_dim + s) : 0.f;
+                }
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    uint32_t raw[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                           (uint32_t)((acc * MT + mt) * BN + cb * 32);
+                    tmem_ld_32x32(taddr, raw);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int n0 = tn * BN + cb * 32;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+                        }
+                        if (p.side_dim) {
+                            for (int s = 0; s < p.side_dim; ++s) {
+                                const float a = sv[s];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = fmaf(a, __ldg(p.side_w + (long long)(n0 + j) * p.side_dim + s), v[j]);
+                            }
+                        }
+                        if (p.add_pre) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.add_pre + ro + n0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u = __ldg(src + q);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __bfloat1622float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (p.act != CB_ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = cb::apply_act(v[j], p.act);
+                        }
+                        if (p.actgrad_src) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.actgrad_src + ro + n0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u = __ldg(src + q);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __bfloat1622float2(h[e]);
+                                    v[q * 8 + e * 2] *= cb::act_grad_from_output(f.x, p.actgrad_act);
+                                    v[q * 8 + e * 2 + 1] *= cb::act_grad_from_output(f.y, p.actgrad_act);
+                                }
+                            }
+                        }
+                        if (p.residual) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.residual + ro + n0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u = __ldg(src + q);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __bfloat1622float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (p.out_bf16) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ro + n0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u;
+                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                                dst[q] = u;
+                            }
+                        }
+                        if (p.out_f32) {
+                            float4* dst = reinterpret_cast<float4*>(p.out_f32 + ro + n0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_thread_sync();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace umma

@@ -1,0 +1,116 @@
+"""The tcgen05 engine forced on (engine='umma' fails loudly if a shape has no specialisation):
+same torch-fp32-on-bf16-operands reference as test_gpu_layers, at sizes that span several tiles
+and more than one wave of the persistent grid."""
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from curiosity_baselines_b200 import _lib as L
+from curiosity_baselines_b200 import layers as LY
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20))
+
+
+@pytest.fixture(autouse=True)
+def _umma_engine():
+    LY.set_engine("umma")
+    yield
+    LY.set_engine("auto")
+
+
+@pytest.mark.parametrize("K,out,act,side_dim,use_res,n", [
+    (512, 512, "relu", 0, False, 37),
+    (512, 512, "none", 0, False, 300),
+    (512, 512, "lrelu", 4, False, 1000),
+    (512, 512, "none", 7, True, 40000),
+    (1024, 512, "relu", 0, False, 513),
+    (512, 64, "none", 0, False, 700),
+    (512, 128, "relu", 0, False, 700),
+    (64, 32, "none", 0, False, 5000),
+])
+def test_linear_forward(K, out, act, side_dim, use_res, n):
+    torch.manual_seed(0)
+    lin = nn.Linear(K + side_dim, out).to(DEV)
+    layer = LY.linear_layer(lin, act, side_dim)
+    x = bf(torch.randn(n, K, device=DEV))
+    side = F.one_hot(torch.randint(0, max(side_dim, 1), (n,), device=DEV), max(side_dim, 1)).float() if side_dim else None
+    res = bf(torch.randn(n, out, device=DEV)) if use_res else None
+    yb, yf = layer.forward(x.to(torch.bfloat16), n, side=side,
+                           residual=res.to(torch.bfloat16) if use_res else None, out_f32=True)
+    W = lin.weight.detach()
+    ref = x @ bf(W[:, :K]).t() + lin.bias
+    if side_dim:
+        ref = ref + side @ W[:, K:].t()
+    ref = {"none": lambda t: t, "relu": F.relu, "lrelu": F.leaky_relu}[act](ref)
+    if use_res:
+        ref = ref + res
+    assert rel(yf, ref) < 2e-5
+    assert rel(yb, ref) < 5e-3
+
+
+@pytest.mark.parametrize("n", [3, 260, 1500])
+def test_fc_over_flattened_map(n):
+    torch.manual_seed(1)
+    lin = nn.Linear(3136, 512).to(DEV)
+    layer = LY.linear_layer(lin, "relu", spatial=(7, 64))
+    a = bf(torch.randn(n, 64, 7, 7, device=DEV))
+    _, yf = layer.forward(a.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), n, out_f32=True)
+    ref = F.relu(a.reshape(n, -1) @ bf(lin.weight).t() + lin.bias)
+    assert rel(yf, ref) < 2e-5
+
+
+@pytest.mark.parametrize("case", [
+    (32, 20, 20, 64, 4, 2, 0, 5), (32, 20, 20, 64, 4, 2, 0, 1000),      # conv2
+    (64, 9, 9, 64, 3, 1, 0, 7), (64, 9, 9, 64, 3, 1, 0, 2001),          # conv3
+    (64, 9, 9, 128, 3, 1, 1, 33),                                       # padded stride-1 conv
+])
+def test_conv_forward(case):
+    in_c, h, w, out_c, k, s, p, n = case
+    torch.manual_seed(2)
+    conv = nn.Conv2d(in_c, out_c, k, s, p).to(DEV)
+    layer = LY.conv_layer(conv, (h, w, in_c), "lrelu")
+    x = bf(torch.randn(n, in_c, h, w, device=DEV))
+    yb, yf = layer.forward(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), n, out_f32=True)
+    ref = F.leaky_relu(F.conv2d(x, bf(conv.weight), conv.bias, stride=s, padding=p))
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, out_c)
+    assert rel(yf, ref) < 2e-5
+    assert rel(yb, ref) < 5e-3
+
+
+@pytest.mark.parametrize("K,out,n", [(512, 512, 129), (512, 512, 3000), (1024, 512, 77), (512, 64, 300)])
+def test_linear_dgrad(K, out, n):
+    torch.manual_seed(3)
+    lin = nn.Linear(K, out).to(DEV)
+    layer = LY.linear_layer(lin, "none")
+    dy = bf(torch.randn(n, out, device=DEV))
+    saved = bf(torch.randn(n, K, device=DEV))
+    add = bf(torch.randn(n, K, device=DEV))
+    dx = layer.dgrad(dy.to(torch.bfloat16), n, x_saved=saved.to(torch.bfloat16), x_act="relu",
+                     dx_add=add.to(torch.bfloat16))
+    ref = (dy @ bf(lin.weight) + add) * (saved > 0)
+    assert rel(dx, ref) < 5e-3
+
+
+@pytest.mark.parametrize("n", [4, 700])
+def test_conv3_dgrad(n):
+    torch.manual_seed(4)
+    conv = nn.Conv2d(64, 64, 3, 1, 0).to(DEV)
+    layer = LY.conv_layer(conv, (9, 9, 64), "lrelu")
+    dy = bf(torch.randn(n, 64, 7, 7, device=DEV))
+    xs = torch.zeros(n, 64, 9, 9, device=DEV, requires_grad=True)
+    F.conv2d(xs, bf(conv.weight), None).backward(dy)
+    saved = bf(torch.randn(n * 81, 64, device=DEV))
+    dx = layer.dgrad(dy.permute(0, 2, 3, 1).reshape(-1, 64).contiguous().to(torch.bfloat16), n,
+                     x_saved=saved.to(torch.bfloat16), x_act="lrelu")
+    ref = xs.grad.permute(0, 2, 3, 1).reshape(-1, 64) * torch.where(saved > 0, 1.0, 0.01)
+    assert rel(dx, ref) < 5e-3
