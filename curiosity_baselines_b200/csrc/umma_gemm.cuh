@@ -72,6 +72,27 @@ __device__ __forceinline__ long long store_row_offset(const GemmParams& p, long 
     return grow * (long long)p.n_total;
 }
 
+// 32 consecutive bf16 of one row -> fp32 (four 16-byte loads)
+__device__ __forceinline__ void load_bf16_row(float (&g)[32], const __nv_bfloat16* src) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 u = __ldg(s4 + q);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            g[q * 8 + e * 2] = f.x; g[q * 8 + e * 2 + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ void add_bf16_row(float (&v)[32], const __nv_bfloat16* src) {
+    float g[32];
+    load_bf16_row(g, src);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += g[j];
+}
+
 template <int BN, int MT>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -193,61 +214,46 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
                         if (p.bias) {
+                            const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = __ldg(bsrc + q);
+                                v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+                            }
                         }
                         if (p.side_dim) {
+                            const float* sw = p.side_w + (long long)n0 * p.side_dim;
                             for (int s = 0; s < p.side_dim; ++s) {
                                 const float a = sv[s];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    v[j] = fmaf(a, __ldg(p.side_w + (long long)(n0 + j) * p.side_dim + s), v[j]);
+                                for (int j = 0; j < 32; ++j) v[j] = fmaf(a, __ldg(sw + j * p.side_dim + s), v[j]);
                             }
                         }
-                        if (p.add_pre) {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.add_pre + ro + n0);
+                        if (p.add_pre) add_bf16_row(v, p.add_pre + ro + n0);
+                        // activation: one branch per 32-column chunk, branch-free per element
+                        if (p.act == CB_ACT_RELU) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(src + q);
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.act == CB_ACT_LRELU) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __bfloat1622float2(h[e]);
-                                    v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y;
-                                }
-                            }
-                        }
-                        if (p.act != CB_ACT_NONE) {
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
+                        } else if (p.act == CB_ACT_ELU) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = cb::apply_act(v[j], p.act);
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
                         }
                         if (p.actgrad_src) {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.actgrad_src + ro + n0);
+                            float g[32];
+                            load_bf16_row(g, p.actgrad_src + ro + n0);
+                            if (p.actgrad_act == CB_ACT_ELU) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(src + q);
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                                for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : g[j] + 1.f;
+                            } else if (p.actgrad_act != CB_ACT_NONE) {
+                                const float slope = p.actgrad_act == CB_ACT_LRELU ? 0.01f : 0.f;
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __bfloat1622float2(h[e]);
-                                    v[q * 8 + e * 2] *= cb::act_grad_from_output(f.x, p.actgrad_act);
-                                    v[q * 8 + e * 2 + 1] *= cb::act_grad_from_output(f.y, p.actgrad_act);
-                                }
+                                for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : slope;
                             }
                         }
-                        if (p.residual) {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.residual + ro + n0);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(src + q);
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __bfloat1622float2(h[e]);
-                                    v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y;
-                                }
-                            }
-                        }
+                        if (p.residual) add_bf16_row(v, p.residual + ro + n0);
                         if (p.out_bf16) {
                             uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ro + n0);
 #pragma unroll

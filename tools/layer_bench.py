@@ -1,0 +1,58 @@
+"""Event-timed micro-benchmark of single layers through the library (used for profiling).
+    python tools/layer_bench.py [--n 131072] [--reps 5] [--only conv2]"""
+import argparse
+import os
+import sys
+
+import torch
+from torch import nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from curiosity_baselines_b200 import layers as LY  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=131072)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--only", default="")
+ap.add_argument("--engine", default="auto")
+args = ap.parse_args()
+dev = "cuda"
+n = args.n
+LY.set_engine(args.engine)
+torch.manual_seed(0)
+
+
+def timeit(fn, flops, name):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.reps
+    print(f"{name:28s} {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+cases = {}
+conv2 = LY.conv_layer(nn.Conv2d(32, 64, 4, 2).to(dev), (20, 20, 32), "lrelu")
+conv3 = LY.conv_layer(nn.Conv2d(64, 64, 3, 1).to(dev), (9, 9, 64), "lrelu")
+fc = LY.linear_layer(nn.Linear(3136, 512).to(dev), "relu", spatial=(7, 64))
+lin = LY.linear_layer(nn.Linear(512, 512).to(dev), "relu")
+a1 = torch.randn(n * 400, 32, device=dev).to(torch.bfloat16)
+a2 = torch.randn(n * 81, 64, device=dev).to(torch.bfloat16)
+a3 = torch.randn(n * 49, 64, device=dev).to(torch.bfloat16)
+h = torch.randn(n, 512, device=dev).to(torch.bfloat16)
+cases["conv2_fwd"] = (lambda: conv2.forward(a1, n), 2.0 * 512 * 64 * 81 * n)
+cases["conv3_fwd"] = (lambda: conv3.forward(a2, n), 2.0 * 576 * 64 * 49 * n)
+cases["fc_fwd"] = (lambda: fc.forward(a3, n), 2.0 * 3136 * 512 * n)
+cases["lin_fwd"] = (lambda: lin.forward(h, n), 2.0 * 512 * 512 * n)
+cases["lin_fwd_f32"] = (lambda: lin.forward(h, n, out_bf16=False, out_f32=True), 2.0 * 512 * 512 * n)
+cases["lin_dgrad"] = (lambda: lin.dgrad(h, n, x_saved=h, x_act="relu"), 2.0 * 512 * 512 * n)
+cases["conv3_dgrad"] = (lambda: conv3.dgrad(a3, n, x_saved=a2, x_act="lrelu"), 2.0 * 576 * 64 * 81 * n)
+for name, (fn, fl) in cases.items():
+    if args.only and args.only not in name:
+        continue
+    timeit(fn, fl, name)
