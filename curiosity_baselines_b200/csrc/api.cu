@@ -13,6 +13,9 @@ int umma_conv_fwd(const cb_conv_desc*, const void*, const void*, const cb_epilog
 int umma_conv_dgrad(const cb_conv_desc*, const void*, const void*, const void*, int, const void*, void*, cudaStream_t);
 int umma_conv_wgrad(const cb_conv_desc*, const void*, const void*, const float*, const float*, float*, float*,
                     float, cudaStream_t);
+int umma_conv_dgrad_s2(const cb_conv_desc*, const void*, const void*, const void*, int, const void*, void*,
+                       cudaStream_t);
+bool umma_supports_dgrad_s2(const cb_conv_desc*);
 bool umma_supports_fwd(const cb_conv_desc*, const cb_epilogue*);
 bool umma_supports_dgrad(const cb_conv_desc*);
 bool umma_supports_wgrad(const cb_conv_desc*);
@@ -66,4 +69,14 @@ extern "C" int cb_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int
     CB_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src_host, (size_t)src_pitch, (size_t)width_bytes,
                               (size_t)rows, cudaMemcpyHostToDevice, cb::as_stream(stream)));
     return CB_OK;
+}
+
+extern "C" int cb_conv_dgrad_s2_supported(const cb_conv_desc* d) {
+    return d && cb::umma_supports_dgrad_s2(d) ? 1 : 0;
+}
+
+extern "C" int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle, const void* x_saved,
+                                int32_t x_act, const void* dx_add, void* dx, void* stream) {
+    CB_REQUIRE(d, CB_E_ARG, "cb_conv_dgrad_s2: null descriptor");
+    return cb::umma_conv_dgrad_s2(d, dy, w_shuffle, x_saved, x_act, dx_add, dx, cb::as_stream(stream));
 }

@@ -303,6 +303,40 @@ int umma_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, cons
     return dispatch(pl, s);
 }
 
+// ------------------------------------------------------------------------------ stride-2 dgrad
+// k = 2*stride = 4, pad 0 (Burda conv2).  With ih = 2a+ph, kh = 2u+ph the four output parities share
+// the same 2x2 taps of dy, so one GEMM computes all of them:
+//   D[(n,a,b), (ph,pw,ci)] = sum_{u,v,co} dy[n, a-u, b-v, co] * W[co, 2u+ph, 2v+pw, ci]
+// (M = n*(in_h/2)*(in_w/2), K = 4*out_c, N = 4*in_c) and the epilogue scatters the four 32-channel
+// chunks of a row to the pixels (2a+ph, 2b+pw) -- a depth-to-space store.
+bool umma_supports_dgrad_s2(const cb_conv_desc* d) {
+    return device_ok() && d->stride == 2 && d->k_h == 4 && d->k_w == 4 && d->pad == 0 && d->in_c == 32 &&
+           d->out_c % 64 == 0 && d->in_h % 2 == 0 && d->in_w % 2 == 0 && (d->in_h / 2) * (d->in_w / 2) <= 256;
+}
+
+int umma_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle, const void* x_saved,
+                       int x_act, const void* dx_add, void* dx, cudaStream_t s) {
+    CB_REQUIRE(dy && w_shuffle && dx, CB_E_ARG, "cb_conv_dgrad_s2: null pointer");
+    CB_REQUIRE(umma_supports_dgrad_s2(d), CB_E_ARG, "cb_conv_dgrad_s2: unsupported shape or device");
+    Plan pl{};
+    pl.bn = 128; pl.mt = 2;
+    umma::GemmParams& p = pl.p;
+    Geo g{d->n, d->out_h, d->out_w, d->out_c, 2, 2, 1, 0, d->in_h / 2, d->in_w / 2};
+    int rc = plan_a(pl, g, dy, pl.mt); if (rc) return rc;
+    p.a_kb.mul[1] = -1; p.a_kb.mul[2] = -1;
+    rc = plan_b(pl, w_shuffle, 4 * d->in_c, 4LL * d->out_c); if (rc) return rc;
+    p.n_total = 4 * d->in_c;
+    p.n_tiles = 1;
+    p.add_pre = (const __nv_bfloat16*)dx_add;
+    p.act = CB_ACT_NONE;
+    p.actgrad_src = (const __nv_bfloat16*)x_saved; p.actgrad_act = x_act;
+    p.out_bf16 = (__nv_bfloat16*)dx;
+    p.shuffle = 1; p.sh_ph = d->in_h / 2; p.sh_pw = d->in_w / 2; p.sh_h = d->in_h; p.sh_w = d->in_w;
+    CB_REQUIRE(aligned16(dx) && aligned16(dx_add) && aligned16(x_saved), CB_E_ALIGN,
+               "cb_conv_dgrad_s2: operands must be 16-byte aligned");
+    return dispatch(pl, s);
+}
+
 // ------------------------------------------------------------------------------ wgrad (not yet on tcgen05)
 bool umma_supports_wgrad(const cb_conv_desc*) { return false; }
 int umma_conv_wgrad(const cb_conv_desc*, const void*, const void*, const float*, const float*, float*, float*,

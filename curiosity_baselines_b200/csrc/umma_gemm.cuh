@@ -42,8 +42,10 @@ struct GemmParams {
     int actgrad_act;
     const __nv_bfloat16* residual;     // added after the activation
     __nv_bfloat16* out_bf16; float* out_f32;
-    // optional pixel-shuffle of the output rows (stride-2 dgrad): 0 = rows are contiguous
-    int shuffle; int sh_a, sh_b, sh_c;       // see store_row_offset
+    // optional pixel shuffle of the output (stride-2 dgrad): row = (n, a, b) over an (sh_ph x sh_pw)
+    // grid per sample, 32-column chunk q = (ph, pw) -> NHWC pixel (2a+ph, 2b+pw) of a [*, sh_h, sh_w, 32]
+    // tensor.  0 = plain row-major [*, n_total].
+    int shuffle; int sh_ph, sh_pw, sh_h, sh_w;
 };
 
 template <int BN, int MT>
@@ -67,9 +69,15 @@ __device__ __forceinline__ int map_coord(const CoordMap& m, int i, int idx) {
     return v * m.mul[i];
 }
 
-// element offset of output row `grow` (global row index) in a row-major [*, n_total] tensor
-__device__ __forceinline__ long long store_row_offset(const GemmParams& p, long long grow) {
-    return grow * (long long)p.n_total;
+// element offset of the 32-column chunk starting at column n0 of output row `grow`
+__device__ __forceinline__ long long chunk_offset(const GemmParams& p, long long grow, int n0) {
+    if (!p.shuffle) return grow * (long long)p.n_total + n0;
+    const int pp = p.sh_ph * p.sh_pw;
+    const long long n = grow / pp;
+    const int rem = (int)(grow - n * pp);
+    const int a = rem / p.sh_pw, b = rem - a * p.sh_pw;
+    const int q = n0 >> 5, ph = q >> 1, pw = q & 1;
+    return ((n * p.sh_h + 2 * a + ph) * p.sh_w + 2 * b + pw) * 32;
 }
 
 // 32 consecutive bf16 of one row -> fp32 (four 16-byte loads)
@@ -194,7 +202,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int r = mt * 128 + quarter * 32 + lane;           // row inside the tile
                 const long long grow = (long long)tm * p.rows_per_tile + r;
                 const bool valid = r < p.rows_per_tile && grow < p.m_total;
-                const long long ro = store_row_offset(p, grow);
                 float sv[16];
                 if (p.side_dim) {
 #pragma unroll
@@ -210,6 +217,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld_wait();
                     if (valid) {
                         const int n0 = tn * BN + cb * 32;
+                        const long long co = chunk_offset(p, grow, n0);
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -229,7 +237,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int j = 0; j < 32; ++j) v[j] = fmaf(a, __ldg(sw + j * p.side_dim + s), v[j]);
                             }
                         }
-                        if (p.add_pre) add_bf16_row(v, p.add_pre + ro + n0);
+                        if (p.add_pre) add_bf16_row(v, p.add_pre + co);
                         // activation: one branch per 32-column chunk, branch-free per element
                         if (p.act == CB_ACT_RELU) {
 #pragma unroll
@@ -243,7 +251,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         if (p.actgrad_src) {
                             float g[32];
-                            load_bf16_row(g, p.actgrad_src + ro + n0);
+                            load_bf16_row(g, p.actgrad_src + co);
                             if (p.actgrad_act == CB_ACT_ELU) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : g[j] + 1.f;
@@ -253,9 +261,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : slope;
                             }
                         }
-                        if (p.residual) add_bf16_row(v, p.residual + ro + n0);
+                        if (p.residual) add_bf16_row(v, p.residual + co);
                         if (p.out_bf16) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ro + n0);
+                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + co);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 uint4 u;
@@ -267,7 +275,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                         if (p.out_f32) {
-                            float4* dst = reinterpret_cast<float4*>(p.out_f32 + ro + n0);
+                            float4* dst = reinterpret_cast<float4*>(p.out_f32 + co);
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
                                 dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);

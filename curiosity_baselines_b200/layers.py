@@ -47,7 +47,9 @@ class GemmLayer:
         self.side_dim = side_dim
         self.trainable = trainable
         self.K = k * k * self.in_c
-        self.w_fwd = self.w_t = self.bias = self.side_w = None
+        # a Linear over a flattened [c,k,k] map: its dgrad is a plain [*, K] linear dgrad
+        self.flat_linear = k > 1 and k == self.in_h == self.in_w and pad == 0
+        self.w_fwd = self.w_t = self.w_shuffle = self.bias = self.side_w = None
         self._version = None
 
     # ---------------------------------------------------------------- weights
@@ -76,6 +78,13 @@ class GemmLayer:
                                    device=dev)
         L.call("cb_prepare_conv_weight", L.ptr(w4), L.ptr(self.w_fwd), L.ptr(self.w_t),
                self.out_c, self.in_c, self.k, self.k, L.stream())
+        if self.flat_linear:        # [K, out_c] with K in (h, w, c) order
+            self.w_t = self.w_fwd.t().contiguous()
+        if self.stride == 2 and self.k == 4 and self.pad == 0 and self.in_c == 32:
+            # depth-to-space dgrad operand: [(ph,pw,ci)][(u,v,co)] = W[co][ci][2u+ph][2v+pw]
+            w6 = w4.view(self.out_c, self.in_c, 2, 2, 2, 2)          # co ci u ph v pw
+            self.w_shuffle = w6.permute(3, 5, 1, 2, 4, 0).reshape(4 * self.in_c, 4 * self.out_c) \
+                .to(torch.bfloat16).contiguous()
         self.bias = self.module.bias.detach()
         self.side_w = side.detach().contiguous() if side is not None else None
         self._version = ver
@@ -125,7 +134,22 @@ class GemmLayer:
         self.prepare()
         dx = torch.empty(n * self.in_h * self.in_w, self.in_c, dtype=torch.bfloat16,
                          device=dy.device)
-        d = self.desc(n)
+        if self.flat_linear:
+            d = L.ConvDesc()
+            d.n, d.in_h, d.in_w, d.in_c = n, 1, 1, self.K
+            d.k_h = d.k_w = d.stride = 1
+            d.out_h = d.out_w = 1
+            d.out_c = self.out_c
+            d.in_dtype = L.BF16
+            d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = self.K, self.K, self.K, 1
+            d.engine = _engine
+        else:
+            d = self.desc(n)
+            if (self.w_shuffle is not None and _engine != L.ENGINE_SIMT
+                    and L.load().cb_conv_dgrad_s2_supported(C.byref(d))):
+                L.call("cb_conv_dgrad_s2", C.byref(d), L.ptr(dy), L.ptr(self.w_shuffle), L.ptr(x_saved),
+                       ACT[x_act], L.ptr(dx_add), L.ptr(dx), L.stream())
+                return dx
         L.call("cb_conv_dgrad", C.byref(d), L.ptr(dy), L.ptr(self.w_t), L.ptr(x_saved), ACT[x_act],
                L.ptr(dx_add), L.ptr(dx), L.stream())
         return dx

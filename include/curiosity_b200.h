@@ -153,6 +153,13 @@ int cb_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_ep
  * at x over a skip connection (icm.py:22), or NULL; dx: bf16 NHWC [n,in_h,in_w,in_c] */
 int cb_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved,
                   int32_t x_act, const void* dx_add, void* dx, void* stream);
+/* tcgen05-only dgrad of a k=4, stride=2, pad=0, in_c=32 convolution (Burda conv2): all four
+ * output parities in one GEMM with a depth-to-space store.  w_shuffle: bf16
+ * [(ph,pw,ci)][(u,v,co)] = W[co][2u+ph][2v+pw][ci].  cb_conv_dgrad_s2_supported() tells whether
+ * the shape/device qualifies (otherwise use cb_conv_dgrad). */
+int cb_conv_dgrad_s2_supported(const cb_conv_desc* d);
+int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle,
+                     const void* x_saved, int32_t x_act, const void* dx_add, void* dx, void* stream);
 /* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise
  * (NULL to skip).  x addressed as in cb_conv_fwd (norm_* honoured for CB_U8). */
 int cb_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,

@@ -114,3 +114,32 @@ def test_conv3_dgrad(n):
                      x_saved=saved.to(torch.bfloat16), x_act="lrelu")
     ref = xs.grad.permute(0, 2, 3, 1).reshape(-1, 64) * torch.where(saved > 0, 1.0, 0.01)
     assert rel(dx, ref) < 5e-3
+
+
+@pytest.mark.parametrize("n", [2, 5, 777])
+def test_conv2_dgrad_depth_to_space(n):
+    torch.manual_seed(5)
+    conv = nn.Conv2d(32, 64, 4, 2, 0).to(DEV)
+    layer = LY.conv_layer(conv, (20, 20, 32), "lrelu")
+    dy = bf(torch.randn(n, 64, 9, 9, device=DEV))
+    xs = torch.zeros(n, 32, 20, 20, device=DEV, requires_grad=True)
+    F.conv2d(xs, bf(conv.weight), None, stride=2).backward(dy)
+    saved = bf(torch.randn(n * 400, 32, device=DEV))
+    add = bf(torch.randn(n * 400, 32, device=DEV))
+    dx = layer.dgrad(dy.permute(0, 2, 3, 1).reshape(-1, 64).contiguous().to(torch.bfloat16), n,
+                     x_saved=saved.to(torch.bfloat16), x_act="lrelu", dx_add=add.to(torch.bfloat16))
+    ref = (xs.grad.permute(0, 2, 3, 1).reshape(-1, 32) + add) * torch.where(saved > 0, 1.0, 0.01)
+    assert rel(dx, ref) < 5e-3
+
+
+@pytest.mark.parametrize("n", [6, 1000])
+def test_fc_dgrad_flat(n):
+    torch.manual_seed(6)
+    lin = nn.Linear(3136, 512).to(DEV)
+    layer = LY.linear_layer(lin, "none", spatial=(7, 64))
+    dy = bf(torch.randn(n, 512, device=DEV))
+    saved = bf(torch.randn(n * 49, 64, device=DEV))
+    dx = layer.dgrad(dy.to(torch.bfloat16), n, x_saved=saved.to(torch.bfloat16), x_act="lrelu")
+    ref = (dy @ bf(lin.weight)).reshape(n, 64, 7, 7).permute(0, 2, 3, 1).reshape(-1, 64)
+    ref = ref * torch.where(saved > 0, 1.0, 0.01)
+    assert rel(dx, ref) < 5e-3

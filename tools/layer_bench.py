@@ -52,6 +52,9 @@ cases["lin_fwd"] = (lambda: lin.forward(h, n), 2.0 * 512 * 512 * n)
 cases["lin_fwd_f32"] = (lambda: lin.forward(h, n, out_bf16=False, out_f32=True), 2.0 * 512 * 512 * n)
 cases["lin_dgrad"] = (lambda: lin.dgrad(h, n, x_saved=h, x_act="relu"), 2.0 * 512 * 512 * n)
 cases["conv3_dgrad"] = (lambda: conv3.dgrad(a3, n, x_saved=a2, x_act="lrelu"), 2.0 * 576 * 64 * 81 * n)
+dy2 = torch.randn(n * 81, 64, device=dev).to(torch.bfloat16)
+cases["conv2_dgrad"] = (lambda: conv2.dgrad(dy2, n, x_saved=a1, x_act="lrelu"), 2.0 * 512 * 64 * 81 * n)
+cases["fc_dgrad"] = (lambda: fc.dgrad(h, n, x_saved=a3, x_act="lrelu"), 2.0 * 3136 * 512 * n)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
         continue
