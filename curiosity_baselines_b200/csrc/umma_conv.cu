@@ -14,6 +14,9 @@
 // S = samples per tile so that S*out_h*out_w <= 256 rows (two M=128 UMMA sub-tiles).
 #include "umma_gemm.cuh"
 #include <mutex>
+#include <string.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace cb {
 
@@ -94,7 +97,7 @@ int launch(const Plan& pl, cudaStream_t s) {
     }
     int tiles = pl.p.m_tiles * pl.p.n_tiles;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    umma::umma_gemm_kernel<BN, MT><<<grid, 192, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+    umma::umma_gemm_kernel<BN, MT><<<grid, umma::kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -225,7 +228,21 @@ bool dense_nhwc(const cb_conv_desc* d) {
 }  // namespace
 
 // ------------------------------------------------------------------------------ forward
+bool window_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e);
+int window_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s);
+bool window_supports_dgrad(const cb_conv_desc* d);
+int window_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved, int x_act,
+                      const void* dx_add, void* dx, cudaStream_t s);
+int window_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle, const void* x_saved,
+                         int x_act, const void* dx_add, void* dx, cudaStream_t s);
+static bool use_window() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CB_NO_WINDOW"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
 bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
+    if (use_window() && window_supports_fwd(d, e)) return true;
     if (!device_ok() || !dense_nhwc(d) || e->norm_mean) return false;
     int mt;
     if (!pick_bn(d->out_c, &mt)) return false;
@@ -239,6 +256,8 @@ bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
 
 int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
     CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
+    if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
+    if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
     Plan pl{};
     pl.bn = pick_bn(d->out_c, &pl.mt);
     Geo g = fwd_geo(d);
@@ -263,6 +282,8 @@ int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_
 // which is a stride-1 forward over dy with the filter walked backwards; linear layers are the 1x1 case.
 bool umma_supports_dgrad(const cb_conv_desc* d) {
     if (!device_ok()) return false;
+    if (use_window() && window_supports_dgrad(d)) return true;
+    if (use_window() && window_supports_dgrad(d)) return true;
     int mt;
     if (!pick_bn(d->in_c, &mt)) return false;
     if (d->k_h == 1 && d->k_w == 1 && d->in_h == 1 && d->in_w == 1 && d->out_c % 8 == 0) return true;
@@ -275,6 +296,7 @@ bool umma_supports_dgrad(const cb_conv_desc* d) {
 int umma_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved, int x_act,
                     const void* dx_add, void* dx, cudaStream_t s) {
     CB_REQUIRE(dy && w_t && dx, CB_E_ARG, "cb_conv_dgrad: null pointer");
+    if (use_window() && window_supports_dgrad(d)) return window_conv_dgrad(d, dy, w_t, x_saved, x_act, dx_add, dx, s);
     Plan pl{};
     pl.bn = pick_bn(d->in_c, &pl.mt);
     umma::GemmParams& p = pl.p;
@@ -318,6 +340,7 @@ int umma_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuf
                        int x_act, const void* dx_add, void* dx, cudaStream_t s) {
     CB_REQUIRE(dy && w_shuffle && dx, CB_E_ARG, "cb_conv_dgrad_s2: null pointer");
     CB_REQUIRE(umma_supports_dgrad_s2(d), CB_E_ARG, "cb_conv_dgrad_s2: unsupported shape or device");
+    if (use_window()) return window_conv_dgrad_s2(d, dy, w_shuffle, x_saved, x_act, dx_add, dx, s);
     Plan pl{};
     pl.bn = 128; pl.mt = 2;
     umma::GemmParams& p = pl.p;
@@ -342,6 +365,207 @@ bool umma_supports_wgrad(const cb_conv_desc*) { return false; }
 int umma_conv_wgrad(const cb_conv_desc*, const void*, const void*, const float*, const float*, float*, float*,
                     float, cudaStream_t) {
     return fail(CB_E_ARG, "umma_conv_wgrad: not built");
+}
+
+}  // namespace cb
+
+// =================================================================================================
+// Window kernels (umma_window.cuh): host-side planning
+// =================================================================================================
+#include "umma_window.cuh"
+
+namespace cb {
+namespace {
+
+constexpr int kSmemBudget = 224 * 1024;      // dynamic shared memory we allow ourselves per CTA
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct WindowGeo {
+    // tensor read through TMA (bf16 NHWC) and its view
+    const void* x; int n, h, w, c;
+    bool s2;                    // stride-2 k4 c32 "two pixels per row" view with two row-parity planes
+    int gh, gw, vh, vw;         // pixel grid per sample and stored part
+    int y0, x0;                 // grid origin in tensor coordinates (negative = zero padding)
+    int ntaps; int tap_plane[umma::kMaxTaps], tap_shift[umma::kMaxTaps];
+};
+
+// encode the slab tensor map (box = one plane of S samples) and fill the slab part of WindowParams
+int plan_slab(CUtensorMap* tm, const WindowGeo& g, int S, umma::WindowParams& p) {
+    p.S = S; p.gh = g.gh; p.gw = g.gw; p.vh = g.vh; p.vw = g.vw; p.n_samples = g.n;
+    p.tiles = (g.n + S - 1) / S;
+    p.plane_rows = S * g.gh * g.gw;
+    p.plane_bytes = round_up(p.plane_rows * 128, 1024);
+    memset(p.a_coord, 0, sizeof(p.a_coord));
+    if (!g.s2) {
+        uint64_t dims[4] = {(uint64_t)g.c, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+        uint64_t strides[3] = {(uint64_t)g.c * 2, (uint64_t)g.w * g.c * 2, (uint64_t)g.h * g.w * g.c * 2};
+        uint32_t box[4] = {64, (uint32_t)g.gw, (uint32_t)g.gh, (uint32_t)S};
+        int rc = encode_bf16(tm, g.x, 4, dims, strides, box); if (rc) return rc;
+        p.a_rank = 4; p.a_sample_dim = 3; p.nplanes = 1;
+        p.a_coord[0][1] = g.x0; p.a_coord[0][2] = g.y0;
+    } else {
+        uint64_t dims[5] = {64, (uint64_t)g.w / 2, 2, (uint64_t)g.h / 2, (uint64_t)g.n};
+        uint64_t strides[4] = {128, (uint64_t)g.w * 64, (uint64_t)g.w * 128, (uint64_t)g.h * g.w * 64};
+        uint32_t box[5] = {64, (uint32_t)g.gw, 1, (uint32_t)g.gh, (uint32_t)S};
+        int rc = encode_bf16(tm, g.x, 5, dims, strides, box); if (rc) return rc;
+        p.a_rank = 5; p.a_sample_dim = 4; p.nplanes = 2;
+        p.a_coord[1][2] = 1;                                 // second plane: odd rows
+    }
+    p.stage_bytes = p.nplanes * p.plane_bytes;
+    p.kb_count = g.ntaps;
+    int max_shift = 0;
+    for (int i = 0; i < g.ntaps; ++i) {
+        p.kb_plane[i] = g.tap_plane[i]; p.kb_shift[i] = g.tap_shift[i];
+        p.kb_off16[i] = (g.tap_plane[i] * p.plane_bytes + g.tap_shift[i] * 128) >> 4;
+        if (g.tap_shift[i] > max_shift) max_shift = g.tap_shift[i];
+    }
+    p.slack_bytes = round_up((256 + max_shift) * 128, 1024);   // a shifted M=256 window may run this far past a plane
+    return CB_OK;
+}
+
+void taps_s1(WindowGeo& g, int k, bool flipped) {
+    g.ntaps = k * k;
+    for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+            int i = kh * k + kw;
+            g.tap_plane[i] = 0;
+            g.tap_shift[i] = flipped ? ((k - 1 - kh) * g.gw + (k - 1 - kw)) : (kh * g.gw + kw);
+        }
+}
+
+template <int BN>
+int launch_window(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
+    const int w_bytes = p.kb_count * BN * 128;
+    int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 512;
+    p.stages = avail / p.stage_bytes;
+    if (p.stages > umma::kMaxStages) p.stages = umma::kMaxStages;
+    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "window conv: slab does not fit shared memory (stage %d B)", p.stage_bytes);
+    const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 512;
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma::umma_window_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+        attr = true;
+    }
+    int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+    umma::umma_window_conv_kernel<BN><<<grid, umma::kGemmThreads, smem, s>>>(tmA, tmW, p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int plan_weights(CUtensorMap* tm, const void* w, int bn, long long k_total) {
+    uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)bn};
+    uint64_t strides[1] = {(uint64_t)k_total * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    return encode_bf16(tm, w, 2, dims, strides, box);
+}
+
+// two stages of one-plane slabs + resident weights + slack must fit the shared-memory budget
+bool window_fits(int ntaps, int bn, int plane_rows, int nplanes, int max_shift) {
+    int w_bytes = ntaps * bn * 128;
+    int stage = nplanes * round_up(plane_rows * 128, 1024);
+    int slack = round_up((256 + max_shift) * 128, 1024);
+    return w_bytes + 2 * stage + slack + 1536 <= kSmemBudget;
+}
+
+bool window_shape_s1(int c, int k, int gh, int gw, int n_out) {
+    if (!(c == 64 && k * k <= umma::kMaxTaps && gh * gw <= 256 && gw <= 256 && gh <= 256 &&
+          (n_out == 64 || n_out == 128)))
+        return false;
+    int S = 256 / (gh * gw);
+    return window_fits(k * k, n_out, S * gh * gw, 1, (k - 1) * gw + k - 1);
+}
+
+}  // namespace
+
+// ---- forward ----------------------------------------------------------------------------------
+bool window_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
+    if (!device_ok() || !dense_nhwc(d) || e->norm_mean || e->side_dim) return false;
+    if (d->stride == 1 && d->k_h == d->k_w && d->k_h > 1 && !(d->k_h == d->in_h && d->pad == 0))
+        return window_shape_s1(d->in_c, d->k_h, d->in_h + 2 * d->pad, d->in_w + 2 * d->pad, d->out_c);
+    if (d->stride == 2 && d->k_h == 4 && d->k_w == 4 && d->pad == 0 && d->in_c == 32 && d->in_h % 2 == 0 &&
+        d->in_w % 2 == 0 && (d->in_h / 2) * (d->in_w / 2) <= 128 && (d->out_c == 64 || d->out_c == 128))
+        return true;
+    return false;
+}
+
+int window_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
+    CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
+    WindowGeo g{};
+    g.x = x; g.n = d->n; g.h = d->in_h; g.w = d->in_w; g.c = d->in_c;
+    g.vh = d->out_h; g.vw = d->out_w;
+    if (d->stride == 1) {
+        g.s2 = false; g.gh = d->in_h + 2 * d->pad; g.gw = d->in_w + 2 * d->pad; g.y0 = g.x0 = -d->pad;
+        taps_s1(g, d->k_h, false);
+    } else {
+        g.s2 = true; g.gh = d->in_h / 2; g.gw = d->in_w / 2;
+        g.ntaps = 8;
+        for (int kh = 0; kh < 4; ++kh)
+            for (int j = 0; j < 2; ++j) { g.tap_plane[kh * 2 + j] = kh & 1; g.tap_shift[kh * 2 + j] = (kh >> 1) * g.gw + j; }
+    }
+    umma::WindowParams p{};
+    CUtensorMap tmA, tmW;
+    int S = 256 / (g.gh * g.gw);
+    int rc = plan_slab(&tmA, g, S, p); if (rc) return rc;
+    rc = plan_weights(&tmW, w, d->out_c, (long long)d->k_h * d->k_w * d->in_c); if (rc) return rc;
+    p.epi.n_total = d->out_c;
+    p.epi.bias = e->bias; p.epi.act = d->act;
+    p.epi.residual = (const __nv_bfloat16*)e->residual;
+    p.epi.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.epi.out_f32 = e->out_f32;
+    return d->out_c == 64 ? launch_window<64>(tmA, tmW, p, s) : launch_window<128>(tmA, tmW, p, s);
+}
+
+// ---- dgrad -------------------------------------------------------------------------------------
+bool window_supports_dgrad(const cb_conv_desc* d) {
+    if (!device_ok()) return false;
+    if (d->stride == 1 && d->k_h == d->k_w && d->k_h > 1 && !(d->k_h == d->in_h && d->pad == 0))
+        return window_shape_s1(d->out_c, d->k_h, d->in_h + d->k_h - 1, d->in_w + d->k_w - 1, d->in_c);
+    return false;
+}
+
+int window_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const void* x_saved, int x_act,
+                      const void* dx_add, void* dx, cudaStream_t s) {
+    CB_REQUIRE(dy && w_t && dx, CB_E_ARG, "cb_conv_dgrad: null pointer");
+    const int k = d->k_h;
+    WindowGeo g{};
+    g.x = dy; g.n = d->n; g.h = d->out_h; g.w = d->out_w; g.c = d->out_c; g.s2 = false;
+    g.gh = d->in_h + k - 1; g.gw = d->in_w + k - 1; g.vh = d->in_h; g.vw = d->in_w;
+    g.y0 = g.x0 = d->pad - (k - 1);
+    taps_s1(g, k, true);
+    umma::WindowParams p{};
+    CUtensorMap tmA, tmW;
+    int S = 256 / (g.gh * g.gw);
+    int rc = plan_slab(&tmA, g, S, p); if (rc) return rc;
+    rc = plan_weights(&tmW, w_t, d->in_c, (long long)k * k * d->out_c); if (rc) return rc;
+    p.epi.n_total = d->in_c;
+    p.epi.add_pre = (const __nv_bfloat16*)dx_add;
+    p.epi.actgrad_src = (const __nv_bfloat16*)x_saved; p.epi.actgrad_act = x_act;
+    p.epi.out_bf16 = (__nv_bfloat16*)dx;
+    return d->in_c == 64 ? launch_window<64>(tmA, tmW, p, s) : launch_window<128>(tmA, tmW, p, s);
+}
+
+int window_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle, const void* x_saved,
+                         int x_act, const void* dx_add, void* dx, cudaStream_t s) {
+    WindowGeo g{};
+    g.x = dy; g.n = d->n; g.h = d->out_h; g.w = d->out_w; g.c = d->out_c; g.s2 = false;
+    g.vh = d->in_h / 2; g.vw = d->in_w / 2; g.gh = g.vh + 1; g.gw = g.vw + 1;
+    g.y0 = g.x0 = -1;
+    g.ntaps = 4;
+    for (int u = 0; u < 2; ++u)
+        for (int v = 0; v < 2; ++v) { g.tap_plane[u * 2 + v] = 0; g.tap_shift[u * 2 + v] = (1 - u) * g.gw + (1 - v); }
+    umma::WindowParams p{};
+    CUtensorMap tmA, tmW;
+    int S = 256 / (g.gh * g.gw);
+    CB_REQUIRE(S >= 1 && d->out_c == 64 && d->in_c == 32, CB_E_ARG, "cb_conv_dgrad_s2: unsupported shape");
+    int rc = plan_slab(&tmA, g, S, p); if (rc) return rc;
+    rc = plan_weights(&tmW, w_shuffle, 128, 4LL * d->out_c); if (rc) return rc;
+    p.epi.n_total = 128;
+    p.epi.add_pre = (const __nv_bfloat16*)dx_add;
+    p.epi.actgrad_src = (const __nv_bfloat16*)x_saved; p.epi.actgrad_act = x_act;
+    p.epi.out_bf16 = (__nv_bfloat16*)dx;
+    p.epi.shuffle = 1; p.epi.sh_ph = g.vh; p.epi.sh_pw = g.vw; p.epi.sh_h = d->in_h; p.epi.sh_w = d->in_w;
+    return launch_window<128>(tmA, tmW, p, s);
 }
 
 }  // namespace cb

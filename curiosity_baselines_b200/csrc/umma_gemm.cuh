@@ -16,6 +16,12 @@
 
 namespace umma {
 
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (one per
+// TMEM lane quarter).  192 threads at one CTA/SM leave the epilogue warps the full 255-register budget,
+// which the operand prefetch needs; more epilogue warps would have to spill.
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
 struct CoordMap {          // coordinate = ((index / div) % mod) * mul   (mod == 0: no modulo)
     int div[5], mod[5], mul[5];
 };
@@ -101,8 +107,159 @@ __device__ __forceinline__ void add_bf16_row(float (&v)[32], const __nv_bfloat16
     for (int j = 0; j < 32; ++j) v[j] += g[j];
 }
 
+// Row-major side operands of one 32-column chunk, fetched ahead of use (they are global-memory
+// reads on the epilogue's critical path: skip gradient, saved activation, residual).
+struct AuxRegs { uint4 other[4], grad[4]; };   // other = add_pre (dgrad) or residual (forward), never both
+
+__device__ __forceinline__ void aux_load(const GemmParams& p, long long co, AuxRegs& a) {
+    const __nv_bfloat16* other = p.add_pre ? p.add_pre : p.residual;
+    if (other) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(other + co);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a.other[q] = __ldg(s4 + q);
+    }
+    if (p.actgrad_src) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(p.actgrad_src + co);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a.grad[q] = __ldg(s4 + q);
+    }
+}
+
+__device__ __forceinline__ void unpack_bf16x32(const uint4 (&u)[4], float (&g)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            g[q * 8 + e * 2] = f.x; g[q * 8 + e * 2 + 1] = f.y;
+        }
+    }
+}
+
+// One 32-column chunk of one output row: accumulator -> bias/side -> (+add_pre) -> activation ->
+// (*act'(saved)) -> (+residual) -> bf16 / fp32 stores.  `co` = element offset of the chunk in every
+// row-major operand, n0 = first column (for bias / side weights), sv = the row's side inputs.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&raw)[32], long long co, int n0,
+                                               const float (&sv)[16], const AuxRegs& aux) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (p.bias) {
+        const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b4 = __ldg(bsrc + q);
+            v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+        }
+    }
+    if (p.side_dim) {
+        const float* sw = p.side_w + (long long)n0 * p.side_dim;
+        for (int s = 0; s < p.side_dim; ++s) {
+            const float a = sv[s];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(a, __ldg(sw + j * p.side_dim + s), v[j]);
+        }
+    }
+    if (p.add_pre) {
+        float g[32];
+        unpack_bf16x32(aux.other, g);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += g[j];
+    }
+    if (p.act == CB_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (p.act == CB_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
+    } else if (p.act == CB_ACT_ELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+    }
+    if (p.actgrad_src) {
+        float g[32];
+        unpack_bf16x32(aux.grad, g);
+        if (p.actgrad_act == CB_ACT_ELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : g[j] + 1.f;
+        } else if (p.actgrad_act != CB_ACT_NONE) {
+            const float slope = p.actgrad_act == CB_ACT_LRELU ? 0.01f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : slope;
+        }
+    }
+    if (p.residual && !p.add_pre) {
+        float g[32];
+        unpack_bf16x32(aux.other, g);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += g[j];
+    }
+    if (p.out_bf16) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + co);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+            dst[q] = u;
+        }
+    }
+    if (p.out_f32) {
+        float4* dst = reinterpret_cast<float4*>(p.out_f32 + co);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    }
+}
+
+// Epilogue of one accumulator stage for one warp: MT*BN/32 (sub-tile, 32-column chunk) items.
+// The loop is deliberately NOT unrolled: the chunk body is ~1.5k instructions and an unrolled
+// epilogue overflows the instruction cache (measured: 2x slower).  Side operands of the first item
+// are requested before the accumulator is awaited and each later item's while the previous one is
+// processed, so their global-memory latency overlaps the MMAs / the math.
+// row_fn(r, valid, grow): maps tile row r to its output row.
+template <int BN, int MT, class RowFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int quarter, int lane,
+                                              int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
+    constexpr int NCH = BN / 32;
+    constexpr int ITEMS = MT * NCH;
+    bool valid[MT]; long long grow[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) row_fn(mt * 128 + quarter * 32 + lane, valid[mt], grow[mt]);
+    float sv[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) sv[s] = 0.f;
+    AuxRegs cur, nxt;
+    if (valid[0]) aux_load(p, chunk_offset(p, grow[0], n_base), cur);
+    mbar_wait(tfull, parity);
+    fence_after_thread_sync();
+#pragma unroll 1
+    for (int it = 0; it < ITEMS; ++it) {
+        const int mt = it / NCH, cb = it - mt * NCH;
+        const bool v_now = MT == 1 ? valid[0] : (mt ? valid[MT - 1] : valid[0]);
+        const long long g_now = MT == 1 ? grow[0] : (mt ? grow[MT - 1] : grow[0]);
+        if (p.side_dim && cb == 0) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s)
+                sv[s] = (v_now && s < p.side_dim) ? __ldg(p.side + g_now * p.side_dim + s) : 0.f;
+        }
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * BN + cb * 32), raw);
+        if (it + 1 < ITEMS) {          // request the next item's side operands while this one is in flight
+            const int mt2 = (it + 1) / NCH, cb2 = (it + 1) - mt2 * NCH;
+            const bool v2 = MT == 1 ? valid[0] : (mt2 ? valid[MT - 1] : valid[0]);
+            const long long g2 = MT == 1 ? grow[0] : (mt2 ? grow[MT - 1] : grow[0]);
+            if (v2) aux_load(p, chunk_offset(p, g2, n_base + cb2 * 32), nxt);
+        }
+        tmem_ld_wait();
+        if (v_now) epilogue_chunk(p, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, cur);
+        cur = nxt;
+    }
+}
+
 template <int BN, int MT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
     using Cfg = GemmConfig<BN, MT>;
@@ -171,16 +328,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(full_bar(stage), phase);
                     fence_after_thread_sync();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    // descriptors differ only in the start-address field: add (bytes >> 4) to the low word
+                    const uint64_t da0 = make_smem_desc(sa, 16, 1024);
+                    const uint64_t db0 = make_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {           // 4 x UMMA_K(16) = 64
-                            const uint64_t da = make_smem_desc(sa + mt * 16384 + k * 32, 16, 1024);
-                            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
-                            mma_f16_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < 4; ++k)             // 4 x UMMA_K(16) = 64
+                            mma_f16_ss(d_tmem, da0 + (uint64_t)(mt * 1024 + k * 2), db0 + (uint64_t)(k * 2), idesc,
+                                       (kb | k) ? 1u : 0u);
                     }
                     mma_commit(empty_bar(stage));             // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -189,100 +346,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+    } else if (warp >= kEpiWarp0) {
+        // ------------------------------------------------------------------ epilogue
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            fence_after_thread_sync();
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int r = mt * 128 + quarter * 32 + lane;           // row inside the tile
-                const long long grow = (long long)tm * p.rows_per_tile + r;
-                const bool valid = r < p.rows_per_tile && grow < p.m_total;
-                float sv[16];
-                if (p.side_dim) {
-#pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        sv[s] = (valid && s < p.side_dim) ? __ldg(p.side + grow * p.side_dim + s) : 0.f;
-                }
-#pragma unroll
-                for (int cb = 0; cb < BN / 32; ++cb) {
-                    uint32_t raw[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                           (uint32_t)((acc * MT + mt) * BN + cb * 32);
-                    tmem_ld_32x32(taddr, raw);
-                    tmem_ld_wait();
-                    if (valid) {
-                        const int n0 = tn * BN + cb * 32;
-                        const long long co = chunk_offset(p, grow, n0);
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                        if (p.bias) {
-                            const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 b4 = __ldg(bsrc + q);
-                                v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
-                            }
-                        }
-                        if (p.side_dim) {
-                            const float* sw = p.side_w + (long long)n0 * p.side_dim;
-                            for (int s = 0; s < p.side_dim; ++s) {
-                                const float a = sv[s];
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = fmaf(a, __ldg(sw + j * p.side_dim + s), v[j]);
-                            }
-                        }
-                        if (p.add_pre) add_bf16_row(v, p.add_pre + co);
-                        // activation: one branch per 32-column chunk, branch-free per element
-                        if (p.act == CB_ACT_RELU) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (p.act == CB_ACT_LRELU) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
-                        } else if (p.act == CB_ACT_ELU) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
-                        }
-                        if (p.actgrad_src) {
-                            float g[32];
-                            load_bf16_row(g, p.actgrad_src + co);
-                            if (p.actgrad_act == CB_ACT_ELU) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : g[j] + 1.f;
-                            } else if (p.actgrad_act != CB_ACT_NONE) {
-                                const float slope = p.actgrad_act == CB_ACT_LRELU ? 0.01f : 0.f;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : slope;
-                            }
-                        }
-                        if (p.residual) add_bf16_row(v, p.residual + co);
-                        if (p.out_bf16) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + co);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u;
-                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-                                dst[q] = u;
-                            }
-                        }
-                        if (p.out_f32) {
-                            float4* dst = reinterpret_cast<float4*>(p.out_f32 + co);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BN, MT>(p, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
+                                  tfull_bar(acc), acc_phase,
+                                  [&](int r, bool& valid, long long& grow) {
+                                      grow = (long long)tm * p.rows_per_tile + r;
+                                      valid = r < p.rows_per_tile && grow < p.m_total;
+                                  });
             fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));

@@ -1,0 +1,311 @@
+// "Window" kernels: convolutions whose input slab is loaded into shared memory ONCE per tile and
+// whose filter taps are read as row-shifted windows of that slab.
+//
+// On B200 the 128-byte swizzle is a pure function of the shared-memory address (pinned by
+// tests/test_gpu_umma_probe.py), so a UMMA descriptor may start at any 128-byte row of a
+// TMA-written slab.  For a stride-1 convolution over a gh x gw pixel grid, the A operand of tap
+// (kh, kw) for "output position = every grid pixel" is the slab itself shifted by kh*gw + kw rows;
+// grid pixels whose window would leave the image produce rows that are simply not stored.  This
+// trades (gh*gw)/(oh*ow) extra MMA rows for a k_h*k_w-fold cut of L2->SM traffic, which is what
+// bounds these skinny-N (32/64 channel) layers.  The weights stay resident in shared memory.
+//
+//   window_conv : K-major A (slab rows = pixels), B = resident [N][K] weights        fwd / dgrad
+//   window_wgrad: MN-major A = slab (M = channel chunk of one or two taps, K = pixels),
+//                 MN-major B = dy on the same grid (zero outside the valid outputs);
+//                 accumulates over all slabs of a CTA in TMEM, then atomically adds to dW
+#pragma once
+#include "umma_gemm.cuh"
+
+namespace umma {
+
+constexpr int kMaxPlanes = 2;
+constexpr int kMaxTaps = 16;
+constexpr int kMaxStages = 8;
+
+struct WindowParams {
+    // slab: nplanes TMA boxes per tile, each `plane_rows` rows of 128 B
+    int nplanes, plane_rows, plane_bytes, stage_bytes, stages, slack_bytes;
+    int a_rank, a_sample_dim, S;           // coord[a_sample_dim] = tile * S
+    int a_coord[kMaxPlanes][5];            // constant start coordinates of each plane
+    // taps (k-blocks of 64): plane and row shift
+    int kb_count, kb_plane[kMaxTaps], kb_shift[kMaxTaps];
+    int kb_off16[kMaxTaps];                // (plane*plane_bytes + shift*128) >> 4, filled by the host
+    // pixel grid per sample and its valid (stored) part
+    int gh, gw, vh, vw, n_samples, tiles;
+    GemmParams epi;                        // epilogue operands (n_total == BN, shuffle fields honoured)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                        const WindowParams p) {
+    constexpr int MT = 2;
+    constexpr int TMEM_COLS = (2 * MT * BN <= 256) ? 256 : 512;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t w_bytes = (uint32_t)p.kb_count * BN * 128;
+    const uint32_t a_base = smem_base + w_bytes;
+    const uint32_t a_bytes = (uint32_t)p.stages * p.stage_bytes + p.slack_bytes;
+    const uint32_t bar_base = a_base + a_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+    const uint32_t w_bar = bar_base + 8u * (2 * kMaxStages + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // one-time zero of the slab area: rows a shifted window reads past a slab are then always finite
+    {
+        uint4* z = reinterpret_cast<uint4*>(gen_base + w_bytes);
+        for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmW);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weights: kb_count boxes of {64, BN}
+            mbar_arrive_expect_tx(w_bar, w_bytes);
+            for (int kb = 0; kb < p.kb_count; ++kb)
+                tma_load_2d(smem_base + kb * BN * 128, &tmW, w_bar, kb * 64, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.nplanes * p.plane_rows * 128));
+                for (int pl = 0; pl < p.nplanes; ++pl) {
+                    int c[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) c[i] = p.a_coord[pl][i];
+                    c[p.a_sample_dim] += tile * p.S;
+                    tma_load(p.a_rank, a_base + stage * p.stage_bytes + pl * p.plane_bytes, &tmA, full_bar(stage), c);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            mbar_wait(w_bar, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                mbar_wait(full_bar(stage), phase);
+                fence_after_thread_sync();
+                const uint64_t da0 = make_smem_desc(a_base + stage * p.stage_bytes, 16, 1024);
+                const uint64_t db0 = make_smem_desc(smem_base, 16, 1024);
+                for (int kb = 0; kb < p.kb_count; ++kb) {
+                    const uint64_t da = da0 + (uint64_t)p.kb_off16[kb];
+                    const uint64_t db = db0 + (uint64_t)(kb * BN * 8);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16_ss(d_tmem, da + (uint64_t)(mt * 1024 + k * 2), db + (uint64_t)(k * 2), idesc,
+                                       (kb | k) ? 1u : 0u);
+                    }
+                }
+                mma_commit(empty_bar(stage));
+                mma_commit(tfull_bar(acc));
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        const int quarter = warp & 3;
+        const int grid_px = p.gh * p.gw;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            epilogue_tile<BN, MT>(p.epi, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
+                                  acc_phase, [&](int r, bool& valid, long long& grow) {
+                                      const int s = r / grid_px, rem = r - s * grid_px;
+                                      const int gy = rem / p.gw, gx = rem - gy * p.gw;
+                                      const long long sample = (long long)tile * p.S + s;
+                                      valid = s < p.S && gy < p.vh && gx < p.vw && sample < p.n_samples;
+                                      grow = (sample * p.vh + gy) * p.vw + gx;
+                                  });
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) { fence_after_thread_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: D_g[M=128][N=BN] += sum over K rows of A_g^T B, both operands MN-major, K = rows
+// (samples or grid pixels) of the stage.  One CTA owns a set of accumulators for its whole K range
+// (split-K across CTAs) and finally atomically adds them into dW.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxAcc = 8;
+
+struct WgradParams {
+    // stage contents: na + nb TMA boxes
+    int na, nb;
+    int a_rank, b_rank;
+    int a_coord[4][5], b_coord[4][5];      // constant start coordinates per box
+    int a_step_dim, b_step_dim, a_step, b_step;     // coord[step_dim] += slab * step
+    int a_box_bytes, b_box_bytes;          // bytes deposited per box
+    int a_box_stride, b_box_stride;        // smem distance between consecutive boxes of an operand
+    int stage_bytes, stages, slack_bytes, b_offset;  // B boxes start at stage + b_offset
+    int k_rows;                            // K rows consumed per slab (multiple of 16)
+    // work partition: CTA -> (unit, split); unit selects coordinate offsets for A/B columns
+    int units, splits, slabs_total;
+    int unit_div;                          // a_unit = unit / unit_div, b_unit = unit % unit_div
+    int a_unit_dim, a_unit_step, b_unit_dim, b_unit_step;
+    // accumulators
+    int n_acc;
+    int acc_a_off[kMaxAcc];                // byte offset of the accumulator's A window inside the stage
+    int acc_a_lbo[kMaxAcc];                // distance between its two 64-wide M chunks
+    // output: dw index = base(lane<64 ? 0 : 1) + (lane%64)*m_stride + col*n_stride (+ unit offsets)
+    long long acc_base0[kMaxAcc], acc_base1[kMaxAcc];      // base1 < 0: upper half unused
+    long long m_stride, n_stride, unit_m_off, unit_n_off;
+    int n_cols_total, n_unit_cols;         // valid columns: min(BN, n_cols_total - unit_n*n_unit_cols)
+    float* dw;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t a_bytes = (uint32_t)p.stages * p.stage_bytes + p.slack_bytes;
+    const uint32_t bar_base = smem_base + a_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    const uint32_t done_bar = bar_base + 8u * (2 * kMaxStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        uint4* z = reinterpret_cast<uint4*>(gen_base);
+        for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int unit = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+    const int a_unit = unit / p.unit_div, b_unit = unit % p.unit_div;
+    // slabs of this split: split, split + splits, ...
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int slab = split; slab < p.slabs_total; slab += p.splits) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.na * p.a_box_bytes + p.nb * p.b_box_bytes));
+                const uint32_t st = smem_base + stage * p.stage_bytes;
+                for (int i = 0; i < p.na; ++i) {
+                    int c[5];
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) c[d] = p.a_coord[i][d];
+                    c[p.a_step_dim] += slab * p.a_step;
+                    c[p.a_unit_dim] += a_unit * p.a_unit_step;
+                    tma_load(p.a_rank, st + i * p.a_box_stride, &tmA, full_bar(stage), c);
+                }
+                for (int i = 0; i < p.nb; ++i) {
+                    int c[5];
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) c[d] = p.b_coord[i][d];
+                    c[p.b_step_dim] += slab * p.b_step;
+                    c[p.b_unit_dim] += b_unit * p.b_unit_step;
+                    tma_load(p.b_rank, st + p.b_offset + i * p.b_box_stride, &tmB, full_bar(stage), c);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            bool first = true;
+            for (int slab = split; slab < p.slabs_total; slab += p.splits) {
+                mbar_wait(full_bar(stage), phase);
+                fence_after_thread_sync();
+                const uint32_t st = smem_base + stage * p.stage_bytes;
+                const int ksteps = p.k_rows / 16;
+                for (int g = 0; g < p.n_acc; ++g) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(g * BN);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t da = make_smem_desc(st + p.acc_a_off[g] + k * 2048, (uint32_t)p.acc_a_lbo[g], 1024);
+                        const uint64_t db = make_smem_desc(st + p.b_offset + k * 2048, (uint32_t)p.b_box_stride, 1024);
+                        mma_f16_ss(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                    }
+                }
+                first = false;
+                mma_commit(empty_bar(stage));
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            mma_commit(done_bar);
+        }
+    } else {
+        // epilogue: wait for the CTA's whole K range, then atomically add into dW
+        const int quarter = warp & 3;
+        const bool any = split < p.slabs_total;
+        if (any) {
+            mbar_wait(done_bar, 0);
+            fence_after_thread_sync();
+            const int row = quarter * 32 + lane;                 // accumulator row (TMEM lane)
+            int ncols = BN;
+            if (p.n_cols_total) {
+                int left = p.n_cols_total - b_unit * p.n_unit_cols;
+                ncols = left < BN ? left : BN;
+            }
+            for (int g = 0; g < p.n_acc; ++g) {
+                const long long base = row < 64 ? p.acc_base0[g] : p.acc_base1[g];
+                const long long o = base + (long long)(row & 63) * p.m_stride + (long long)a_unit * p.unit_m_off +
+                                    (long long)b_unit * p.unit_n_off;
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * BN + cb * 32), raw);
+                    tmem_ld_wait();
+                    if (base >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = cb * 32 + j;
+                            if (col < ncols) atomicAdd(p.dw + o + (long long)col * p.n_stride, __uint_as_float(raw[j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) { fence_after_thread_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace umma

@@ -230,6 +230,16 @@ int cb_unprepare_conv_grad(const float* g, float* dst, int32_t o, int32_t i, int
 int cb_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch,
               int64_t width_bytes, int64_t rows, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Kernel-author diagnostics (not on the product path): run `ksteps` tcgen05.mma over raw
+ * shared-memory images with explicit descriptor fields {start, lbo, sbo, base_offset, kstep}
+ * (bytes) and return the [128][N] fp32 accumulator.  Used by tests/test_gpu_umma_probe.py to pin
+ * the MN-major / base_offset descriptor semantics on the installed hardware.
+ * ---------------------------------------------------------------------------------- */
+int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, const int* a_desc_host,
+                  const int* b_desc_host, int a_mn_major, int b_mn_major, int M, int N, int ksteps,
+                  float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
