@@ -211,6 +211,23 @@ int check_desc(const cb_conv_desc* d, const char* who) {
 
 namespace cb {
 
+// x = beta * x (beta == 0 stores zeros); used to pre-scale atomically accumulated outputs
+int scale_buffer(float* x, int64_t n, float beta, cudaStream_t s) {
+    scale_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(x, n, beta);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// out[c] = beta*out[c] + sum_rows dy[rows][c]   (bias gradient)
+int colsum_bf16(const void* dy, int64_t rows, int c, float* out, float beta, cudaStream_t s) {
+    int rc = scale_buffer(out, c, beta, s); if (rc) return rc;
+    int64_t rpb = std::max<int64_t>(64, ceil_div<int64_t>(rows, 148 * 4));
+    dim3 g2((unsigned)ceil_div<int64_t>(rows, rpb), (unsigned)ceil_div(c, 128));
+    colsum_kernel<<<g2, 128, 0, s>>>((const __nv_bfloat16*)dy, rows, c, out, rpb);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 int simt_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
     int rc = check_desc(d, "cb_conv_fwd"); if (rc) return rc;
     CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");

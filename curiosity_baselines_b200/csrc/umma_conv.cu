@@ -360,13 +360,6 @@ int umma_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuf
     return dispatch(pl, s);
 }
 
-// ------------------------------------------------------------------------------ wgrad (not yet on tcgen05)
-bool umma_supports_wgrad(const cb_conv_desc*) { return false; }
-int umma_conv_wgrad(const cb_conv_desc*, const void*, const void*, const float*, const float*, float*, float*,
-                    float, cudaStream_t) {
-    return fail(CB_E_ARG, "umma_conv_wgrad: not built");
-}
-
 }  // namespace cb
 
 // =================================================================================================
@@ -566,6 +559,175 @@ int window_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_sh
     p.epi.out_bf16 = (__nv_bfloat16*)dx;
     p.epi.shuffle = 1; p.epi.sh_ph = g.vh; p.epi.sh_pw = g.vw; p.epi.sh_h = d->in_h; p.epi.sh_w = d->in_w;
     return launch_window<128>(tmA, tmW, p, s);
+}
+
+}  // namespace cb
+
+// =================================================================================================
+// Weight gradients on tcgen05 (umma_wgrad_kernel): MN-major operands, split-K over CTAs
+// =================================================================================================
+namespace cb {
+
+int scale_buffer(float* x, int64_t n, float beta, cudaStream_t s);
+int colsum_bf16(const void* dy, int64_t rows, int c, float* out, float beta, cudaStream_t s);
+
+namespace {
+
+enum WgradKind { WG_NONE = 0, WG_ROWS, WG_CONV_S1, WG_CONV_S2 };
+
+WgradKind wgrad_kind(const cb_conv_desc* d) {
+    if (!device_ok() || !dense_nhwc(d)) return WG_NONE;
+    const long long K = (long long)d->k_h * d->k_w * d->in_c;
+    if (d->k_h == d->in_h && d->k_w == d->in_w && d->pad == 0 && d->out_h == 1 && d->out_w == 1 &&
+        d->out_c % 128 == 0 && K % 8 == 0)
+        return WG_ROWS;
+    if (d->stride == 1 && d->k_h == d->k_w && d->k_h > 1 && d->k_h * d->k_w <= 2 * umma::kMaxAcc &&
+        d->in_c == 64 && d->out_c == 64 && (d->in_h + 2 * d->pad) * (d->in_w + 2 * d->pad) <= 81)
+        return WG_CONV_S1;
+    if (d->stride == 2 && d->k_h == 4 && d->k_w == 4 && d->pad == 0 && d->in_c == 32 && d->out_c == 64 &&
+        d->in_h % 2 == 0 && d->in_w % 2 == 0 && (d->in_h / 2) * (d->in_w / 2) <= 100)
+        return WG_CONV_S2;
+    return WG_NONE;
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const umma::WgradParams& p, cudaStream_t s) {
+    const int smem = p.stages * p.stage_bytes + p.slack_bytes + 1024 + 512;
+    CB_REQUIRE(smem <= kSmemBudget && p.stages >= 2, CB_E_ARG, "wgrad: stages do not fit shared memory");
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma::umma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBudget));
+        attr = true;
+    }
+    umma::umma_wgrad_kernel<BN><<<p.units * p.splits, 192, smem, s>>>(tmA, tmB, p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+}  // namespace
+
+bool umma_supports_wgrad(const cb_conv_desc* d) { return wgrad_kind(d) != WG_NONE; }
+
+int umma_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* mean, const float* rstd,
+                    float* dw, float* dbias, float beta, cudaStream_t s) {
+    CB_REQUIRE(x && dy && dw, CB_E_ARG, "cb_conv_wgrad: null pointer");
+    CB_REQUIRE(!mean && !rstd, CB_E_ARG, "cb_conv_wgrad: normalised uint8 input has no tcgen05 path");
+    const WgradKind kind = wgrad_kind(d);
+    const long long K = (long long)d->k_h * d->k_w * d->in_c;
+    int rc = scale_buffer(dw, (int64_t)d->out_c * K, beta, s); if (rc) return rc;
+    if (dbias) {
+        rc = colsum_bf16(dy, (int64_t)d->n * d->out_h * d->out_w, d->out_c, dbias, beta, s); if (rc) return rc;
+    }
+    umma::WgradParams p{};
+    CUtensorMap tmA, tmB;
+    p.dw = dw;
+    p.unit_div = 1;
+    if (kind == WG_ROWS) {
+        // dW[out][K] = dy^T x : A = dy [n, out] (M = out chunk), B = x [n, K] (N = 256 columns)
+        uint64_t da[2] = {(uint64_t)d->out_c, (uint64_t)d->n}; uint64_t sa[1] = {(uint64_t)d->out_c * 2};
+        uint64_t db[2] = {(uint64_t)K, (uint64_t)d->n};        uint64_t sb[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {64, 64};
+        rc = encode_bf16(&tmA, dy, 2, da, sa, box); if (rc) return rc;
+        rc = encode_bf16(&tmB, x, 2, db, sb, box); if (rc) return rc;
+        p.na = 2; p.nb = 4; p.a_rank = p.b_rank = 2;
+        for (int i = 0; i < 4; ++i) { p.a_coord[i][0] = i * 64; p.b_coord[i][0] = i * 64; }
+        p.a_step_dim = p.b_step_dim = 1; p.a_step = p.b_step = 64;
+        p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = 128; p.b_unit_step = 256;
+        p.a_box_bytes = p.b_box_bytes = 8192; p.a_box_stride = p.b_box_stride = 8192;
+        p.b_offset = 2 * 8192; p.stage_bytes = 6 * 8192; p.stages = 4; p.slack_bytes = 0; p.k_rows = 64;
+        const int n_tiles = (int)((K + 255) / 256);
+        p.units = (d->out_c / 128) * n_tiles; p.unit_div = n_tiles;
+        p.slabs_total = (d->n + 63) / 64;
+        p.n_acc = 1; p.acc_a_off[0] = 0; p.acc_a_lbo[0] = 8192;
+        p.acc_base0[0] = 0; p.acc_base1[0] = 64 * K;
+        p.m_stride = K; p.n_stride = 1; p.unit_m_off = 128 * K; p.unit_n_off = 256;
+        p.n_cols_total = (int)K; p.n_unit_cols = 256;
+        int splits = (2 * sm_count()) / p.units; if (splits < 1) splits = 1;
+        if (splits > p.slabs_total) splits = p.slabs_total;
+        p.splits = splits;
+        return launch_wgrad<256>(tmA, tmB, p, s);
+    }
+    if (kind == WG_CONV_S1) {
+        const int k = d->k_h, gh = d->in_h + 2 * d->pad, gw = d->in_w + 2 * d->pad;
+        const int S = 256 / (gh * gw) > 0 ? 256 / (gh * gw) : 1;
+        const int rows = S * gh * gw;
+        uint64_t dx4[4] = {64, (uint64_t)d->in_w, (uint64_t)d->in_h, (uint64_t)d->n};
+        uint64_t sx[3] = {128, (uint64_t)d->in_w * 128, (uint64_t)d->in_h * d->in_w * 128};
+        uint64_t dy4[4] = {64, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n};
+        uint64_t sy[3] = {128, (uint64_t)d->out_w * 128, (uint64_t)d->out_h * d->out_w * 128};
+        uint32_t box[4] = {64, (uint32_t)gw, (uint32_t)gh, (uint32_t)S};
+        rc = encode_bf16(&tmA, x, 4, dx4, sx, box); if (rc) return rc;
+        rc = encode_bf16(&tmB, dy, 4, dy4, sy, box); if (rc) return rc;     // beyond out_h/out_w: zero fill
+        p.na = 1; p.nb = 1; p.a_rank = p.b_rank = 4;
+        p.a_coord[0][1] = -d->pad; p.a_coord[0][2] = -d->pad;
+        p.a_step_dim = p.b_step_dim = 3; p.a_step = p.b_step = S;
+        p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = p.b_unit_step = 0;
+        p.k_rows = round_up(rows, 16);
+        const int max_shift = (k - 1) * gw + (k - 1);
+        const int a_region = round_up((p.k_rows + max_shift + 1) * 128, 1024);
+        const int b_region = round_up(p.k_rows * 128, 1024);
+        p.a_box_bytes = p.b_box_bytes = rows * 128;
+        p.a_box_stride = a_region; p.b_box_stride = b_region;
+        p.b_offset = a_region; p.stage_bytes = a_region + b_region; p.slack_bytes = 0;
+        p.stages = (kSmemBudget - 1536) / p.stage_bytes; if (p.stages > 4) p.stages = 4;
+        p.units = 1; p.slabs_total = (d->n + S - 1) / S;
+        p.splits = p.slabs_total < sm_count() ? p.slabs_total : sm_count();
+        const int taps = k * k;
+        p.n_acc = (taps + 1) / 2;
+        for (int g = 0; g < p.n_acc; ++g) {
+            const int t0 = 2 * g, t1 = 2 * g + 1;
+            const int s0 = (t0 / k) * gw + (t0 % k);
+            p.acc_a_off[g] = s0 * 128;
+            p.acc_base0[g] = (long long)t0 * 64;
+            if (t1 < taps) {
+                const int s1 = (t1 / k) * gw + (t1 % k);
+                p.acc_a_lbo[g] = (s1 - s0) * 128;
+                p.acc_base1[g] = (long long)t1 * 64;
+            } else {
+                p.acc_a_lbo[g] = 128;            // upper half computed from a neighbouring window and discarded
+                p.acc_base1[g] = -1;
+            }
+        }
+        p.m_stride = 1; p.n_stride = K;
+        return launch_wgrad<64>(tmA, tmB, p, s);
+    }
+    if (kind == WG_CONV_S2) {
+        const int gh = d->in_h / 2, gw = d->in_w / 2;
+        const int S = 2 * gh * gw <= 208 ? 2 : 1;
+        const int rows = S * gh * gw;
+        uint64_t dx5[5] = {64, (uint64_t)gw, 2, (uint64_t)gh, (uint64_t)d->n};
+        uint64_t sx[4] = {128, (uint64_t)d->in_w * 64, (uint64_t)d->in_w * 128, (uint64_t)d->in_h * d->in_w * 64};
+        uint32_t boxa[5] = {64, (uint32_t)gw, 1, (uint32_t)gh, (uint32_t)S};
+        uint64_t dy4[4] = {64, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n};
+        uint64_t sy[3] = {128, (uint64_t)d->out_w * 128, (uint64_t)d->out_h * d->out_w * 128};
+        uint32_t boxb[4] = {64, (uint32_t)gw, (uint32_t)gh, (uint32_t)S};
+        rc = encode_bf16(&tmA, x, 5, dx5, sx, boxa); if (rc) return rc;
+        rc = encode_bf16(&tmB, dy, 4, dy4, sy, boxb); if (rc) return rc;
+        p.na = 2; p.nb = 1; p.a_rank = 5; p.b_rank = 4;
+        p.a_coord[1][2] = 1;
+        p.a_step_dim = 4; p.b_step_dim = 3; p.a_step = p.b_step = S;
+        p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = p.b_unit_step = 0;
+        p.k_rows = round_up(rows, 16);
+        const int max_shift = gw + 1;
+        const int a_region = round_up((p.k_rows + max_shift + 1) * 128, 1024);
+        const int b_region = round_up(p.k_rows * 128, 1024);
+        p.a_box_bytes = p.b_box_bytes = rows * 128;
+        p.a_box_stride = a_region; p.b_box_stride = b_region;
+        p.b_offset = 2 * a_region; p.stage_bytes = 2 * a_region + b_region; p.slack_bytes = 0;
+        p.stages = (kSmemBudget - 1536) / p.stage_bytes; if (p.stages > 4) p.stages = 4;
+        p.units = 1; p.slabs_total = (d->n + S - 1) / S;
+        p.splits = p.slabs_total < sm_count() ? p.slabs_total : sm_count();
+        p.n_acc = 4;
+        for (int kh = 0; kh < 4; ++kh) {
+            p.acc_a_off[kh] = (kh & 1) * a_region + (kh >> 1) * gw * 128;
+            p.acc_a_lbo[kh] = 128;                      // kw pairs j = 0, 1 are one grid column apart
+            p.acc_base0[kh] = kh * 128; p.acc_base1[kh] = kh * 128 + 64;
+        }
+        p.m_stride = 1; p.n_stride = K;
+        return launch_wgrad<64>(tmA, tmB, p, s);
+    }
+    return fail(CB_E_ARG, "cb_conv_wgrad: no tcgen05 specialisation for this shape");
 }
 
 }  // namespace cb

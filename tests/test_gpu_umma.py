@@ -143,3 +143,47 @@ def test_fc_dgrad_flat(n):
     ref = (dy @ bf(lin.weight)).reshape(n, 64, 7, 7).permute(0, 2, 3, 1).reshape(-1, 64)
     ref = ref * torch.where(saved > 0, 1.0, 0.01)
     assert rel(dx, ref) < 5e-3
+
+
+@pytest.mark.parametrize("K,out,n", [(512, 512, 100), (512, 512, 5000), (1024, 512, 333), (512, 128, 70)])
+def test_linear_wgrad(K, out, n):
+    torch.manual_seed(7)
+    lin = nn.Linear(K, out).to(DEV)
+    layer = LY.linear_layer(lin, "none")
+    x = bf(torch.randn(n, K, device=DEV))
+    dy = bf(torch.randn(n, out, device=DEV))
+    layer.wgrad(x.to(torch.bfloat16), dy.to(torch.bfloat16), n)
+    assert rel(lin.weight.grad, dy.t() @ x) < 1e-4
+    assert rel(lin.bias.grad, dy.sum(0)) < 1e-4
+    layer.wgrad(x.to(torch.bfloat16), dy.to(torch.bfloat16), n, accumulate=True)
+    assert rel(lin.weight.grad, 2 * (dy.t() @ x)) < 1e-4
+
+
+@pytest.mark.parametrize("n", [5, 1000])
+def test_fc_wgrad(n):
+    torch.manual_seed(8)
+    lin = nn.Linear(3136, 512).to(DEV)
+    layer = LY.linear_layer(lin, "none", spatial=(7, 64))
+    a = bf(torch.randn(n, 64, 7, 7, device=DEV))
+    dy = bf(torch.randn(n, 512, device=DEV))
+    layer.wgrad(a.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), dy.to(torch.bfloat16), n)
+    assert rel(lin.weight.grad, dy.t() @ a.reshape(n, -1)) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(64, 9, 9, 64, 3, 1, 0, 4), (64, 9, 9, 64, 3, 1, 0, 1001),
+                                  (32, 20, 20, 64, 4, 2, 0, 3), (32, 20, 20, 64, 4, 2, 0, 777),
+                                  (64, 7, 7, 64, 3, 1, 1, 50)])
+def test_conv_wgrad(case):
+    in_c, h, w, out_c, k, s, p, n = case
+    torch.manual_seed(9)
+    conv = nn.Conv2d(in_c, out_c, k, s, p).to(DEV)
+    layer = LY.conv_layer(conv, (h, w, in_c), "lrelu")
+    x = bf(torch.randn(n, in_c, h, w, device=DEV))
+    dy = bf(torch.randn(n, out_c, layer.out_h, layer.out_w, device=DEV))
+    wq = bf(conv.weight).detach().requires_grad_(True)
+    bq = conv.bias.detach().clone().requires_grad_(True)
+    F.conv2d(x, wq, bq, stride=s, padding=p).backward(dy)
+    layer.wgrad(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
+                dy.permute(0, 2, 3, 1).reshape(-1, out_c).contiguous().to(torch.bfloat16), n)
+    assert rel(conv.weight.grad, wq.grad) < 1e-4
+    assert rel(conv.bias.grad, bq.grad) < 1e-4

@@ -55,6 +55,10 @@ cases["conv3_dgrad"] = (lambda: conv3.dgrad(a3, n, x_saved=a2, x_act="lrelu"), 2
 dy2 = torch.randn(n * 81, 64, device=dev).to(torch.bfloat16)
 cases["conv2_dgrad"] = (lambda: conv2.dgrad(dy2, n, x_saved=a1, x_act="lrelu"), 2.0 * 512 * 64 * 81 * n)
 cases["fc_dgrad"] = (lambda: fc.dgrad(h, n, x_saved=a3, x_act="lrelu"), 2.0 * 3136 * 512 * n)
+cases["lin_wgrad"] = (lambda: lin.wgrad(h, h, n), 2.0 * 512 * 512 * n)
+cases["fc_wgrad"] = (lambda: fc.wgrad(a3, h, n), 2.0 * 3136 * 512 * n)
+cases["conv3_wgrad"] = (lambda: conv3.wgrad(a2, a3, n), 2.0 * 576 * 64 * 49 * n)
+cases["conv2_wgrad"] = (lambda: conv2.wgrad(a1, dy2, n), 2.0 * 512 * 64 * 81 * n)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
         continue
