@@ -49,7 +49,7 @@ class GemmLayer:
         self.K = k * k * self.in_c
         # a Linear over a flattened [c,k,k] map: its dgrad is a plain [*, K] linear dgrad
         self.flat_linear = k > 1 and k == self.in_h == self.in_w and pad == 0
-        self.w_fwd = self.w_t = self.w_shuffle = self.bias = self.side_w = None
+        self.w_fwd = self.w_t = self.w_shuffle = self.w_native = self.bias = self.side_w = None
         self._version = None
 
     # ---------------------------------------------------------------- weights
@@ -78,6 +78,9 @@ class GemmLayer:
                                    device=dev)
         L.call("cb_prepare_conv_weight", L.ptr(w4), L.ptr(self.w_fwd), L.ptr(self.w_t),
                self.out_c, self.in_c, self.k, self.k, L.stream())
+        if self.k == 8 and self.stride == 4 and self.pad == 0 and self.out_c == 32 and self.in_c <= 4:
+            # first Burda conv: the uint8 tcgen05 kernel consumes torch's own (c, kh, kw) order
+            self.w_native = w4.reshape(self.out_c, -1).to(torch.bfloat16).contiguous()
         if self.flat_linear:        # [K, out_c] with K in (h, w, c) order
             self.w_t = self.w_fwd.t().contiguous()
         if self.stride == 2 and self.k == 4 and self.pad == 0 and self.in_c == 32:
@@ -125,8 +128,15 @@ class GemmLayer:
         e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
         d = self.desc(n, in_dtype, strides)
         xp = x if isinstance(x, int) else L.ptr(x)
-        L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(self.w_fwd), C.byref(e), L.stream())
+        if self._use_conv1(d) and yb is not None and yf is None:
+            L.call("cb_conv1_fwd", C.byref(d), xp, L.ptr(self.w_native), C.byref(e), L.stream())
+        else:
+            L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(self.w_fwd), C.byref(e), L.stream())
         return yb, yf
+
+    def _use_conv1(self, d):
+        return (self.w_native is not None and d.in_dtype == L.U8 and _engine != L.ENGINE_SIMT
+                and bool(L.load().cb_conv1_supported(C.byref(d))))
 
     # ---------------------------------------------------------------- backward
     def dgrad(self, dy, n, x_saved=None, x_act="none", dx_add=None):
@@ -171,6 +181,10 @@ class GemmLayer:
         d = self.desc(n, in_dtype, strides)
         xp = x if isinstance(x, int) else L.ptr(x)
         mean, rstd = (L.ptr(norm[0]), L.ptr(norm[1])) if norm is not None else (None, None)
+        if self._use_conv1(d):      # gradient lands directly in the torch layout
+            L.call("cb_conv1_wgrad", C.byref(d), xp, L.ptr(dy), mean, rstd, L.ptr(w.grad), L.ptr(b.grad), beta,
+                   L.stream())
+            return
         if direct or not accumulate:
             L.call("cb_conv_wgrad", C.byref(d), xp, L.ptr(dy), mean, rstd, L.ptr(dw),
                    L.ptr(b.grad), beta if direct else 0.0, L.stream())

@@ -160,6 +160,15 @@ int cb_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, const 
 int cb_conv_dgrad_s2_supported(const cb_conv_desc* d);
 int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle,
                      const void* x_saved, int32_t x_act, const void* dx_add, void* dx, void* stream);
+/* tcgen05 first convolution of the Burda / RND encoders: 8x8 stride 4, uint8 NCHW frames read in
+ * place (in_stride_w == 1, in_stride_h == in_w), 1..4 input channels, 32 output channels; the RND
+ * normalisation (e->norm_mean / norm_rstd) is applied while the patch tile is built.
+ * w_native / dw_native use torch's own [32][in_c][8][8] order (bf16 / fp32). */
+int cb_conv1_supported(const cb_conv_desc* d);
+int cb_conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e,
+                 void* stream);
+int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
+                   const float* norm_rstd, float* dw_native, float* dbias, float beta, void* stream);
 /* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise
  * (NULL to skip).  x addressed as in cb_conv_fwd (norm_* honoured for CB_U8). */
 int cb_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,

@@ -187,3 +187,39 @@ def test_conv_wgrad(case):
                 dy.permute(0, 2, 3, 1).reshape(-1, out_c).contiguous().to(torch.bfloat16), n)
     assert rel(conv.weight.grad, wq.grad) < 1e-4
     assert rel(conv.bias.grad, bq.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,n,norm", [(1, 3, True), (1, 700, True), (4, 2, False), (4, 301, False), (1, 5, False)])
+def test_conv1_uint8_fwd_wgrad(cin, n, norm):
+    """Burda / RND conv1 on tcgen05: uint8 NCHW frames read in place, normalisation in the loader."""
+    torch.manual_seed(10)
+    C = 4
+    frames = torch.randint(0, 256, (n, C, 84, 84), dtype=torch.uint8, device=DEV)
+    mean = torch.rand(84 * 84, device=DEV) * 255
+    rstd = 1.0 / (torch.rand(84 * 84, device=DEV) * 60 + 20)
+    conv = nn.Conv2d(cin, 32, 8, 4).to(DEV)
+    layer = LY.conv_layer(conv, (84, 84, cin), "lrelu")
+    if cin == 1:
+        base = frames.data_ptr() + (C - 1) * 7056
+        strides = (C * 7056, 84, 1, 7056)
+        xin = frames[:, -1:].float()
+    else:
+        base = frames.data_ptr()
+        strides = (C * 7056, 84, 1, 7056)
+        xin = frames.float()
+    nm = (mean, rstd) if norm else None
+    if norm:
+        xin = ((xin - mean.view(1, 1, 84, 84)) * rstd.view(1, 1, 84, 84)).clamp(-5, 5)
+    yb, _ = layer.forward(base, n, in_dtype=L.U8, strides=strides, norm=nm)
+    ref = F.leaky_relu(F.conv2d(bf(xin), bf(conv.weight), conv.bias, stride=4))
+    assert rel(yb, ref.permute(0, 2, 3, 1).reshape(-1, 32)) < 5e-3
+    dy = bf(torch.randn(n, 32, 20, 20, device=DEV))
+    dyb = dy.permute(0, 2, 3, 1).reshape(-1, 32).contiguous().to(torch.bfloat16)
+    wq = bf(conv.weight).detach().requires_grad_(True)
+    bq = conv.bias.detach().clone().requires_grad_(True)
+    F.conv2d(bf(xin), wq, bq, stride=4).backward(dy)
+    layer.wgrad(base, dyb, n, in_dtype=L.U8, strides=strides, norm=nm)
+    assert rel(conv.weight.grad, wq.grad) < 1e-4
+    assert rel(conv.bias.grad, bq.grad) < 1e-4
+    layer.wgrad(base, dyb, n, in_dtype=L.U8, strides=strides, norm=nm, accumulate=True)
+    assert rel(conv.weight.grad, 2 * wq.grad) < 1e-4

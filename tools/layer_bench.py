@@ -59,6 +59,14 @@ cases["lin_wgrad"] = (lambda: lin.wgrad(h, h, n), 2.0 * 512 * 512 * n)
 cases["fc_wgrad"] = (lambda: fc.wgrad(a3, h, n), 2.0 * 3136 * 512 * n)
 cases["conv3_wgrad"] = (lambda: conv3.wgrad(a2, a3, n), 2.0 * 576 * 64 * 49 * n)
 cases["conv2_wgrad"] = (lambda: conv2.wgrad(a1, dy2, n), 2.0 * 512 * 64 * 81 * n)
+from curiosity_baselines_b200 import _lib as L
+conv1 = LY.conv_layer(nn.Conv2d(1, 32, 8, 4).to(dev), (84, 84, 1), "lrelu")
+frames = torch.randint(0, 256, (n, 1, 84, 84), dtype=torch.uint8, device=dev)
+nm = (torch.rand(7056, device=dev) * 255, torch.rand(7056, device=dev) / 50 + 0.01)
+st1 = (7056, 84, 1, 7056)
+dy1 = torch.randn(n * 400, 32, device=dev).to(torch.bfloat16)
+cases["conv1_fwd"] = (lambda: conv1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm), 2.0 * 64 * 32 * 400 * n)
+cases["conv1_wgrad"] = (lambda: conv1.wgrad(frames.data_ptr(), dy1, n, in_dtype=L.U8, strides=st1, norm=nm), 2.0 * 64 * 32 * 400 * n)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
         continue
