@@ -14,94 +14,91 @@
 // Warp roles: 0-3 converters (one tile row per thread), 4 = TMEM owner + MMA issuer, 5-8 epilogue.
 #include "common.cuh"
 #include "umma_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int kThreads = 288;
+constexpr int kConvWarps = 8;           // converter warps
+constexpr int kConvThreads = kConvWarps * 32;
+constexpr int kMmaWarp = kConvWarps;   // MMA issuer / TMEM owner
+constexpr int kThreads = (kConvWarps + 1 + 4) * 32;    // + 4 epilogue warps
 constexpr int kMaxStages1 = 4;
 constexpr int kMaxCin = 4;
+constexpr int kConvBar = 1;            // named barrier of the converter threads
 
 struct Conv1Params {
-    const uint8_t* x; long long stride_n, stride_c; int h, w, cin, oh, ow;
-    long long total_rows; int tiles, stages;
+    const uint8_t* x; long long stride_n, stride_c; int h, w, cin, oh, ow, n;
+    int rows, row_tiles;               // oh*ow output positions per sample, ceil(rows/128)
+    int pitch;                         // bytes per row of the normalised bf16 frame in shared memory
+    int units, stages, a_stage_bytes;  // units = n*cin (one channel of one sample each)
     const float* mean; const float* rstd;
-    // forward
-    const __nv_bfloat16* w_bf16;        // [32][cin*64] K-major (torch layout cast to bf16)
-    const float* bias; int act; __nv_bfloat16* out;
+    // forward: one or two networks sharing the input (RND target + predictor)
+    int nets; const __nv_bfloat16* w_bf16[2]; const float* bias[2]; int act; __nv_bfloat16* out[2];
     // wgrad
     const __nv_bfloat16* dy; float* dw;
+    int debug;                         // CB_CONV1_DEBUG bits (profiling only): 1 no stats, 2 no stores, 4 no assemble, 8 no frame loads
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kConvBar), "n"(kConvThreads) : "memory"); }
 
-// builds row r of the A tile (all k-blocks) in shared memory; a_stage = generic pointer to the stage
-__device__ __forceinline__ void convert_row(const Conv1Params& p, uint8_t* a_stage, int r, long long grow) {
-    const bool valid = grow < p.total_rows;
-    int n = 0, oy = 0, ox = 0;
-    if (valid) {
-        const int pp = p.oh * p.ow;
-        n = (int)(grow / pp);
-        const int rem = (int)(grow - (long long)n * pp);
-        oy = rem / p.ow; ox = rem - oy * p.ow;
+constexpr int kMaxGroups = 8;          // 4-pixel groups per converter thread: ceil(h*w/4/256) (84x84 -> 7)
+
+// one channel of one sample: global uint8 -> registers (issued early so the latency overlaps other work)
+__device__ __forceinline__ void frame_prefetch(const Conv1Params& p, int unit, int tid, uint32_t (&px)[kMaxGroups]) {
+    const int groups = p.h * p.w / 4;
+    const int s = unit / p.cin, c = unit - s * p.cin;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.x + s * p.stride_n + c * p.stride_c);
+#pragma unroll
+    for (int i = 0; i < kMaxGroups; ++i) {
+        const int g = tid + i * kConvThreads;
+        px[i] = (unit < p.units && g < groups && !(p.debug & 8)) ? __ldg(src + g) : 0u;
     }
-    const int px0 = (4 * oy) * p.w + 4 * ox;
-    for (int c = 0; c < p.cin; ++c) {
-        const uint8_t* src = p.x + n * p.stride_n + c * p.stride_c + px0;
-        uint8_t* dst_row = a_stage + c * 16384 + r * 128;
-        // all loads of the patch first (8 rows x 8 bytes, plus the statistics), so their latencies overlap
-        uint32_t lo[8], hi[8];
+}
+
+// registers -> normalised bf16 frame F[h][pitch] in shared memory
+__device__ __forceinline__ void frame_store(const Conv1Params& p, int tid, const uint32_t (&px)[kMaxGroups], uint8_t* F,
+                                            const float4* s_mean, const float4* s_rstd) {
+    const int groups = p.h * p.w / 4, w4 = p.w / 4;
+    int y = tid / w4, x4 = tid - y * w4;
+    const int dy = kConvThreads / w4, dx = kConvThreads - dy * w4;
 #pragma unroll
-        for (int kh = 0; kh < 8; ++kh) {
-            lo[kh] = valid ? __ldg(reinterpret_cast<const uint32_t*>(src + kh * p.w)) : 0u;
-            hi[kh] = valid ? __ldg(reinterpret_cast<const uint32_t*>(src + kh * p.w + 4)) : 0u;
-        }
-        if (p.mean && valid) {
+    for (int i = 0; i < kMaxGroups; ++i) {
+        const int g = tid + i * kConvThreads;
+        if (g < groups) {
+            float v[4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float4 m[8], sd[8];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int kh = half * 4 + q;
-                    const float4* m4 = reinterpret_cast<const float4*>(p.mean + px0 + kh * p.w);
-                    const float4* r4 = reinterpret_cast<const float4*>(p.rstd + px0 + kh * p.w);
-                    m[2 * q] = __ldg(m4); m[2 * q + 1] = __ldg(m4 + 1);
-                    sd[2 * q] = __ldg(r4); sd[2 * q + 1] = __ldg(r4 + 1);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int kh = half * 4 + q;
-                    const float mm[8] = {m[2 * q].x, m[2 * q].y, m[2 * q].z, m[2 * q].w,
-                                         m[2 * q + 1].x, m[2 * q + 1].y, m[2 * q + 1].z, m[2 * q + 1].w};
-                    const float ss[8] = {sd[2 * q].x, sd[2 * q].y, sd[2 * q].z, sd[2 * q].w,
-                                         sd[2 * q + 1].x, sd[2 * q + 1].y, sd[2 * q + 1].z, sd[2 * q + 1].w};
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j] = (float)((lo[kh] >> (8 * j)) & 0xffu);
-                        v[4 + j] = (float)((hi[kh] >> (8 * j)) & 0xffu);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf((v[j] - mm[j]) * ss[j], -5.f), 5.f);
-                    *reinterpret_cast<uint4*>(dst_row + ((kh ^ (r & 7)) << 4)) =
-                        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-                }
+            for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+            if (p.mean && !(p.debug & 1)) {
+                const float4 m = s_mean[g], r = s_rstd[g];        // statistics staged in shared memory
+                v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
             }
-        } else {
-#pragma unroll
-            for (int kh = 0; kh < 8; ++kh) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    v[j] = (float)((lo[kh] >> (8 * j)) & 0xffu);
-                    v[4 + j] = (float)((hi[kh] >> (8 * j)) & 0xffu);
-                }
-                *reinterpret_cast<uint4*>(dst_row + ((kh ^ (r & 7)) << 4)) =
-                    make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-            }
+            *reinterpret_cast<uint2*>(F + y * p.pitch + x4 * 8) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
         }
+        y += dy; x4 += dx;
+        if (x4 >= w4) { x4 -= w4; ++y; }
+    }
+}
+
+// F -> patch tile: row (oy, ox), 16-byte chunk kh = 8 bf16 of frame row 4*oy+kh starting at pixel 4*ox
+__device__ __forceinline__ void assemble(const Conv1Params& p, int tid, const uint8_t* F, uint8_t* A) {
+    const int kh = tid & 7;
+    int row = tid >> 3;
+    int oy = row / p.ow, ox = row - oy * p.ow;
+    constexpr int RS = kConvThreads / 8;       // rows covered per sweep
+    const int step_y = RS / p.ow, step_x = RS - step_y * p.ow;
+    for (; row < p.rows; row += RS) {
+        const uint2* src = reinterpret_cast<const uint2*>(F + (4 * oy + kh) * p.pitch + 8 * ox);
+        const uint2 lo = src[0], hi = src[1];
+        *reinterpret_cast<uint4*>(A + row * 128 + ((kh ^ (row & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        oy += step_y; ox += step_x;
+        if (ox >= p.ow) { ox -= p.ow; ++oy; }
     }
 }
 
@@ -110,154 +107,188 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
-    // layout: [W: cin*4096 (fwd)] [stages: A cin*16384 (+ B 16384 for wgrad)] [barriers]
-    const uint32_t w_bytes = WGRAD ? 0u : (uint32_t)p.cin * 4096u;
-    const uint32_t a_bytes = (uint32_t)p.cin * 16384u;
-    const uint32_t stage_bytes = a_bytes + (WGRAD ? 16384u : 0u);
+    // layout: [W (fwd): cin * N*128] [stages: A (+ dy rows for wgrad)] [F] [barriers]
+    const int N = WGRAD ? 64 : 32 * p.nets;
+    const uint32_t w_bytes = WGRAD ? 0u : (uint32_t)(p.cin * N * 128);
+    const uint32_t stage_bytes = (uint32_t)p.a_stage_bytes * (WGRAD ? 2u : 1u);
     const uint32_t st_base = smem_base + w_bytes;
-    const int kStages = p.stages;
-    const uint32_t bar_base = st_base + kStages * stage_bytes;
+    const uint32_t f_off = w_bytes + p.stages * stage_bytes;
+    const uint32_t f_bytes = (uint32_t)((p.h * p.pitch + 1023) & ~1023);
+    const uint32_t t_off = f_off + f_bytes;                                   // per-pixel mean | rstd (fp32)
+    const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
+    const uint32_t bar_base = smem_base + t_off + t_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages1 + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages1 + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages1 + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages1 + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
+    const uint32_t tmem_cols = WGRAD ? 256u : (N == 64 ? 512u : 256u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // weights (forward): converter threads copy W[32][cin*64] into the swizzled K-major layout
-    if (!WGRAD) {
-        for (int i = threadIdx.x; i < p.cin * 32 * 8; i += blockDim.x) {      // 16-byte chunks
-            const int chunk = i & 7, row = (i >> 3) & 31, c = i >> 8;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w_bf16 + (long long)row * p.cin * 64 + c * 64) + chunk);
-            *reinterpret_cast<uint4*>(gen + c * 4096 + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+    // zero all stages once (rows past `rows` and the padded half of the dy rows stay zero / finite)
+    {
+        uint4* z = reinterpret_cast<uint4*>(gen + w_bytes);
+        for (uint32_t i = threadIdx.x; i < p.stages * stage_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (!WGRAD) {     // weights: [net][32][cin*64] -> per channel a K-major swizzled [N rows][64] block
+        for (int i = threadIdx.x; i < p.cin * N * 8; i += blockDim.x) {
+            const int chunk = i & 7, row = (i >> 3) % N, c = (i >> 3) / N;
+            const __nv_bfloat16* wsrc = p.w_bf16[row >> 5] + (long long)(row & 31) * p.cin * 64 + c * 64;
+            *reinterpret_cast<uint4*>(gen + c * N * 128 + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                __ldg(reinterpret_cast<const uint4*>(wsrc) + chunk);
         }
-    } else {      // zero the dy stages once: their upper 64 bytes of every row stay zero (N padded 32 -> 64)
-        for (int s = 0; s < kStages; ++s) {
-            uint4* z = reinterpret_cast<uint4*>(gen + w_bytes + s * stage_bytes + a_bytes);
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.mean) {
+        float4* tm = reinterpret_cast<float4*>(gen + t_off);
+        const int g4 = p.h * p.w / 4;
+        for (int i = threadIdx.x; i < g4; i += blockDim.x) {
+            tm[i] = __ldg(reinterpret_cast<const float4*>(p.mean) + i);
+            tm[g4 + i] = __ldg(reinterpret_cast<const float4*>(p.rstd) + i);
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { umma::mbar_init(full_bar(s), 128); umma::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 4); }
         umma::fence_barrier_init();
     }
-    if (warp == 4) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
+    // CTA b owns the samples b, b+grid, ... ; a unit is one input channel of one sample
+    if (warp < kConvWarps) {
         // ------------------------------------------------------------ converters
-        const int r = threadIdx.x;
+        const int tid = threadIdx.x;
+        uint8_t* F = gen + f_off;
+        const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
+        const float4* s_rstd = s_mean + p.h * p.w / 4;
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        uint32_t px[kMaxGroups];
+        int s = blockIdx.x, c = 0;
+        frame_prefetch(p, s * p.cin + c, tid, px);
+        while (s < p.n) {
+            frame_store(p, tid, px, F, s_mean, s_rstd);
+            conv_bar_sync();                                   // F complete
+            int s2 = s, c2 = c + 1;
+            if (c2 == p.cin) { c2 = 0; s2 += gridDim.x; }
+            frame_prefetch(p, s2 < p.n ? s2 * p.cin + c2 : p.units, tid, px);      // next unit's pixels in flight
             umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-            uint8_t* a_stage = gen + w_bytes + stage * stage_bytes;
-            const long long grow = (long long)tile * 128 + r;
-            convert_row(p, a_stage, r, grow);
-            if (WGRAD) {
-                uint8_t* b_row = a_stage + a_bytes + r * 128;
-                const bool valid = grow < p.total_rows;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (valid) v = __ldg(reinterpret_cast<const uint4*>(p.dy + grow * 32) + j);
-                    *reinterpret_cast<uint4*>(b_row + ((j ^ (r & 7)) << 4)) = v;
+            uint8_t* A = gen + w_bytes + stage * stage_bytes;
+            if (!(p.debug & 4)) assemble(p, tid, F, A);
+            if (WGRAD) {       // dy rows of this sample: 64 B each into the lower half of 128-byte rows
+                uint8_t* Bs = A + p.a_stage_bytes;
+                const __nv_bfloat16* dys = p.dy + (long long)s * p.rows * 32;
+                for (int i = tid; i < p.rows * 4; i += kConvThreads) {
+                    const int row = i >> 2, j = i & 3;
+                    *reinterpret_cast<uint4*>(Bs + row * 128 + ((j ^ (row & 7)) << 4)) =
+                        __ldg(reinterpret_cast<const uint4*>(dys + row * 32) + j);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             umma::mbar_arrive(full_bar(stage));
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            conv_bar_sync();                                   // everyone has finished reading F
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            s = s2; c = c2;
         }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            bool first = true;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            bool seen[kMaxCin] = {false, false, false, false};
+            const uint32_t idesc_f = N == 64 ? umma::make_idesc(128, 64, 0, 0) : umma::make_idesc(128, 32, 0, 0);
+            constexpr uint32_t idesc_w = umma::make_idesc(64, 64, 1, 1);
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
                 if (!WGRAD) umma::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                umma::mbar_wait(full_bar(stage), phase);
-                umma::fence_after_thread_sync();
-                const uint32_t sa = st_base + stage * stage_bytes;
-                if (!WGRAD) {
-                    constexpr uint32_t idesc = umma::make_idesc(128, 32, 0, 0);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
-                    for (int c = 0; c < p.cin; ++c)
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(full_bar(stage), phase);
+                    umma::fence_after_thread_sync();
+                    const uint32_t sa = st_base + stage * stage_bytes;
+                    if (!WGRAD) {
+                        const uint32_t wb = smem_base + c * N * 128;
+                        for (int mt = 0; mt < p.row_tiles; ++mt) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 4 + mt) * N);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma::mma_f16_ss(d_tmem, umma::make_smem_desc(sa + c * 16384 + k * 32, 16, 1024),
-                                             umma::make_smem_desc(smem_base + c * 4096 + k * 32, 16, 1024), idesc,
-                                             (c | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)
+                                umma::mma_f16_ss(d_tmem, umma::make_smem_desc(sa + mt * 16384 + k * 32, 16, 1024),
+                                                 umma::make_smem_desc(wb + k * 32, 16, 1024), idesc_f, (c | k) ? 1u : 0u);
+                        }
+                    } else {
+                        const int ksteps = (p.rows + 15) / 16;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma::mma_f16_ss(tmem_base + (uint32_t)(c * 64),
+                                             umma::make_smem_desc(sa + k * 2048, 8192, 1024),
+                                             umma::make_smem_desc(sa + p.a_stage_bytes + k * 2048, 8192, 1024), idesc_w,
+                                             (!seen[c] && k == 0) ? 0u : 1u);
+                        seen[c] = true;
+                    }
                     umma::mma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                if (!WGRAD) {
                     umma::mma_commit(tfull_bar(acc));
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                } else {
-                    constexpr uint32_t idesc = umma::make_idesc(64, 64, 1, 1);
-                    for (int c = 0; c < p.cin; ++c)
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)     // 128 positions / 16
-                            umma::mma_f16_ss(tmem_base + (uint32_t)(c * 64),
-                                             umma::make_smem_desc(sa + c * 16384 + k * 2048, 8192, 1024),
-                                             umma::make_smem_desc(sa + p.cin * 16384 + k * 2048, 8192, 1024), idesc,
-                                             (first && k == 0) ? 0u : 1u);
-                    first = false;
-                    umma::mma_commit(empty_bar(stage));
                 }
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
             if (WGRAD) umma::mma_commit(tfull_bar(0));
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 5..8)
+        // ------------------------------------------------------------ epilogue (4 warps, one per TMEM lane quarter)
         const int quarter = warp & 3;
         if (!WGRAD) {
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
                 umma::mbar_wait(tfull_bar(acc), acc_phase);
                 umma::fence_after_thread_sync();
-                uint32_t raw[32];
-                umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32), raw);
-                umma::tmem_ld_wait();
-                const long long grow = (long long)tile * 128 + quarter * 32 + lane;
-                if (grow < p.total_rows) {
-                    float v[32];
+#pragma unroll 1
+                for (int it = 0; it < p.row_tiles * p.nets; ++it) {
+                    const int mt = it / p.nets, net = it - mt * p.nets;
+                    uint32_t raw[32];
+                    umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32),
+                                        raw);
+                    umma::tmem_ld_wait();
+                    const int row = mt * 128 + quarter * 32 + lane;
+                    if (row < p.rows && !(p.debug & 2)) {
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    if (p.bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                        const float* bsrc = net ? p.bias[1] : p.bias[0];
+                        if (bsrc) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bsrc);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b = __ldg(b4 + q);
-                            v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b = __ldg(b4 + q);
+                                v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+                            }
                         }
+                        if (p.act == CB_ACT_LRELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
+                        } else if (p.act == CB_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (p.act == CB_ACT_ELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                        }
+                        __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + row) * 32;
+                        uint4* dst = reinterpret_cast<uint4*>(o);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dst[q] = make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
+                                                pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
                     }
-                    if (p.act == CB_ACT_LRELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
-                    } else if (p.act == CB_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (p.act == CB_ACT_ELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + grow * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        dst[q] = make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
-                                            pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
                 }
                 umma::fence_before_thread_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-        } else if (blockIdx.x < p.tiles) {
+        } else if (blockIdx.x < p.n) {
             // M = 64 accumulator: patch element i lives in TMEM lane (i/16)*32 + i%16
             umma::mbar_wait(tfull_bar(0), 0);
             umma::fence_after_thread_sync();
@@ -276,33 +307,40 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     }
     umma::fence_before_thread_sync();
     __syncthreads();
-    if (warp == 4) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, 256); }
+    if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 bool shape_ok(const cb_conv_desc* d) {
     return d->in_dtype == CB_U8 && d->k_h == 8 && d->k_w == 8 && d->stride == 4 && d->pad == 0 && d->out_c == 32 &&
            d->in_c >= 1 && d->in_c <= kMaxCin && d->in_stride_w == 1 && d->in_stride_h == d->in_w && d->in_w % 4 == 0 &&
-           d->in_stride_n % 4 == 0 && d->in_stride_c % 4 == 0;
+           d->in_stride_n % 4 == 0 && d->in_stride_c % 4 == 0 && d->out_h * d->out_w <= 512 &&
+           (d->in_h * d->in_w / 4 + kConvThreads - 1) / kConvThreads <= kMaxGroups && d->out_w <= 32;
 }
 
 int fill(Conv1Params& p, const cb_conv_desc* d, const void* x, const float* mean, const float* rstd) {
     CB_REQUIRE(((uintptr_t)x & 3) == 0, CB_E_ALIGN, "conv1: frames must be 4-byte aligned");
     CB_REQUIRE(!mean || ((((uintptr_t)mean | (uintptr_t)rstd) & 15) == 0), CB_E_ALIGN, "conv1: mean/rstd 16-byte aligned");
     p.x = (const uint8_t*)x; p.stride_n = d->in_stride_n; p.stride_c = d->in_stride_c;
-    p.h = d->in_h; p.w = d->in_w; p.cin = d->in_c; p.oh = d->out_h; p.ow = d->out_w;
-    p.total_rows = (long long)d->n * d->out_h * d->out_w;
-    p.tiles = (int)((p.total_rows + 127) / 128);
+    p.h = d->in_h; p.w = d->in_w; p.cin = d->in_c; p.oh = d->out_h; p.ow = d->out_w; p.n = d->n;
+    p.rows = d->out_h * d->out_w; p.row_tiles = (p.rows + 127) / 128;
+    p.pitch = (d->in_w * 2 + 15) / 16 * 16;
+    if (p.pitch % 128 == 0) p.pitch += 16;
+    p.units = d->n * d->in_c;
     p.mean = mean; p.rstd = rstd;
+    { const char* e = getenv("CB_CONV1_DEBUG"); p.debug = e ? atoi(e) : 0; }
     return CB_OK;
 }
 
 template <bool WGRAD>
 int launch(Conv1Params& p, cudaStream_t s) {
-    const int stage_bytes = p.cin * 16384 + (WGRAD ? 16384 : 0);
-    const int fixed = (WGRAD ? 0 : p.cin * 4096) + 1024 + 256;
-    p.stages = (220 * 1024 - fixed) / stage_bytes;
+    // forward: rows padded to whole M=128 tiles; wgrad: K = rows rounded to 16, patches and dy rows per stage
+    p.a_stage_bytes = WGRAD ? ((p.rows + 15) / 16 * 16 * 128 + 1023) / 1024 * 1024 : p.row_tiles * 16384;
+    const int stage_bytes = p.a_stage_bytes * (WGRAD ? 2 : 1);
+    const int fixed = (WGRAD ? 0 : p.cin * 32 * p.nets * 128) + ((p.h * p.pitch + 1023) & ~1023) +
+                      (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
+    p.stages = (224 * 1024 - fixed) / stage_bytes;
     if (p.stages > kMaxStages1) p.stages = kMaxStages1;
-    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1: tile does not fit shared memory");
+    CB_REQUIRE(p.stages >= 1, CB_E_ARG, "conv1: tile does not fit shared memory");
     const int smem = fixed + p.stages * stage_bytes;
     static bool attr = false;
     if (!attr) {
@@ -312,7 +350,7 @@ int launch(Conv1Params& p, cudaStream_t s) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = p.tiles < sms ? p.tiles : sms;
+    int grid = p.n < sms ? p.n : sms;
     umma_conv1_kernel<WGRAD><<<grid, kThreads, smem, s>>>(p);
     CB_LAUNCH_CHECK();
     return CB_OK;
@@ -327,13 +365,19 @@ int colsum_bf16(const void* dy, int64_t rows, int c, float* out, float beta, cud
 
 bool conv1_supports(const cb_conv_desc* d) { return cb_device_supports_umma() && shape_ok(d); }
 
-// w_native: bf16 copy of the torch weight [32][cin][8][8] (K order c, kh, kw)
-int conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e, cudaStream_t s) {
+// w_native: bf16 copy of the torch weight [32][cin][8][8] (K order c, kh, kw).  A second network
+// (w2/bias2/out2) may share the same input pass (RND target + predictor, rnd.py:174-177).
+int conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e, const void* w2,
+              const float* bias2, void* out2, cudaStream_t s) {
     CB_REQUIRE(x && w_native && e && e->out_bf16 && !e->out_f32 && !e->residual && !e->side_dim, CB_E_ARG,
                "conv1 forward: needs a bf16 output and no residual/side operands");
+    CB_REQUIRE(!w2 || out2, CB_E_ARG, "conv1 forward: second network needs an output");
     Conv1Params p{};
     int rc = fill(p, d, x, e->norm_mean, e->norm_rstd); if (rc) return rc;
-    p.w_bf16 = (const __nv_bfloat16*)w_native; p.bias = e->bias; p.act = d->act; p.out = (__nv_bfloat16*)e->out_bf16;
+    p.nets = w2 ? 2 : 1;
+    p.w_bf16[0] = (const __nv_bfloat16*)w_native; p.bias[0] = e->bias; p.out[0] = (__nv_bfloat16*)e->out_bf16;
+    p.w_bf16[1] = (const __nv_bfloat16*)w2; p.bias[1] = bias2; p.out[1] = (__nv_bfloat16*)out2;
+    p.act = d->act;
     return launch<false>(p, s);
 }
 
@@ -343,9 +387,9 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
     CB_REQUIRE(x && dy && dw, CB_E_ARG, "conv1 wgrad: null pointer");
     Conv1Params p{};
     int rc = fill(p, d, x, mean, rstd); if (rc) return rc;
-    p.dy = (const __nv_bfloat16*)dy; p.dw = dw;
+    p.dy = (const __nv_bfloat16*)dy; p.dw = dw; p.nets = 1;
     rc = scale_buffer(dw, (int64_t)32 * d->in_c * 64, beta, s); if (rc) return rc;
-    if (dbias) { rc = colsum_bf16(dy, p.total_rows, 32, dbias, beta, s); if (rc) return rc; }
+    if (dbias) { rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s); if (rc) return rc; }
     return launch<true>(p, s);
 }
 
@@ -354,9 +398,9 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
 extern "C" int cb_conv1_supported(const cb_conv_desc* d) { return d && cb::conv1_supports(d) ? 1 : 0; }
 
 extern "C" int cb_conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e,
-                            void* stream) {
+                            const void* w2_native, const float* bias2, void* out2_bf16, void* stream) {
     CB_REQUIRE(d && cb::conv1_supports(d), CB_E_ARG, "cb_conv1_fwd: unsupported shape or device");
-    return cb::conv1_fwd(d, x, w_native, e, cb::as_stream(stream));
+    return cb::conv1_fwd(d, x, w_native, e, w2_native, bias2, out2_bf16, cb::as_stream(stream));
 }
 
 extern "C" int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,

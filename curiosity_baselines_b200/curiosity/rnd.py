@@ -131,8 +131,11 @@ class RND(nn.Module):
         obs, T, B, base, strides = self._frame_view(obs)
         n = T * B
         pred, targ = self._chains
-        _, phi = targ.forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm)
-        acts, phi_hat = pred.forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm)
+        # target and predictor read the same normalised frame: one fused first-conv pass for both
+        a1_p, _, a1_t = pred.layers[0].forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm,
+                                               twin=targ.layers[0])
+        _, phi = targ.forward(base, n, first_out=a1_t)
+        acts, phi_hat = pred.forward(base, n, first_out=a1_p)
         return obs, T, B, base, strides, phi, phi_hat, (acts if keep_acts else None)
 
     # ------------------------------------------------------------------ bonus

@@ -110,8 +110,10 @@ class GemmLayer:
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, n, in_dtype=L.BF16, strides=None, side=None, residual=None, norm=None,
-                out_bf16=True, out_f32=False):
-        """Returns (bf16 NHWC output or None, fp32 output or None), each [n*out_h*out_w, out_c]."""
+                out_bf16=True, out_f32=False, twin=None):
+        """Returns (bf16 NHWC output or None, fp32 output or None), each [n*out_h*out_w, out_c].
+        ``twin``: a second first-conv layer of identical shape reading the same uint8 input (RND
+        target + predictor); its bf16 output is then returned as a third element."""
         self.prepare()
         m = n * self.out_h * self.out_w
         dev = self.w_fwd.device
@@ -129,9 +131,19 @@ class GemmLayer:
         d = self.desc(n, in_dtype, strides)
         xp = x if isinstance(x, int) else L.ptr(x)
         if self._use_conv1(d) and yb is not None and yf is None:
-            L.call("cb_conv1_fwd", C.byref(d), xp, L.ptr(self.w_native), C.byref(e), L.stream())
+            y2 = None
+            if twin is not None:
+                twin.prepare()
+                y2 = torch.empty_like(yb)
+                L.call("cb_conv1_fwd", C.byref(d), xp, L.ptr(self.w_native), C.byref(e), L.ptr(twin.w_native),
+                       L.ptr(twin.bias), L.ptr(y2), L.stream())
+                return yb, yf, y2
+            L.call("cb_conv1_fwd", C.byref(d), xp, L.ptr(self.w_native), C.byref(e), None, None, None, L.stream())
         else:
             L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(self.w_fwd), C.byref(e), L.stream())
+        if twin is not None:      # no fused kernel for this shape/engine: run the twin separately
+            y2, _ = twin.forward(x, n, in_dtype=in_dtype, strides=strides, norm=norm)
+            return yb, yf, y2
         return yb, yf
 
     def _use_conv1(self, d):
@@ -169,6 +181,7 @@ class GemmLayer:
         torch layout."""
         if not self.trainable:
             return
+        self.prepare()
         dev = dy.device
         w, b = self.module.weight, self.module.bias
         if w.grad is None:
@@ -240,12 +253,17 @@ class Chain:
         self.layers = layers
 
     def forward(self, x, n, in_dtype=L.BF16, strides=None, norm=None, last_f32=True,
-                last_bf16=False):
+                last_bf16=False, first_out=None):
+        """``first_out``: bf16 output of layer 0 computed elsewhere (fused twin first conv)."""
         acts = []
         cur = x
         last = len(self.layers) - 1
         out_f32 = None
         for i, layer in enumerate(self.layers):
+            if i == 0 and first_out is not None:
+                acts.append(first_out)
+                cur = first_out
+                continue
             kw = dict(in_dtype=in_dtype, strides=strides, norm=norm) if i == 0 else {}
             want_f32 = last_f32 and i == last
             want_bf16 = (i != last) or last_bf16 or not last_f32

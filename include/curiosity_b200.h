@@ -163,10 +163,12 @@ int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffl
 /* tcgen05 first convolution of the Burda / RND encoders: 8x8 stride 4, uint8 NCHW frames read in
  * place (in_stride_w == 1, in_stride_h == in_w), 1..4 input channels, 32 output channels; the RND
  * normalisation (e->norm_mean / norm_rstd) is applied while the patch tile is built.
- * w_native / dw_native use torch's own [32][in_c][8][8] order (bf16 / fp32). */
+ * w_native / dw_native use torch's own [32][in_c][8][8] order (bf16 / fp32).  A second network
+ * sharing the input (w2_native, bias2, out2_bf16; NULL to skip) is computed in the same pass:
+ * RND's target and predictor read the same normalised frame (rnd.py:174-177). */
 int cb_conv1_supported(const cb_conv_desc* d);
 int cb_conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e,
-                 void* stream);
+                 const void* w2_native, const float* bias2, void* out2_bf16, void* stream);
 int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
                    const float* norm_rstd, float* dw_native, float* dbias, float beta, void* stream);
 /* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise
