@@ -1,0 +1,319 @@
+"""ICM and Disagreement on B200 -- drop-ins for rlpyt/models/curiosity/icm.py:45-145 and
+disagreement.py:44-167: same constructors, ``state_dict`` keys, ``feature_size`` attribute and
+``compute_bonus`` / ``compute_loss`` signatures.  The ``torch.nn`` sub-modules are parameter
+holders; forward and backward run in libcuriosity_b200.so.
+
+Reference behaviours kept on purpose: pixels are fed raw 0..255 (the obs_stats
+normalisation is dead code, icm.py:107-112); the forward model sees detached features; Disagreement
+has four forward models whatever ``ensemble_size`` says, unbiased variance, and an always-on
+dropout(p=0.2) on the squared error of its loss (masks can be injected for parity tests).
+"""
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import dist
+from ..layers import linear_layer
+from .encoders import make_encoder, frame_input
+
+ENC_LAST_ACT = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}
+
+
+class ResBlock(nn.Module):
+    """icm.py:9-21 (holder)."""
+
+    def __init__(self, feature_size, action_size):
+        super().__init__()
+        self.lin_1 = nn.Linear(feature_size + action_size, feature_size)
+        self.lin_2 = nn.Linear(feature_size + action_size, feature_size)
+
+
+class ResForward(nn.Module):
+    """icm.py:23-43 (holder) + executor over the library's linear layers with the one-hot action as
+    a side input of every layer (icm.py:19-21: torch.cat([x, action], 2))."""
+
+    def __init__(self, feature_size, action_size):
+        super().__init__()
+        self.feature_size, self.action_size = feature_size, action_size
+        self.lin_1 = nn.Linear(feature_size + action_size, feature_size)
+        self.res_block_1 = ResBlock(feature_size, action_size)
+        self.res_block_2 = ResBlock(feature_size, action_size)
+        self.res_block_3 = ResBlock(feature_size, action_size)
+        self.res_block_4 = ResBlock(feature_size, action_size)
+        self.lin_last = nn.Linear(feature_size + action_size, feature_size)
+        self._layers = None
+
+    def _build(self):
+        if self._layers is None:
+            A = self.action_size
+            blocks = [self.res_block_1, self.res_block_2, self.res_block_3, self.res_block_4]
+            self._layers = dict(
+                first=linear_layer(self.lin_1, "lrelu", A),
+                a=[linear_layer(b.lin_1, "lrelu", A) for b in blocks],
+                b=[linear_layer(b.lin_2, "none", A) for b in blocks],
+                last=linear_layer(self.lin_last, "none", A))
+        return self._layers
+
+    def run_forward(self, phi1_bf16, action, n):
+        """-> (saved activations, predicted phi2 fp32 [n,F])."""
+        ly = self._build()
+        x, _ = ly["first"].forward(phi1_bf16, n, side=action)
+        saved = dict(x=[x], r=[])
+        for i in range(4):
+            r, _ = ly["a"][i].forward(x, n, side=action)
+            x_new, _ = ly["b"][i].forward(r, n, side=action, residual=x)     # r2 + x   (icm.py:22)
+            saved["r"].append(r)
+            saved["x"].append(x_new)
+            x = x_new
+        _, pred = ly["last"].forward(x, n, side=action, out_bf16=False, out_f32=True)
+        return saved, pred
+
+    def run_backward(self, phi1_bf16, action, saved, dpred_bf16, n, accumulate=False):
+        ly = self._build()
+        xs, rs = saved["x"], saved["r"]
+        ly["last"].wgrad(xs[4], dpred_bf16, n, side=action, accumulate=accumulate)
+        g = ly["last"].dgrad(dpred_bf16, n)                                   # x4 = r2 + x3: no activation
+        for i in range(3, -1, -1):
+            ly["b"][i].wgrad(rs[i], g, n, side=action, accumulate=accumulate)
+            dr = ly["b"][i].dgrad(g, n, x_saved=rs[i], x_act="lrelu")
+            ly["a"][i].wgrad(xs[i], dr, n, side=action, accumulate=accumulate)
+            # skip connection: total gradient at x_i = (dr W_a + g); x_0 alone carries a LeakyReLU
+            g = ly["a"][i].dgrad(dr, n, dx_add=g, x_saved=xs[0] if i == 0 else None,
+                                 x_act="lrelu" if i == 0 else "none")
+        ly["first"].wgrad(phi1_bf16, g, n, side=action, accumulate=accumulate)
+
+
+class _IcmLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, args, *params):
+        need = any(p.requires_grad for p in params)
+        inv, fwd, g_inv, g_fwd = model._loss_and_grads(*args, need_grad=need)
+        ctx.g_inv, ctx.g_fwd = g_inv, g_fwd
+        return inv, fwd
+
+    @staticmethod
+    def backward(ctx, d_inv, d_fwd):
+        out = []
+        for gi, gf in zip(ctx.g_inv, ctx.g_fwd):
+            if gi is not None:
+                out.append(gi * d_inv)
+            elif gf is not None:
+                out.append(gf * d_fwd)
+            else:
+                out.append(None)
+        return (None, None) + tuple(out)
+
+
+class _IcmBase(nn.Module):
+    n_forward_models = 1
+
+    def _init_common(self, image_shape, action_size, feature_encoding, batch_norm, prediction_beta, obs_stats,
+                     forward_loss_wt):
+        self.prediction_beta = prediction_beta
+        self.feature_encoding = feature_encoding
+        self.obs_stats = obs_stats
+        self.action_size = action_size
+        if forward_loss_wt == -1.0:                       # icm.py:70-75
+            self.forward_loss_wt, self.inverse_loss_wt = 1.0, 1.0
+        else:
+            self.forward_loss_wt, self.inverse_loss_wt = forward_loss_wt, 1 - forward_loss_wt
+        self.encoder, self.feature_size = make_encoder(feature_encoding, image_shape, batch_norm)
+        self.inverse_model = nn.Sequential(nn.Linear(self.feature_size * 2, self.feature_size), nn.ReLU(),
+                                           nn.Linear(self.feature_size, action_size))
+        self._exec = None
+
+    # ------------------------------------------------------------------ executors
+    def _forward_models(self):
+        raise NotImplementedError
+
+    def _build(self):
+        dev = self.inverse_model[0].weight.device
+        if dev.type != "cuda":
+            raise L.CuriosityLibError("curiosity model parameters must be on a CUDA device (no CPU fallback)")
+        if self._exec is None or self._exec["dev"] != dev:
+            chain, perm = self.encoder.build_chain(True)
+            self._exec = dict(dev=dev, chain=chain,
+                              perm=None if perm is None else perm.to(dev),
+                              inv_perm=None if perm is None else torch.argsort(perm).to(dev),
+                              inv0=linear_layer(self.inverse_model[0], "relu"),
+                              inv2=linear_layer(self.inverse_model[2], "none"))
+        return self._exec
+
+    def _encode(self, frames, n):
+        ex = self._exec
+        keep, x, dtype, strides = frame_input(frames)
+        acts, phi_f = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=True, last_bf16=True)
+        phi_b = acts[-1].reshape(n, -1)
+        phi_f = phi_f.reshape(n, -1)
+        if ex["perm"] is not None:                         # NHWC -> the reference's CHW feature order
+            phi_f = phi_f.index_select(1, ex["perm"])
+            phi_b = phi_b.index_select(1, ex["perm"])
+        return dict(keep=keep, x=x, dtype=dtype, strides=strides, acts=acts), phi_f, phi_b
+
+    def _encode_backward(self, enc, dphi_bf16, n, accumulate):
+        ex = self._exec
+        if ex["inv_perm"] is not None:
+            dphi_bf16 = dphi_bf16.index_select(1, ex["inv_perm"])
+        last = ex["chain"].layers[-1]
+        dphi_bf16 = dphi_bf16.reshape(n * last.out_h * last.out_w, last.out_c)      # back to NHWC rows
+        ex["chain"].backward(enc["x"], enc["acts"], dphi_bf16.contiguous(), n, in_dtype=enc["dtype"],
+                             strides=enc["strides"], accumulate=accumulate)
+
+    def _features(self, observations, next_observations, actions):
+        """Shared by bonus and loss: (T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action[n,A])."""
+        self._build()
+        if observations.dim() != 5:
+            raise ValueError("expected [T,B,C,H,W] observations")
+        T, B = observations.shape[:2]
+        n = T * B
+        shp = observations.shape[2:]
+        enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n)
+        enc2, phi2_f, phi2_b = self._encode(next_observations.reshape(n, *shp), n)
+        action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
+        return T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action
+
+    # ------------------------------------------------------------------ loss
+    def _loss_and_grads(self, observations, next_observations, actions, valid, masks, need_grad, inplace=False):
+        if actions.dim() == 2:
+            actions = actions.unsqueeze(1)                  # icm.py:138
+        T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action = self._features(observations, next_observations,
+                                                                              actions)
+        ex, st, dev, F = self._exec, L.stream(), self._exec["dev"], self.feature_size
+        valid = valid.to(dev, torch.float32).reshape(n).contiguous()
+        denom = dist.all_reduce_sum_(valid.sum().reshape(1)) if dist.world_size() > 1 else None
+        # inverse model (icm.py:88-92, 125)
+        cat = torch.cat([phi1_b, phi2_b], 1)
+        h, _ = ex["inv0"].forward(cat, n)
+        _, logits = ex["inv2"].forward(h, n, out_bf16=False, out_f32=True)
+        ce = torch.empty(n, dtype=torch.float32, device=dev)
+        coef_inv = torch.empty(n, dtype=torch.float32, device=dev)
+        L.call("cb_loss_coef", L.ptr(valid), None, float(self.inverse_loss_wt), L.ptr(denom), L.ptr(coef_inv), n, st)
+        dlogits = torch.empty_like(logits) if need_grad else None
+        L.call("cb_cross_entropy", L.ptr(logits), L.ptr(action), L.ptr(coef_inv), L.ptr(ce), L.ptr(dlogits), n,
+               self.action_size, st)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        L.call("cb_dot", L.ptr(ce), L.ptr(coef_inv), L.ptr(losses[0:1]), n, st)
+        # forward model(s) on detached features (icm.py:126)
+        coef_fwd = torch.empty(n, dtype=torch.float32, device=dev)
+        L.call("cb_loss_coef", L.ptr(valid), None, float(self.forward_loss_wt), L.ptr(denom), L.ptr(coef_fwd), n, st)
+        fwd_terms = torch.empty(self.n_forward_models, dtype=torch.float32, device=dev)
+        fm_saved = []
+        for e, fm in enumerate(self._forward_models()):
+            saved, pred = fm.run_forward(phi1_b, action, n)
+            err = torch.empty(n, dtype=torch.float32, device=dev)
+            mask = None if masks is None else masks[e].to(dev, torch.float32).reshape(n, F).contiguous()
+            if mask is None:
+                L.call("cb_rowwise_sqerr", L.ptr(pred), L.ptr(phi2_f), 1.0 / F, L.ptr(err), n, F, st)
+            else:
+                L.call("cb_rowwise_sqerr_masked", L.ptr(pred), L.ptr(phi2_f), L.ptr(mask), self._mask_scale, 1.0 / F,
+                       L.ptr(err), n, F, st)
+            L.call("cb_dot", L.ptr(err), L.ptr(coef_fwd), L.ptr(fwd_terms[e:e + 1]), n, st)
+            fm_saved.append((fm, saved, pred, mask))
+        losses[1] = fwd_terms.sum()
+        params = list(self.parameters())
+        if not need_grad:
+            return losses[0], losses[1], [None] * len(params), [None] * len(params)
+        saved_grads = [p.grad for p in params]
+        if not inplace:
+            for p in params:
+                p.grad = None
+        # ---- backward: forward models
+        for fm, saved, pred, mask in fm_saved:
+            dpred = torch.empty(n, F, dtype=torch.bfloat16, device=dev)
+            L.call("cb_sqerr_grad", L.ptr(pred), L.ptr(phi2_f), L.ptr(coef_fwd), 1.0 / F, L.ptr(mask),
+                   self._mask_scale if mask is not None else 1.0, L.ptr(dpred), n, F, st)
+            fm.run_backward(phi1_b, action, saved, dpred, n)
+        # ---- backward: inverse model -> both encoder passes
+        dlog_b = dlogits.to(torch.bfloat16)
+        ex["inv2"].wgrad(h, dlog_b, n)
+        dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
+        ex["inv0"].wgrad(cat, dh, n)
+        dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
+        self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False)
+        self._encode_backward(enc2, dcat[:, F:].contiguous(), n, accumulate=True)
+        if inplace:
+            return losses[0], losses[1], None, None
+        g_inv, g_fwd = [], []
+        fwd_ids = {id(p) for fm in self._forward_models() for p in fm.parameters()}
+        for p, old in zip(params, saved_grads):
+            g = p.grad
+            p.grad = old
+            g_inv.append(None if id(p) in fwd_ids else g)
+            g_fwd.append(g if id(p) in fwd_ids else None)
+        return losses[0], losses[1], g_inv, g_fwd
+
+    _mask_scale = 1.0
+
+    def _default_masks(self, T, B):
+        return None
+
+    def compute_loss(self, observations, next_observations, actions, valid, dropout_masks="default"):
+        """icm.py:136-145 / disagreement.py:142-167 -> (inverse_loss_wt*inv, forward_loss_wt*fwd)."""
+        masks = self._default_masks(*observations.shape[:2]) if isinstance(dropout_masks, str) else dropout_masks
+        return _IcmLoss.apply(self, (observations, next_observations, actions, valid, masks), *self.parameters())
+
+    def loss_and_grads_(self, observations, next_observations, actions, valid, dropout_masks="default"):
+        """Fused training entry: losses + gradients left in ``.grad`` (no autograd graph)."""
+        masks = self._default_masks(*observations.shape[:2]) if isinstance(dropout_masks, str) else dropout_masks
+        inv, fwd, _, _ = self._loss_and_grads(observations, next_observations, actions, valid, masks, True, inplace=True)
+        return inv, fwd
+
+
+class ICM(_IcmBase):
+    """icm.py:45-145."""
+
+    def __init__(self, image_shape, action_size, feature_encoding="idf", batch_norm=False, prediction_beta=1.0,
+                 obs_stats=None, forward_loss_wt=0.2):
+        super().__init__()
+        self._init_common(image_shape, action_size, feature_encoding, batch_norm, prediction_beta, obs_stats,
+                          forward_loss_wt)
+        self.forward_model = ResForward(feature_size=self.feature_size, action_size=action_size)
+
+    def _forward_models(self):
+        return [self.forward_model]
+
+    @torch.no_grad()
+    def compute_bonus(self, observations, next_observations, actions):
+        """icm.py:131-134: beta * sum_f (pred_phi2 - phi2)^2 / F -> fp32 [T,B]."""
+        T, B, n, _, _, phi1_b, phi2_f, _, action = self._features(observations, next_observations, actions)
+        _, pred = self.forward_model.run_forward(phi1_b, action, n)
+        out = torch.empty(T, B, dtype=torch.float32, device=self._exec["dev"])
+        L.call("cb_rowwise_sqerr", L.ptr(pred), L.ptr(phi2_f), float(self.prediction_beta) / self.feature_size,
+               L.ptr(out), n, self.feature_size, L.stream())
+        return out
+
+
+class Disagreement(_IcmBase):
+    """disagreement.py:44-167."""
+
+    n_forward_models = 4
+    _mask_scale = 1.0 / 0.8          # F.dropout(p=0.2) rescales the kept elements
+
+    def __init__(self, image_shape, action_size, ensemble_size=5, feature_encoding="idf", batch_norm=False,
+                 prediction_beta=1.0, obs_stats=None, device="cpu", forward_loss_wt=0.2):
+        super().__init__()
+        self.ensemble_size = ensemble_size      # accepted and ignored, like the reference (disagreement.py:97-100)
+        self._init_common(image_shape, action_size, feature_encoding, batch_norm, prediction_beta, obs_stats,
+                          forward_loss_wt)
+        for e in range(1, 5):
+            setattr(self, f"forward_model_{e}", ResForward(feature_size=self.feature_size, action_size=action_size))
+
+    def _forward_models(self):
+        return [getattr(self, f"forward_model_{e}") for e in range(1, 5)]
+
+    def _default_masks(self, T, B):
+        """disagreement.py:155-164: dropout is always in training mode."""
+        dev = self.inverse_model[0].weight.device
+        return [(torch.rand(T * B, self.feature_size, device=dev) > 0.2).float() for _ in range(4)]
+
+    @torch.no_grad()
+    def compute_bonus(self, observations, next_observations, actions):
+        """disagreement.py:136-140: beta * mean_f var_e(pred_e) with the unbiased variance."""
+        T, B, n, _, _, phi1_b, _, _, action = self._features(observations, next_observations, actions)
+        preds = [fm.run_forward(phi1_b, action, n)[1] for fm in self._forward_models()]
+        dev = self._exec["dev"]
+        ptrs = torch.tensor([p.data_ptr() for p in preds], dtype=torch.int64, device=dev)
+        out = torch.empty(T, B, dtype=torch.float32, device=dev)
+        L.call("cb_ensemble_variance", L.ptr(ptrs), len(preds), float(self.prediction_beta), L.ptr(out), n,
+               self.feature_size, L.stream())
+        return out

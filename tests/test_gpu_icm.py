@@ -1,0 +1,112 @@
+"""ICM and Disagreement on the GPU vs the reference's golden vectors and the oracle.
+Tolerance (north_star): bonus / loss within 1e-2 relative (bf16 operands, fp32 accumulation)."""
+import pytest
+import torch
+
+import recipes as R
+from helpers import golden, check_grads
+from oracle import curiosity_oracle as O
+from curiosity_baselines_b200.curiosity.icm import ICM, Disagreement
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def relmax(a, b):
+    a, b = a.detach().cpu().double(), torch.as_tensor(b).double()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-12)).max())
+
+
+def test_state_dict_keys_match_reference():
+    m = ICM(image_shape=(4, 84, 84), action_size=4, feature_encoding="idf_burda")
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(R.icm_shapes(4, "idf_burda"))
+    m = ICM(image_shape=(4, 84, 84), action_size=7, feature_encoding="idf")
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(R.icm_shapes(7, "idf"))
+    d = Disagreement(image_shape=(4, 84, 84), action_size=7, feature_encoding="idf_burda")
+    assert {k: tuple(v.shape) for k, v in d.state_dict().items()} == dict(R.disagreement_shapes(7, "idf_burda"))
+    assert m.feature_size == 288 and d.feature_size == 512
+
+
+@pytest.mark.parametrize("enc,A", [("idf_burda", 4), ("idf", 7)])
+def test_icm_golden(enc, A):
+    g = golden(f"icm_{enc}")
+    T, B, seed = int(g["T"]), int(g["B"]), int(g["seed"])
+    m = ICM(image_shape=(4, 84, 84), action_size=A, feature_encoding=enc, prediction_beta=0.7,
+            forward_loss_wt=0.2).to(DEV)
+    m.load_state_dict(R.make_params(R.icm_shapes(A, enc), seed))
+    obs, nxt = R.make_frames(seed + 1, T, B).to(DEV), R.make_frames(seed + 2, T, B).to(DEV)
+    act = R.onehot(R.make_actions(seed + 3, T, B, A), A).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 4, T, B, frac=0.5)).to(DEV)
+    bonus = m.compute_bonus(obs, nxt, act)
+    assert relmax(bonus, g["bonus"]) < 1e-2
+    inv, fwd = m.compute_loss(obs, nxt, act, valid)
+    (inv + fwd).backward()
+    assert abs(float(inv) - float(g["inv_loss"])) / float(g["inv_loss"]) < 1e-2
+    assert abs(float(fwd) - float(g["fwd_loss"])) / float(g["fwd_loss"]) < 1e-2
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert len(grads) == len(list(m.parameters()))
+    # 12-15 samples and raw 0..255 inputs: deepest conv gradients see bf16 mask flips; norm within 5%
+    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)
+    assert not bad, bad
+
+
+def test_disagreement_golden():
+    g = golden("disagreement")
+    T, B, A, seed = int(g["T"]), int(g["B"]), int(g["A"]), int(g["seed"])
+    m = Disagreement(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda", prediction_beta=1.0,
+                     forward_loss_wt=0.2).to(DEV)
+    m.load_state_dict(R.make_params(R.disagreement_shapes(A, "idf_burda"), seed))
+    obs, nxt = R.make_frames(seed + 1, T, B).to(DEV), R.make_frames(seed + 2, T, B).to(DEV)
+    act = R.onehot(R.make_actions(seed + 3, T, B, A), A).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 4, T, B, frac=0.5)).to(DEV)
+    bonus = m.compute_bonus(obs, nxt, act)
+    # ensemble variance of nearly equal predictions: differences of bf16-rounded features -> 3e-2
+    assert relmax(bonus, g["bonus"]) < 3e-2
+    masks = [R.make_mask(seed + 10 + e, (T, B, 512), 0.2).to(DEV) for e in range(4)]
+    inv, fwd = m.compute_loss(obs, nxt, act, valid, dropout_masks=masks)
+    (inv + fwd).backward()
+    assert abs(float(inv) - float(g["inv_loss"])) / float(g["inv_loss"]) < 1e-2
+    assert abs(float(fwd) - float(g["fwd_loss"])) / float(g["fwd_loss"]) < 1e-2
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)
+    assert not bad, bad
+    inv2, fwd2 = m.compute_loss(obs, nxt, act, valid, dropout_masks=None)
+    assert abs(float(fwd2) - float(g["fwd_loss_nodrop"])) / float(g["fwd_loss_nodrop"]) < 1e-2
+    _, fwd3 = m.compute_loss(obs, nxt, act, valid)          # default: random dropout, same expectation
+    assert abs(float(fwd3) - float(fwd2)) / float(fwd2) < 0.1
+
+
+@pytest.mark.parametrize("enc,A,T,B", [("idf_burda", 4, 16, 8), ("idf_maze", 5, 12, 6)])
+def test_icm_oracle_parity(enc, A, T, B):
+    seed = 300 + T
+    shape = (4, 84, 84) if enc != "idf_maze" else (3, 5, 5)
+    params = R.make_params(R.icm_shapes(A, enc, c_in=shape[0]) if enc != "idf_maze" else
+                           R.maze_shapes("encoder.model.", 3) + R.icm_shapes(A, "idf_burda")[8:12] +
+                           R.res_forward_shapes("forward_model.", 256, A), seed)
+    if enc == "idf_maze":      # rebuild the inverse-model shapes for F = 256
+        shapes = R.maze_shapes("encoder.model.", 3) + [
+            ("inverse_model.0.weight", (256, 512)), ("inverse_model.0.bias", (256,)),
+            ("inverse_model.2.weight", (A, 256)), ("inverse_model.2.bias", (A,))] + R.res_forward_shapes("forward_model.", 256, A)
+        params = R.make_params(shapes, seed)
+        obs, nxt = R.make_binary_frames(seed + 1, T, B), R.make_binary_frames(seed + 2, T, B)
+    else:
+        obs, nxt = R.make_frames(seed + 1, T, B), R.make_frames(seed + 2, T, B)
+    m = ICM(image_shape=shape, action_size=A, feature_encoding=enc, prediction_beta=1.0, forward_loss_wt=0.2).to(DEV)
+    m.load_state_dict(params)
+    act = R.onehot(R.make_actions(seed + 3, T, B, A), A)
+    valid = 1 - R.make_suffix_done(seed + 4, T, B, frac=0.3)
+    b_ref = O.icm_bonus(params, obs, nxt, act, enc, 1.0)
+    assert relmax(m.compute_bonus(obs.to(DEV), nxt.to(DEV), act.to(DEV)), b_ref) < 1e-2
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    inv_r, fwd_r = O.icm_loss(p, obs, nxt, act, valid, enc, 0.2)
+    (inv_r + fwd_r).backward()
+    inv, fwd = m.compute_loss(obs.to(DEV), nxt.to(DEV), act.to(DEV), valid.to(DEV))
+    (inv + fwd).backward()
+    assert abs(float(inv) - float(inv_r)) / float(inv_r) < 1e-2
+    assert abs(float(fwd) - float(fwd_r)) / float(fwd_r) < 1e-2
+    for k, prm in m.named_parameters():
+        gref, gg = p[k].grad.flatten(), prm.grad.cpu().flatten()
+        cos = float(gg @ gref / (gg.norm() * gref.norm()).clamp_min(1e-30))
+        # bias gradients are signed sums of bf16-rounded dy rows (cancellation): allow 8% on their norm
+        tol = 8e-2 if gg.numel() <= 64 else 3e-2
+        assert cos > 0.99 and abs(float(gg.norm() / gref.norm()) - 1) < tol, (k, cos, float(gg.norm() / gref.norm()))
