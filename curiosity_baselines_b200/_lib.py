@@ -64,6 +64,7 @@ _SIGS = {
     "cb_rowwise_sqerr_masked": [_P, _P, _P, _F, _F, _P, _L, _I, _P],
     "cb_ensemble_variance": [_P, _I, _F, _P, _L, _I, _P],
     "cb_cross_entropy": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "cb_bce_logits": [_P, _P, _F, _P, _F, _P, _L, _I, _P],
     "cb_weighted_mean": [_P, _P, _P, _L, _P],
     "cb_loss_coef": [_P, _P, _F, _P, _P, _L, _P],
     "cb_dot": [_P, _P, _P, _L, _P],

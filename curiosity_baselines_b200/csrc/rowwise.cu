@@ -57,6 +57,25 @@ __global__ void ensemble_variance_kernel(const float* const* __restrict__ preds,
     if (lane == 0) out[row] = beta * acc / (float)f;
 }
 
+// binary_cross_entropy(sigmoid(z), y) as torch computes it (fp32 sigmoid, log clamped at -100):
+// row[m] = scale * sum_f bce ; dz = gscale * (p - y)           (ndigo.py:197-206, 265-268)
+__global__ void bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y, float scale,
+                                  float* __restrict__ row, float gscale, float* __restrict__ dz, int64_t m, int f) {
+    int64_t r = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (r >= m) return;
+    int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int j = lane; j < f; j += 32) {
+        const float zz = z[r * f + j], yy = y[r * f + j];
+        const float p = 1.f / (1.f + expf(-zz));
+        const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+        acc -= yy * lp + (1.f - yy) * lq;
+        if (dz) dz[r * f + j] = gscale * (p - yy);
+    }
+    acc = cb::warp_sum(acc);
+    if (lane == 0 && row) row[r] = acc * scale;
+}
+
 // one thread per row; A (actions) is small
 __global__ void cross_entropy_kernel(const float* __restrict__ logits, const float* __restrict__ onehot,
                                      const float* __restrict__ coef, float* __restrict__ loss,
@@ -252,6 +271,15 @@ extern "C" int cb_cross_entropy(const float* logits, const float* onehot, const 
     CB_REQUIRE(!dlogits || coef, CB_E_ARG, "cb_cross_entropy: dlogits needs coef");
     cross_entropy_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, 128), 128, 0, cb::as_stream(stream)>>>(
         logits, onehot, coef, loss, dlogits, m, a);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_bce_logits(const float* logits, const float* target, float scale, float* row_loss, float gscale,
+                             float* dlogits, int64_t m, int32_t f, void* stream) {
+    CB_REQUIRE(logits && target && (row_loss || dlogits) && m >= 1 && f >= 1, CB_E_ARG, "cb_bce_logits: bad argument");
+    bce_logits_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, kRowThreads / 32), kRowThreads, 0, cb::as_stream(stream)>>>(
+        logits, target, scale, row_loss, gscale, dlogits, m, f);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

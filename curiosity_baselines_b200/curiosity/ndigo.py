@@ -1,0 +1,215 @@
+"""NDIGO on B200 -- drop-in for rlpyt/models/curiosity/ndigo.py:36-274 (same constructor,
+``state_dict`` keys, ``compute_bonus`` / ``compute_loss`` signatures and quirks: the GRU state is
+reset every call, ``valid`` and ``prediction_beta`` are ignored, horizon 10 has no predictor).
+
+The encoder, the multi-horizon predictor MLPs (the action window enters as a side input of the first
+Linear instead of a concatenation) and the BCE run in libcuriosity_b200.so; the 128-unit GRU between
+them is ``torch.nn.GRU`` (cuDNN) for now -- SURVEY 8(f) rank 3 -- so the pieces are tied together
+through ``torch.autograd.Function`` wrappers.
+"""
+import torch
+from torch import nn
+
+from .. import _lib as L
+from ..layers import linear_layer
+from .encoders import make_encoder, frame_input
+
+
+class _EncoderFn(torch.autograd.Function):
+    """features = encoder(obs); obs carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, model, frames, n, *params):
+        ex = model._exec
+        keep, x, dtype, strides = frame_input(frames)
+        acts, phi = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=True, last_bf16=True)
+        ctx.model, ctx.n = model, n
+        ctx.enc = dict(keep=keep, x=x, dtype=dtype, strides=strides, acts=acts)
+        ctx.params = params
+        return phi.reshape(n, -1)
+
+    @staticmethod
+    def backward(ctx, dphi):
+        m, n, enc = ctx.model, ctx.n, ctx.enc
+        chain = m._exec["chain"]
+        last = chain.layers[-1]
+        # gradient w.r.t. the last layer's pre-activation output
+        dy = dphi.reshape(-1, last.out_c)
+        y = enc["acts"][-1].float()
+        if m._enc_last_act == "relu":
+            dy = dy * (y > 0)
+        elif m._enc_last_act == "elu":
+            dy = dy * torch.where(y > 0, torch.ones_like(y), y + 1)
+        saved = [p.grad for p in ctx.params]
+        for p in ctx.params:
+            p.grad = None
+        chain.backward(enc["x"], enc["acts"], dy.to(torch.bfloat16).contiguous(), n, in_dtype=enc["dtype"],
+                       strides=enc["strides"])
+        grads = [p.grad for p in ctx.params]
+        for p, g in zip(ctx.params, saved):
+            p.grad = g
+        return (None, None, None) + tuple(grads)
+
+
+class _PredictorFn(torch.autograd.Function):
+    """logits = Linear(64->D)(relu(Linear(G + kA -> 64)([belief, action window])))."""
+
+    @staticmethod
+    def forward(ctx, layers, belief, window, *params):
+        l1, l2 = layers
+        n = belief.shape[0]
+        xb = belief.to(torch.bfloat16).contiguous()
+        window = window.contiguous()
+        h, _ = l1.forward(xb, n, side=window)
+        _, logits = l2.forward(h, n, out_bf16=False, out_f32=True)
+        ctx.layers, ctx.saved, ctx.params = layers, (xb, window, h, n), params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        l1, l2 = ctx.layers
+        xb, window, h, n = ctx.saved
+        saved = [p.grad for p in ctx.params]
+        for p in ctx.params:
+            p.grad = None
+        dy = dlogits.to(torch.bfloat16).contiguous()
+        l2.wgrad(h, dy, n)
+        dh = l2.dgrad(dy, n, x_saved=h, x_act="relu")
+        l1.wgrad(xb, dh, n, side=window)
+        dx = l1.dgrad(dh, n)
+        grads = [p.grad for p in ctx.params]
+        for p, g in zip(ctx.params, saved):
+            p.grad = g
+        return (None, dx.float(), None) + tuple(grads)
+
+
+class _BceMeanFn(torch.autograd.Function):
+    """mean over all elements of binary_cross_entropy(sigmoid(logits), target)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        m, f = logits.shape
+        rows = torch.empty(m, dtype=torch.float32, device=logits.device)
+        dz = torch.empty_like(logits)
+        L.call("cb_bce_logits", L.ptr(logits.contiguous()), L.ptr(target.contiguous()), 1.0 / (m * f), L.ptr(rows),
+               1.0 / (m * f), L.ptr(dz), m, f, L.stream())
+        ctx.save_for_backward(dz)
+        return rows.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return dz * g, None
+
+
+class NdigoForward(nn.Module):
+    """ndigo.py:17-34 (holder)."""
+
+    def __init__(self, feature_size, action_size, output_size):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(feature_size + action_size, 64), nn.ReLU(), nn.Linear(64, output_size))
+
+
+class NDIGO(nn.Module):
+    def __init__(self, image_shape, action_size, horizon, feature_encoding="idf_maze", gru_size=128, batch_norm=False,
+                 obs_stats=None, num_predictors=10, device="cpu"):
+        super().__init__()
+        assert num_predictors >= horizon
+        self.action_size, self.horizon = action_size, horizon
+        self.feature_encoding, self.obs_stats, self.num_predictors = feature_encoding, obs_stats, num_predictors
+        self.encoder, self.feature_size = make_encoder(feature_encoding, image_shape, batch_norm)
+        self._enc_last_act = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}[feature_encoding]
+        self.gru_size = gru_size
+        self.gru = nn.GRU(self.feature_size + action_size, gru_size)
+        self.gru_states = None
+        self.obs_dim = image_shape[0] * image_shape[1] * image_shape[2]
+        for k in range(1, 11):          # ndigo.py:82-111: always ten predictors
+            setattr(self, f"forward_model_{k}", NdigoForward(gru_size, action_size * k, self.obs_dim))
+        self._exec = None
+
+    def _build(self):
+        dev = self.gru.weight_ih_l0.device
+        if dev.type != "cuda":
+            raise L.CuriosityLibError("NDIGO parameters must be on a CUDA device (no CPU fallback)")
+        if self._exec is None or self._exec["dev"] != dev:
+            chain, perm = self.encoder.build_chain(True)
+            preds = {}
+            for k in range(1, 11):
+                seq = getattr(self, f"forward_model_{k}").model
+                preds[k] = (linear_layer(seq[0], "relu", side_dim=k * self.action_size), linear_layer(seq[2], "none"))
+            self._exec = dict(dev=dev, chain=chain, perm=None if perm is None else perm.to(dev), preds=preds)
+        return self._exec
+
+    # ------------------------------------------------------------------
+    def _beliefs(self, observations, prev_actions):
+        ex = self._build()
+        T, B = observations.shape[:2]
+        n = T * B
+        phi = _EncoderFn.apply(self, observations.reshape(n, *observations.shape[2:]), n, *self.encoder.parameters())
+        if ex["perm"] is not None:
+            phi = phi.index_select(1, ex["perm"])
+        gru_in = torch.cat([phi.reshape(T, B, -1), prev_actions.to(ex["dev"], torch.float32)], dim=2)
+        belief, _ = self.gru(gru_in, None)                 # zero state every call (ndigo.py:127,145)
+        return belief
+
+    def _logits(self, belief, actions, k):
+        """predictor k on belief[:T-k] with the k-step action window starting at each step."""
+        T, B = actions.shape[:2]
+        window = torch.cat([actions[j:T - k + j] for j in range(k)], dim=2)            # ndigo.py:154-163
+        l1, l2 = self._exec["preds"][k]
+        params = list(getattr(self, f"forward_model_{k}").parameters())
+        return _PredictorFn.apply((l1, l2), belief[:T - k].reshape((T - k) * B, -1),
+                                  window.reshape((T - k) * B, -1).detach(), *params)
+
+    @torch.no_grad()
+    def compute_bonus(self, observations, prev_actions, actions):
+        """ndigo.py:132-217: r[H:T-1] = L_{t-1} - L_t[1:], zero elsewhere."""
+        self._build()
+        dev = self._exec["dev"]
+        if prev_actions.dim() == 1:
+            prev_actions = prev_actions.view(1, 1, -1)
+        if actions.dim() == 1:
+            actions = actions.view(1, 1, -1)
+        T, B = observations.shape[:2]
+        H = self.horizon
+        if H + 1 > 10:
+            raise AttributeError("'NDIGO' object has no attribute 'forward_model_11'")    # ndigo.py:194
+        actions = actions.to(dev, torch.float32)
+        belief = self._beliefs(observations, prev_actions)
+        flat = observations.to(dev, torch.float32).reshape(T, B, -1)
+
+        # ndigo.py:194-206: M_H(bel[:T-H]) vs obs[H:], M_{H+1}(bel[:T-H-1]) vs obs[H:-1]
+        loss_t = _row_losses(self, belief, actions, H, flat[H:], dev, B)
+        loss_tm1 = _row_losses(self, belief, actions, H + 1, flat[H:-1], dev, B)
+        r = torch.zeros(T, B, dtype=torch.float32, device=dev)
+        r[H:T - 1] = loss_tm1 - loss_t[1:]
+        return r
+
+    def compute_loss(self, observations, prev_actions, actions, valid):
+        """ndigo.py:220-274: sum over k of the mean BCE of predictor k; ``valid`` is ignored."""
+        self._build()
+        dev = self._exec["dev"]
+        if prev_actions.dim() == 2:
+            prev_actions = prev_actions.unsqueeze(1)
+        if actions.dim() == 2:
+            actions = actions.unsqueeze(1)
+        T, B = observations.shape[:2]
+        actions = actions.to(dev, torch.float32)
+        belief = self._beliefs(observations, prev_actions)
+        flat = observations.to(dev, torch.float32).reshape(T, B, -1)
+        loss = None
+        for k in range(1, self.num_predictors + 1):
+            logits = self._logits(belief, actions, k)
+            term = _BceMeanFn.apply(logits, flat[k:].reshape(logits.shape[0], -1))
+            loss = term if loss is None else loss + term
+        return loss
+
+
+def _row_losses(model, belief, actions, k, target, dev, B):
+    """Per-(t,b) mean BCE of predictor k against ``target`` ([T-k, B, D])."""
+    logits = model._logits(belief, actions, k)
+    m, f = logits.shape
+    rows = torch.empty(m, dtype=torch.float32, device=dev)
+    L.call("cb_bce_logits", L.ptr(logits), L.ptr(target.reshape(m, f).contiguous()), 1.0 / f, L.ptr(rows), 0.0, None, m,
+           f, L.stream())
+    return rows.reshape(-1, B)

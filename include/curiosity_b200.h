@@ -202,6 +202,11 @@ int cb_ensemble_variance(const float* const* preds, int32_t e, float beta, float
  * dlogits (fp32, may be NULL) = coef[m]*(softmax-onehot_of_argmax) */
 int cb_cross_entropy(const float* logits, const float* onehot, const float* coef, float* loss,
                      float* dlogits, int64_t m, int32_t a, void* stream);
+/* ndigo.py:197-206, 265-268: binary_cross_entropy(sigmoid(logits), target) per element as torch
+ * evaluates it (fp32 sigmoid, logs clamped at -100); row_loss[m] = scale * sum_f bce (NULL to skip),
+ * dlogits[m,f] = gscale * (sigmoid - target) (NULL to skip). */
+int cb_bce_logits(const float* logits, const float* target, float scale, float* row_loss, float gscale,
+                  float* dlogits, int64_t m, int32_t f, void* stream);
 /* utils/tensor.py:39-46: out[0] = sum(x*w)/sum(w) (w NULL -> mean); deterministic order.
  * Also writes out[1] = sum(w). */
 int cb_weighted_mean(const float* x, const float* w, float* out, int64_t n, void* stream);
