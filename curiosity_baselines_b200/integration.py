@@ -1,0 +1,60 @@
+"""Drop-in wiring: make an importable rlpyt (the reference checkout) run its intrinsic-reward hot
+path on this package without touching launch.py.
+
+    import curiosity_baselines_b200.integration as cbi
+    cbi.install()            # before launch.start_experiment(...)
+
+What gets replaced (reference file:line -> ours):
+  rlpyt/models/curiosity/{icm,disagreement,rnd,ndigo}.py classes      -> curiosity.{ICM,Disagreement,RND,NDIGO}
+  the same names inside rlpyt/models/pg/atari_lstm_model.py:45-78     (it constructs them by name)
+  rlpyt/algos/utils.py:8-40,104-112 discount_return / GAE / valid_from_done -> algos.utils
+  PolicyGradientAlgo.process_returns  (algos/pg/base.py:53-108)       -> algos.pg_base.process_returns
+  RecurrentCategoricalPgAgentBase.curiosity_step / curiosity_loss
+                                      (agents/pg/categorical.py:83-130) -> agents.hooks
+The policy network itself (AtariLstmModel conv + LSTM heads) stays the reference's torch code: it is
+SURVEY 8(f) rank 1, the next row after the hot path.
+"""
+import importlib
+
+
+def install(strict=True):
+    """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
+    that fail to import (e.g. optional dependencies missing)."""
+    from .curiosity.icm import ICM, Disagreement
+    from .curiosity.rnd import RND
+    from .curiosity.ndigo import NDIGO
+    from .algos import utils as U
+    from .algos.pg_base import process_returns
+    from .agents import hooks
+
+    patched = []
+
+    def patch(modname, **attrs):
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            if strict:
+                raise
+            return
+        for k, v in attrs.items():
+            target = mod
+            *path, leaf = k.split(".")
+            for part in path:
+                target = getattr(target, part)
+            setattr(target, leaf, v)
+            patched.append(f"{modname}.{k}")
+
+    patch("rlpyt.models.curiosity.icm", ICM=ICM)
+    patch("rlpyt.models.curiosity.disagreement", Disagreement=Disagreement)
+    patch("rlpyt.models.curiosity.rnd", RND=RND)
+    patch("rlpyt.models.curiosity.ndigo", NDIGO=NDIGO)
+    patch("rlpyt.models.pg.atari_lstm_model", ICM=ICM, Disagreement=Disagreement, RND=RND, NDIGO=NDIGO)
+    patch("rlpyt.algos.utils", discount_return=U.discount_return,
+          generalized_advantage_estimation=U.generalized_advantage_estimation, valid_from_done=U.valid_from_done)
+    patch("rlpyt.algos.pg.base", discount_return=U.discount_return,
+          generalized_advantage_estimation=U.generalized_advantage_estimation, valid_from_done=U.valid_from_done,
+          **{"PolicyGradientAlgo.process_returns": process_returns})
+    patch("rlpyt.agents.pg.categorical",
+          **{"RecurrentCategoricalPgAgentBase.curiosity_step": hooks.curiosity_step,
+             "RecurrentCategoricalPgAgentBase.curiosity_loss": hooks.curiosity_loss})
+    return patched

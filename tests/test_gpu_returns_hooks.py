@@ -1,0 +1,100 @@
+"""process_returns (algos/pg/base.py:53-108) and the agent hooks (agents/pg/categorical.py:83-130)
+against the reference's golden vectors, driven through stub algo / agent objects the way the
+reference classes would call them."""
+from collections import namedtuple
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import recipes as R
+from helpers import golden
+from oracle import curiosity_oracle as O
+from curiosity_baselines_b200.algos.pg_base import process_returns
+from curiosity_baselines_b200.agents import hooks
+from curiosity_baselines_b200.curiosity.rnd import RND
+from curiosity_baselines_b200.curiosity.icm import ICM
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+Step = namedtuple("Step", ["r_int", "agent_curiosity_info"])
+Env = namedtuple("Env", ["reward", "done", "observation", "next_observation"])
+AgentInfo = namedtuple("AgentInfo", ["value"])
+Ag = namedtuple("Ag", ["agent_info", "bootstrap_value", "action", "prev_action"])
+Samples = namedtuple("Samples", ["env", "agent"])
+
+
+@pytest.mark.parametrize("tag,nr,na,lam", [("plain", False, False, 0.95), ("norm", True, True, 0.95),
+                                           ("lam1", False, True, 1.0)])
+def test_process_returns_golden(tag, nr, na, lam):
+    g = golden(f"process_returns_{tag}")
+    T, B, seed = int(g["T"]), int(g["B"]), int(g["seed"])
+
+    class Agent:
+        recurrent = True
+        calls = 0
+
+        def curiosity_step(self, kind, *args):
+            self.calls += 1
+            return Step(R.make_normal(seed + 7 * self.calls, T, B).abs() * 0.1, None)
+
+    algo = SimpleNamespace(curiosity_type="icm", agent=Agent(), normalize_reward=nr, normalize_advantage=na,
+                           gae_lambda=lam, discount=0.99, mid_batch_reset=False, kernel_params=None)
+    for it in range(2):
+        reward = R.make_normal(seed + 1000 * it, T, B) * 0.0
+        done = R.make_suffix_done(seed + 1000 * it + 1, T, B) > 0.5
+        value = R.make_normal(seed + 1000 * it + 2, T, B)
+        boot = R.make_normal(seed + 1000 * it + 3, 1, B)
+        obs = torch.zeros(T, B, 1)
+        act = torch.zeros(T, B, dtype=torch.long)
+        s = Samples(Env(reward, done, obs, obs), Ag(AgentInfo(value), boot, act, act))
+        ret, adv, valid = process_returns(algo, s)
+        assert ret.device.type == "cpu"
+        np.testing.assert_allclose(ret.numpy(), g[f"ret{it}"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(adv.numpy(), g[f"adv{it}"], rtol=2e-5, atol=2e-5)
+        assert np.array_equal(valid.numpy(), g[f"valid{it}"])
+        np.testing.assert_allclose(reward.numpy(), g[f"reward_after{it}"], rtol=1e-6)     # in-place add (base.py:66)
+        assert algo.intrinsic_rewards.shape == (T, B)
+
+
+def _agent(model, A):
+    return SimpleNamespace(model=SimpleNamespace(curiosity_model=model), device=torch.device(DEV),
+                           distribution=SimpleNamespace(dim=A))
+
+
+def test_hooks_rnd_host_buffers():
+    """Host (pinned) uint8 stacks in, CPU tensors out -- the reference's calling convention."""
+    T, B, seed = 6, 4, 5
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m.load_state_dict(params)
+    agent = _agent(m, 4)
+    frames = R.make_frames(seed, T, B).pin_memory()
+    done = R.make_suffix_done(seed + 1, T, B, frac=0.5)
+    step = hooks.curiosity_step(agent, "rnd", frames, done)
+    assert step.r_int.device.type == "cpu" and step.r_int.shape == (T, B)
+    o = O.RndOracle(drop_probability=0.0)
+    ref = o.compute_bonus(params, frames, done)
+    nz = ref.abs() > 0
+    assert float(((step.r_int - ref).abs()[nz] / ref.abs()[nz]).max()) < 1e-2
+    loss = hooks.curiosity_loss(agent, "rnd", frames, torch.ones(T, B))
+    assert loss.device.type == "cpu" and loss.requires_grad
+    loss.backward()
+    assert m.forward_model[0].weight.grad is not None
+
+
+def test_hooks_icm_index_actions():
+    T, B, A, seed = 4, 3, 4, 9
+    m = ICM(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+    params = R.make_params(R.icm_shapes(A, "idf_burda"), seed)
+    m.load_state_dict(params)
+    agent = _agent(m, A)
+    obs, nxt = R.make_frames(seed + 1, T, B), R.make_frames(seed + 2, T, B)
+    idx = R.make_actions(seed + 3, T, B, A)
+    step = hooks.curiosity_step(agent, "icm", obs, nxt, idx)
+    ref = O.icm_bonus(params, obs, nxt, R.onehot(idx, A), "idf_burda", 1.0)
+    assert float(((step.r_int - ref).abs() / ref.abs()).max()) < 1e-2
+    inv, fwd = hooks.curiosity_loss(agent, "icm", obs, nxt, idx, torch.ones(T, B))
+    (inv + fwd).backward()
+    assert inv.device.type == "cpu" and m.encoder.model[0].weight.grad is not None
