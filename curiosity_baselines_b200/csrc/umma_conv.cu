@@ -86,20 +86,35 @@ struct Plan {
     int bn, mt;
 };
 
-template <int BN, int MT>
-int launch(const Plan& pl, cudaStream_t s) {
+int epi_mode(const umma::GemmParams& p) {
+    if (p.add_pre || p.actgrad_src) return umma::EPI_DGRAD;
+    if (p.side_dim || p.residual || p.out_f32 || !p.out_bf16) return umma::EPI_FULL;
+    return umma::EPI_SIMPLE;
+}
+
+template <int BN, int MT, int EPI>
+int launch_epi(const Plan& pl, cudaStream_t s) {
     using Cfg = umma::GemmConfig<BN, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        CB_CUDA(cudaFuncSetAttribute(umma::umma_gemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB_CUDA(cudaFuncSetAttribute(umma::umma_gemm_kernel<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
         attr_set = true;
     }
     int tiles = pl.p.m_tiles * pl.p.n_tiles;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    umma::umma_gemm_kernel<BN, MT><<<grid, umma::kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+template <int BN, int MT>
+int launch(const Plan& pl, cudaStream_t s) {
+    switch (epi_mode(pl.p)) {
+        case umma::EPI_DGRAD: return launch_epi<BN, MT, umma::EPI_DGRAD>(pl, s);
+        case umma::EPI_FULL:  return launch_epi<BN, MT, umma::EPI_FULL>(pl, s);
+        default:              return launch_epi<BN, MT, umma::EPI_SIMPLE>(pl, s);
+    }
 }
 
 int dispatch(const Plan& pl, cudaStream_t s) {
@@ -427,8 +442,9 @@ void taps_s1(WindowGeo& g, int k, bool flipped) {
         }
 }
 
-template <int BN>
-int launch_window(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
+template <int BN, int EPI>
+int launch_window_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CB_EPI_DEBUG"); dbg = e ? atoi(e) : 0; } p.epi.debug = dbg; }
     const int w_bytes = p.kb_count * BN * 128;
     int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 512;
     p.stages = avail / p.stage_bytes;
@@ -437,14 +453,23 @@ int launch_window(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowPa
     const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 512;
     static bool attr = false;
     if (!attr) {
-        CB_CUDA(cudaFuncSetAttribute(umma::umma_window_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB_CUDA(cudaFuncSetAttribute(umma::umma_window_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kSmemBudget));
         attr = true;
     }
     int grid = p.tiles < sm_count() ? p.tiles : sm_count();
-    umma::umma_window_conv_kernel<BN><<<grid, umma::kGemmThreads, smem, s>>>(tmA, tmW, p);
+    umma::umma_window_conv_kernel<BN, EPI><<<grid, umma::kGemmThreads, smem, s>>>(tmA, tmW, p);
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+template <int BN>
+int launch_window(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
+    switch (epi_mode(p.epi)) {
+        case umma::EPI_DGRAD: return launch_window_epi<BN, umma::EPI_DGRAD>(tmA, tmW, p, s);
+        case umma::EPI_FULL:  return launch_window_epi<BN, umma::EPI_FULL>(tmA, tmW, p, s);
+        default:              return launch_window_epi<BN, umma::EPI_SIMPLE>(tmA, tmW, p, s);
+    }
 }
 
 int plan_weights(CUtensorMap* tm, const void* w, int bn, long long k_total) {

@@ -48,6 +48,7 @@ struct GemmParams {
     int actgrad_act;
     const __nv_bfloat16* residual;     // added after the activation
     __nv_bfloat16* out_bf16; float* out_f32;
+    int debug;                         // CB_EPI_DEBUG (profiling only): 1 = skip the epilogue math and stores
     // optional pixel shuffle of the output (stride-2 dgrad): row = (n, a, b) over an (sh_ph x sh_pw)
     // grid per sample, 32-column chunk q = (ph, pw) -> NHWC pixel (2a+ph, 2b+pw) of a [*, sh_h, sh_w, 32]
     // tensor.  0 = plain row-major [*, n_total].
@@ -112,7 +113,7 @@ __device__ __forceinline__ void add_bf16_row(float (&v)[32], const __nv_bfloat16
 struct AuxRegs { uint4 other[4], grad[4]; };   // other = add_pre (dgrad) or residual (forward), never both
 
 __device__ __forceinline__ void aux_load(const GemmParams& p, long long co, AuxRegs& a) {
-    const __nv_bfloat16* other = p.add_pre ? p.add_pre : p.residual;
+    const __nv_bfloat16* other = p.add_pre ? p.add_pre : p.residual;     // skip gradient (dgrad) or residual (forward)
     if (other) {
         const uint4* s4 = reinterpret_cast<const uint4*>(other + co);
 #pragma unroll
@@ -137,15 +138,21 @@ __device__ __forceinline__ void unpack_bf16x32(const uint4 (&u)[4], float (&g)[3
     }
 }
 
-// One 32-column chunk of one output row: accumulator -> bias/side -> (+add_pre) -> activation ->
-// (*act'(saved)) -> (+residual) -> bf16 / fp32 stores.  `co` = element offset of the chunk in every
-// row-major operand, n0 = first column (for bias / side weights), sv = the row's side inputs.
+// Epilogue specialisations (compile-time pruning keeps the hot loop small enough for the I-cache):
+//   EPI_SIMPLE  bias + activation -> bf16                       (conv layers, most Linears)
+//   EPI_FULL    bias + side input + activation + residual -> bf16 and/or fp32
+//   EPI_DGRAD   (+ skip gradient) * act'(saved output) -> bf16   (optionally depth-to-space)
+enum { EPI_SIMPLE = 0, EPI_FULL = 1, EPI_DGRAD = 2 };
+
+// One 32-column chunk of one output row.  `co` = element offset of the chunk in every row-major
+// operand, n0 = first column (for bias / side weights), sv = the row's side inputs.
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&raw)[32], long long co, int n0,
                                                const float (&sv)[16], const AuxRegs& aux) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-    if (p.bias) {
+    if (EPI != EPI_DGRAD && p.bias) {
         const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -153,7 +160,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
         }
     }
-    if (p.side_dim) {
+    if (EPI == EPI_FULL && p.side_dim) {
         const float* sw = p.side_w + (long long)n0 * p.side_dim;
         for (int s = 0; s < p.side_dim; ++s) {
             const float a = sv[s];
@@ -161,23 +168,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             for (int j = 0; j < 32; ++j) v[j] = fmaf(a, __ldg(sw + j * p.side_dim + s), v[j]);
         }
     }
-    if (p.add_pre) {
+    if (EPI == EPI_DGRAD && p.add_pre) {
         float g[32];
         unpack_bf16x32(aux.other, g);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += g[j];
     }
-    if (p.act == CB_ACT_RELU) {
+    if (EPI != EPI_DGRAD) {
+        if (p.act == CB_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (p.act == CB_ACT_LRELU) {
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == CB_ACT_LRELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
-    } else if (p.act == CB_ACT_ELU) {
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
+        } else if (p.act == CB_ACT_ELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+        }
     }
-    if (p.actgrad_src) {
+    if (EPI == EPI_DGRAD && p.actgrad_src) {
         float g[32];
         unpack_bf16x32(aux.grad, g);
         if (p.actgrad_act == CB_ACT_ELU) {
@@ -189,13 +198,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             for (int j = 0; j < 32; ++j) v[j] *= g[j] > 0.f ? 1.f : slope;
         }
     }
-    if (p.residual && !p.add_pre) {
+    if (EPI == EPI_FULL && p.residual) {
         float g[32];
         unpack_bf16x32(aux.other, g);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += g[j];
     }
-    if (p.out_bf16) {
+    if (EPI != EPI_FULL || p.out_bf16) {
         uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + co);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -206,20 +215,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             dst[q] = u;
         }
     }
-    if (p.out_f32) {
+    if (EPI == EPI_FULL && p.out_f32) {
         float4* dst = reinterpret_cast<float4*>(p.out_f32 + co);
 #pragma unroll
         for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
     }
 }
 
-// Epilogue of one accumulator stage for one warp: MT*BN/32 (sub-tile, 32-column chunk) items.
-// The loop is deliberately NOT unrolled: the chunk body is ~1.5k instructions and an unrolled
-// epilogue overflows the instruction cache (measured: 2x slower).  Side operands of the first item
-// are requested before the accumulator is awaited and each later item's while the previous one is
-// processed, so their global-memory latency overlaps the MMAs / the math.
+// Epilogue of one accumulator stage for one warp: MT*BN/32 (sub-tile, 32-column chunk) items, rolled
+// (an unrolled epilogue overflows the instruction cache).  For the modes with global side operands
+// the loop is software-pipelined two items deep with alternating register buffers: the operands of
+// item i+1 are requested before item i is processed, and of item 0 before the accumulator is awaited,
+// so their HBM latency overlaps the MMAs and the math.  (Copying a prefetch buffer would stall on the
+// pending loads -- the buffers are only ever consumed.)
 // row_fn(r, valid, grow): maps tile row r to its output row.
-template <int BN, int MT, class RowFn>
+template <int BN, int MT, int EPI, class RowFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int quarter, int lane,
                                               int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
     constexpr int NCH = BN / 32;
@@ -230,35 +240,49 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     float sv[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) sv[s] = 0.f;
-    AuxRegs cur, nxt;
-    if (valid[0]) aux_load(p, chunk_offset(p, grow[0], n_base), cur);
-    mbar_wait(tfull, parity);
-    fence_after_thread_sync();
-#pragma unroll 1
-    for (int it = 0; it < ITEMS; ++it) {
+    auto row_valid = [&](int mt) { return MT == 1 ? valid[0] : (mt ? valid[MT - 1] : valid[0]); };
+    auto row_index = [&](int mt) { return MT == 1 ? grow[0] : (mt ? grow[MT - 1] : grow[0]); };
+    auto request = [&](int it, AuxRegs& buf) {
+        if (EPI == EPI_SIMPLE || it >= ITEMS) return;
         const int mt = it / NCH, cb = it - mt * NCH;
-        const bool v_now = MT == 1 ? valid[0] : (mt ? valid[MT - 1] : valid[0]);
-        const long long g_now = MT == 1 ? grow[0] : (mt ? grow[MT - 1] : grow[0]);
-        if (p.side_dim && cb == 0) {
+        if (row_valid(mt)) aux_load(p, chunk_offset(p, row_index(mt), n_base + cb * 32), buf);
+    };
+    auto process = [&](int it, const AuxRegs& buf) {
+        const int mt = it / NCH, cb = it - mt * NCH;
+        const bool v_now = row_valid(mt);
+        const long long g_now = row_index(mt);
+        if (EPI == EPI_FULL && p.side_dim && cb == 0) {
 #pragma unroll
             for (int s = 0; s < 16; ++s)
                 sv[s] = (v_now && s < p.side_dim) ? __ldg(p.side + g_now * p.side_dim + s) : 0.f;
         }
         uint32_t raw[32];
         tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * BN + cb * 32), raw);
-        if (it + 1 < ITEMS) {          // request the next item's side operands while this one is in flight
-            const int mt2 = (it + 1) / NCH, cb2 = (it + 1) - mt2 * NCH;
-            const bool v2 = MT == 1 ? valid[0] : (mt2 ? valid[MT - 1] : valid[0]);
-            const long long g2 = MT == 1 ? grow[0] : (mt2 ? grow[MT - 1] : grow[0]);
-            if (v2) aux_load(p, chunk_offset(p, g2, n_base + cb2 * 32), nxt);
-        }
         tmem_ld_wait();
-        if (v_now) epilogue_chunk(p, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, cur);
-        cur = nxt;
+        if (v_now && !(p.debug & 1))
+            epilogue_chunk<EPI>(p, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, buf);
+    };
+    AuxRegs b0, b1;
+    request(0, b0);
+    mbar_wait(tfull, parity);
+    fence_after_thread_sync();
+    if (EPI == EPI_SIMPLE) {
+#pragma unroll 1
+        for (int it = 0; it < ITEMS; ++it) process(it, b0);
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < ITEMS; it += 2) {
+            request(it + 1, b1);
+            process(it, b0);
+            if (it + 1 < ITEMS) {
+                request(it + 2, b0);
+                process(it + 1, b1);
+            }
+        }
     }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -352,7 +376,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
-            epilogue_tile<BN, MT>(p, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
+            epilogue_tile<BN, MT, EPI>(p, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
                                   tfull_bar(acc), acc_phase,
                                   [&](int r, bool& valid, long long& grow) {
                                       grow = (long long)tm * p.rows_per_tile + r;

@@ -35,7 +35,7 @@ struct WindowParams {
     GemmParams epi;                        // epilogue operands (n_total == BN, shuffle fields honoured)
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                         const WindowParams p) {
@@ -132,7 +132,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int grid_px = p.gh * p.gw;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            epilogue_tile<BN, MT>(p.epi, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
+            epilogue_tile<BN, MT, EPI>(p.epi, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
                                   acc_phase, [&](int r, bool& valid, long long& grow) {
                                       const int s = r / grid_px, rem = r - s * grid_px;
                                       const int gy = rem / p.gw, gx = rem - gy * p.gw;

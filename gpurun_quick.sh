@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_returns_hooks.py -x -q 2>&1 | grep -E "^E|passed|failed|Error" | head -12
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/layer_bench.py 2>&1 | tee gpurun_out/layer_bench.log
