@@ -21,7 +21,9 @@ namespace {
 constexpr int kConvWarps = 8;           // converter warps
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kMmaWarp = kConvWarps;   // MMA issuer / TMEM owner
-constexpr int kThreads = (kConvWarps + 1 + 4) * 32;    // + 4 epilogue warps
+constexpr int kStagePitch = 80;         // bytes per staged output row (64 + 16: conflict-free 16-byte stores)
+constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, splitting the (row tile, net) items
+constexpr int kThreads = (kConvWarps + 1 + kEpiWarps) * 32;
 constexpr int kMaxStages1 = 4;
 constexpr int kMaxCin = 4;
 constexpr int kConvBar = 1;            // named barrier of the converter threads
@@ -116,7 +118,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     const uint32_t f_bytes = (uint32_t)((p.h * p.pitch + 1023) & ~1023);
     const uint32_t t_off = f_off + f_bytes;                                   // per-pixel mean | rstd (fp32)
     const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
-    const uint32_t bar_base = smem_base + t_off + t_bytes;
+    const uint32_t o_off = t_off + t_bytes;                                   // epilogue staging: 32 rows x 80 B per warp
+    const uint32_t o_bytes = WGRAD ? 0u : (uint32_t)(kEpiWarps * kStagePitch * 32);
+    const uint32_t bar_base = smem_base + o_off + ((o_bytes + 1023u) & ~1023u);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages1 + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages1 + a); };
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEpiWarps); }
         umma::fence_barrier_init();
     }
     if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
@@ -239,13 +243,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     } else {
         // ------------------------------------------------------------ epilogue (4 warps, one per TMEM lane quarter)
         const int quarter = warp & 3;
+        const int half = (warp - kMmaWarp - 1) >> 2;          // which of the two warps sharing this quarter
+        uint8_t* stage_o = gen + o_off + (warp - kMmaWarp - 1) * (kStagePitch * 32);
         if (!WGRAD) {
             int acc = 0; uint32_t acc_phase = 0;
             for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
                 umma::mbar_wait(tfull_bar(acc), acc_phase);
                 umma::fence_after_thread_sync();
 #pragma unroll 1
-                for (int it = 0; it < p.row_tiles * p.nets; ++it) {
+                for (int it = half; it < p.row_tiles * p.nets; it += kEpiWarps / 4) {
                     const int mt = it / p.nets, net = it - mt * p.nets;
                     uint32_t raw[32];
                     umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32),
@@ -275,20 +281,34 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
                         }
-                        __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + row) * 32;
-                        uint4* dst = reinterpret_cast<uint4*>(o);
+                        uint8_t* my = stage_o + lane * kStagePitch;
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            dst[q] = make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
-                                                pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
+                            *reinterpret_cast<uint4*>(my + q * 16) =
+                                make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
+                                           pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
                     }
+                    __syncwarp();
+                    // coalesced write-out: each store instruction covers 8 rows x 64 B = 512 contiguous bytes
+                    {
+                        const int row0 = mt * 128 + quarter * 32;
+                        __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + row0) * 32;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = j * 8 + (lane >> 2);
+                            if (row0 + rr < p.rows && !(p.debug & 2))
+                                reinterpret_cast<uint4*>(o)[rr * 4 + (lane & 3)] =
+                                    *reinterpret_cast<const uint4*>(stage_o + rr * kStagePitch + (lane & 3) * 16);
+                        }
+                    }
+                    __syncwarp();
                 }
                 umma::fence_before_thread_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-        } else if (blockIdx.x < p.n) {
+        } else if (blockIdx.x < p.n && half == 0) {
             // M = 64 accumulator: patch element i lives in TMEM lane (i/16)*32 + i%16
             umma::mbar_wait(tfull_bar(0), 0);
             umma::fence_after_thread_sync();
@@ -334,10 +354,11 @@ int fill(Conv1Params& p, const cb_conv_desc* d, const void* x, const float* mean
 template <bool WGRAD>
 int launch(Conv1Params& p, cudaStream_t s) {
     // forward: rows padded to whole M=128 tiles; wgrad: K = rows rounded to 16, patches and dy rows per stage
-    p.a_stage_bytes = WGRAD ? ((p.rows + 15) / 16 * 16 * 128 + 1023) / 1024 * 1024 : p.row_tiles * 16384;
+    p.a_stage_bytes = ((p.rows + 15) / 16 * 16 * 128 + 1023) / 1024 * 1024;   // the last M tile may read past it (finite bytes)
     const int stage_bytes = p.a_stage_bytes * (WGRAD ? 2 : 1);
     const int fixed = (WGRAD ? 0 : p.cin * 32 * p.nets * 128) + ((p.h * p.pitch + 1023) & ~1023) +
-                      (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
+                      (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) +
+                      (WGRAD ? 0 : ((kEpiWarps * kStagePitch * 32 + 1023) & ~1023)) + 1024 + 256;
     p.stages = (224 * 1024 - fixed) / stage_bytes;
     if (p.stages > kMaxStages1) p.stages = kMaxStages1;
     CB_REQUIRE(p.stages >= 1, CB_E_ARG, "conv1: tile does not fit shared memory");

@@ -1,2 +1,3 @@
 #!/bin/bash
-for d in 0 1; do echo "epi debug=$d"; CB_EPI_DEBUG=$d timeout 120 python tools/layer_bench.py --only conv 2>&1 | grep -E "conv2_fwd|conv3_fwd|conv3_dgrad|conv2_dgrad"; done
+timeout 600 python -m pytest tests/test_gpu_umma.py tests/test_gpu_rnd.py -k "conv1 or golden or oracle" -x -q 2>&1 | tail -2
+timeout 120 python tools/layer_bench.py --only conv1 2>&1 | tail -3

@@ -66,6 +66,8 @@ nm = (torch.rand(7056, device=dev) * 255, torch.rand(7056, device=dev) / 50 + 0.
 st1 = (7056, 84, 1, 7056)
 dy1 = torch.randn(n * 400, 32, device=dev).to(torch.bfloat16)
 cases["conv1_fwd"] = (lambda: conv1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm), 2.0 * 64 * 32 * 400 * n)
+conv1b = LY.conv_layer(nn.Conv2d(1, 32, 8, 4).to(dev), (84, 84, 1), "lrelu")
+cases["conv1_twin_fwd"] = (lambda: conv1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm, twin=conv1b), 2.0 * 64 * 64 * 400 * n)
 cases["conv1_wgrad"] = (lambda: conv1.wgrad(frames.data_ptr(), dy1, n, in_dtype=L.U8, strides=st1, norm=nm), 2.0 * 64 * 32 * 400 * n)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
