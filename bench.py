@@ -247,9 +247,13 @@ def main():
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / reps
     kern_tflops = 2.0 * 512 * 64 * 81 * n / (kern_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv2 forward (32->64, k4 s2) implicit GEMM",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if os.path.exists(tpath) and n == 131072:      # dram__bytes_read+write of this kernel at this size (ncu --set full)
+        traffic = json.load(open(tpath))["conv2_fwd_window_n131072"]["dram_bytes_per_launch"]
+    roofline = {"bound": "tensor", "kernel": "conv2 forward (32->64, k4 s2) window implicit GEMM (umma_window_conv_kernel<64>)",
                 "achieved": kern_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": kern_tflops / tf_burst,
-                "traffic": None, "peak_source": f"{src} bf16 burst", "kernel_ms": kern_ms,
+                "traffic": traffic, "peak_source": f"{src} bf16 burst", "kernel_ms": kern_ms,
                 "step_tflops": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12 / tf_sust}
 

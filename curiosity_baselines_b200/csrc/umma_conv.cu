@@ -446,11 +446,11 @@ template <int BN, int EPI>
 int launch_window_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CB_EPI_DEBUG"); dbg = e ? atoi(e) : 0; } p.epi.debug = dbg; }
     const int w_bytes = p.kb_count * BN * 128;
-    int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 512;
+    int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 1024;
     p.stages = avail / p.stage_bytes;
     if (p.stages > umma::kMaxStages) p.stages = umma::kMaxStages;
     CB_REQUIRE(p.stages >= 2, CB_E_ARG, "window conv: slab does not fit shared memory (stage %d B)", p.stage_bytes);
-    const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 512;
+    const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 1024;     // + barriers + bias[BN]
     static bool attr = false;
     if (!attr) {
         CB_CUDA(cudaFuncSetAttribute(umma::umma_window_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -484,7 +484,7 @@ bool window_fits(int ntaps, int bn, int plane_rows, int nplanes, int max_shift) 
     int w_bytes = ntaps * bn * 128;
     int stage = nplanes * round_up(plane_rows * 128, 1024);
     int slack = round_up((256 + max_shift) * 128, 1024);
-    return w_bytes + 2 * stage + slack + 1536 <= kSmemBudget;
+    return w_bytes + 2 * stage + slack + 2048 <= kSmemBudget;
 }
 
 bool window_shape_s1(int c, int k, int gh, int gw, int n_out) {

@@ -22,6 +22,8 @@ namespace umma {
 constexpr int kGemmThreads = 192;
 constexpr int kEpiWarp0 = 2;
 
+constexpr int kBiasSmemFloats = 4096;   // bias vectors up to this length are staged in shared memory
+
 struct CoordMap {          // coordinate = ((index / div) % mod) * mul   (mod == 0: no modulo)
     int div[5], mod[5], mul[5];
 };
@@ -64,7 +66,7 @@ struct GemmConfig {
     static constexpr int ACC_COLS = MT * BN;                       // one accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                      : 2 * ACC_COLS <= 256 ? 256 : 512;   // allocation: power of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + kBiasSmemFloats * 4;
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -138,6 +140,16 @@ __device__ __forceinline__ void unpack_bf16x32(const uint4 (&u)[4], float (&g)[3
     }
 }
 
+// Copies the bias vector into shared memory (all threads; visible after the kernel's first
+// __syncthreads) and returns the pointer the epilogue should read: smem copy, global, or null.
+__device__ __forceinline__ const float* stage_bias(const GemmParams& p, uint8_t* smem_area) {
+    if (!p.bias) return nullptr;
+    if (p.n_total > kBiasSmemFloats) return p.bias;
+    float* sb = reinterpret_cast<float*>(smem_area);
+    for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sb[i] = __ldg(p.bias + i);
+    return sb;
+}
+
 // Epilogue specialisations (compile-time pruning keeps the hot loop small enough for the I-cache):
 //   EPI_SIMPLE  bias + activation -> bf16                       (conv layers, most Linears)
 //   EPI_FULL    bias + side input + activation + residual -> bf16 and/or fp32
@@ -147,16 +159,16 @@ enum { EPI_SIMPLE = 0, EPI_FULL = 1, EPI_DGRAD = 2 };
 // One 32-column chunk of one output row.  `co` = element offset of the chunk in every row-major
 // operand, n0 = first column (for bias / side weights), sv = the row's side inputs.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&raw)[32], long long co, int n0,
-                                               const float (&sv)[16], const AuxRegs& aux) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* bias, const uint32_t (&raw)[32],
+                                               long long co, int n0, const float (&sv)[16], const AuxRegs& aux) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-    if (EPI != EPI_DGRAD && p.bias) {
-        const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n0);
+    if (EPI != EPI_DGRAD && bias) {          // `bias` points at the shared-memory copy when it fits
+        const float4* bsrc = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 b4 = __ldg(bsrc + q);
+            const float4 b4 = bsrc[q];
             v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
         }
     }
@@ -230,8 +242,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 // pending loads -- the buffers are only ever consumed.)
 // row_fn(r, valid, grow): maps tile row r to its output row.
 template <int BN, int MT, int EPI, class RowFn>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int quarter, int lane,
-                                              int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* bias, uint32_t tmem_acc, int quarter,
+                                              int lane, int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
     constexpr int NCH = BN / 32;
     constexpr int ITEMS = MT * NCH;
     bool valid[MT]; long long grow[MT];
@@ -260,7 +272,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * BN + cb * 32), raw);
         tmem_ld_wait();
         if (v_now && !(p.debug & 1))
-            epilogue_chunk<EPI>(p, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, buf);
+            epilogue_chunk<EPI>(p, bias, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, buf);
     };
     AuxRegs b0, b1;
     request(0, b0);
@@ -301,6 +313,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* bias = stage_bias(p, smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
@@ -376,7 +389,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
-            epilogue_tile<BN, MT, EPI>(p, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
+            epilogue_tile<BN, MT, EPI>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
                                   tfull_bar(acc), acc_phase,
                                   [&](int r, bool& valid, long long& grow) {
                                       grow = (long long)tm * p.rows_per_tile + r;

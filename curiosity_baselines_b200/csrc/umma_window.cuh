@@ -57,6 +57,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* bias = stage_bias(p.epi, gen_base + (bar_base + 256u - smem_base));
     // one-time zero of the slab area: rows a shifted window reads past a slab are then always finite
     {
         uint4* z = reinterpret_cast<uint4*>(gen_base + w_bytes);
@@ -132,7 +133,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int grid_px = p.gh * p.gw;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            epilogue_tile<BN, MT, EPI>(p.epi, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
+            epilogue_tile<BN, MT, EPI>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
                                   acc_phase, [&](int r, bool& valid, long long& grow) {
                                       const int s = r / grid_px, rem = r - s * grid_px;
                                       const int gy = rem / p.gw, gx = rem - gy * p.gw;
