@@ -126,6 +126,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------ 256-bit global access
+// sm_100 has 32-byte per-thread global loads / stores (LDG/STG.E.ENL2.256): a lane that owns a
+// 64-byte output row writes it as two full 32-byte sectors instead of four half sectors.
+struct alignas(32) U256 { uint32_t w[8]; };
+__device__ __forceinline__ void st_global_256(void* ptr, const U256& v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                 "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
+}
+__device__ __forceinline__ U256 ld_global_nc_256(const void* ptr) {
+    U256 v;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]),
+                 "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(ptr));
+    return v;
+}
+
 // ------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (sm_100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout [61,64) (2 = SWIZZLE_128B).

@@ -281,27 +281,16 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
                         }
-                        uint8_t* my = stage_o + lane * kStagePitch;
+                        // this lane owns one 64-byte NHWC output row: two full-sector 32-byte stores
+                        __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + row) * 32;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<uint4*>(my + q * 16) =
-                                make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
-                                           pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
-                    }
-                    __syncwarp();
-                    // coalesced write-out: each store instruction covers 8 rows x 64 B = 512 contiguous bytes
-                    {
-                        const int row0 = mt * 128 + quarter * 32;
-                        __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + row0) * 32;
+                        for (int q = 0; q < 2; ++q) {
+                            umma::U256 u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int rr = j * 8 + (lane >> 2);
-                            if (row0 + rr < p.rows && !(p.debug & 2))
-                                reinterpret_cast<uint4*>(o)[rr * 4 + (lane & 3)] =
-                                    *reinterpret_cast<const uint4*>(stage_o + rr * kStagePitch + (lane & 3) * 16);
+                            for (int e = 0; e < 8; ++e) u.w[e] = pack2(v[q * 16 + e * 2], v[q * 16 + e * 2 + 1]);
+                            umma::st_global_256(o + q * 16, u);
                         }
                     }
-                    __syncwarp();
                 }
                 umma::fence_before_thread_sync();
                 __syncwarp();
@@ -328,6 +317,232 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
     umma::fence_before_thread_sync();
     __syncthreads();
     if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, space-to-depth form: the 8x8/stride-4 convolution is a 2x2/stride-1 convolution over 4x4
+// pixel blocks.  The converter writes the normalised frame ONCE as [block row = by*(w/4)+bx][16 px]
+// (32-byte rows, SWIZZLE_32B) and each of the four taps is a UMMA descriptor shifted by
+// bh*(w/4)+bw rows into that image -- no im2col copy in shared memory at all.  Block positions in the
+// last block row / column produce rows that are not stored (400 of 441 are kept for 84x84).
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2dStageBytes = 18 * 1024;       // (4*128 + 22) rows x 32 B, rounded
+constexpr int kS2dMaxStages = 6;
+
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
+    uint64_t d = umma::make_smem_desc(saddr, 16, 256);
+    return (d & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);          // SWIZZLE_32B
+}
+__device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
+
+__global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
+    const int N = 32 * p.nets;
+    const int bwc = p.w / 4;                                   // blocks per frame row
+    const int brows = (p.h / 4) * bwc;                         // block positions per sample
+    const uint32_t w_bytes = (uint32_t)(p.cin * 4 * N * 32);
+    const uint32_t t_off = w_bytes;
+    const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
+    const uint32_t st_off = t_off + t_bytes;
+    const uint32_t bar_base = smem_base + st_off + p.stages * kS2dStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kS2dMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kS2dMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kS2dMaxStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kS2dMaxStages + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
+    const uint32_t tmem_cols = N == 64 ? 512u : 256u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    {   // zero the stages once (block rows past the frame stay zero)
+        uint4* z = reinterpret_cast<uint4*>(gen + st_off);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * kS2dStageBytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    // weights: per (channel, tap) a [N rows][16 = (py,px)] block, K-major, 32-byte swizzle
+    for (int i = threadIdx.x; i < p.cin * 4 * N * 16; i += blockDim.x) {
+        const int e = i & 15, n = (i >> 4) % N, t = ((i >> 4) / N) & 3, c = (i >> 4) / (4 * N);
+        const int kh = 4 * (t >> 1) + (e >> 2), kw = 4 * (t & 1) + (e & 3);
+        const __nv_bfloat16 v = p.w_bf16[n >> 5][(long long)(n & 31) * p.cin * 64 + c * 64 + kh * 8 + kw];
+        *reinterpret_cast<__nv_bfloat16*>(gen + (c * 4 + t) * N * 32 + swz32((uint32_t)(n * 32 + e * 2))) = v;
+    }
+    if (p.mean) {
+        float4* tm = reinterpret_cast<float4*>(gen + t_off);
+        const int g4 = p.h * p.w / 4;
+        for (int i = threadIdx.x; i < g4; i += blockDim.x) {
+            tm[i] = __ldg(reinterpret_cast<const float4*>(p.mean) + i);
+            tm[g4 + i] = __ldg(reinterpret_cast<const float4*>(p.rstd) + i);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEpiWarps); }
+        umma::fence_barrier_init();
+    }
+    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int row_tiles = (brows + 127) / 128;
+
+    if (warp < kConvWarps) {
+        // ------------------------------------------------------------ converters: uint8 -> s2d bf16 image
+        const int tid = threadIdx.x;
+        const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
+        const float4* s_rstd = s_mean + p.h * p.w / 4;
+        const int groups = p.h * p.w / 4;
+        int stage = 0; uint32_t phase = 0;
+        uint32_t px[kMaxGroups];
+        int s = blockIdx.x, c = 0;
+        frame_prefetch(p, s * p.cin + c, tid, px);
+        while (s < p.n) {
+            umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+            uint8_t* A = gen + st_off + stage * kS2dStageBytes;
+            int y = tid / bwc, x4 = tid - y * bwc;
+            const int dy = kConvThreads / bwc, dx = kConvThreads - dy * bwc;
+#pragma unroll
+            for (int i = 0; i < kMaxGroups; ++i) {
+                const int g = tid + i * kConvThreads;
+                if (g < groups) {
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+                    if (p.mean && !(p.debug & 1)) {
+                        const float4 m = s_mean[g], r = s_rstd[g];
+                        v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                        v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                        v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                        v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                    }
+                    const uint32_t off = (uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8);
+                    *reinterpret_cast<uint2*>(A + swz32(off)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+                }
+                y += dy; x4 += dx;
+                if (x4 >= bwc) { x4 -= bwc; ++y; }
+            }
+            int s2 = s, c2 = c + 1;
+            if (c2 == p.cin) { c2 = 0; s2 += gridDim.x; }
+            frame_prefetch(p, s2 < p.n ? s2 * p.cin + c2 : p.units, tid, px);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            umma::mbar_arrive(full_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            s = s2; c = c2;
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t idesc = N == 64 ? umma::make_idesc(128, 64, 0, 0) : umma::make_idesc(128, 32, 0, 0);
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
+                umma::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(full_bar(stage), phase);
+                    umma::fence_after_thread_sync();
+                    const uint64_t da0 = desc_sw32(smem_base + st_off + stage * kS2dStageBytes);
+                    const uint64_t db0 = desc_sw32(smem_base + c * 4 * N * 32);
+                    for (int mt = 0; mt < row_tiles; ++mt) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 4 + mt) * N);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int shift = (t >> 1) * bwc + (t & 1);
+                            umma::mma_f16_ss(d_tmem, da0 + (uint64_t)((mt * 128 + shift) * 2), db0 + (uint64_t)(t * N * 2),
+                                             idesc, (c | t) ? 1u : 0u);
+                        }
+                    }
+                    umma::mma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma::mma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;
+        const int half = (warp - kMmaWarp - 1) >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
+            umma::mbar_wait(tfull_bar(acc), acc_phase);
+            umma::fence_after_thread_sync();
+#pragma unroll 1
+            for (int it = half; it < row_tiles * p.nets; it += kEpiWarps / 4) {
+                const int mt = it / p.nets, net = it - mt * p.nets;
+                uint32_t raw[32];
+                umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32), raw);
+                umma::tmem_ld_wait();
+                const int r = mt * 128 + quarter * 32 + lane;
+                const int by = r / bwc, bx = r - by * bwc;
+                if (by < p.oh && bx < p.ow && !(p.debug & 2)) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    const float* bsrc = net ? p.bias[1] : p.bias[0];
+                    if (bsrc) {
+                        const float4* b4 = reinterpret_cast<const float4*>(bsrc);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = __ldg(b4 + q);
+                            v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+                        }
+                    }
+                    if (p.act == CB_ACT_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
+                    } else if (p.act == CB_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == CB_ACT_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                    }
+                    __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + by * p.ow + bx) * 32;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        umma::U256 u;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) u.w[e] = pack2(v[q * 16 + e * 2], v[q * 16 + e * 2 + 1]);
+                        umma::st_global_256(o + q * 16, u);
+                    }
+                }
+            }
+            umma::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
+    const int N = 32 * p.nets;
+    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
+    p.stages = (224 * 1024 - fixed) / kS2dStageBytes;
+    if (p.stages > kS2dMaxStages) p.stages = kS2dMaxStages;
+    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1: does not fit shared memory");
+    const int smem = fixed + p.stages * kS2dStageBytes;
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = p.n < sms ? p.n : sms;
+    umma_conv1s_fwd_kernel<<<grid, kThreads, smem, s>>>(p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+bool s2d_ok(const cb_conv_desc* d) {      // block grid must fit four M tiles plus the largest tap shift
+    const int bwc = d->in_w / 4, brows = (d->in_h / 4) * bwc;
+    return d->in_h % 4 == 0 && brows <= 512 && (brows + 127) / 128 * 128 + bwc + 1 <= kS2dStageBytes / 32;
 }
 
 bool shape_ok(const cb_conv_desc* d) {
@@ -399,6 +614,9 @@ int conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const 
     p.w_bf16[0] = (const __nv_bfloat16*)w_native; p.bias[0] = e->bias; p.out[0] = (__nv_bfloat16*)e->out_bf16;
     p.w_bf16[1] = (const __nv_bfloat16*)w2; p.bias[1] = bias2; p.out[1] = (__nv_bfloat16*)out2;
     p.act = d->act;
+    static int im2col = -1;
+    if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
+    if (!im2col && s2d_ok(d)) return launch_s2d_fwd(p, s);
     return launch<false>(p, s);
 }
 

@@ -117,14 +117,14 @@ struct AuxRegs { uint4 other[4], grad[4]; };   // other = add_pre (dgrad) or res
 __device__ __forceinline__ void aux_load(const GemmParams& p, long long co, AuxRegs& a) {
     const __nv_bfloat16* other = p.add_pre ? p.add_pre : p.residual;     // skip gradient (dgrad) or residual (forward)
     if (other) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(other + co);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a.other[q] = __ldg(s4 + q);
+        const U256 lo = ld_global_nc_256(other + co), hi = ld_global_nc_256(other + co + 16);
+        a.other[0] = make_uint4(lo.w[0], lo.w[1], lo.w[2], lo.w[3]); a.other[1] = make_uint4(lo.w[4], lo.w[5], lo.w[6], lo.w[7]);
+        a.other[2] = make_uint4(hi.w[0], hi.w[1], hi.w[2], hi.w[3]); a.other[3] = make_uint4(hi.w[4], hi.w[5], hi.w[6], hi.w[7]);
     }
     if (p.actgrad_src) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(p.actgrad_src + co);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a.grad[q] = __ldg(s4 + q);
+        const U256 lo = ld_global_nc_256(p.actgrad_src + co), hi = ld_global_nc_256(p.actgrad_src + co + 16);
+        a.grad[0] = make_uint4(lo.w[0], lo.w[1], lo.w[2], lo.w[3]); a.grad[1] = make_uint4(lo.w[4], lo.w[5], lo.w[6], lo.w[7]);
+        a.grad[2] = make_uint4(hi.w[0], hi.w[1], hi.w[2], hi.w[3]); a.grad[3] = make_uint4(hi.w[4], hi.w[5], hi.w[6], hi.w[7]);
     }
 }
 
@@ -216,21 +216,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += g[j];
     }
-    if (EPI != EPI_FULL || p.out_bf16) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + co);
+    if (EPI != EPI_FULL || p.out_bf16) {        // 64 B per row chunk: two 32-byte stores
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+        for (int q = 0; q < 2; ++q) {
+            U256 u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-            dst[q] = u;
+            for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 16 + e * 2], v[q * 16 + e * 2 + 1]);
+                u.w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            st_global_256(p.out_bf16 + co + q * 16, u);
         }
     }
     if (EPI == EPI_FULL && p.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(p.out_f32 + co);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        for (int q = 0; q < 4; ++q) {
+            U256 u;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u.w[e] = __float_as_uint(v[q * 8 + e]);
+            st_global_256(p.out_f32 + co + q * 8, u);
+        }
     }
 }
 

@@ -10,15 +10,16 @@ namespace {
 
 struct ProbeParams {
     const uint8_t* a_img; const uint8_t* b_img; int a_bytes, b_bytes;   // images copied to smem (1024-aligned bases)
-    int a_start, a_lbo, a_sbo, a_base_off, a_kstep;                   // A descriptor fields (bytes)
-    int b_start, b_lbo, b_sbo, b_base_off, b_kstep;
+    int a_start, a_lbo, a_sbo, a_base_off, a_kstep, a_layout;         // A descriptor fields (bytes; layout 0 = SW128)
+    int b_start, b_lbo, b_sbo, b_base_off, b_kstep, b_layout;
     int a_mn_major, b_mn_major, M, N, ksteps;
     float* d_out;                                                     // [128][N] fp32 (TMEM lanes x columns)
 };
 
-__device__ __forceinline__ uint64_t probe_desc(uint32_t saddr, int lbo, int sbo, int base_off) {
+__device__ __forceinline__ uint64_t probe_desc(uint32_t saddr, int lbo, int sbo, int base_off, int layout) {
     uint64_t d = umma::make_smem_desc(saddr, (uint32_t)lbo, (uint32_t)sbo);
     d |= (uint64_t)(base_off & 7) << 49;
+    if (layout) d = (d & ~((uint64_t)7 << 61)) | ((uint64_t)(layout & 7) << 61);
     return d;
 }
 
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeParams p)
         const uint32_t idesc = umma::make_idesc(p.M, p.N, p.a_mn_major, p.b_mn_major);
         const uint32_t sa = umma::smem_u32(a_s), sb = umma::smem_u32(b_s);
         for (int k = 0; k < p.ksteps; ++k) {
-            uint64_t da = probe_desc(sa + p.a_start + k * p.a_kstep, p.a_lbo, p.a_sbo, p.a_base_off);
-            uint64_t db = probe_desc(sb + p.b_start + k * p.b_kstep, p.b_lbo, p.b_sbo, p.b_base_off);
+            uint64_t da = probe_desc(sa + p.a_start + k * p.a_kstep, p.a_lbo, p.a_sbo, p.a_base_off, p.a_layout);
+            uint64_t db = probe_desc(sb + p.b_start + k * p.b_kstep, p.b_lbo, p.b_sbo, p.b_base_off, p.b_layout);
             umma::mma_f16_ss(tmem, da, db, idesc, k ? 1u : 0u);
         }
         umma::mma_commit(umma::smem_u32(&bar));
@@ -78,8 +79,8 @@ extern "C" int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, 
                CB_E_ARG, "cb_umma_probe: bad sizes");
     ProbeParams p{};
     p.a_img = (const uint8_t*)a_img; p.b_img = (const uint8_t*)b_img; p.a_bytes = a_bytes; p.b_bytes = b_bytes;
-    p.a_start = a_desc[0]; p.a_lbo = a_desc[1]; p.a_sbo = a_desc[2]; p.a_base_off = a_desc[3]; p.a_kstep = a_desc[4];
-    p.b_start = b_desc[0]; p.b_lbo = b_desc[1]; p.b_sbo = b_desc[2]; p.b_base_off = b_desc[3]; p.b_kstep = b_desc[4];
+    p.a_start = a_desc[0]; p.a_lbo = a_desc[1]; p.a_sbo = a_desc[2]; p.a_base_off = a_desc[3]; p.a_kstep = a_desc[4]; p.a_layout = a_desc[5];
+    p.b_start = b_desc[0]; p.b_lbo = b_desc[1]; p.b_sbo = b_desc[2]; p.b_base_off = b_desc[3]; p.b_kstep = b_desc[4]; p.b_layout = b_desc[5];
     p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.M = M; p.N = N; p.ksteps = ksteps; p.d_out = d_out;
     int smem = a_bytes + b_bytes + 4096;
     CB_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -248,8 +248,8 @@ int cb_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pi
 
 /* ------------------------------------------------------------------------------------
  * Kernel-author diagnostics (not on the product path): run `ksteps` tcgen05.mma over raw
- * shared-memory images with explicit descriptor fields {start, lbo, sbo, base_offset, kstep}
- * (bytes) and return the [128][N] fp32 accumulator.  Used by tests/test_gpu_umma_probe.py to pin
+ * shared-memory images with explicit descriptor fields {start, lbo, sbo, base_offset, kstep, layout}
+ * (bytes; layout 0 = SWIZZLE_128B, else the raw 3-bit layout code) and return the [128][N] fp32 accumulator.  Used by tests/test_gpu_umma_probe.py to pin
  * the MN-major / base_offset descriptor semantics on the installed hardware.
  * ---------------------------------------------------------------------------------- */
 int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, const int* a_desc_host,

@@ -28,8 +28,8 @@ def run(a_img, b_img, a_desc, b_desc, a_mn, b_mn, M, N, ksteps):
     a = torch.from_numpy(a_img.view(np.int16)).to(dev)
     b = torch.from_numpy(b_img.view(np.int16)).to(dev)
     out = torch.full((128, N), float("nan"), device=dev)
-    ad = (C.c_int * 5)(*a_desc)
-    bd = (C.c_int * 5)(*b_desc)
+    ad = (C.c_int * 6)(*(tuple(a_desc) + (0,) * (6 - len(a_desc))))
+    bd = (C.c_int * 6)(*(tuple(b_desc) + (0,) * (6 - len(b_desc))))
     L.call("cb_umma_probe", L.ptr(a), a.numel() * 2, L.ptr(b), b.numel() * 2, ad, bd, a_mn, b_mn, M, N, ksteps,
            L.ptr(out), L.stream())
     torch.cuda.synchronize()
@@ -114,3 +114,23 @@ for bo in (0,):
     d = run(x_img, b2, (0, 128, 1024, bo, 2048), (0, 8192, 1024, 0, 2048), 1, 1, 128, 64, 4)
     ref = torch.cat([X[:, 0:64], X[:, 1:65]], 0) @ B2.t()
     print(f"E5 MN-major A two overlapping chunks (LBO=128): err {rel(d, ref):.3e}  (first half {rel(d[:64], ref[:64]):.3e})")
+
+# E6: K-major SWIZZLE_32B (layout code 6): rows of 32 B (K = 16), 8-row atoms of 256 B, row-shifted starts
+def swz32(off):
+    return off ^ (((off >> 7) & 1) << 4)
+
+
+def kmajor32_image(mat, rows_alloc, swz_fn):
+    b = bf16_bits(mat)
+    img = np.zeros(rows_alloc * 16, dtype=np.int16)
+    r, k = np.meshgrid(np.arange(mat.shape[0]), np.arange(16), indexing="ij")
+    img[swz_fn(r * 32 + k * 2) // 2] = b
+    return img
+
+
+A6 = rb(200, 16); B6 = rb(64, 16)
+for name, fn in (("addr-swizzle", swz32), ("no-swizzle", lambda o: o)):
+    a6 = kmajor32_image(A6, 256, fn); b6 = kmajor32_image(B6, 64, fn)
+    for shift in (0, 1, 5, 21, 22):
+        d = run(a6, b6, (shift * 32, 16, 256, 0, 0, 6), (0, 16, 256, 0, 0, 6), 0, 0, 128, 64, 1)
+        print(f"E6 SW32 K-major {name} shift={shift}: err {rel(d, A6[shift:shift + 128] @ B6.t()):.3e}")
