@@ -209,18 +209,24 @@ def main():
     h_out = [torch.empty(T, B).pin_memory() for _ in range(3)]
     h_loss = torch.empty(1).pin_memory()
 
+    from curiosity_baselines_b200.agents.hooks import FrameStager
+    stager = FrameStager(dev)
+
     def e2e_step():
-        d_frames = newest_frame_to_device(h_frames, dev)            # only the newest frame is read by RND
+        """Host buffers in, host results out.  The strided upload of the NEXT step's frames runs on a
+        side stream under this step's compute (double buffered), as a training loop would do it."""
+        d_frames = stager.get()
+        stager.prefetch(h_frames)
         d_done, d_value, d_boot, d_mask = (t.to(dev, non_blocking=True) for t in h_small)
         loss, r_int, adv, ret = step(d_frames, d_done, torch.zeros(T, B, device=dev), d_value, d_boot, d_mask)
         h_out[0].copy_(r_int, non_blocking=True); h_out[1].copy_(adv, non_blocking=True)
         h_out[2].copy_(ret, non_blocking=True); h_loss.copy_(loss.reshape(1), non_blocking=True)
-        torch.cuda.synchronize()
 
+    stager.prefetch(h_frames)
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(2, min(args.steps, 5))
+    n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
         e2e_step()
     barrier()

@@ -46,6 +46,39 @@ def newest_frame_to_device(frames, dev):
     return out
 
 
+class FrameStager:
+    """Double-buffered host->device staging of the newest frame of pinned uint8 stacks on a side
+    stream: ``prefetch(frames)`` starts the strided copy of the NEXT batch while the
+    current one is being processed; ``get()`` makes the compute stream wait for it and returns it."""
+
+    def __init__(self, device):
+        self.dev = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.bufs, self.events, self.k = [None, None], [None, None], 0
+        self.pending = None
+
+    def prefetch(self, frames):
+        from .. import _lib as L
+        T, B, C, H, W = frames.shape
+        i = self.k
+        if self.bufs[i] is None or self.bufs[i].shape != (T, B, 1, H, W):
+            self.bufs[i] = torch.empty((T, B, 1, H, W), dtype=torch.uint8, device=self.dev)
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # buffer i is free once earlier compute is queued
+        with torch.cuda.stream(self.stream):
+            L.call("cb_h2d_2d", self.bufs[i].data_ptr(), H * W, frames.data_ptr() + (C - 1) * H * W, C * H * W, H * W,
+                   T * B, self.stream.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.events[i] = ev
+        self.pending = i
+        self.k ^= 1
+
+    def get(self):
+        i = self.pending
+        torch.cuda.current_stream(self.dev).wait_event(self.events[i])
+        return self.bufs[i]
+
+
 @torch.no_grad()
 def curiosity_step(self, curiosity_type, *args):
     dev = _device(self)

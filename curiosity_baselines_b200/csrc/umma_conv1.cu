@@ -540,6 +540,201 @@ int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
     return CB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient, space-to-depth form.  dW[n][tap t, element e] = sum over block positions r of
+// dy_grid[r][n] * image[r + shift_t][e].
+//   A = dy rows laid on the same (w/4)-wide block grid, MN-major SWIZZLE_128B, M = 64 (32 channels +
+//       32 zero columns; grid positions without an output stay zero);
+//   B = the s2d image read MN-major with SWIZZLE_32B.  The converter stores the image four times,
+//       copy t pre-shifted by shift_t rows, so ONE descriptor with LBO = copy stride presents the four
+//       taps as the four 16-element chunks of an N = 64 operand (tiny N = 16 MMAs are issue-bound).
+// One TMEM accumulator [64 x 64] per input channel, accumulated over all samples of the CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2dDyBytes = 56 * 1024;          // 448 grid rows x 128 B
+constexpr int kS2dCopyBytes = 15 * 1024;        // one pre-shifted image copy: 480 rows x 32 B
+constexpr int kS2dWgradStage = 4 * kS2dCopyBytes + kS2dDyBytes;
+
+__global__ void __launch_bounds__(kThreads, 1) umma_conv1s_wgrad_kernel(const Conv1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
+    const int bwc = p.w / 4;
+    const int brows = (p.h / 4) * bwc;
+    const int ksteps = (brows + 15) / 16;
+    const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
+    const uint32_t stage_bytes = kS2dWgradStage;
+    const uint32_t st_off = t_bytes;
+    const uint32_t bar_base = smem_base + st_off + p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kS2dMaxStages + s); };
+    const uint32_t done_bar = bar_base + 8u * (2 * kS2dMaxStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kS2dMaxStages + 1);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
+    const uint32_t tmem_cols = p.cin * 64 <= 64 ? 64u : (p.cin * 64 <= 128 ? 128u : 256u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        uint4* z = reinterpret_cast<uint4*>(gen + st_off);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * stage_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.mean) {
+        float4* tm = reinterpret_cast<float4*>(gen);
+        const int g4 = p.h * p.w / 4;
+        for (int i = threadIdx.x; i < g4; i += blockDim.x) {
+            tm[i] = __ldg(reinterpret_cast<const float4*>(p.mean) + i);
+            tm[g4 + i] = __ldg(reinterpret_cast<const float4*>(p.rstd) + i);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
+        umma::mbar_init(done_bar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < kConvWarps) {
+        const int tid = threadIdx.x;
+        const float4* s_mean = reinterpret_cast<const float4*>(gen);
+        const float4* s_rstd = s_mean + p.h * p.w / 4;
+        const int groups = p.h * p.w / 4;
+        int stage = 0; uint32_t phase = 0;
+        uint32_t px[kMaxGroups];
+        int s = blockIdx.x, c = 0;
+        frame_prefetch(p, s * p.cin + c, tid, px);
+        while (s < p.n) {
+            // dy rows of this sample first (global loads in flight while the image is converted)
+            uint4 dyv[8];
+            const __nv_bfloat16* dys = p.dy + (long long)s * p.rows * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = tid + i * kConvThreads;
+                dyv[i] = q < p.rows * 4 ? __ldg(reinterpret_cast<const uint4*>(dys) + q) : make_uint4(0, 0, 0, 0);
+            }
+            umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+            uint8_t* A = gen + st_off + stage * stage_bytes;           // four pre-shifted s2d image copies
+            uint8_t* D = A + 4 * kS2dCopyBytes;                        // dy on the block grid
+            int y = tid / bwc, x4 = tid - y * bwc;
+            const int dy_ = kConvThreads / bwc, dx_ = kConvThreads - dy_ * bwc;
+#pragma unroll
+            for (int i = 0; i < kMaxGroups; ++i) {
+                const int g = tid + i * kConvThreads;
+                if (g < groups) {
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+                    if (p.mean) {
+                        const float4 m = s_mean[g], r = s_rstd[g];
+                        v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                        v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                        v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                        v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                    }
+                    const uint2 val = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+                    const int row = (y >> 2) * bwc + x4;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {               // copy t holds image rows shifted up by shift_t
+                        const int rt = row - ((t >> 1) * bwc + (t & 1));
+                        if (rt >= 0)
+                            *reinterpret_cast<uint2*>(A + t * kS2dCopyBytes + swz32((uint32_t)(rt * 32 + (y & 3) * 8))) = val;
+                    }
+                }
+                y += dy_; x4 += dx_;
+                if (x4 >= bwc) { x4 -= bwc; ++y; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = tid + i * kConvThreads;
+                if (q < p.rows * 4) {
+                    const int pos = q >> 2, j = q & 3;
+                    const int oy = pos / p.ow, ox = pos - oy * p.ow;
+                    const int row = oy * bwc + ox;
+                    *reinterpret_cast<uint4*>(D + row * 128 + ((j ^ (row & 7)) << 4)) = dyv[i];
+                }
+            }
+            int s2 = s, c2 = c + 1;
+            if (c2 == p.cin) { c2 = 0; s2 += gridDim.x; }
+            frame_prefetch(p, s2 < p.n ? s2 * p.cin + c2 : p.units, tid, px);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            umma::mbar_arrive(full_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            s = s2; c = c2;
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            bool seen[kMaxCin] = {false, false, false, false};
+            constexpr uint32_t idesc = umma::make_idesc(64, 64, 1, 1);
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(full_bar(stage), phase);
+                    umma::fence_after_thread_sync();
+                    const uint32_t img = smem_base + st_off + stage * stage_bytes;
+                    uint64_t db0 = umma::make_smem_desc(img, kS2dCopyBytes, 256);          // LBO = copy stride
+                    db0 = (db0 & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);               // SWIZZLE_32B
+                    const uint64_t da0 = umma::make_smem_desc(img + 4 * kS2dCopyBytes, 8192, 1024);
+                    for (int k = 0; k < ksteps; ++k)
+                        umma::mma_f16_ss(tmem_base + (uint32_t)(c * 64), da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 32), idesc,
+                                         (!seen[c] && k == 0) ? 0u : 1u);
+                    seen[c] = true;
+                    umma::mma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            umma::mma_commit(done_bar);
+        }
+    } else if (warp - kMmaWarp - 1 < 4 && blockIdx.x < p.n) {
+        // M = 64 accumulator: channel n lives in TMEM lane (n/16)*32 + n%16; only n < 32 is real
+        const int quarter = warp & 3;
+        umma::mbar_wait(done_bar, 0);
+        umma::fence_after_thread_sync();
+        const int K = p.cin * 64;
+        for (int c = 0; c < p.cin; ++c) {
+#pragma unroll 1
+            for (int hb = 0; hb < 2; ++hb) {
+                uint32_t raw[32];
+                umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 64 + hb * 32), raw);
+                umma::tmem_ld_wait();
+                if (quarter < 2 && lane < 16) {
+                    const int n = quarter * 16 + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int t = hb * 2 + (j >> 4), e = j & 15;
+                        const int kh = 4 * (t >> 1) + (e >> 2), kw = 4 * (t & 1) + (e & 3);
+                        atomicAdd(p.dw + (long long)n * K + c * 64 + kh * 8 + kw, __uint_as_float(raw[j]));
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
+    const int fixed = (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
+    p.stages = (224 * 1024 - fixed) / kS2dWgradStage;
+    if (p.stages > kS2dMaxStages) p.stages = kS2dMaxStages;
+    CB_REQUIRE(p.stages >= 1, CB_E_ARG, "conv1 wgrad: does not fit shared memory");
+    const int smem = fixed + p.stages * kS2dWgradStage;
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = p.n < sms ? p.n : sms;
+    umma_conv1s_wgrad_kernel<<<grid, kThreads, smem, s>>>(p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 bool s2d_ok(const cb_conv_desc* d) {      // block grid must fit four M tiles plus the largest tap shift
     const int bwc = d->in_w / 4, brows = (d->in_h / 4) * bwc;
     return d->in_h % 4 == 0 && brows <= 512 && (brows + 127) / 128 * 128 + bwc + 1 <= kS2dStageBytes / 32;
@@ -629,6 +824,12 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
     p.dy = (const __nv_bfloat16*)dy; p.dw = dw; p.nets = 1;
     rc = scale_buffer(dw, (int64_t)32 * d->in_c * 64, beta, s); if (rc) return rc;
     if (dbias) { rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s); if (rc) return rc; }
+    static int im2col = -1;
+    if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
+    // the s2d kernel prefetches a sample's dy rows into 8 registers per converter thread
+    if (!im2col && s2d_ok(d) && p.rows * 4 <= 8 * kConvThreads && ((d->in_h / 4) * (d->in_w / 4) + 15) / 16 * 16 * 128 <= kS2dDyBytes &&
+        (((d->in_h / 4) * (d->in_w / 4) + 15) / 16 * 16 + 1) * 32 <= kS2dCopyBytes)
+        return launch_s2d_wgrad(p, s);
     return launch<true>(p, s);
 }
 

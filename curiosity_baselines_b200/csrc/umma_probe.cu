@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeParams p)
     }
     umma::mbar_wait(umma::smem_u32(&bar), 0);
     umma::fence_after_thread_sync();
-    for (int c0 = 0; c0 < p.N; c0 += 32) {
+    for (int c0 = 0; c0 < p.N; c0 += 32) {      // reads whole 32-column groups; columns >= N are not stored
         uint32_t raw[32];
         umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, raw);
         umma::tmem_ld_wait();
@@ -75,7 +75,7 @@ extern "C" int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, 
                              float* d_out, void* stream) {
     CB_REQUIRE(a_img && b_img && a_desc && b_desc && d_out, CB_E_ARG, "cb_umma_probe: null pointer");
     CB_REQUIRE(cb_device_supports_umma(), CB_E_ARCH, "cb_umma_probe: needs sm_100");
-    CB_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_bytes + b_bytes <= 200 * 1024 && N % 32 == 0 && N <= 256,
+    CB_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_bytes + b_bytes <= 200 * 1024 && N % 8 == 0 && N <= 256,
                CB_E_ARG, "cb_umma_probe: bad sizes");
     ProbeParams p{};
     p.a_img = (const uint8_t*)a_img; p.b_img = (const uint8_t*)b_img; p.a_bytes = a_bytes; p.b_bytes = b_bytes;

@@ -134,3 +134,24 @@ for name, fn in (("addr-swizzle", swz32), ("no-swizzle", lambda o: o)):
     for shift in (0, 1, 5, 21, 22):
         d = run(a6, b6, (shift * 32, 16, 256, 0, 0, 6), (0, 16, 256, 0, 0, 6), 0, 0, 128, 64, 1)
         print(f"E6 SW32 K-major {name} shift={shift}: err {rel(d, A6[shift:shift + 128] @ B6.t()):.3e}")
+
+# E7: MN-major SWIZZLE_32B B operand with N = 16 (one 32-byte chunk per K row), K-row-shifted start,
+#     against an MN-major SWIZZLE_128B A operand with M = 64
+def mn32_image(mat, krows_alloc):
+    """mat [16, K] -> K rows of 32 B (16 MN elements), 32-byte swizzle."""
+    b = bf16_bits(mat)
+    img = np.zeros(krows_alloc * 16, dtype=np.int16)
+    m, k = np.meshgrid(np.arange(16), np.arange(mat.shape[1]), indexing="ij")
+    img[swz32(k * 32 + m * 2) // 2] = b
+    return img
+
+
+A7 = rb(64, 64)                       # [M, K]  (dy channels x positions)
+B7 = rb(16, 96)                       # [N, K]  (patch elements x block rows)
+a7 = mnmajor_image(A7, 64, 8192)
+b7 = mn32_image(B7, 128)
+for shift in (0, 1, 21, 22):
+    d = run(a7, b7, (0, 8192, 1024, 0, 2048, 0), (shift * 32, 16, 256, 0, 512, 6), 1, 1, 64, 16, 4)
+    ref = A7 @ B7[:, shift:shift + 64].t()            # [64, 16]
+    got = torch.stack([d[(i // 16) * 32 + i % 16, :16] for i in range(64)])
+    print(f"E7 MN-major SW32 N=16 shift={shift}: err {rel(got, ref):.3e}")
