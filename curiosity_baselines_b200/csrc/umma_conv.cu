@@ -59,6 +59,31 @@ int encode_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
     return CB_OK;
 }
 
+}  // namespace
+
+// bf16 tensor map with a chosen swizzle (0 = none, 1 = 32 B, 2 = 64 B, 3 = 128 B); used by umma_conv1.cu
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle) {
+    EncodeFn enc = get_encode();
+    CB_REQUIRE(enc, CB_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    CB_REQUIRE(((uintptr_t)base & 15) == 0, CB_E_ALIGN, "TMA base address not 16-byte aligned");
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        CB_REQUIRE(strides_bytes[i] % 16 == 0, CB_E_ALIGN, "TMA stride %d not a multiple of 16", i);
+        gs[i] = strides_bytes[i];
+    }
+    const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CB_REQUIRE(r == CUDA_SUCCESS, CB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CB_OK;
+}
+
+namespace {
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -103,7 +128,7 @@ int launch_epi(const Plan& pl, cudaStream_t s) {
     }
     int tiles = pl.p.m_tiles * pl.p.n_tiles;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::gemm_threads<EPI>(), Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -458,7 +483,7 @@ int launch_window_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::Wind
         attr = true;
     }
     int grid = p.tiles < sm_count() ? p.tiles : sm_count();
-    umma::umma_window_conv_kernel<BN, EPI><<<grid, umma::kGemmThreads, smem, s>>>(tmA, tmW, p);
+    umma::umma_window_conv_kernel<BN, EPI><<<grid, umma::gemm_threads<EPI>(), smem, s>>>(tmA, tmW, p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

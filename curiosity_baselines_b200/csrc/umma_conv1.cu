@@ -16,6 +16,11 @@
 #include "umma_common.cuh"
 #include <stdlib.h>
 
+namespace cb {
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle);
+}
+
 namespace {
 
 constexpr int kConvWarps = 8;           // converter warps
@@ -24,6 +29,9 @@ constexpr int kMmaWarp = kConvWarps;   // MMA issuer / TMEM owner
 constexpr int kStagePitch = 80;         // bytes per staged output row (64 + 16: conflict-free 16-byte stores)
 constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, splitting the (row tile, net) items
 constexpr int kThreads = (kConvWarps + 1 + kEpiWarps) * 32;
+constexpr int kLoadWarp = kConvWarps + 1 + kEpiWarps;   // s2d forward: raw-frame loader (cp.async.bulk ring)
+constexpr int kThreadsS2d = kThreads + 32;
+constexpr int kMaxRaw = 8;             // raw uint8 frames in flight per CTA
 constexpr int kMaxStages1 = 4;
 constexpr int kMaxCin = 4;
 constexpr int kConvBar = 1;            // named barrier of the converter threads
@@ -33,6 +41,7 @@ struct Conv1Params {
     int rows, row_tiles;               // oh*ow output positions per sample, ceil(rows/128)
     int pitch;                         // bytes per row of the normalised bf16 frame in shared memory
     int units, stages, a_stage_bytes;  // units = n*cin (one channel of one sample each)
+    int raw_slots;                     // s2d kernels: depth of the raw-frame ring
     const float* mean; const float* rstd;
     // forward: one or two networks sharing the input (RND target + predictor)
     int nets; const __nv_bfloat16* w_bf16[2]; const float* bias[2]; int act; __nv_bfloat16* out[2];
@@ -46,6 +55,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kConvBar), "n"(kConvThreads) : "memory"); }
+
+// global -> shared bulk copy (TMA, no tensor map): `bytes` % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 constexpr int kMaxGroups = 8;          // 4-pixel groups per converter thread: ceil(h*w/4/256) (84x84 -> 7)
 
@@ -335,7 +350,10 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
 }
 __device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
 
-__global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv1Params p) {
+constexpr int kEpiBar = 2;             // named barrier of the epilogue threads
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBar), "n"(kEpiWarps * 32) : "memory"); }
+
+__global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const Conv1Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
@@ -346,12 +364,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
     const uint32_t t_off = w_bytes;
     const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
     const uint32_t st_off = t_off + t_bytes;
-    const uint32_t bar_base = smem_base + st_off + p.stages * kS2dStageBytes;
+    const uint32_t raw_off = st_off + p.stages * kS2dStageBytes;              // ring of raw uint8 frames
+    const uint32_t raw_bytes = (uint32_t)((p.h * p.w + 127) & ~127);
+    const uint32_t b_off = raw_off + p.raw_slots * raw_bytes;                  // biases: [net][32] fp32
+    const uint32_t bar_base = smem_base + b_off + 256u;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kS2dMaxStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kS2dMaxStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kS2dMaxStages + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kS2dMaxStages + 4);
+    auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kS2dMaxStages + 5 + s); };
+    auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kS2dMaxStages + 5 + kMaxRaw + s); };
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
     const uint32_t tmem_cols = N == 64 ? 512u : 256u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -375,10 +398,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
             tm[g4 + i] = __ldg(reinterpret_cast<const float4*>(p.rstd) + i);
         }
     }
+    if (threadIdx.x < 64) {
+        const float* b = p.bias[threadIdx.x >> 5];
+        reinterpret_cast<float*>(gen + b_off)[threadIdx.x] = (b && (int)(threadIdx.x >> 5) < p.nets) ? __ldg(b + (threadIdx.x & 31)) : 0.f;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEpiWarps); }
+        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kConvThreads); }
         umma::fence_barrier_init();
     }
     if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
@@ -395,10 +423,22 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
         const float4* s_rstd = s_mean + p.h * p.w / 4;
         const int groups = p.h * p.w / 4;
         int stage = 0; uint32_t phase = 0;
+        int rslot = 0; uint32_t rphase = 0;
         uint32_t px[kMaxGroups];
         int s = blockIdx.x, c = 0;
-        frame_prefetch(p, s * p.cin + c, tid, px);
         while (s < p.n) {
+            // this unit's raw pixels: staged by the loader warp several units ahead (HBM latency hidden)
+            umma::mbar_wait(rfull_bar(rslot), rphase);
+            {
+                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
+#pragma unroll
+                for (int i = 0; i < kMaxGroups; ++i) {
+                    const int g = tid + i * kConvThreads;
+                    px[i] = g < groups ? raw[g] : 0u;
+                }
+            }
+            umma::mbar_arrive(rempty_bar(rslot));
+            if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
             umma::mbar_wait(empty_bar(stage), phase ^ 1u);
             uint8_t* A = gen + st_off + stage * kS2dStageBytes;
             int y = tid / bwc, x4 = tid - y * bwc;
@@ -423,13 +463,23 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
                 y += dy; x4 += dx;
                 if (x4 >= bwc) { x4 -= bwc; ++y; }
             }
-            int s2 = s, c2 = c + 1;
-            if (c2 == p.cin) { c2 = 0; s2 += gridDim.x; }
-            frame_prefetch(p, s2 < p.n ? s2 * p.cin + c2 : p.units, tid, px);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             umma::mbar_arrive(full_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            s = s2; c = c2;
+            if (++c == p.cin) { c = 0; s += gridDim.x; }
+        }
+    } else if (warp == kLoadWarp) {
+        // ------------------------------------------------------------ raw-frame loader
+        if (lane == 0) {
+            int rslot = 0; uint32_t rphase = 0;
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x)
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(rempty_bar(rslot), rphase ^ 1u);
+                    umma::mbar_arrive_expect_tx(rfull_bar(rslot), (uint32_t)(p.h * p.w));
+                    bulk_load(smem_base + raw_off + rslot * raw_bytes, p.x + s * p.stride_n + c * p.stride_c,
+                              (uint32_t)(p.h * p.w), rfull_bar(rslot));
+                    if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
+                }
         }
     } else if (warp == kMmaWarp) {
         if (lane == 0) {
@@ -461,44 +511,60 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
         }
     } else {
         // ------------------------------------------------------------ epilogue
+        // TMEM reads run at 64 B/clk/SM (a 32x32 fp32 block takes 64 cycles), so each warp keeps the NEXT
+        // block's tcgen05.ld in flight while it applies bias/activation to the current one and stores it.
         const int quarter = warp & 3;
         const int half = (warp - kMmaWarp - 1) >> 2;
+        const float* s_bias = reinterpret_cast<const float*>(gen + b_off);
+        // The block-grid row of this lane in each row tile (and whether it is stored) never changes: hoisted
+        // out of the sample loop so the per-block work is tcgen05.ld + bias/activation + pack + two stores.
+        int out_row[4];                                  // by*ow + bx, or -1
+        bool tile_live[4];                               // any of the warp's 32 rows inside the block grid
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = mt * 128 + quarter * 32 + lane;
+            const int by = r / bwc, bx = r - by * bwc;
+            out_row[mt] = (mt < row_tiles && by < p.oh && bx < p.ow) ? by * p.ow + bx : -1;
+            tile_live[mt] = mt < row_tiles && mt * 128 + quarter * 32 < brows;
+        }
+        const int act = p.act;
         int acc = 0; uint32_t acc_phase = 0;
         for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
             umma::mbar_wait(tfull_bar(acc), acc_phase);
             umma::fence_after_thread_sync();
+            const long long obase = (long long)s * p.rows;
+            // (row tile, net) blocks alternate between the two warps of a quarter; mt is unrolled so that
+            // out_row / tile_live stay in registers (a dynamically indexed copy lands in local memory: +30 % time).
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                if (!tile_live[mt]) continue;
 #pragma unroll 1
-            for (int it = half; it < row_tiles * p.nets; it += kEpiWarps / 4) {
-                const int mt = it / p.nets, net = it - mt * p.nets;
-                uint32_t raw[32];
-                umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32), raw);
-                umma::tmem_ld_wait();
-                const int r = mt * 128 + quarter * 32 + lane;
-                const int by = r / bwc, bx = r - by * bwc;
-                if (by < p.oh && bx < p.ow && !(p.debug & 2)) {
+                for (int net = 0; net < p.nets; ++net) {
+                    if (((mt * p.nets + net) & 1) != half) continue;
+                    uint32_t raw[32];
+                    umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32), raw);
+                    umma::tmem_ld_wait();
+                    if (out_row[mt] < 0 || (p.debug & 2)) continue;
                     float v[32];
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + net * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    const float* bsrc = net ? p.bias[1] : p.bias[0];
-                    if (bsrc) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bsrc);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b = __ldg(b4 + q);
-                            v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = b4[q];
+                        v[q * 4] = __uint_as_float(raw[q * 4]) + b.x; v[q * 4 + 1] = __uint_as_float(raw[q * 4 + 1]) + b.y;
+                        v[q * 4 + 2] = __uint_as_float(raw[q * 4 + 2]) + b.z; v[q * 4 + 3] = __uint_as_float(raw[q * 4 + 3]) + b.w;
                     }
-                    if (p.act == CB_ACT_LRELU) {
+                    if (act == CB_ACT_LRELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
-                    } else if (p.act == CB_ACT_RELU) {
+                    } else if (act == CB_ACT_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (p.act == CB_ACT_ELU) {
+                    } else if (act == CB_ACT_ELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
                     }
-                    __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + ((long long)s * p.rows + by * p.ow + bx) * 32;
+                    // this lane owns one 64-byte NHWC output row: two full-sector 32-byte stores
+                    __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + (obase + out_row[mt]) * 32;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         umma::U256 u;
@@ -521,11 +587,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_fwd_kernel(const Conv
 
 int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
     const int N = 32 * p.nets;
-    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
-    p.stages = (224 * 1024 - fixed) / kS2dStageBytes;
-    if (p.stages > kS2dMaxStages) p.stages = kS2dMaxStages;
+    const int raw_bytes = (p.h * p.w + 127) & ~127;
+    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256 + 512;
+    p.stages = (224 * 1024 - fixed - 4 * raw_bytes) / kS2dStageBytes;
+    if (p.stages > 4) p.stages = 4;
     CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1: does not fit shared memory");
-    const int smem = fixed + p.stages * kS2dStageBytes;
+    p.raw_slots = (224 * 1024 - fixed - p.stages * kS2dStageBytes) / raw_bytes;
+    if (p.raw_slots > kMaxRaw) p.raw_slots = kMaxRaw;
+    const int smem = fixed + p.stages * kS2dStageBytes + p.raw_slots * raw_bytes;
     static bool attr = false;
     if (!attr) {
         CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -535,7 +604,7 @@ int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = p.n < sms ? p.n : sms;
-    umma_conv1s_fwd_kernel<<<grid, kThreads, smem, s>>>(p);
+    umma_conv1s_fwd_kernel<<<grid, kThreadsS2d, smem, s>>>(p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -737,7 +806,8 @@ int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
 
 bool s2d_ok(const cb_conv_desc* d) {      // block grid must fit four M tiles plus the largest tap shift
     const int bwc = d->in_w / 4, brows = (d->in_h / 4) * bwc;
-    return d->in_h % 4 == 0 && brows <= 512 && (brows + 127) / 128 * 128 + bwc + 1 <= kS2dStageBytes / 32;
+    return d->in_h % 4 == 0 && brows <= 512 && (brows + 127) / 128 * 128 + bwc + 1 <= kS2dStageBytes / 32 &&
+           (d->in_h * d->in_w) % 16 == 0 && d->in_stride_n % 16 == 0 && d->in_stride_c % 16 == 0;   // cp.async.bulk
 }
 
 bool shape_ok(const cb_conv_desc* d) {
@@ -811,7 +881,7 @@ int conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const 
     p.act = d->act;
     static int im2col = -1;
     if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
-    if (!im2col && s2d_ok(d)) return launch_s2d_fwd(p, s);
+    if (!im2col && s2d_ok(d) && ((uintptr_t)x & 15) == 0) return launch_s2d_fwd(p, s);
     return launch<false>(p, s);
 }
 

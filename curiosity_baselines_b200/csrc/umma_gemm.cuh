@@ -16,11 +16,14 @@
 
 namespace umma {
 
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (one per
-// TMEM lane quarter).  192 threads at one CTA/SM leave the epilogue warps the full 255-register budget,
-// which the operand prefetch needs; more epilogue warps would have to spill.
-constexpr int kGemmThreads = 192;
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = epilogue.  A warp may
+// only read the TMEM lane quarter (warp % 4), so the epilogue warps come in groups of four; the
+// kEpiGroups warps sharing a quarter split a tile's (sub-tile, 32-column chunk) items between them.
+// With one warp per scheduler every tcgen05.ld / global-load latency is exposed (ncu: issue slots 22 %
+// busy, tensor pipe 46 %); several warps per scheduler hide it.
 constexpr int kEpiWarp0 = 2;
+template <int EPI> struct EpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 2; };   // SIMPLE needs few registers
+template <int EPI> constexpr int gemm_threads() { return (kEpiWarp0 + 4 * EpiWarps<EPI>::GROUPS) * 32; }
 
 constexpr int kBiasSmemFloats = 4096;   // bias vectors up to this length are staged in shared memory
 
@@ -248,13 +251,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 // row_fn(r, valid, grow): maps tile row r to its output row.
 template <int BN, int MT, int EPI, class RowFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* bias, uint32_t tmem_acc, int quarter,
-                                              int lane, int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
+                                              int sub, int lane, int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
     constexpr int NCH = BN / 32;
     constexpr int ITEMS = MT * NCH;
+    constexpr int G = EpiWarps<EPI>::GROUPS;       // this warp handles items sub, sub + G, ...
     bool valid[MT]; long long grow[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) row_fn(mt * 128 + quarter * 32 + lane, valid[mt], grow[mt]);
     float sv[16];
+    int sv_mt = -1;
 #pragma unroll
     for (int s = 0; s < 16; ++s) sv[s] = 0.f;
     auto row_valid = [&](int mt) { return MT == 1 ? valid[0] : (mt ? valid[MT - 1] : valid[0]); };
@@ -268,7 +273,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         const int mt = it / NCH, cb = it - mt * NCH;
         const bool v_now = row_valid(mt);
         const long long g_now = row_index(mt);
-        if (EPI == EPI_FULL && p.side_dim && cb == 0) {
+        if (EPI == EPI_FULL && p.side_dim && mt != sv_mt) {      // the row's side inputs, once per sub-tile
+            sv_mt = mt;
 #pragma unroll
             for (int s = 0; s < 16; ++s)
                 sv[s] = (v_now && s < p.side_dim) ? __ldg(p.side + g_now * p.side_dim + s) : 0.f;
@@ -280,27 +286,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
             epilogue_chunk<EPI>(p, bias, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, buf);
     };
     AuxRegs b0, b1;
-    request(0, b0);
+    request(sub, b0);
     mbar_wait(tfull, parity);
     fence_after_thread_sync();
     if (EPI == EPI_SIMPLE) {
 #pragma unroll 1
-        for (int it = 0; it < ITEMS; ++it) process(it, b0);
+        for (int it = sub; it < ITEMS; it += G) process(it, b0);
     } else {
 #pragma unroll 1
-        for (int it = 0; it < ITEMS; it += 2) {
-            request(it + 1, b1);
+        for (int it = sub; it < ITEMS; it += 2 * G) {
+            request(it + G, b1);
             process(it, b0);
-            if (it + 1 < ITEMS) {
-                request(it + 2, b0);
-                process(it + 1, b1);
+            if (it + G < ITEMS) {
+                request(it + 2 * G, b0);
+                process(it + G, b1);
             }
         }
     }
 }
 
 template <int BN, int MT, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
     using Cfg = GemmConfig<BN, MT>;
@@ -323,7 +329,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EpiWarps<EPI>::GROUPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -391,10 +397,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= kEpiWarp0) {
         // ------------------------------------------------------------------ epilogue
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+        const int sub = (warp - kEpiWarp0) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
-            epilogue_tile<BN, MT, EPI>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, tn * BN,
+            epilogue_tile<BN, MT, EPI>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, tn * BN,
                                   tfull_bar(acc), acc_phase,
                                   [&](int r, bool& valid, long long& grow) {
                                       grow = (long long)tm * p.rows_per_tile + r;

@@ -36,7 +36,7 @@ struct WindowParams {
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                         const WindowParams p) {
     constexpr int MT = 2;
@@ -68,7 +68,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EpiWarps<EPI>::GROUPS); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -130,10 +130,11 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
     } else if (warp >= kEpiWarp0) {
         const int quarter = warp & 3;
+        const int sub = (warp - kEpiWarp0) >> 2;
         const int grid_px = p.gh * p.gw;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            epilogue_tile<BN, MT, EPI>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, lane, 0, tfull_bar(acc),
+            epilogue_tile<BN, MT, EPI>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, 0, tfull_bar(acc),
                                   acc_phase, [&](int r, bool& valid, long long& grow) {
                                       const int s = r / grid_px, rem = r - s * grid_px;
                                       const int gy = rem / p.gw, gx = rem - gy * p.gw;

@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_umma.py tests/test_gpu_rnd.py tests/test_gpu_icm.py -k "conv1 or golden or oracle" -x -q 2>&1 | tail -3
-timeout 120 python tools/layer_bench.py --only conv1 2>&1 | tail -3
+for d in 0 2 1 3; do echo "CB_CONV1_DEBUG=$d"; CB_CONV1_DEBUG=$d timeout 300 python tools/layer_bench.py --only conv1 2>&1 | grep -v wgrad; done
