@@ -46,7 +46,7 @@ struct Conv1Params {
     // forward: one or two networks sharing the input (RND target + predictor)
     int nets; const __nv_bfloat16* w_bf16[2]; const float* bias[2]; int act; __nv_bfloat16* out[2];
     // wgrad
-    const __nv_bfloat16* dy; float* dw;
+    const __nv_bfloat16* dy; float* dw; float* dbias;
     int debug;                         // CB_CONV1_DEBUG bits (profiling only): 1 no stats, 2 no stores, 4 no assemble, 8 no frame loads
 };
 
@@ -610,43 +610,75 @@ int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradient, space-to-depth form.  dW[n][tap t, element e] = sum over block positions r of
-// dy_grid[r][n] * image[r + shift_t][e].
-//   A = dy rows laid on the same (w/4)-wide block grid, MN-major SWIZZLE_128B, M = 64 (32 channels +
-//       32 zero columns; grid positions without an output stay zero);
-//   B = the s2d image read MN-major with SWIZZLE_32B.  The converter stores the image four times,
-//       copy t pre-shifted by shift_t rows, so ONE descriptor with LBO = copy stride presents the four
-//       taps as the four 16-element chunks of an N = 64 operand (tiny N = 16 MMAs are issue-bound).
-// One TMEM accumulator [64 x 64] per input channel, accumulated over all samples of the CTA.
+// Weight gradient, space-to-depth form.  With block rows r = by*(w/4)+bx and tap shifts {0, 1, G, G+1}
+// (G = w/4):   dW[n][tap, e] = sum_r dy_grid[r][n] * image[r + shift_tap][e].
+// ONE tcgen05.mma per 16 block rows yields all four taps from a single copy of each operand, because
+// the two 32-wide halves of M and the two 16-wide halves of N may be overlapping windows of the same
+// shared-memory image (descriptor LBO = window distance; pinned by tools/probe_wgrad1.py):
+//   A = dyP, the sample's dy rows on the block grid with G zero rows in front, written by ONE TMA tensor
+//       load (out-of-range grid positions are zero-filled): MN-major SWIZZLE_64B, M = 64, LBO = G rows;
+//   B = the s2d frame written once by the converters: MN-major SWIZZLE_32B, N = 32, LBO = 1 row;
+//   D[(j,n)][(i,e)] = sum_q dyP[q + G j][n] * img[q + i][e]   ->   tap (bh, bw) = (1 - j, i).
+// Per input channel one [64 x 32] TMEM accumulator over all samples of the CTA.  Raw uint8 frames and dy
+// arrive through asynchronous copies several units ahead, so HBM latency is never exposed.
 // ------------------------------------------------------------------------------------------------
-constexpr int kS2dDyBytes = 56 * 1024;          // 448 grid rows x 128 B
-constexpr int kS2dCopyBytes = 15 * 1024;        // one pre-shifted image copy: 480 rows x 32 B
-constexpr int kS2dWgradStage = 4 * kS2dCopyBytes + kS2dDyBytes;
+constexpr int kWgConvWarps = 8;
+constexpr int kWgConvThreads = kWgConvWarps * 32;
+constexpr int kWgMmaWarp = kWgConvWarps;            // + 4 epilogue warps, raw-frame loader, dy loader
+constexpr int kWgRawWarp = kWgConvWarps + 5;
+constexpr int kWgDyWarp = kWgConvWarps + 6;
+constexpr int kWgThreads = (kWgConvWarps + 7) * 32; // 15 warps: 128 registers per thread
+constexpr int kWgMaxStages = 4;
 
-__global__ void __launch_bounds__(kThreads, 1) umma_conv1s_wgrad_kernel(const Conv1Params p) {
+struct WgGeo { int dy_rows, dy_bytes, img_bytes, stage_bytes, ksteps; };
+
+__host__ __device__ inline WgGeo wg_geo(int h, int w) {
+    WgGeo g;
+    const int G = w / 4, brows = (h / 4) * G;
+    g.ksteps = (brows + G + 15) / 16;
+    g.dy_rows = G * (h / 4 + 3);
+    g.dy_bytes = (g.dy_rows * 64 + 1023) & ~1023;
+    g.img_bytes = ((g.ksteps * 16 + 1) * 32 + 1023) & ~1023;
+    g.stage_bytes = g.dy_bytes + g.img_bytes;
+    return g;
+}
+
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    uint64_t d = umma::make_smem_desc(saddr, lbo, sbo);
+    return (d & ~((uint64_t)7 << 61)) | ((uint64_t)layout << 61);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
     const int bwc = p.w / 4;
-    const int brows = (p.h / 4) * bwc;
-    const int ksteps = (brows + 15) / 16;
+    const WgGeo geo = wg_geo(p.h, p.w);
+    // layout: [stages: dyP | image] [mean|rstd table] [raw ring] [barriers]
+    const uint32_t t_off = (uint32_t)(p.stages * geo.stage_bytes);
     const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
-    const uint32_t stage_bytes = kS2dWgradStage;
-    const uint32_t st_off = t_bytes;
-    const uint32_t bar_base = smem_base + st_off + p.stages * stage_bytes;
+    const uint32_t raw_off = t_off + t_bytes;
+    const uint32_t raw_bytes = (uint32_t)((p.h * p.w + 127) & ~127);
+    const uint32_t ones_off = (raw_off + p.raw_slots * raw_bytes + 1023u) & ~1023u;   // 16 K rows x 16 bf16 ones (bias gradient)
+    const uint32_t bar_base = smem_base + ones_off + 512u;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kS2dMaxStages + s); };
-    const uint32_t done_bar = bar_base + 8u * (2 * kS2dMaxStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kS2dMaxStages + 1);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kWgMaxStages + s); };
+    auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kWgMaxStages + s); };
+    auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kWgMaxStages + kMaxRaw + s); };
+    const uint32_t done_bar = bar_base + 8u * (2 * kWgMaxStages + 2 * kMaxRaw);
+    const uint32_t tmem_slot = done_bar + 8u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
-    const uint32_t tmem_cols = p.cin * 64 <= 64 ? 64u : (p.cin * 64 <= 128 ? 128u : 256u);
+    const uint32_t tmem_need = (uint32_t)(p.cin * 32 + 16);         // + the bias-gradient accumulator [64 x 16]
+    const uint32_t tmem_cols = tmem_need <= 32 ? 32u : tmem_need <= 64 ? 64u : tmem_need <= 128 ? 128u : 256u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {
-        uint4* z = reinterpret_cast<uint4*>(gen + st_off);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * stage_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 128) reinterpret_cast<uint32_t*>(gen + ones_off)[threadIdx.x] = 0x3f803f80u;   // bf16 1.0 pairs
+    {   // zero the stages once: image rows past the frame are read by the last k-steps and must stay zero
+        uint4* z = reinterpret_cast<uint4*>(gen);
+        for (uint32_t i = threadIdx.x; i < t_off / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (p.mean) {
-        float4* tm = reinterpret_cast<float4*>(gen);
+        float4* tm = reinterpret_cast<float4*>(gen + t_off);
         const int g4 = p.h * p.w / 4;
         for (int i = threadIdx.x; i < g4; i += blockDim.x) {
             tm[i] = __ldg(reinterpret_cast<const float4*>(p.mean) + i);
@@ -655,99 +687,115 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_wgrad_kernel(const Co
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
+        umma::prefetch_tmap(&tmDy);
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kWgConvThreads + 1); umma::mbar_init(empty_bar(s), 1); }
+        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kWgConvThreads); }
         umma::mbar_init(done_bar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == kWgMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < kConvWarps) {
+    if (warp < kWgConvWarps) {
+        // ------------------------------------------------------------ converters: uint8 -> s2d bf16 image
         const int tid = threadIdx.x;
-        const float4* s_mean = reinterpret_cast<const float4*>(gen);
+        const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
         const float4* s_rstd = s_mean + p.h * p.w / 4;
         const int groups = p.h * p.w / 4;
         int stage = 0; uint32_t phase = 0;
-        uint32_t px[kMaxGroups];
-        int s = blockIdx.x, c = 0;
-        frame_prefetch(p, s * p.cin + c, tid, px);
-        while (s < p.n) {
-            // dy rows of this sample first (global loads in flight while the image is converted)
-            uint4 dyv[8];
-            const __nv_bfloat16* dys = p.dy + (long long)s * p.rows * 32;
+        int rslot = 0; uint32_t rphase = 0;
+        for (int s = blockIdx.x; s < p.n; s += gridDim.x)
+            for (int c = 0; c < p.cin; ++c) {
+                uint32_t px[kMaxGroups];
+                umma::mbar_wait(rfull_bar(rslot), rphase);
+                {
+                    const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q = tid + i * kConvThreads;
-                dyv[i] = q < p.rows * 4 ? __ldg(reinterpret_cast<const uint4*>(dys) + q) : make_uint4(0, 0, 0, 0);
-            }
-            umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-            uint8_t* A = gen + st_off + stage * stage_bytes;           // four pre-shifted s2d image copies
-            uint8_t* D = A + 4 * kS2dCopyBytes;                        // dy on the block grid
-            int y = tid / bwc, x4 = tid - y * bwc;
-            const int dy_ = kConvThreads / bwc, dx_ = kConvThreads - dy_ * bwc;
-#pragma unroll
-            for (int i = 0; i < kMaxGroups; ++i) {
-                const int g = tid + i * kConvThreads;
-                if (g < groups) {
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
-                    if (p.mean) {
-                        const float4 m = s_mean[g], r = s_rstd[g];
-                        v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
-                        v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
-                        v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
-                        v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
-                    }
-                    const uint2 val = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
-                    const int row = (y >> 2) * bwc + x4;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {               // copy t holds image rows shifted up by shift_t
-                        const int rt = row - ((t >> 1) * bwc + (t & 1));
-                        if (rt >= 0)
-                            *reinterpret_cast<uint2*>(A + t * kS2dCopyBytes + swz32((uint32_t)(rt * 32 + (y & 3) * 8))) = val;
+                    for (int i = 0; i < kMaxGroups; ++i) {
+                        const int g = tid + i * kWgConvThreads;
+                        px[i] = g < groups ? raw[g] : 0u;
                     }
                 }
-                y += dy_; x4 += dx_;
-                if (x4 >= bwc) { x4 -= bwc; ++y; }
-            }
+                umma::mbar_arrive(rempty_bar(rslot));
+                if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
+                umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+                uint8_t* A = gen + stage * geo.stage_bytes + geo.dy_bytes;
+                int y = tid / bwc, x4 = tid - y * bwc;
+                const int dy_ = kWgConvThreads / bwc, dx_ = kWgConvThreads - dy_ * bwc;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q = tid + i * kConvThreads;
-                if (q < p.rows * 4) {
-                    const int pos = q >> 2, j = q & 3;
-                    const int oy = pos / p.ow, ox = pos - oy * p.ow;
-                    const int row = oy * bwc + ox;
-                    *reinterpret_cast<uint4*>(D + row * 128 + ((j ^ (row & 7)) << 4)) = dyv[i];
+                for (int i = 0; i < kMaxGroups; ++i) {
+                    const int g = tid + i * kWgConvThreads;
+                    if (g < groups) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+                        if (p.mean) {
+                            const float4 m = s_mean[g], r = s_rstd[g];
+                            v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                            v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                            v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                            v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                        }
+                        const uint32_t off = (uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8);
+                        *reinterpret_cast<uint2*>(A + swz32(off)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+                    }
+                    y += dy_; x4 += dx_;
+                    if (x4 >= bwc) { x4 -= bwc; ++y; }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                umma::mbar_arrive(full_bar(stage));
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            int s2 = s, c2 = c + 1;
-            if (c2 == p.cin) { c2 = 0; s2 += gridDim.x; }
-            frame_prefetch(p, s2 < p.n ? s2 * p.cin + c2 : p.units, tid, px);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            umma::mbar_arrive(full_bar(stage));
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            s = s2; c = c2;
+    } else if (warp == kWgRawWarp) {
+        // ------------------------------------------------------------ raw-frame loader (cp.async.bulk ring)
+        if (lane == 0) {
+            int rslot = 0; uint32_t rphase = 0;
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x)
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(rempty_bar(rslot), rphase ^ 1u);
+                    umma::mbar_arrive_expect_tx(rfull_bar(rslot), (uint32_t)(p.h * p.w));
+                    bulk_load(smem_base + raw_off + rslot * raw_bytes, p.x + s * p.stride_n + c * p.stride_c,
+                              (uint32_t)(p.h * p.w), rfull_bar(rslot));
+                    if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
+                }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kWgDyWarp) {
+        // ------------------------------------------------------------ dy loader: one tensor box per unit
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int s = blockIdx.x; s < p.n; s += gridDim.x)
+                for (int c = 0; c < p.cin; ++c) {
+                    umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    umma::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(geo.dy_rows * 64));
+                    umma::tma_load_4d(smem_base + stage * geo.stage_bytes, &tmDy, full_bar(stage), 0, 0, -1, s);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+        }
+    } else if (warp == kWgMmaWarp) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             bool seen[kMaxCin] = {false, false, false, false};
-            constexpr uint32_t idesc = umma::make_idesc(64, 64, 1, 1);
+            constexpr uint32_t idesc = umma::make_idesc(64, 32, 1, 1);
+            constexpr uint32_t idesc_b = umma::make_idesc(64, 16, 1, 1);
             for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
                 for (int c = 0; c < p.cin; ++c) {
                     umma::mbar_wait(full_bar(stage), phase);
                     umma::fence_after_thread_sync();
-                    const uint32_t img = smem_base + st_off + stage * stage_bytes;
-                    uint64_t db0 = umma::make_smem_desc(img, kS2dCopyBytes, 256);          // LBO = copy stride
-                    db0 = (db0 & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);               // SWIZZLE_32B
-                    const uint64_t da0 = umma::make_smem_desc(img + 4 * kS2dCopyBytes, 8192, 1024);
-                    for (int k = 0; k < ksteps; ++k)
-                        umma::mma_f16_ss(tmem_base + (uint32_t)(c * 64), da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 32), idesc,
+                    const uint32_t st = smem_base + stage * geo.stage_bytes;
+                    const uint64_t da0 = desc_mn(st, (uint32_t)(bwc * 64), 512, 4);              // SWIZZLE_64B, windows G rows apart
+                    const uint64_t db0 = desc_mn(st + geo.dy_bytes, 32, 256, 6);                 // SWIZZLE_32B, windows 1 row apart
+                    for (int k = 0; k < geo.ksteps; ++k)
+                        umma::mma_f16_ss(tmem_base + (uint32_t)(c * 32), da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * 32), idesc,
                                          (!seen[c] && k == 0) ? 0u : 1u);
+                    if (c == 0 && p.dbias) {     // column sums of dy: the same A windows times a block of ones
+                        const uint64_t d1 = desc_mn(smem_base + ones_off, 32, 256, 6);
+                        for (int k = 0; k < geo.ksteps; ++k)
+                            umma::mma_f16_ss(tmem_base + (uint32_t)(p.cin * 32), da0 + (uint64_t)(k * 64), d1, idesc_b,
+                                             (!seen[0] && k == 0) ? 0u : 1u);
+                    }
                     seen[c] = true;
                     umma::mma_commit(empty_bar(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -755,41 +803,64 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1s_wgrad_kernel(const Co
             }
             umma::mma_commit(done_bar);
         }
-    } else if (warp - kMmaWarp - 1 < 4 && blockIdx.x < p.n) {
-        // M = 64 accumulator: channel n lives in TMEM lane (n/16)*32 + n%16; only n < 32 is real
+    } else if (warp < kWgRawWarp && blockIdx.x < p.n) {
+        // ------------------------------------------------------------ epilogue: TMEM -> atomics into dW
+        // M = 64 accumulator: row i = (j, n) lives in TMEM lane (i/16)*32 + i%16
         const int quarter = warp & 3;
         umma::mbar_wait(done_bar, 0);
         umma::fence_after_thread_sync();
         const int K = p.cin * 64;
         for (int c = 0; c < p.cin; ++c) {
-#pragma unroll 1
-            for (int hb = 0; hb < 2; ++hb) {
-                uint32_t raw[32];
-                umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 64 + hb * 32), raw);
-                umma::tmem_ld_wait();
-                if (quarter < 2 && lane < 16) {
-                    const int n = quarter * 16 + lane;
+            uint32_t raw[32];
+            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), raw);
+            umma::tmem_ld_wait();
+            if (lane < 16) {
+                const int i = quarter * 16 + lane, j = i >> 5, n = i & 31, bh = 1 - j;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int t = hb * 2 + (j >> 4), e = j & 15;
-                        const int kh = 4 * (t >> 1) + (e >> 2), kw = 4 * (t & 1) + (e & 3);
-                        atomicAdd(p.dw + (long long)n * K + c * 64 + kh * 8 + kw, __uint_as_float(raw[j]));
-                    }
+                for (int col = 0; col < 32; ++col) {
+                    const int bw = col >> 4, e = col & 15;
+                    const int kh = 4 * bh + (e >> 2), kw = 4 * bw + (e & 3);
+                    atomicAdd(p.dw + (long long)n * K + c * 64 + kh * 8 + kw, __uint_as_float(raw[col]));
                 }
             }
+        }
+        if (p.dbias) {      // rows (j = 1, n): the window that covers every real dy row
+            uint32_t raw[16];
+            umma::tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p.cin * 32), raw);
+            umma::tmem_ld_wait();
+            if (lane < 16 && quarter >= 2) atomicAdd(p.dbias + (quarter - 2) * 16 + lane, __uint_as_float(raw[0]));
         }
     }
     umma::fence_before_thread_sync();
     __syncthreads();
-    if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+    if (warp == kWgMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+bool s2d_wgrad_ok(const cb_conv_desc* d) {
+    const int G = d->in_w / 4;
+    const WgGeo g = wg_geo(d->in_h, d->in_w);
+    return G >= 15 && G <= 256 && d->in_h / 4 + 3 <= 256 && g.ksteps * 16 + G <= g.dy_rows &&
+           d->out_h == d->in_h / 4 - 1 && d->out_w == G - 1;
 }
 
 int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
-    const int fixed = (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256;
-    p.stages = (224 * 1024 - fixed) / kS2dWgradStage;
-    if (p.stages > kS2dMaxStages) p.stages = kS2dMaxStages;
-    CB_REQUIRE(p.stages >= 1, CB_E_ARG, "conv1 wgrad: does not fit shared memory");
-    const int smem = fixed + p.stages * kS2dWgradStage;
+    const WgGeo g = wg_geo(p.h, p.w);
+    const int raw_bytes = (p.h * p.w + 127) & ~127;
+    const int fixed = (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 1024 + 512 + 512;
+    p.stages = (224 * 1024 - fixed - 3 * raw_bytes) / g.stage_bytes;
+    if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
+    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1 wgrad: does not fit shared memory");
+    p.raw_slots = (224 * 1024 - fixed - p.stages * g.stage_bytes) / raw_bytes;
+    if (p.raw_slots > kMaxRaw) p.raw_slots = kMaxRaw;
+    const int smem = fixed + p.stages * g.stage_bytes + p.raw_slots * raw_bytes;
+    // dy [n][oh][ow][32] bf16; one box = a sample's rows on the (w/4)-wide block grid with a zero row block in front
+    CUtensorMap tmDy;
+    {
+        uint64_t dims[4] = {32, (uint64_t)p.ow, (uint64_t)p.oh, (uint64_t)p.n};
+        uint64_t strides[3] = {64, (uint64_t)p.ow * 64, (uint64_t)p.oh * p.ow * 64};
+        uint32_t box[4] = {32, (uint32_t)(p.w / 4), (uint32_t)(p.h / 4 + 3), 1};
+        int rc = cb::encode_tmap_bf16(&tmDy, p.dy, 4, dims, strides, box, 2); if (rc) return rc;
+    }
     static bool attr = false;
     if (!attr) {
         CB_CUDA(cudaFuncSetAttribute(umma_conv1s_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -799,7 +870,7 @@ int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = p.n < sms ? p.n : sms;
-    umma_conv1s_wgrad_kernel<<<grid, kThreads, smem, s>>>(p);
+    umma_conv1s_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmDy, p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -893,12 +964,15 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
     int rc = fill(p, d, x, mean, rstd); if (rc) return rc;
     p.dy = (const __nv_bfloat16*)dy; p.dw = dw; p.nets = 1;
     rc = scale_buffer(dw, (int64_t)32 * d->in_c * 64, beta, s); if (rc) return rc;
-    if (dbias) { rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s); if (rc) return rc; }
     static int im2col = -1;
     if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
+    const bool s2d = !im2col && s2d_ok(d) && s2d_wgrad_ok(d) && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0;
+    // Bias gradient: a separate column-sum pass.  (Summing dy on the tensor cores with an extra N = 16 block of
+    // ones -- p.dbias -- works but the 29 extra M=64 MMAs per unit cost more than the pass: each tiny MN-major
+    // MMA takes ~70 cycles of operand fetch whatever its N.)
+    if (dbias) { rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s); if (rc) return rc; }
     // the s2d kernel prefetches a sample's dy rows into 8 registers per converter thread
-    if (!im2col && s2d_ok(d) && p.rows * 4 <= 8 * kConvThreads && ((d->in_h / 4) * (d->in_w / 4) + 15) / 16 * 16 * 128 <= kS2dDyBytes &&
-        (((d->in_h / 4) * (d->in_w / 4) + 15) / 16 * 16 + 1) * 32 <= kS2dCopyBytes)
+    if (s2d)
         return launch_s2d_wgrad(p, s);
     return launch<true>(p, s);
 }
