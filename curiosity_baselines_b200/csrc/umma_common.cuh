@@ -94,6 +94,10 @@ __device__ __forceinline__ void tma_load(int rank, uint32_t dst, const CUtensorM
     }
 }
 
+// ask L2 to fetch a contiguous global range (16-byte aligned, size % 16 == 0); no destination, no completion
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // smem -> global tensor store (bulk async group): the TMA engine writes whole lines, no LSU traffic
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

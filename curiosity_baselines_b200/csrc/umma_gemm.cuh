@@ -81,15 +81,21 @@ __device__ __forceinline__ int map_coord(const CoordMap& m, int i, int idx) {
     return v * m.mul[i];
 }
 
-// element offset of the 32-column chunk starting at column n0 of output row `grow`
-__device__ __forceinline__ long long chunk_offset(const GemmParams& p, long long grow, int n0) {
-    if (!p.shuffle) return grow * (long long)p.n_total + n0;
+// Element offset of the 32-column chunk starting at column n0 of an output row = row_base + chunk_delta:
+//   plain layout    row_base = grow * n_total,                       delta = n0
+//   depth-to-space  row_base = pixel (2a, 2b) of the NHWC output,    delta = ((ph * sh_w) + pw) * 32, chunk q = (ph, pw)
+__device__ __forceinline__ long long row_base(const GemmParams& p, long long grow) {
+    if (!p.shuffle) return grow * (long long)p.n_total;
     const int pp = p.sh_ph * p.sh_pw;
     const long long n = grow / pp;
     const int rem = (int)(grow - n * pp);
     const int a = rem / p.sh_pw, b = rem - a * p.sh_pw;
-    const int q = n0 >> 5, ph = q >> 1, pw = q & 1;
-    return ((n * p.sh_h + 2 * a + ph) * p.sh_w + 2 * b + pw) * 32;
+    return ((n * p.sh_h + 2 * a) * p.sh_w + 2 * b) * 32;
+}
+__device__ __forceinline__ int chunk_delta(const GemmParams& p, int n0) {
+    if (!p.shuffle) return n0;
+    const int q = n0 >> 5;
+    return ((q >> 1) * p.sh_w + (q & 1)) * 32;
 }
 
 // 32 consecutive bf16 of one row -> fp32 (four 16-byte loads)
@@ -248,26 +254,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 // item i+1 are requested before item i is processed, and of item 0 before the accumulator is awaited,
 // so their HBM latency overlaps the MMAs and the math.  (Copying a prefetch buffer would stall on the
 // pending loads -- the buffers are only ever consumed.)
-// row_fn(r, valid, grow): maps tile row r to its output row.
+// row_fn(mt, valid, grow, base): output row of this lane in sub-tile mt, and its element offset (row_base).
 template <int BN, int MT, int EPI, class RowFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* bias, uint32_t tmem_acc, int quarter,
                                               int sub, int lane, int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
     constexpr int NCH = BN / 32;
     constexpr int ITEMS = MT * NCH;
     constexpr int G = EpiWarps<EPI>::GROUPS;       // this warp handles items sub, sub + G, ...
-    bool valid[MT]; long long grow[MT];
+    bool valid[MT]; long long grow[MT], base[MT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) row_fn(mt * 128 + quarter * 32 + lane, valid[mt], grow[mt]);
+    for (int mt = 0; mt < MT; ++mt) row_fn(mt, valid[mt], grow[mt], base[mt]);
     float sv[16];
     int sv_mt = -1;
 #pragma unroll
     for (int s = 0; s < 16; ++s) sv[s] = 0.f;
     auto row_valid = [&](int mt) { return MT == 1 ? valid[0] : (mt ? valid[MT - 1] : valid[0]); };
     auto row_index = [&](int mt) { return MT == 1 ? grow[0] : (mt ? grow[MT - 1] : grow[0]); };
+    auto row_off = [&](int mt) { return MT == 1 ? base[0] : (mt ? base[MT - 1] : base[0]); };
     auto request = [&](int it, AuxRegs& buf) {
         if (EPI == EPI_SIMPLE || it >= ITEMS) return;
         const int mt = it / NCH, cb = it - mt * NCH;
-        if (row_valid(mt)) aux_load(p, chunk_offset(p, row_index(mt), n_base + cb * 32), buf);
+        if (row_valid(mt)) aux_load(p, row_off(mt) + chunk_delta(p, n_base + cb * 32), buf);
     };
     auto process = [&](int it, const AuxRegs& buf) {
         const int mt = it / NCH, cb = it - mt * NCH;
@@ -283,7 +290,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * BN + cb * 32), raw);
         tmem_ld_wait();
         if (v_now && !(p.debug & 1))
-            epilogue_chunk<EPI>(p, bias, raw, chunk_offset(p, g_now, n_base + cb * 32), n_base + cb * 32, sv, buf);
+            epilogue_chunk<EPI>(p, bias, raw, row_off(mt) + chunk_delta(p, n_base + cb * 32), n_base + cb * 32, sv, buf);
     };
     AuxRegs b0, b1;
     request(sub, b0);
@@ -403,9 +410,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
             epilogue_tile<BN, MT, EPI>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, tn * BN,
                                   tfull_bar(acc), acc_phase,
-                                  [&](int r, bool& valid, long long& grow) {
+                                  [&](int mt, bool& valid, long long& grow, long long& base) {
+                                      const int r = mt * 128 + quarter * 32 + lane;
                                       grow = (long long)tm * p.rows_per_tile + r;
                                       valid = r < p.rows_per_tile && grow < p.m_total;
+                                      base = row_base(p, grow);
                                   });
             fence_before_thread_sync();
             __syncwarp();

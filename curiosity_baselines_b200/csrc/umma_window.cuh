@@ -85,8 +85,22 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int kb = 0; kb < p.kb_count; ++kb)
                 tma_load_2d(smem_base + kb * BN * 128, &tmW, w_bar, kb * 64, 0);
             int stage = 0; uint32_t phase = 0;
+            // The epilogue's row-major side operands (saved activation, skip gradient, residual) of a tile are
+            // one contiguous range: ask L2 for it when the tile's slab is requested, `stages` tiles before the
+            // epilogue reads it, so those per-thread loads hit L2 instead of paying HBM latency.
+            const __nv_bfloat16* aux0 = p.epi.add_pre ? p.epi.add_pre : p.epi.residual;
+            const __nv_bfloat16* aux1 = p.epi.actgrad_src;
+            const long long per_sample = p.epi.shuffle ? (long long)p.epi.sh_h * p.epi.sh_w * 32
+                                                       : (long long)p.vh * p.vw * p.epi.n_total;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (EPI != EPI_SIMPLE && (aux0 || aux1)) {
+                    const int s0 = tile * p.S;
+                    const int ns = p.n_samples - s0 < p.S ? p.n_samples - s0 : p.S;
+                    const uint32_t bytes = (uint32_t)((ns * per_sample * 2) & ~15ll);
+                    if (aux0) prefetch_l2_bulk(aux0 + s0 * per_sample, bytes);
+                    if (aux1) prefetch_l2_bulk(aux1 + s0 * per_sample, bytes);
+                }
                 mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.nplanes * p.plane_rows * 128));
                 for (int pl = 0; pl < p.nplanes; ++pl) {
                     int c[5];
@@ -132,15 +146,30 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int quarter = warp & 3;
         const int sub = (warp - kEpiWarp0) >> 2;
         const int grid_px = p.gh * p.gw;
+        // Which output pixel a lane's row of each sub-tile is never changes from tile to tile: the divisions
+        // are done once here, per tile only the sample base is added.
+        bool ok[MT]; int smp[MT]; long long rel_row[MT], rel_base[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r = mt * 128 + quarter * 32 + lane;
+            const int s = r / grid_px, rem = r - s * grid_px;
+            const int gy = rem / p.gw, gx = rem - gy * p.gw;
+            ok[mt] = s < p.S && gy < p.vh && gx < p.vw;
+            smp[mt] = s;
+            rel_row[mt] = ((long long)s * p.vh + gy) * p.vw + gx;
+            rel_base[mt] = p.epi.shuffle ? (((long long)s * p.epi.sh_h + 2 * gy) * p.epi.sh_w + 2 * gx) * 32
+                                         : rel_row[mt] * p.epi.n_total;
+        }
+        const long long tile_rows = (long long)p.S * p.vh * p.vw;
+        const long long tile_elems = p.epi.shuffle ? (long long)p.S * p.epi.sh_h * p.epi.sh_w * 32 : tile_rows * p.epi.n_total;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             epilogue_tile<BN, MT, EPI>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, 0, tfull_bar(acc),
-                                  acc_phase, [&](int r, bool& valid, long long& grow) {
-                                      const int s = r / grid_px, rem = r - s * grid_px;
-                                      const int gy = rem / p.gw, gx = rem - gy * p.gw;
-                                      const long long sample = (long long)tile * p.S + s;
-                                      valid = s < p.S && gy < p.vh && gx < p.vw && sample < p.n_samples;
-                                      grow = (sample * p.vh + gy) * p.vw + gx;
+                                  acc_phase, [&](int mt, bool& valid, long long& grow, long long& base) {
+                                      const int m = MT == 1 ? 0 : (mt ? MT - 1 : 0);
+                                      valid = ok[m] && tile * p.S + smp[m] < p.n_samples;
+                                      grow = tile * tile_rows + rel_row[m];
+                                      base = tile * tile_elems + rel_base[m];
                                   });
             fence_before_thread_sync();
             __syncwarp();
