@@ -59,6 +59,12 @@ _SIGS = {
     "cb_conv1_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_conv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_side_wgrad": [_P, _P, _P, _L, _I, _I, _F, _P],
+    "cb_grouped_linear_fwd": [_I, _I, _I, _I, _I, _P, _P, _I, C.POINTER(Epilogue), _P],
+    "cb_grouped_linear_dgrad": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
+    "cb_grouped_linear_wgrad": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P],
+    "cb_ensemble_sqerr": [_P, _P, _P, _F, _F, _P, _L, _I, _I, _P],
+    "cb_ensemble_sqerr_grad": [_P, _P, _P, _F, _P, _F, _P, _L, _I, _I, _P],
+    "cb_ensemble_variance_packed": [_P, _I, _F, _P, _L, _I, _P],
     "cb_rowwise_sqerr": [_P, _P, _F, _P, _L, _I, _P],
     "cb_sqerr_grad": [_P, _P, _P, _F, _P, _F, _P, _L, _I, _P],
     "cb_rowwise_sqerr_masked": [_P, _P, _P, _F, _F, _P, _L, _I, _P],

@@ -19,7 +19,24 @@ bool umma_supports_dgrad_s2(const cb_conv_desc*);
 bool umma_supports_fwd(const cb_conv_desc*, const cb_epilogue*);
 bool umma_supports_dgrad(const cb_conv_desc*);
 bool umma_supports_wgrad(const cb_conv_desc*);
+int umma_grouped_fwd(int, int, int, int, int, const void*, const void*, int, const cb_epilogue*, cudaStream_t);
+int umma_grouped_dgrad(int, int, int, int, const void*, const void*, const void*, int, const void*, void*, cudaStream_t);
+int umma_grouped_wgrad(int, int, int, int, int, const void*, const void*, float*, float*, float, cudaStream_t);
 }  // namespace cb
+
+extern "C" int cb_grouped_linear_fwd(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
+                                     const void* w_all, int32_t act, const cb_epilogue* e, void* stream) {
+    return cb::umma_grouped_fwd(n, groups, k, f, x_shared, x, w_all, act, e, cb::as_stream(stream));
+}
+extern "C" int cb_grouped_linear_dgrad(int32_t n, int32_t groups, int32_t k, int32_t f, const void* dy,
+                                       const void* w_t_all, const void* x_saved, int32_t x_act, const void* dx_add,
+                                       void* dx, void* stream) {
+    return cb::umma_grouped_dgrad(n, groups, k, f, dy, w_t_all, x_saved, x_act, dx_add, dx, cb::as_stream(stream));
+}
+extern "C" int cb_grouped_linear_wgrad(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
+                                       const void* dy, float* dw_all, float* dbias_all, float beta, void* stream) {
+    return cb::umma_grouped_wgrad(n, groups, k, f, x_shared, x, dy, dw_all, dbias_all, beta, cb::as_stream(stream));
+}
 
 extern "C" const char* cb_last_error(void) { return cb::g_err; }
 extern "C" int cb_version(void) { return 100; }

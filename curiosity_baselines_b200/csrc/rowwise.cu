@@ -57,6 +57,62 @@ __global__ void ensemble_variance_kernel(const float* const* __restrict__ preds,
     if (lane == 0) out[row] = beta * acc / (float)f;
 }
 
+// Ensemble predictions packed side by side, pred [m, e*f] (the grouped-GEMM layout):
+//   out[k][row] = scale * sum_j mask_k[row,j]*elem_scale * (pred[row, k*f+j] - target[row,j])^2
+__global__ void ensemble_sqerr_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                      const float* __restrict__ masks, float elem_scale, float scale,
+                                      float* __restrict__ out, int64_t m, int f, int e) {
+    int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= m) return;
+    int lane = threadIdx.x & 31;
+    const float* t = target + row * f;
+    for (int k = 0; k < e; ++k) {
+        const float* p = pred + (row * e + k) * f;
+        const float* mk = masks ? masks + ((int64_t)k * m + row) * f : nullptr;
+        float acc = 0.f;
+        for (int j = lane; j < f; j += 32) {
+            float d = p[j] - t[j];
+            float v = d * d;
+            if (mk) v *= mk[j] * elem_scale;
+            acc += v;
+        }
+        acc = cb::warp_sum(acc);
+        if (lane == 0) out[(int64_t)k * m + row] = acc * scale;
+    }
+}
+
+__global__ void ensemble_sqerr_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                           const float* __restrict__ coef, float scale,
+                                           const float* __restrict__ masks, float elem_scale,
+                                           __nv_bfloat16* __restrict__ dpred, int64_t m, int f, int e) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // over m * e * f
+    if (i >= m * e * f) return;
+    const int64_t row = i / ((int64_t)e * f);
+    const int rem = (int)(i - row * e * f), k = rem / f, j = rem - k * f;
+    float g = 2.f * scale * coef[row] * (pred[i] - target[row * f + j]);
+    if (masks) g *= masks[((int64_t)k * m + row) * f + j] * elem_scale;
+    dpred[i] = cb::f2bf(g);
+}
+
+__global__ void ensemble_variance_packed_kernel(const float* __restrict__ pred, int e, float beta,
+                                                float* __restrict__ out, int64_t m, int f) {
+    int64_t row = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (row >= m) return;
+    int lane = threadIdx.x & 31;
+    const float* p = pred + row * e * f;
+    float acc = 0.f;
+    for (int j = lane; j < f; j += 32) {
+        float mean = 0.f;
+        for (int k = 0; k < e; ++k) mean += p[k * f + j];
+        mean /= (float)e;
+        float v = 0.f;
+        for (int k = 0; k < e; ++k) { float d = p[k * f + j] - mean; v += d * d; }
+        acc += v / (float)(e - 1);                          // unbiased (torch.var default)
+    }
+    acc = cb::warp_sum(acc);
+    if (lane == 0) out[row] = beta * acc / (float)f;
+}
+
 // binary_cross_entropy(sigmoid(z), y) as torch computes it (fp32 sigmoid, log clamped at -100):
 // row[m] = scale * sum_f bce ; dz = gscale * (p - y)           (ndigo.py:197-206, 265-268)
 __global__ void bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y, float scale,
@@ -261,6 +317,35 @@ extern "C" int cb_ensemble_variance(const float* const* preds, int32_t e, float 
     CB_REQUIRE(preds && out && e >= 2 && m >= 1 && f >= 1, CB_E_ARG, "cb_ensemble_variance: bad argument");
     ensemble_variance_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, kRowThreads / 32), kRowThreads, 0,
                                cb::as_stream(stream)>>>(preds, e, beta, out, m, f);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_ensemble_sqerr(const float* pred, const float* target, const float* masks, float elem_scale,
+                                 float scale, float* out, int64_t m, int32_t f, int32_t e, void* stream) {
+    CB_REQUIRE(pred && target && out && m >= 1 && f >= 1 && e >= 1, CB_E_ARG, "cb_ensemble_sqerr: bad argument");
+    ensemble_sqerr_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, kRowThreads / 32), kRowThreads, 0,
+                            cb::as_stream(stream)>>>(pred, target, masks, elem_scale, scale, out, m, f, e);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_ensemble_sqerr_grad(const float* pred, const float* target, const float* coef, float scale,
+                                      const float* masks, float elem_scale, void* dpred_bf16, int64_t m, int32_t f,
+                                      int32_t e, void* stream) {
+    CB_REQUIRE(pred && target && coef && dpred_bf16 && m >= 1 && f >= 1 && e >= 1, CB_E_ARG,
+               "cb_ensemble_sqerr_grad: bad argument");
+    ensemble_sqerr_grad_kernel<<<(unsigned)cb::ceil_div<int64_t>(m * e * f, 256), 256, 0, cb::as_stream(stream)>>>(
+        pred, target, coef, scale, masks, elem_scale, (__nv_bfloat16*)dpred_bf16, m, f, e);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_ensemble_variance_packed(const float* pred, int32_t e, float beta, float* out, int64_t m,
+                                           int32_t f, void* stream) {
+    CB_REQUIRE(pred && out && e >= 2 && m >= 1 && f >= 1, CB_E_ARG, "cb_ensemble_variance_packed: bad argument");
+    ensemble_variance_packed_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, kRowThreads / 32), kRowThreads, 0,
+                                      cb::as_stream(stream)>>>(pred, e, beta, out, m, f);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -365,6 +365,68 @@ int umma_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, cons
     return dispatch(pl, s);
 }
 
+// ------------------------------------------------------------------------------ grouped linear layers
+// E independent Linear(K -> F) problems over the same n rows as ONE launch (Disagreement's ensemble of
+// forward models, disagreement.py:97-100,127-130).  Activations of all problems live side by side in one
+// row-major tensor [n, E*F]; weights are stacked along their output dimension.  The product is then a
+// block-diagonal GEMM: output column block g reads A columns [g*K, (g+1)*K) (or [0, K) when every
+// problem reads the same input), so only the producer's K coordinate depends on the group.
+bool umma_supports_grouped(int groups, int k, int f) {
+    int mt;
+    return device_ok() && groups >= 1 && k % 64 == 0 && f % 64 == 0 && pick_bn(f, &mt) != 0 && f % pick_bn(f, &mt) == 0;
+}
+
+int umma_grouped_fwd(int n, int groups, int k, int f, int x_shared, const void* x, const void* w_all, int act,
+                     const cb_epilogue* e, cudaStream_t s) {
+    CB_REQUIRE(x && w_all && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_grouped_linear_fwd: null pointer");
+    CB_REQUIRE(umma_supports_grouped(groups, k, f) && e->side_dim <= 16 && !e->norm_mean, CB_E_ARG,
+               "cb_grouped_linear_fwd: unsupported shape or device");
+    Plan pl{};
+    pl.bn = pick_bn(f, &pl.mt);
+    Geo g{n, 1, 1, x_shared ? k : groups * k, 1, 1, 1, 0, 1, 1};
+    int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
+    rc = plan_b(pl, w_all, groups * f, k); if (rc) return rc;
+    umma::GemmParams& p = pl.p;
+    p.kb_count = k / 64;
+    p.n_total = groups * f;
+    p.n_tiles = groups * f / pl.bn;
+    p.group_tiles = f / pl.bn;
+    p.a_group_koff = x_shared ? 0 : k;
+    p.bias = e->bias;
+    p.side = e->side; p.side_w = e->side_w; p.side_dim = e->side_dim;
+    p.act = act;
+    p.residual = (const __nv_bfloat16*)e->residual;
+    p.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.out_f32 = e->out_f32;
+    CB_REQUIRE(aligned16(p.out_bf16) && aligned16(p.out_f32) && aligned16(p.residual), CB_E_ALIGN,
+               "cb_grouped_linear_fwd: outputs must be 16-byte aligned");
+    return dispatch(pl, s);
+}
+
+// dx[n, E*K] block g = (dy[:, g*F:(g+1)*F] W_g + dx_add) .* act'(x_saved);  w_t_all: bf16 [E*K, F]
+int umma_grouped_dgrad(int n, int groups, int k, int f, const void* dy, const void* w_t_all, const void* x_saved,
+                       int x_act, const void* dx_add, void* dx, cudaStream_t s) {
+    CB_REQUIRE(dy && w_t_all && dx, CB_E_ARG, "cb_grouped_linear_dgrad: null pointer");
+    CB_REQUIRE(umma_supports_grouped(groups, f, k), CB_E_ARG, "cb_grouped_linear_dgrad: unsupported shape or device");
+    Plan pl{};
+    pl.bn = pick_bn(k, &pl.mt);
+    Geo g{n, 1, 1, groups * f, 1, 1, 1, 0, 1, 1};
+    int rc = plan_a(pl, g, dy, pl.mt); if (rc) return rc;
+    rc = plan_b(pl, w_t_all, groups * k, f); if (rc) return rc;
+    umma::GemmParams& p = pl.p;
+    p.kb_count = f / 64;
+    p.n_total = groups * k;
+    p.n_tiles = groups * k / pl.bn;
+    p.group_tiles = k / pl.bn;
+    p.a_group_koff = f;
+    p.add_pre = (const __nv_bfloat16*)dx_add;
+    p.act = CB_ACT_NONE;
+    p.actgrad_src = (const __nv_bfloat16*)x_saved; p.actgrad_act = x_act;
+    p.out_bf16 = (__nv_bfloat16*)dx;
+    CB_REQUIRE(aligned16(dx) && aligned16(dx_add) && aligned16(x_saved), CB_E_ALIGN,
+               "cb_grouped_linear_dgrad: operands must be 16-byte aligned");
+    return dispatch(pl, s);
+}
+
 // ------------------------------------------------------------------------------ stride-2 dgrad
 // k = 2*stride = 4, pad 0 (Burda conv2).  With ih = 2a+ph, kh = 2u+ph the four output parities share
 // the same 2x2 taps of dy, so one GEMM computes all of them:
@@ -655,9 +717,54 @@ int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const umma::Wgr
     return CB_OK;
 }
 
+// dW[g][out][K] = dy_g^T x_g for `groups` problems stacked as dy [n, groups*out], x [n, groups*K] (or the
+// shared [n, K]), dw [groups*out, K]:  A = dy (M = 128-row chunks of the stacked output dimension),
+// B = x (N = 256 columns of the group's K range), split-K over CTAs.
+int wgrad_rows(int n, int out_c, int K, int groups, int x_shared, const void* x, const void* dy, float* dw,
+               cudaStream_t s) {
+    umma::WgradParams p{};
+    CUtensorMap tmA, tmB;
+    p.dw = dw;
+    const int out_all = groups * out_c, k_all = (groups > 1 && !x_shared) ? groups * K : K;
+    uint64_t da[2] = {(uint64_t)out_all, (uint64_t)n}; uint64_t sa[1] = {(uint64_t)out_all * 2};
+    uint64_t db[2] = {(uint64_t)k_all, (uint64_t)n};   uint64_t sb[1] = {(uint64_t)k_all * 2};
+    uint32_t box[2] = {64, 64};
+    int rc = encode_bf16(&tmA, dy, 2, da, sa, box); if (rc) return rc;
+    rc = encode_bf16(&tmB, x, 2, db, sb, box); if (rc) return rc;
+    p.na = 2; p.nb = 4; p.a_rank = p.b_rank = 2;
+    for (int i = 0; i < 4; ++i) { p.a_coord[i][0] = i * 64; p.b_coord[i][0] = i * 64; }
+    p.a_step_dim = p.b_step_dim = 1; p.a_step = p.b_step = 64;
+    p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = 128; p.b_unit_step = 256;
+    p.a_box_bytes = p.b_box_bytes = 8192; p.a_box_stride = p.b_box_stride = 8192;
+    p.b_offset = 2 * 8192; p.stage_bytes = 6 * 8192; p.stages = 4; p.slack_bytes = 0; p.k_rows = 64;
+    const int n_tiles = (K + 255) / 256;
+    p.units = (out_all / 128) * n_tiles; p.unit_div = n_tiles;
+    if (groups > 1) { p.group_units = out_c / 128; p.b_group_koff = x_shared ? 0 : K; }
+    p.slabs_total = (n + 63) / 64;
+    p.n_acc = 1; p.acc_a_off[0] = 0; p.acc_a_lbo[0] = 8192;
+    p.acc_base0[0] = 0; p.acc_base1[0] = 64LL * K;
+    p.m_stride = K; p.n_stride = 1; p.unit_m_off = 128LL * K; p.unit_n_off = 256;
+    p.n_cols_total = K; p.n_unit_cols = 256;
+    int splits = (2 * sm_count()) / p.units; if (splits < 1) splits = 1;
+    if (splits > p.slabs_total) splits = p.slabs_total;
+    p.splits = splits;
+    return launch_wgrad<256>(tmA, tmB, p, s);
+}
+
 }  // namespace
 
 bool umma_supports_wgrad(const cb_conv_desc* d) { return wgrad_kind(d) != WG_NONE; }
+
+// dw_all [groups*F, K] = beta*dw_all + per-group dy_g^T x_g;  dbias_all [groups*F] likewise
+int umma_grouped_wgrad(int n, int groups, int k, int f, int x_shared, const void* x, const void* dy, float* dw_all,
+                       float* dbias_all, float beta, cudaStream_t s) {
+    CB_REQUIRE(x && dy && dw_all, CB_E_ARG, "cb_grouped_linear_wgrad: null pointer");
+    CB_REQUIRE(device_ok() && f % 128 == 0 && k % 8 == 0 && (x_shared || k % 64 == 0), CB_E_ARG,
+               "cb_grouped_linear_wgrad: unsupported shape or device");
+    int rc = scale_buffer(dw_all, (int64_t)groups * f * k, beta, s); if (rc) return rc;
+    if (dbias_all) { rc = colsum_bf16(dy, n, groups * f, dbias_all, beta, s); if (rc) return rc; }
+    return wgrad_rows(n, f, k, groups, x_shared, x, dy, dw_all, s);
+}
 
 int umma_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* mean, const float* rstd,
                     float* dw, float* dbias, float beta, cudaStream_t s) {
@@ -673,31 +780,7 @@ int umma_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const 
     CUtensorMap tmA, tmB;
     p.dw = dw;
     p.unit_div = 1;
-    if (kind == WG_ROWS) {
-        // dW[out][K] = dy^T x : A = dy [n, out] (M = out chunk), B = x [n, K] (N = 256 columns)
-        uint64_t da[2] = {(uint64_t)d->out_c, (uint64_t)d->n}; uint64_t sa[1] = {(uint64_t)d->out_c * 2};
-        uint64_t db[2] = {(uint64_t)K, (uint64_t)d->n};        uint64_t sb[1] = {(uint64_t)K * 2};
-        uint32_t box[2] = {64, 64};
-        rc = encode_bf16(&tmA, dy, 2, da, sa, box); if (rc) return rc;
-        rc = encode_bf16(&tmB, x, 2, db, sb, box); if (rc) return rc;
-        p.na = 2; p.nb = 4; p.a_rank = p.b_rank = 2;
-        for (int i = 0; i < 4; ++i) { p.a_coord[i][0] = i * 64; p.b_coord[i][0] = i * 64; }
-        p.a_step_dim = p.b_step_dim = 1; p.a_step = p.b_step = 64;
-        p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = 128; p.b_unit_step = 256;
-        p.a_box_bytes = p.b_box_bytes = 8192; p.a_box_stride = p.b_box_stride = 8192;
-        p.b_offset = 2 * 8192; p.stage_bytes = 6 * 8192; p.stages = 4; p.slack_bytes = 0; p.k_rows = 64;
-        const int n_tiles = (int)((K + 255) / 256);
-        p.units = (d->out_c / 128) * n_tiles; p.unit_div = n_tiles;
-        p.slabs_total = (d->n + 63) / 64;
-        p.n_acc = 1; p.acc_a_off[0] = 0; p.acc_a_lbo[0] = 8192;
-        p.acc_base0[0] = 0; p.acc_base1[0] = 64 * K;
-        p.m_stride = K; p.n_stride = 1; p.unit_m_off = 128 * K; p.unit_n_off = 256;
-        p.n_cols_total = (int)K; p.n_unit_cols = 256;
-        int splits = (2 * sm_count()) / p.units; if (splits < 1) splits = 1;
-        if (splits > p.slabs_total) splits = p.slabs_total;
-        p.splits = splits;
-        return launch_wgrad<256>(tmA, tmB, p, s);
-    }
+    if (kind == WG_ROWS) return wgrad_rows(d->n, d->out_c, (int)K, 1, 0, x, dy, dw, s);
     if (kind == WG_CONV_S1) {
         const int k = d->k_h, gh = d->in_h + 2 * d->pad, gw = d->in_w + 2 * d->pad;
         const int S = 256 / (gh * gw) > 0 ? 256 / (gh * gw) : 1;

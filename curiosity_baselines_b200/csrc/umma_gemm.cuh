@@ -41,6 +41,9 @@ struct GemmParams {
     int kb_count;          // K / 64
     // tiling
     int m_tiles, n_tiles;
+    // grouped (block-diagonal) GEMM: n-tiles [g*group_tiles, (g+1)*group_tiles) belong to problem g, whose
+    // A operand starts a_group_koff elements further along K (0: all problems share A).  group_tiles == 0: off.
+    int group_tiles, a_group_koff;
     int rows_per_tile;     // valid rows of each tile (<= MT*128)
     long long m_total;     // total output rows
     int n_total;           // total output columns (row stride of all row-major operands below)
@@ -357,6 +360,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int tc[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) tc[i] = p.a_off[i] + map_coord(p.a_tile, i, tm);
+                if (p.group_tiles) tc[0] += (tn / p.group_tiles) * p.a_group_koff;
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));

@@ -203,6 +203,9 @@ struct WgradParams {
     int units, splits, slabs_total;
     int unit_div;                          // a_unit = unit / unit_div, b_unit = unit % unit_div
     int a_unit_dim, a_unit_step, b_unit_dim, b_unit_step;
+    // grouped weight gradient: a_units [g*group_units, ...) belong to problem g, whose B (input) columns start
+    // b_group_koff further (0: shared input).  group_units == 0: off.
+    int group_units, b_group_koff;
     // accumulators
     int n_acc;
     int acc_a_off[kMaxAcc];                // byte offset of the accumulator's A window inside the stage
@@ -272,6 +275,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int d = 0; d < 5; ++d) c[d] = p.b_coord[i][d];
                     c[p.b_step_dim] += slab * p.b_step;
                     c[p.b_unit_dim] += b_unit * p.b_unit_step;
+                    if (p.group_units) c[p.b_unit_dim] += (a_unit / p.group_units) * p.b_group_koff;
                     tma_load(p.b_rank, st + p.b_offset + i * p.b_box_stride, &tmB, full_bar(stage), c);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }

@@ -8,12 +8,14 @@ normalisation is dead code, icm.py:107-112); the forward model sees detached fea
 has four forward models whatever ``ensemble_size`` says, unbiased variance, and an always-on
 dropout(p=0.2) on the squared error of its loss (masks can be injected for parity tests).
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
 from .. import _lib as L
 from .. import dist
-from ..layers import linear_layer
+from ..layers import linear_layer, ACT
 from .encoders import make_encoder, frame_input
 
 ENC_LAST_ACT = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}
@@ -81,6 +83,116 @@ class ResForward(nn.Module):
             g = ly["a"][i].dgrad(dr, n, dx_add=g, x_saved=xs[0] if i == 0 else None,
                                  x_act="lrelu" if i == 0 else "none")
         ly["first"].wgrad(phi1_bf16, g, n, side=action, accumulate=accumulate)
+
+
+class GroupedResForward:
+    """E ResForward models over the same batch, every layer position as ONE grouped tcgen05 launch
+    (cb_grouped_linear_*): activations packed [n, E*F], weights stacked along the output dimension.
+    The reference evaluates forward_model_1..4 one after the other (disagreement.py:127-130).
+    Shapes the grouped kernels do not cover (F not a multiple of 128) run model by model into the same
+    packed layout."""
+
+    POSITIONS = ["first"] + [f"a{i}" for i in range(4)] + [f"b{i}" for i in range(4)] + ["last"]
+
+    def __init__(self, models):
+        self.models = list(models)
+        self.E = len(self.models)
+        self.F, self.A = self.models[0].feature_size, self.models[0].action_size
+        self.grouped = self.F % 128 == 0
+        self._key = None
+        self._stk = None
+
+    def _layer(self, fm, pos):
+        ly = fm._build()
+        return ly[pos] if pos in ("first", "last") else ly[pos[0]][int(pos[1])]
+
+    def _stacks(self):
+        """bf16 weights of all models stacked per layer position (rebuilt when a master weight changed)."""
+        for fm in self.models:
+            for pos in self.POSITIONS:
+                self._layer(fm, pos).prepare()
+        key = tuple(self._layer(fm, pos)._version for fm in self.models for pos in self.POSITIONS)
+        if key != self._key:
+            stk = {}
+            for pos in self.POSITIONS:
+                ls = [self._layer(fm, pos) for fm in self.models]
+                stk[pos] = dict(w=torch.cat([l.w_fwd for l in ls]).contiguous(),
+                                w_t=torch.cat([l.w_t for l in ls]).contiguous(),
+                                bias=torch.cat([l.bias for l in ls]).contiguous(),
+                                side_w=torch.cat([l.side_w for l in ls]).contiguous(),
+                                act=ls[0].act)
+            self._stk, self._key = stk, key
+        return self._stk
+
+    def _fwd(self, pos, x, n, action, shared=False, residual=None, f32=False):
+        st = self._stk[pos]
+        dev = x.device
+        EF = self.E * self.F
+        yb = None if f32 else torch.empty(n, EF, dtype=torch.bfloat16, device=dev)
+        yf = torch.empty(n, EF, dtype=torch.float32, device=dev) if f32 else None
+        e = L.Epilogue()
+        e.bias, e.residual = L.ptr(st["bias"]), L.ptr(residual)
+        e.side, e.side_w, e.side_dim = L.ptr(action), L.ptr(st["side_w"]), self.A
+        e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
+        L.call("cb_grouped_linear_fwd", n, self.E, self.F, self.F, 1 if shared else 0, L.ptr(x), L.ptr(st["w"]),
+               st["act"], C.byref(e), L.stream())
+        return yf if f32 else yb
+
+    def _dgrad(self, pos, dy, n, x_saved=None, x_act="none", dx_add=None):
+        dx = torch.empty(n, self.E * self.F, dtype=torch.bfloat16, device=dy.device)
+        L.call("cb_grouped_linear_dgrad", n, self.E, self.F, self.F, L.ptr(dy), L.ptr(self._stk[pos]["w_t"]),
+               L.ptr(x_saved), ACT[x_act], L.ptr(dx_add), L.ptr(dx), L.stream())
+        return dx
+
+    def _wgrad(self, pos, x, dy, n, action, shared=False):
+        dev, E, F, A = dy.device, self.E, self.F, self.A
+        dw = torch.empty(E * F, F, dtype=torch.float32, device=dev)
+        db = torch.empty(E * F, dtype=torch.float32, device=dev)
+        dsw = torch.empty(E * F, A, dtype=torch.float32, device=dev)
+        L.call("cb_grouped_linear_wgrad", n, E, F, F, 1 if shared else 0, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db),
+               0.0, L.stream())
+        L.call("cb_side_wgrad", L.ptr(dy), L.ptr(action), L.ptr(dsw), n, E * F, A, 0.0, L.stream())
+        for e, fm in enumerate(self.models):
+            mod = self._layer(fm, pos).module
+            if mod.weight.grad is None:
+                mod.weight.grad = torch.zeros_like(mod.weight)
+            if mod.bias.grad is None:
+                mod.bias.grad = torch.zeros_like(mod.bias)
+            mod.weight.grad[:, :F].copy_(dw[e * F:(e + 1) * F])
+            mod.weight.grad[:, F:].copy_(dsw[e * F:(e + 1) * F])
+            mod.bias.grad.copy_(db[e * F:(e + 1) * F])
+
+    def run_forward(self, phi1_bf16, action, n):
+        """-> (saved activations, predictions fp32 packed [n, E*F])."""
+        if not self.grouped:
+            outs = [fm.run_forward(phi1_bf16, action, n) for fm in self.models]
+            return [o[0] for o in outs], torch.cat([o[1] for o in outs], 1).contiguous()
+        self._stacks()
+        x = self._fwd("first", phi1_bf16, n, action, shared=True)
+        saved = dict(x=[x], r=[])
+        for i in range(4):
+            r = self._fwd(f"a{i}", x, n, action)
+            x = self._fwd(f"b{i}", r, n, action, residual=x)
+            saved["r"].append(r)
+            saved["x"].append(x)
+        return saved, self._fwd("last", x, n, action, f32=True)
+
+    def run_backward(self, phi1_bf16, action, saved, dpred_bf16, n):
+        if not self.grouped:
+            F = self.F
+            for e, fm in enumerate(self.models):
+                fm.run_backward(phi1_bf16, action, saved[e], dpred_bf16[:, e * F:(e + 1) * F].contiguous(), n)
+            return
+        xs, rs = saved["x"], saved["r"]
+        self._wgrad("last", xs[4], dpred_bf16, n, action)
+        g = self._dgrad("last", dpred_bf16, n)
+        for i in range(3, -1, -1):
+            self._wgrad(f"b{i}", rs[i], g, n, action)
+            dr = self._dgrad(f"b{i}", g, n, x_saved=rs[i], x_act="lrelu")
+            self._wgrad(f"a{i}", xs[i], dr, n, action)
+            g = self._dgrad(f"a{i}", dr, n, dx_add=g, x_saved=xs[0] if i == 0 else None,
+                            x_act="lrelu" if i == 0 else "none")
+        self._wgrad("first", phi1_bf16, g, n, action, shared=True)
 
 
 class _IcmLoss(torch.autograd.Function):
@@ -196,19 +308,18 @@ class _IcmBase(nn.Module):
         # forward model(s) on detached features (icm.py:126)
         coef_fwd = torch.empty(n, dtype=torch.float32, device=dev)
         L.call("cb_loss_coef", L.ptr(valid), None, float(self.forward_loss_wt), L.ptr(denom), L.ptr(coef_fwd), n, st)
-        fwd_terms = torch.empty(self.n_forward_models, dtype=torch.float32, device=dev)
-        fm_saved = []
-        for e, fm in enumerate(self._forward_models()):
-            saved, pred = fm.run_forward(phi1_b, action, n)
-            err = torch.empty(n, dtype=torch.float32, device=dev)
-            mask = None if masks is None else masks[e].to(dev, torch.float32).reshape(n, F).contiguous()
-            if mask is None:
-                L.call("cb_rowwise_sqerr", L.ptr(pred), L.ptr(phi2_f), 1.0 / F, L.ptr(err), n, F, st)
-            else:
-                L.call("cb_rowwise_sqerr_masked", L.ptr(pred), L.ptr(phi2_f), L.ptr(mask), self._mask_scale, 1.0 / F,
-                       L.ptr(err), n, F, st)
-            L.call("cb_dot", L.ptr(err), L.ptr(coef_fwd), L.ptr(fwd_terms[e:e + 1]), n, st)
-            fm_saved.append((fm, saved, pred, mask))
+        E = self.n_forward_models
+        fwd_terms = torch.empty(E, dtype=torch.float32, device=dev)
+        fmx = self._forward_exec()
+        saved, pred = fmx.run_forward(phi1_b, action, n)                 # pred fp32, packed [n, E*F]
+        mask = None
+        if masks is not None:
+            mask = torch.stack([m.to(dev, torch.float32).reshape(n, F) for m in masks]).contiguous()
+        err = torch.empty(E, n, dtype=torch.float32, device=dev)
+        L.call("cb_ensemble_sqerr", L.ptr(pred), L.ptr(phi2_f), L.ptr(mask), self._mask_scale, 1.0 / F, L.ptr(err),
+               n, F, E, st)
+        for e in range(E):
+            L.call("cb_dot", L.ptr(err[e]), L.ptr(coef_fwd), L.ptr(fwd_terms[e:e + 1]), n, st)
         losses[1] = fwd_terms.sum()
         params = list(self.parameters())
         if not need_grad:
@@ -218,11 +329,10 @@ class _IcmBase(nn.Module):
             for p in params:
                 p.grad = None
         # ---- backward: forward models
-        for fm, saved, pred, mask in fm_saved:
-            dpred = torch.empty(n, F, dtype=torch.bfloat16, device=dev)
-            L.call("cb_sqerr_grad", L.ptr(pred), L.ptr(phi2_f), L.ptr(coef_fwd), 1.0 / F, L.ptr(mask),
-                   self._mask_scale if mask is not None else 1.0, L.ptr(dpred), n, F, st)
-            fm.run_backward(phi1_b, action, saved, dpred, n)
+        dpred = torch.empty(n, E * F, dtype=torch.bfloat16, device=dev)
+        L.call("cb_ensemble_sqerr_grad", L.ptr(pred), L.ptr(phi2_f), L.ptr(coef_fwd), 1.0 / F, L.ptr(mask),
+               self._mask_scale if mask is not None else 1.0, L.ptr(dpred), n, F, E, st)
+        fmx.run_backward(phi1_b, action, saved, dpred, n)
         # ---- backward: inverse model -> both encoder passes
         dlog_b = dlogits.to(torch.bfloat16)
         ex["inv2"].wgrad(h, dlog_b, n)
@@ -272,6 +382,9 @@ class ICM(_IcmBase):
     def _forward_models(self):
         return [self.forward_model]
 
+    def _forward_exec(self):
+        return self.forward_model
+
     @torch.no_grad()
     def compute_bonus(self, observations, next_observations, actions):
         """icm.py:131-134: beta * sum_f (pred_phi2 - phi2)^2 / F -> fp32 [T,B]."""
@@ -301,6 +414,11 @@ class Disagreement(_IcmBase):
     def _forward_models(self):
         return [getattr(self, f"forward_model_{e}") for e in range(1, 5)]
 
+    def _forward_exec(self):
+        if getattr(self, "_grouped", None) is None:
+            self._grouped = GroupedResForward(self._forward_models())
+        return self._grouped
+
     def _default_masks(self, T, B):
         """disagreement.py:155-164: dropout is always in training mode."""
         dev = self.inverse_model[0].weight.device
@@ -310,10 +428,8 @@ class Disagreement(_IcmBase):
     def compute_bonus(self, observations, next_observations, actions):
         """disagreement.py:136-140: beta * mean_f var_e(pred_e) with the unbiased variance."""
         T, B, n, _, _, phi1_b, _, _, action = self._features(observations, next_observations, actions)
-        preds = [fm.run_forward(phi1_b, action, n)[1] for fm in self._forward_models()]
-        dev = self._exec["dev"]
-        ptrs = torch.tensor([p.data_ptr() for p in preds], dtype=torch.int64, device=dev)
-        out = torch.empty(T, B, dtype=torch.float32, device=dev)
-        L.call("cb_ensemble_variance", L.ptr(ptrs), len(preds), float(self.prediction_beta), L.ptr(out), n,
-               self.feature_size, L.stream())
+        _, pred = self._forward_exec().run_forward(phi1_b, action, n)       # packed [n, 4*F]
+        out = torch.empty(T, B, dtype=torch.float32, device=self._exec["dev"])
+        L.call("cb_ensemble_variance_packed", L.ptr(pred), self.n_forward_models, float(self.prediction_beta),
+               L.ptr(out), n, self.feature_size, L.stream())
         return out

@@ -175,6 +175,20 @@ int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const f
  * (NULL to skip).  x addressed as in cb_conv_fwd (norm_* honoured for CB_U8). */
 int cb_conv_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
                   const float* norm_rstd, float* dw, float* dbias, float beta, void* stream);
+/* Grouped Linear layers: `groups` independent Linear(k -> f) problems over the same n rows in ONE tcgen05
+ * launch (the ensemble of forward models of Disagreement, disagreement.py:97-100,127-130 -- the reference runs
+ * them one after the other).  Activations of all problems are packed side by side, row-major [n, groups*f];
+ * weights are stacked along the output dimension: w_all bf16 [groups*f, k], w_t_all bf16 [groups*k, f],
+ * dw_all fp32 [groups*f, k].  x_shared != 0: every problem reads the same x [n, k] (first layer).
+ * The epilogue operands of cb_epilogue are the packed / stacked ones (bias [groups*f], side_w [groups*f, side_dim],
+ * residual / outputs [n, groups*f]; `side` [n, side_dim] is shared).  tcgen05 only (k, f multiples of 64). */
+int cb_grouped_linear_fwd(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
+                          const void* w_all, int32_t act, const cb_epilogue* e, void* stream);
+/* dx [n, groups*k] block g = (dy[:, g*f:(g+1)*f] W_g + dx_add) .* act'(x_saved) */
+int cb_grouped_linear_dgrad(int32_t n, int32_t groups, int32_t k, int32_t f, const void* dy, const void* w_t_all,
+                            const void* x_saved, int32_t x_act, const void* dx_add, void* dx, void* stream);
+int cb_grouped_linear_wgrad(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
+                            const void* dy, float* dw_all, float* dbias_all, float beta, void* stream);
 /* side-input weight gradient: dsw[out_c,side_dim] = beta*dsw + dy^T side */
 int cb_side_wgrad(const void* dy, const float* side, float* dsw, int64_t m, int32_t out_c,
                   int32_t side_dim, float beta, void* stream);
@@ -198,6 +212,16 @@ int cb_rowwise_sqerr_masked(const float* pred, const float* target, const float*
  * preds: E pointers to fp32 [m,f] packed in a device array of pointers */
 int cb_ensemble_variance(const float* const* preds, int32_t e, float beta, float* out,
                          int64_t m, int32_t f, void* stream);
+/* The same three reductions for ensemble predictions packed as pred [m, e*f] (the grouped layout):
+ * out [e, m] per-model masked squared errors (masks fp32 [e, m, f] or NULL); their gradient dpred bf16 [m, e*f];
+ * and the unbiased ensemble variance. */
+int cb_ensemble_sqerr(const float* pred, const float* target, const float* masks, float elem_scale, float scale,
+                      float* out, int64_t m, int32_t f, int32_t e, void* stream);
+int cb_ensemble_sqerr_grad(const float* pred, const float* target, const float* coef, float scale,
+                           const float* masks, float elem_scale, void* dpred_bf16, int64_t m, int32_t f, int32_t e,
+                           void* stream);
+int cb_ensemble_variance_packed(const float* pred, int32_t e, float beta, float* out, int64_t m, int32_t f,
+                                void* stream);
 /* icm.py:141: per-row cross entropy of logits[m,a] against argmax(onehot[m,:]);
  * dlogits (fp32, may be NULL) = coef[m]*(softmax-onehot_of_argmax) */
 int cb_cross_entropy(const float* logits, const float* onehot, const float* coef, float* loss,

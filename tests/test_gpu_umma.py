@@ -223,3 +223,52 @@ def test_conv1_uint8_fwd_wgrad(cin, n, norm):
     assert rel(conv.bias.grad, bq.grad) < 1e-4
     layer.wgrad(base, dyb, n, in_dtype=L.U8, strides=strides, norm=nm, accumulate=True)
     assert rel(conv.weight.grad, 2 * wq.grad) < 1e-4
+
+
+@pytest.mark.parametrize("E,n,shared", [(4, 300, True), (4, 1000, False), (2, 40, False)])
+def test_grouped_linear(E, n, shared):
+    """cb_grouped_linear_{fwd,dgrad,wgrad}: E Linear(512+A -> 512) problems in one launch against E
+    separate fp32 matmuls on the same bf16 operands (disagreement.py:97-100)."""
+    import ctypes as C
+    torch.manual_seed(5)
+    Fd, A = 512, 7
+    W = bf(torch.randn(E, Fd, Fd, device=DEV) * 0.05)
+    Ws = torch.randn(E, Fd, A, device=DEV) * 0.1
+    b = torch.randn(E, Fd, device=DEV)
+    x = bf(torch.randn(n, Fd if shared else E * Fd, device=DEV))
+    res = bf(torch.randn(n, E * Fd, device=DEV))
+    side = F.one_hot(torch.randint(0, A, (n,), device=DEV), A).float()
+    yb = torch.empty(n, E * Fd, dtype=torch.bfloat16, device=DEV)
+    yf = torch.empty(n, E * Fd, dtype=torch.float32, device=DEV)
+    e = L.Epilogue()
+    w_all = W.reshape(E * Fd, Fd).to(torch.bfloat16).contiguous()
+    b_all, sw_all = b.reshape(-1).contiguous(), Ws.reshape(E * Fd, A).contiguous()
+    xb, resb = x.to(torch.bfloat16).contiguous(), res.to(torch.bfloat16).contiguous()
+    e.bias, e.residual, e.side, e.side_w, e.side_dim = L.ptr(b_all), L.ptr(resb), L.ptr(side), L.ptr(sw_all), A
+    e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
+    L.call("cb_grouped_linear_fwd", n, E, Fd, Fd, int(shared), L.ptr(xb), L.ptr(w_all), L.ACT_LRELU, C.byref(e), L.stream())
+    xs = [x if shared else x[:, g * Fd:(g + 1) * Fd] for g in range(E)]
+    ref = torch.cat([F.leaky_relu(xs[g] @ W[g].t() + b[g] + side @ Ws[g].t()) + res[:, g * Fd:(g + 1) * Fd]
+                     for g in range(E)], 1)
+    assert rel(yf, ref) < 2e-5
+    assert rel(yb, ref) < 5e-3
+    # dgrad: dx_g = (dy_g W_g + add_g) * lrelu'(saved_g)
+    dy = bf(torch.randn(n, E * Fd, device=DEV))
+    add = bf(torch.randn(n, E * Fd, device=DEV))
+    saved = bf(torch.randn(n, E * Fd, device=DEV))
+    w_t_all = W.transpose(1, 2).reshape(E * Fd, Fd).to(torch.bfloat16).contiguous()     # [g*K + i][j] = W_g[j][i]
+    dx = torch.empty(n, E * Fd, dtype=torch.bfloat16, device=DEV)
+    dyb, savedb, addb = (t.to(torch.bfloat16).contiguous() for t in (dy, saved, add))    # keep the operands alive
+    L.call("cb_grouped_linear_dgrad", n, E, Fd, Fd, L.ptr(dyb), L.ptr(w_t_all), L.ptr(savedb), L.ACT_LRELU,
+           L.ptr(addb), L.ptr(dx), L.stream())
+    ref = torch.cat([(dy[:, g * Fd:(g + 1) * Fd] @ W[g] + add[:, g * Fd:(g + 1) * Fd]) *
+                     torch.where(saved[:, g * Fd:(g + 1) * Fd] > 0, 1.0, 0.01) for g in range(E)], 1)
+    assert rel(dx, ref) < 5e-3
+    # wgrad: dW_g = dy_g^T x_g, db_g = column sums
+    dw = torch.empty(E * Fd, Fd, device=DEV)
+    db = torch.empty(E * Fd, device=DEV)
+    L.call("cb_grouped_linear_wgrad", n, E, Fd, Fd, int(shared), L.ptr(xb), L.ptr(dyb), L.ptr(dw), L.ptr(db), 0.0,
+           L.stream())
+    ref = torch.cat([dy[:, g * Fd:(g + 1) * Fd].t() @ xs[g] for g in range(E)], 0)
+    assert rel(dw, ref) < 1e-4
+    assert rel(db, dy.sum(0)) < 1e-4
