@@ -112,6 +112,100 @@ def cpu_reference(T, B, steps, warmup, seconds_cap=120.0):
     return T * B / dt, dt * 1e3, done_steps
 
 
+# ------------------------------------------------------------------------------ ICM / Disagreement
+# algorithmic MFLOP per sample, bonus + one-epoch update = 2*fwd + bwd (Burda encoder)
+ENC_MAC = 256 * 32 * 400 + 512 * 64 * 81 + 576 * 64 * 49 + 3136 * 512          # 4-channel conv1
+
+
+def icm_flops(A, E):
+    F = 512
+    resf = 10 * (F + A) * F
+    inv = 2 * F * F + F * A
+    fwd = 2 * ENC_MAC + inv + E * resf
+    # backward: wgrad of every layer; dgrad of every layer whose input needs a gradient (no conv1 dgrad,
+    # no dgrad into the detached features entering the forward models' first layer)
+    enc_b = 2 * (2 * ENC_MAC - 256 * 32 * 400)
+    inv_b = 2 * inv
+    resf_b = E * (2 * resf - (F + A) * F)
+    return 2 * (2 * fwd + enc_b + inv_b + resf_b)
+
+
+def other_model(args, rank, world, local):
+    import torch.distributed as dist
+    from curiosity_baselines_b200 import _lib as L
+    from curiosity_baselines_b200 import layers as LY
+    from curiosity_baselines_b200.curiosity.icm import ICM, Disagreement
+    from curiosity_baselines_b200.trainer import IcmStep
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    LY.set_engine(args.engine)
+    T, B = args.T, args.B
+    A = args.A or (4 if args.model == "icm" else 7)
+    E = 1 if args.model == "icm" else 4
+    torch.manual_seed(0)
+    cls = ICM if args.model == "icm" else Disagreement
+    model = cls(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(dev)
+    step = IcmStep(model, lr=1e-4)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    obs = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    nxt = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    act = torch.nn.functional.one_hot(torch.randint(0, A, (T, B), device=dev, generator=g), A).float()
+    first = torch.randint(1, T + 1, (B,), device=dev, generator=g)
+    has = torch.rand(B, device=dev, generator=g) < 0.01
+    first = torch.where(has, first, torch.full_like(first, T))
+    done = (torch.arange(T, device=dev).unsqueeze(1) >= first.unsqueeze(0)).float()
+    value = torch.randn(T, B, device=dev, generator=g)
+    boot = torch.randn(B, device=dev, generator=g)
+
+    def one_step():
+        return step(obs, nxt, act, done, torch.zeros(T, B, device=dev), value, boot)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    l0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss, r_int, adv, ret = one_step()
+    ev1.record()
+    barrier()
+    launches = L.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    hbm, tf_burst, tf_sust, src = peaks()
+    flop = icm_flops(A, E)
+    if rank == 0:
+        tfl = flop * T * B / (ms_per_step * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "intrinsic-reward samples/sec (bonus+update)", "value": world * T * B / (ms_per_step * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} bonus+update, T={T}, B={B}/GPU, 4x84x84 uint8, A={A}, E={E} forward models",
+                       "global_B": B * world, "l2": "inputs (7.4 GB frames/GPU) larger than L2", "engine": args.engine,
+                       "parallelism": f"dp{world} over B"},
+            "clocks": clocks, "gpu_launches": launches, "e2e": None,
+            "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": tfl, "peak": tf_sust, "unit": "TFLOP/s",
+                         "frac": tfl / tf_sust, "traffic": None, "peak_source": f"{src} bf16 sustained",
+                         "mflop_per_sample": flop / 1e6},
+            "cpu_baseline": None, "loss": float(loss)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------ B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -123,6 +217,10 @@ def main():
     ap.add_argument("--B", type=int, default=1024, help="env columns per GPU (weak scaling)")
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement"],
+                    help="rnd = BASELINE configs[1] (the headline line); icm / disagreement: the same unit of work "
+                         "for the other two conv curiosity models (device-resident inputs only)")
+    ap.add_argument("--A", type=int, default=None, help="number of discrete actions (icm: 4, disagreement: 7)")
     ap.add_argument("--cpu-B", type=int, default=8)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -145,6 +243,8 @@ def main():
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    if args.model != "rnd":
+        return other_model(args, rank, world, local)
     import torch.distributed as dist
     from curiosity_baselines_b200 import _lib as L
     from curiosity_baselines_b200 import layers as LY

@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("residual", C.c_void_p), ("side", C.c_void_p),
                 ("side_w", C.c_void_p), ("side_dim", C.c_int32), ("norm_mean", C.c_void_p),
-                ("norm_rstd", C.c_void_p), ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p)]
+                ("norm_rstd", C.c_void_p), ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
+                ("side_bf16", C.c_void_p)]
 
 
 class CuriosityLibError(RuntimeError):

@@ -52,6 +52,9 @@ extern "C" int cb_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, 
                            void* stream) {
     CB_REQUIRE(d && e, CB_E_ARG, "cb_conv_fwd: null descriptor");
     cudaStream_t s = cb::as_stream(stream);
+    CB_REQUIRE(!e->side_bf16 || (d->engine != CB_ENGINE_SIMT && cb::umma_supports_fwd(d, e) &&
+                                 ((long long)d->k_h * d->k_w * d->in_c) % 64 == 0 && d->k_h == 1 && d->in_h == 1),
+               CB_E_ARG, "cb_conv_fwd: side_bf16 needs a tcgen05 Linear layer with K % 64 == 0");
     if (d->engine == CB_ENGINE_SIMT) return cb::simt_conv_fwd(d, x, w, e, s);
     if (cb::umma_supports_fwd(d, e)) return cb::umma_conv_fwd(d, x, w, e, s);
     CB_REQUIRE(d->engine != CB_ENGINE_UMMA, CB_E_ARG, "cb_conv_fwd: no tcgen05 specialisation for this shape");

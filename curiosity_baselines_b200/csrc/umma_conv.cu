@@ -106,7 +106,7 @@ void identity_map(umma::CoordMap& m) {
 }
 
 struct Plan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmS;      // tmS: side-input block (GemmParams::side_kb), else unused
     umma::GemmParams p;
     int bn, mt;
 };
@@ -128,7 +128,8 @@ int launch_epi(const Plan& pl, cudaStream_t s) {
     }
     int tiles = pl.p.m_tiles * pl.p.n_tiles;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::gemm_threads<EPI>(), Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::gemm_threads<EPI>(), Cfg::SMEM_BYTES, s>>>(
+        pl.tmA, pl.tmB, pl.p.side_kb ? pl.tmS : pl.tmA, pl.p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -256,6 +257,22 @@ int plan_b(Plan& pl, const void* w, int n_total, long long k_total) {
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// Fold the side input into the GEMM as one more k-block (see GemmParams::side_kb).  side_bf16: [rows, 64].
+// Returns the epilogue's side_dim (0 when folded).
+int plan_side(Plan& pl, const cb_epilogue* e, int rows, int* side_dim_out) {
+    *side_dim_out = e->side_dim;
+    if (!e->side_bf16 || !e->side_dim) return CB_OK;
+    CB_REQUIRE(e->side_dim <= 64 && pl.p.a_rank == 2, CB_E_ARG, "side_bf16: side_dim must be <= 64 on a plain Linear");
+    uint64_t dims[2] = {64, (uint64_t)rows};
+    uint64_t strides[1] = {128};
+    uint32_t box[2] = {64, (uint32_t)(pl.mt * 128)};
+    int rc = encode_bf16(&pl.tmS, e->side_bf16, 2, dims, strides, box); if (rc) return rc;
+    pl.p.side_kb = 1;
+    pl.p.kb_count += 1;
+    *side_dim_out = 0;
+    return CB_OK;
+}
+
 Geo fwd_geo(const cb_conv_desc* d) {
     return Geo{d->n, d->in_h, d->in_w, d->in_c, d->k_h, d->k_w, d->stride, d->pad, d->out_h, d->out_w};
 }
@@ -303,12 +320,14 @@ int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_
     Geo g = fwd_geo(d);
     int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
     const long long K = (long long)d->k_h * d->k_w * d->in_c;
-    rc = plan_b(pl, w, d->out_c, K); if (rc) return rc;
+    int side_dim = e->side_dim;
+    if (e->side_bf16 && K % 64 == 0) { rc = plan_side(pl, e, d->n, &side_dim); if (rc) return rc; }
+    rc = plan_b(pl, w, d->out_c, pl.p.side_kb ? K + 64 : K); if (rc) return rc;
     umma::GemmParams& p = pl.p;
     p.n_total = d->out_c;
     p.n_tiles = d->out_c / pl.bn;
     p.bias = e->bias;
-    p.side = e->side; p.side_w = e->side_w; p.side_dim = e->side_dim;
+    p.side = e->side; p.side_w = e->side_w; p.side_dim = side_dim;
     p.act = d->act;
     p.residual = (const __nv_bfloat16*)e->residual;
     p.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.out_f32 = e->out_f32;
@@ -385,15 +404,17 @@ int umma_grouped_fwd(int n, int groups, int k, int f, int x_shared, const void* 
     pl.bn = pick_bn(f, &pl.mt);
     Geo g{n, 1, 1, x_shared ? k : groups * k, 1, 1, 1, 0, 1, 1};
     int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
-    rc = plan_b(pl, w_all, groups * f, k); if (rc) return rc;
     umma::GemmParams& p = pl.p;
     p.kb_count = k / 64;
+    int side_dim = e->side_dim;
+    rc = plan_side(pl, e, n, &side_dim); if (rc) return rc;
+    rc = plan_b(pl, w_all, groups * f, p.side_kb ? k + 64 : k); if (rc) return rc;
     p.n_total = groups * f;
     p.n_tiles = groups * f / pl.bn;
     p.group_tiles = f / pl.bn;
     p.a_group_koff = x_shared ? 0 : k;
     p.bias = e->bias;
-    p.side = e->side; p.side_w = e->side_w; p.side_dim = e->side_dim;
+    p.side = e->side; p.side_w = e->side_w; p.side_dim = side_dim;
     p.act = act;
     p.residual = (const __nv_bfloat16*)e->residual;
     p.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.out_f32 = e->out_f32;

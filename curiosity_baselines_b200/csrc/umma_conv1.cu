@@ -425,6 +425,19 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
         int stage = 0; uint32_t phase = 0;
         int rslot = 0; uint32_t rphase = 0;
         uint32_t px[kMaxGroups];
+        // where this thread's 4-pixel groups land in the s2d image never changes: computed once
+        uint32_t soff[kMaxGroups];
+        {
+            int y = tid / bwc, x4 = tid - y * bwc;
+            const int dy = kConvThreads / bwc, dx = kConvThreads - dy * bwc;
+#pragma unroll
+            for (int i = 0; i < kMaxGroups; ++i) {
+                soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
+                y += dy; x4 += dx;
+                if (x4 >= bwc) { x4 -= bwc; ++y; }
+            }
+        }
+        const bool norm = p.mean && !(p.debug & 1);
         int s = blockIdx.x, c = 0;
         while (s < p.n) {
             // this unit's raw pixels: staged by the loader warp several units ahead (HBM latency hidden)
@@ -441,8 +454,6 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
             if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
             umma::mbar_wait(empty_bar(stage), phase ^ 1u);
             uint8_t* A = gen + st_off + stage * kS2dStageBytes;
-            int y = tid / bwc, x4 = tid - y * bwc;
-            const int dy = kConvThreads / bwc, dx = kConvThreads - dy * bwc;
 #pragma unroll
             for (int i = 0; i < kMaxGroups; ++i) {
                 const int g = tid + i * kConvThreads;
@@ -450,18 +461,15 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
                     float v[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
-                    if (p.mean && !(p.debug & 1)) {
+                    if (norm) {
                         const float4 m = s_mean[g], r = s_rstd[g];
                         v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
                         v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
                         v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
                         v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
                     }
-                    const uint32_t off = (uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8);
-                    *reinterpret_cast<uint2*>(A + swz32(off)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+                    *reinterpret_cast<uint2*>(A + soff[i]) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                 }
-                y += dy; x4 += dx;
-                if (x4 >= bwc) { x4 -= bwc; ++y; }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             umma::mbar_arrive(full_bar(stage));
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
                     umma::fence_after_thread_sync();
                     const uint64_t da0 = desc_sw32(smem_base + st_off + stage * kS2dStageBytes);
                     const uint64_t db0 = desc_sw32(smem_base + c * 4 * N * 32);
-                    for (int mt = 0; mt < row_tiles; ++mt) {
+                    for (int mt = 0; mt < ((p.debug & 16) ? 1 : row_tiles); ++mt) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 4 + mt) * N);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
@@ -707,6 +715,17 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         const int groups = p.h * p.w / 4;
         int stage = 0; uint32_t phase = 0;
         int rslot = 0; uint32_t rphase = 0;
+        uint32_t soff[kMaxGroups];                         // fixed landing offsets of this thread's pixel groups
+        {
+            int y = tid / bwc, x4 = tid - y * bwc;
+            const int dy_ = kWgConvThreads / bwc, dx_ = kWgConvThreads - dy_ * bwc;
+#pragma unroll
+            for (int i = 0; i < kMaxGroups; ++i) {
+                soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
+                y += dy_; x4 += dx_;
+                if (x4 >= bwc) { x4 -= bwc; ++y; }
+            }
+        }
         for (int s = blockIdx.x; s < p.n; s += gridDim.x)
             for (int c = 0; c < p.cin; ++c) {
                 uint32_t px[kMaxGroups];
@@ -723,8 +742,6 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                 if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 umma::mbar_wait(empty_bar(stage), phase ^ 1u);
                 uint8_t* A = gen + stage * geo.stage_bytes + geo.dy_bytes;
-                int y = tid / bwc, x4 = tid - y * bwc;
-                const int dy_ = kWgConvThreads / bwc, dx_ = kWgConvThreads - dy_ * bwc;
 #pragma unroll
                 for (int i = 0; i < kMaxGroups; ++i) {
                     const int g = tid + i * kWgConvThreads;
@@ -739,11 +756,8 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                             v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
                             v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
                         }
-                        const uint32_t off = (uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8);
-                        *reinterpret_cast<uint2*>(A + swz32(off)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+                        *reinterpret_cast<uint2*>(A + soff[i]) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                     }
-                    y += dy_; x4 += dx_;
-                    if (x4 >= bwc) { x4 -= bwc; ++y; }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 umma::mbar_arrive(full_bar(stage));

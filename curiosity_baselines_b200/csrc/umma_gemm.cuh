@@ -44,6 +44,11 @@ struct GemmParams {
     // grouped (block-diagonal) GEMM: n-tiles [g*group_tiles, (g+1)*group_tiles) belong to problem g, whose
     // A operand starts a_group_koff elements further along K (0: all problems share A).  group_tiles == 0: off.
     int group_tiles, a_group_koff;
+    // side input folded into the GEMM: the LAST k-block of A comes from the tmS tensor map (bf16 [rows, 64],
+    // the one-hot action zero-padded to 64 columns) and B carries the matching 64 weight columns -- the
+    // torch.cat([x, action]) of icm.py:19-21 done by the tensor cores instead of 32*side_dim FMAs per
+    // output chunk in the epilogue.
+    int side_kb;
     int rows_per_tile;     // valid rows of each tile (<= MT*128)
     long long m_total;     // total output rows
     int n_total;           // total output columns (row stride of all row-major operands below)
@@ -318,7 +323,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
 template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmS, const GemmParams p) {
     using Cfg = GemmConfig<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -338,6 +343,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (p.side_kb) prefetch_tmap(&tmS);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EpiWarps<EPI>::GROUPS); }
         fence_barrier_init();
@@ -368,7 +374,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 5; ++i) c[i] = tc[i] + map_coord(p.a_kb, i, kb);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    tma_load(p.a_rank, sa, &tmA, full_bar(stage), c);
+                    if (p.side_kb && kb == kb_count - 1) tma_load_2d(sa, &tmS, full_bar(stage), 0, tc[1]);
+                    else tma_load(p.a_rank, sa, &tmA, full_bar(stage), c);
                     tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * 64, tn * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }

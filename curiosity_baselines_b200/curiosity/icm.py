@@ -15,7 +15,7 @@ from torch import nn
 
 from .. import _lib as L
 from .. import dist
-from ..layers import linear_layer, ACT
+from ..layers import linear_layer, pad_side, ACT
 from .encoders import make_encoder, frame_input
 
 ENC_LAST_ACT = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}
@@ -59,15 +59,16 @@ class ResForward(nn.Module):
     def run_forward(self, phi1_bf16, action, n):
         """-> (saved activations, predicted phi2 fp32 [n,F])."""
         ly = self._build()
-        x, _ = ly["first"].forward(phi1_bf16, n, side=action)
+        sp = pad_side(action) if self.action_size <= 64 else None      # one-hot as a bf16 k-block, built once
+        x, _ = ly["first"].forward(phi1_bf16, n, side=action, side_pad=sp)
         saved = dict(x=[x], r=[])
         for i in range(4):
-            r, _ = ly["a"][i].forward(x, n, side=action)
-            x_new, _ = ly["b"][i].forward(r, n, side=action, residual=x)     # r2 + x   (icm.py:22)
+            r, _ = ly["a"][i].forward(x, n, side=action, side_pad=sp)
+            x_new, _ = ly["b"][i].forward(r, n, side=action, residual=x, side_pad=sp)     # r2 + x   (icm.py:22)
             saved["r"].append(r)
             saved["x"].append(x_new)
             x = x_new
-        _, pred = ly["last"].forward(x, n, side=action, out_bf16=False, out_f32=True)
+        _, pred = ly["last"].forward(x, n, side=action, out_bf16=False, out_f32=True, side_pad=sp)
         return saved, pred
 
     def run_backward(self, phi1_bf16, action, saved, dpred_bf16, n, accumulate=False):
@@ -98,8 +99,9 @@ class GroupedResForward:
         self.models = list(models)
         self.E = len(self.models)
         self.F, self.A = self.models[0].feature_size, self.models[0].action_size
-        self.grouped = self.F % 128 == 0
+        self.grouped = self.F % 128 == 0 and self.A <= 64
         self._key = None
+        self._sp = None
         self._stk = None
 
     def _layer(self, fm, pos):
@@ -116,7 +118,7 @@ class GroupedResForward:
             stk = {}
             for pos in self.POSITIONS:
                 ls = [self._layer(fm, pos) for fm in self.models]
-                stk[pos] = dict(w=torch.cat([l.w_fwd for l in ls]).contiguous(),
+                stk[pos] = dict(w=torch.cat([l.w_ext for l in ls]).contiguous(),
                                 w_t=torch.cat([l.w_t for l in ls]).contiguous(),
                                 bias=torch.cat([l.bias for l in ls]).contiguous(),
                                 side_w=torch.cat([l.side_w for l in ls]).contiguous(),
@@ -126,6 +128,8 @@ class GroupedResForward:
 
     def _fwd(self, pos, x, n, action, shared=False, residual=None, f32=False):
         st = self._stk[pos]
+        if self._sp is None:
+            self._sp = pad_side(action)
         dev = x.device
         EF = self.E * self.F
         yb = None if f32 else torch.empty(n, EF, dtype=torch.bfloat16, device=dev)
@@ -133,6 +137,7 @@ class GroupedResForward:
         e = L.Epilogue()
         e.bias, e.residual = L.ptr(st["bias"]), L.ptr(residual)
         e.side, e.side_w, e.side_dim = L.ptr(action), L.ptr(st["side_w"]), self.A
+        e.side_bf16 = L.ptr(self._sp)
         e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
         L.call("cb_grouped_linear_fwd", n, self.E, self.F, self.F, 1 if shared else 0, L.ptr(x), L.ptr(st["w"]),
                st["act"], C.byref(e), L.stream())
@@ -168,6 +173,7 @@ class GroupedResForward:
             outs = [fm.run_forward(phi1_bf16, action, n) for fm in self.models]
             return [o[0] for o in outs], torch.cat([o[1] for o in outs], 1).contiguous()
         self._stacks()
+        self._sp = None
         x = self._fwd("first", phi1_bf16, n, action, shared=True)
         saved = dict(x=[x], r=[])
         for i in range(4):
@@ -356,6 +362,17 @@ class _IcmBase(nn.Module):
 
     def _default_masks(self, T, B):
         return None
+
+    def invalidate_weights(self):
+        """Call after the fp32 master weights were updated outside torch's version tracking (FlatAdam)."""
+        if self._exec is None:
+            return
+        layers = list(self._exec["chain"].layers) + [self._exec["inv0"], self._exec["inv2"]]
+        for fm in self._forward_models():
+            ly = fm._build()
+            layers += [ly["first"], ly["last"]] + ly["a"] + ly["b"]
+        for layer in layers:
+            layer._version = None
 
     def compute_loss(self, observations, next_observations, actions, valid, dropout_masks="default"):
         """icm.py:136-145 / disagreement.py:142-167 -> (inverse_loss_wt*inv, forward_loss_wt*fwd)."""

@@ -90,6 +90,12 @@ class GemmLayer:
                 .to(torch.bfloat16).contiguous()
         self.bias = self.module.bias.detach()
         self.side_w = side.detach().contiguous() if side is not None else None
+        self.w_ext = None
+        if side is not None and self.k == 1 and self.K % 64 == 0 and self.side_dim <= 64:
+            # [out, K + 64]: the side weights as one more 64-wide k-block (cb_epilogue.side_bf16)
+            self.w_ext = torch.zeros(self.out_c, self.K + 64, dtype=torch.bfloat16, device=dev)
+            self.w_ext[:, : self.K] = self.w_fwd
+            self.w_ext[:, self.K: self.K + self.side_dim] = self.side_w.to(torch.bfloat16)
         self._version = ver
 
     # ---------------------------------------------------------------- descriptors
@@ -110,7 +116,7 @@ class GemmLayer:
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, n, in_dtype=L.BF16, strides=None, side=None, residual=None, norm=None,
-                out_bf16=True, out_f32=False, twin=None):
+                out_bf16=True, out_f32=False, twin=None, side_pad=None):
         """Returns (bf16 NHWC output or None, fp32 output or None), each [n*out_h*out_w, out_c].
         ``twin``: a second first-conv layer of identical shape reading the same uint8 input (RND
         target + predictor); its bf16 output is then returned as a third element."""
@@ -122,9 +128,13 @@ class GemmLayer:
         e = L.Epilogue()
         e.bias = L.ptr(self.bias)
         e.residual = L.ptr(residual)
+        w_fwd = self.w_fwd
         if self.side_dim:
             assert side is not None and side.shape[-1] == self.side_dim
             e.side, e.side_w, e.side_dim = L.ptr(side), L.ptr(self.side_w), self.side_dim
+            if side_pad is not None and self.w_ext is not None and _engine != L.ENGINE_SIMT:
+                e.side_bf16 = L.ptr(side_pad)        # concatenation on the tensor cores (one more k-block)
+                w_fwd = self.w_ext
         if norm is not None:
             e.norm_mean, e.norm_rstd = L.ptr(norm[0]), L.ptr(norm[1])
         e.out_bf16, e.out_f32 = L.ptr(yb), L.ptr(yf)
@@ -140,7 +150,7 @@ class GemmLayer:
                 return yb, yf, y2
             L.call("cb_conv1_fwd", C.byref(d), xp, L.ptr(self.w_native), C.byref(e), None, None, None, L.stream())
         else:
-            L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(self.w_fwd), C.byref(e), L.stream())
+            L.call("cb_conv_fwd", C.byref(d), xp, L.ptr(w_fwd), C.byref(e), L.stream())
         if twin is not None:      # no fused kernel for this shape/engine: run the twin separately
             y2, _ = twin.forward(x, n, in_dtype=in_dtype, strides=strides, norm=norm)
             return yb, yf, y2
@@ -223,6 +233,14 @@ class GemmLayer:
         else:
             w.grad[:, : self.K].copy_(dw)
             w.grad[:, self.K:].copy_(dsw)
+
+def pad_side(side):
+    """fp32 [n, A] side input (one-hot action) -> bf16 [n, 64] zero padded: the extra k-block operand."""
+    n, a = side.shape
+    out = torch.zeros(n, 64, dtype=torch.bfloat16, device=side.device)
+    out[:, :a] = side
+    return out
+
 
 def conv_layer(module, in_shape, act, trainable=True):
     k, s, p = module.kernel_size[0], module.stride[0], module.padding[0]

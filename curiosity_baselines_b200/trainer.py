@@ -73,3 +73,23 @@ class RndStep:
         self.opt.step()
         m.invalidate_weights()
         return loss, r_int, adv, ret
+
+
+class IcmStep:
+    """bonus + returns + update for ICM / Disagreement (BASELINE configs[0], [2]): the same unit of work as
+    ``RndStep`` with the (observation, next_observation, one-hot action) inputs of icm.py:131-145."""
+
+    def __init__(self, model, lr=1e-4, discount=0.99, gae_lambda=0.95, clip_grad_norm=1.0):
+        self.model = model
+        self.opt = FlatAdam(model.parameters(), lr=lr, max_norm=clip_grad_norm)
+        self.discount, self.gae_lambda = discount, gae_lambda
+
+    def __call__(self, obs, next_obs, action, done, reward, value, bootstrap, dropout_masks="default"):
+        m = self.model
+        r_int = m.compute_bonus(obs, next_obs, action)
+        reward.add_(r_int)
+        ret, adv, valid, _ = returns_on_device(reward, done, value, bootstrap, self.discount, self.gae_lambda)
+        inv, fwd = m.loss_and_grads_(obs, next_obs, action, valid, dropout_masks)
+        self.opt.step()
+        m.invalidate_weights()
+        return inv + fwd, r_int, adv, ret

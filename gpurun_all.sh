@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --model icm --steps 5 --warmup 3 > gpurun_out/bench_icm.log 2>&1; tail -n 1 gpurun_out/bench_icm.log | cut -c1-330
+timeout 600 python bench.py --model disagreement --steps 5 --warmup 3 > gpurun_out/bench_dis.log 2>&1; tail -n 1 gpurun_out/bench_dis.log | cut -c1-330

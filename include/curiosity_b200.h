@@ -142,6 +142,11 @@ typedef struct cb_epilogue {
     const float*   norm_rstd;        /* per-pixel 1/sqrt(var); input clamped to [-5,5] */
     void*          out_bf16;         /* bf16 [M,out_c] or NULL */
     float*         out_f32;          /* fp32 [M,out_c] or NULL */
+    const void*    side_bf16;        /* optional, Linear layers on tcgen05 with K % 64 == 0: the side input as bf16
+                                        [M,64] (zero padded).  When given, `w` must be [out_c, K+64] with the side
+                                        weights in columns K..K+side_dim-1 (zero padded): the concatenation of
+                                        icm.py:19-21 then runs on the tensor cores as one more k-block and
+                                        side / side_w are not read. */
 } cb_epilogue;
 
 /* y = act(conv(x, w) + bias + side*side_w) + residual.   w: bf16 [out_c][k_h][k_w][in_c] */

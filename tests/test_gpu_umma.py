@@ -272,3 +272,25 @@ def test_grouped_linear(E, n, shared):
     ref = torch.cat([dy[:, g * Fd:(g + 1) * Fd].t() @ xs[g] for g in range(E)], 0)
     assert rel(dw, ref) < 1e-4
     assert rel(db, dy.sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("A,n,use_res", [(4, 1000, False), (7, 513, True), (12, 37, False)])
+def test_linear_side_as_kblock(A, n, use_res):
+    """cb_epilogue.side_bf16: the one-hot action concatenated on the tensor cores (icm.py:19-21) must equal
+    the fp32-epilogue path up to the bf16 rounding of the side weights."""
+    torch.manual_seed(11)
+    lin = nn.Linear(512 + A, 512).to(DEV)
+    layer = LY.linear_layer(lin, "lrelu", A)
+    x = bf(torch.randn(n, 512, device=DEV))
+    side = F.one_hot(torch.randint(0, A, (n,), device=DEV), A).float()
+    res = bf(torch.randn(n, 512, device=DEV)) if use_res else None
+    resb = res.to(torch.bfloat16) if use_res else None
+    sp = LY.pad_side(side)
+    _, yf = layer.forward(x.to(torch.bfloat16), n, side=side, residual=resb, out_f32=True, side_pad=sp)
+    W = lin.weight.detach()
+    ref = F.leaky_relu(x @ bf(W[:, :512]).t() + lin.bias + side @ bf(W[:, 512:]).t())
+    if use_res:
+        ref = ref + res
+    assert rel(yf, ref) < 2e-5
+    _, y_epi = layer.forward(x.to(torch.bfloat16), n, side=side, residual=resb, out_f32=True)
+    assert rel(yf, y_epi) < 5e-3

@@ -31,10 +31,10 @@ def test_ctypes_table_matches_header():
 
 
 def test_struct_layout_matches_header():
-    # cb_conv_desc: 12 int32, 4 int64, 2 int32 ; cb_epilogue: 4 ptr, int32(+pad), 4 ptr
+    # cb_conv_desc: 12 int32, 4 int64, 2 int32 ; cb_epilogue: 4 ptr, int32(+pad), 5 ptr
     import ctypes as C
     assert C.sizeof(L.ConvDesc) == 12 * 4 + 4 * 8 + 2 * 4
-    assert C.sizeof(L.Epilogue) == 4 * 8 + 8 + 4 * 8
+    assert C.sizeof(L.Epilogue) == 4 * 8 + 8 + 5 * 8
     assert L.ConvDesc.in_stride_n.offset == 48 and L.Epilogue.norm_mean.offset == 40
 
 

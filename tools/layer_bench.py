@@ -69,6 +69,12 @@ cases["conv1_fwd"] = (lambda: conv1.forward(frames.data_ptr(), n, in_dtype=L.U8,
 conv1b = LY.conv_layer(nn.Conv2d(1, 32, 8, 4).to(dev), (84, 84, 1), "lrelu")
 cases["conv1_twin_fwd"] = (lambda: conv1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm, twin=conv1b), 2.0 * 64 * 64 * 400 * n)
 cases["conv1_wgrad"] = (lambda: conv1.wgrad(frames.data_ptr(), dy1, n, in_dtype=L.U8, strides=st1, norm=nm), 2.0 * 64 * 32 * 400 * n)
+conv1c4 = LY.conv_layer(nn.Conv2d(4, 32, 8, 4).to(dev), (84, 84, 4), "lrelu")
+if args.only and "c4" in args.only:      # ICM-shaped first conv: 4-channel stacks, raw pixels (3.7 GB of frames)
+    frames4 = torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device=dev)
+    st4 = (4 * 7056, 84, 1, 7056)
+    cases["conv1c4_fwd"] = (lambda: conv1c4.forward(frames4.data_ptr(), n, in_dtype=L.U8, strides=st4), 2.0 * 256 * 32 * 400 * n)
+    cases["conv1c4_wgrad"] = (lambda: conv1c4.wgrad(frames4.data_ptr(), dy1, n, in_dtype=L.U8, strides=st4), 2.0 * 256 * 32 * 400 * n)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
         continue
