@@ -316,13 +316,14 @@ def main():
         """Host buffers in, host results out.  The strided upload of the NEXT step's frames runs on a
         side stream under this step's compute (double buffered), as a training loop would do it."""
         d_frames = stager.get()
-        stager.prefetch(h_frames)
-        d_done, d_value, d_boot, d_mask = (t.to(dev, non_blocking=True) for t in h_small)
+        d_done, d_value, d_boot, d_mask = stager.get_extras()
         loss, r_int, adv, ret = step(d_frames, d_done, torch.zeros(T, B, device=dev), d_value, d_boot, d_mask)
+        stager.done()
         h_out[0].copy_(r_int, non_blocking=True); h_out[1].copy_(adv, non_blocking=True)
         h_out[2].copy_(ret, non_blocking=True); h_loss.copy_(loss.reshape(1), non_blocking=True)
+        stager.prefetch(h_frames, h_small)
 
-    stager.prefetch(h_frames)
+    stager.prefetch(h_frames, h_small)
     e2e_step()
     barrier()
     t0 = time.perf_counter()

@@ -1,0 +1,3 @@
+#!/bin/bash
+python tools/h2d_probe.py 2>&1 | tail -1
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e'])"
