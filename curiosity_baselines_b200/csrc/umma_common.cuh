@@ -58,6 +58,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp (elect.sync).  The MMA-issuing warp runs its loops with all 32 lanes so that
+// loop state, barrier phases and descriptors stay provably warp-uniform (uniform registers, no per-MMA
+// "waterfall" loop moving operands into them); only the tcgen05 instructions themselves are predicated on this.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -42,6 +42,7 @@ struct Conv1Params {
     int pitch;                         // bytes per row of the normalised bf16 frame in shared memory
     int units, stages, a_stage_bytes;  // units = n*cin (one channel of one sample each)
     int raw_slots;                     // s2d kernels: depth of the raw-frame ring
+    int s2d_stage_bytes;               // s2d forward: bytes of one pipeline stage (CPK channels of one sample)
     const float* mean; const float* rstd;
     // forward: one or two networks sharing the input (RND target + predictor)
     int nets; const __nv_bfloat16* w_bf16[2]; const float* bias[2]; int act; __nv_bfloat16* out[2];
@@ -54,6 +55,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// Four uint8 pixels -> fp32 without I2F (a quarter-rate conversion-pipe instruction: 7056 of them per frame
+// cost ~440 cycles per SM).  PRMT builds the bits of 2^23 + x (exact in fp32), one FADD removes 2^23.
+__device__ __forceinline__ void u8x4_to_f32(uint32_t px, float (&v)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u | j)) - 8388608.f;
+}
+
 __device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kConvBar), "n"(kConvThreads) : "memory"); }
 
 // global -> shared bulk copy (TMA, no tensor map): `bytes` % 16 == 0, both addresses 16-byte aligned
@@ -62,6 +70,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+constexpr int kConvGroups = 2;                         // s2d forward: converter warp groups working on alternate units
+constexpr int kGrpThreads = kConvThreads / kConvGroups;
+constexpr int kGrpMaxGroups = 14;                      // 4-pixel groups per thread of a group (84x84 -> 1764 / 128)
 constexpr int kMaxGroups = 8;          // 4-pixel groups per converter thread: ceil(h*w/4/256) (84x84 -> 7)
 
 // one channel of one sample: global uint8 -> registers (issued early so the latency overlaps other work)
@@ -87,8 +98,7 @@ __device__ __forceinline__ void frame_store(const Conv1Params& p, int tid, const
         const int g = tid + i * kConvThreads;
         if (g < groups) {
             float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+            u8x4_to_f32(px[i], v);
             if (p.mean && !(p.debug & 1)) {
                 const float4 m = s_mean[g], r = s_rstd[g];        // statistics staged in shared memory
                 v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
@@ -349,11 +359,28 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
     return (d & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);          // SWIZZLE_32B
 }
 __device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
+// Block rows may interleave CPK input channels (rows of 32*CPK bytes): SWIZZLE_32B for one channel,
+// SWIZZLE_128B for four.  Address-based XOR swizzle of such an image and the matching descriptor constants.
+template <int CPK> struct Pack {
+    static_assert(CPK == 1 || CPK == 4, "CPK");
+    static constexpr int RB = 32 * CPK;                         // bytes per block row
+    static constexpr uint32_t MASK = CPK == 1 ? 1u : 7u;
+    static constexpr uint32_t LAYOUT = CPK == 1 ? 6u : 2u;      // descriptor swizzle code
+    static constexpr uint32_t SBO = 8u * RB;
+    __device__ static __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & MASK) << 4); }
+};
+__device__ __forceinline__ uint64_t desc_any(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    uint64_t d = umma::make_smem_desc(saddr, lbo, sbo);
+    return (d & ~((uint64_t)7 << 61)) | ((uint64_t)layout << 61);
+}
 
 constexpr int kEpiBar = 2;             // named barrier of the epilogue threads
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBar), "n"(kEpiWarps * 32) : "memory"); }
 
+template <int CPK>
 __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const Conv1Params p) {
+    using PK = Pack<CPK>;
+    constexpr int RB = PK::RB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
@@ -364,7 +391,9 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
     const uint32_t t_off = w_bytes;
     const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
     const uint32_t st_off = t_off + t_bytes;
-    const uint32_t raw_off = st_off + p.stages * kS2dStageBytes;              // ring of raw uint8 frames
+    const int ups = p.cin / CPK;                               // pipeline units (stages) per sample
+    const uint32_t stage_bytes = (uint32_t)p.s2d_stage_bytes;
+    const uint32_t raw_off = st_off + p.stages * stage_bytes;                 // ring of raw uint8 frames
     const uint32_t raw_bytes = (uint32_t)((p.h * p.w + 127) & ~127);
     const uint32_t b_off = raw_off + p.raw_slots * raw_bytes;                  // biases: [net][32] fp32
     const uint32_t bar_base = smem_base + b_off + 256u;
@@ -381,14 +410,15 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
 
     {   // zero the stages once (block rows past the frame stay zero)
         uint4* z = reinterpret_cast<uint4*>(gen + st_off);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * kS2dStageBytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * stage_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
-    // weights: per (channel, tap) a [N rows][16 = (py,px)] block, K-major, 32-byte swizzle
+    // weights: per (unit, tap) a K-major [N rows][CPK channels x 16 = (py,px)] block in the image's swizzle
     for (int i = threadIdx.x; i < p.cin * 4 * N * 16; i += blockDim.x) {
         const int e = i & 15, n = (i >> 4) % N, t = ((i >> 4) / N) & 3, c = (i >> 4) / (4 * N);
         const int kh = 4 * (t >> 1) + (e >> 2), kw = 4 * (t & 1) + (e & 3);
         const __nv_bfloat16 v = p.w_bf16[n >> 5][(long long)(n & 31) * p.cin * 64 + c * 64 + kh * 8 + kw];
-        *reinterpret_cast<__nv_bfloat16*>(gen + (c * 4 + t) * N * 32 + swz32((uint32_t)(n * 32 + e * 2))) = v;
+        const int u = c / CPK, cc = c - u * CPK;
+        *reinterpret_cast<__nv_bfloat16*>(gen + PK::swz((uint32_t)(((u * 4 + t) * N + n) * RB + cc * 32 + e * 2))) = v;
     }
     if (p.mean) {
         float4* tm = reinterpret_cast<float4*>(gen + t_off);
@@ -404,9 +434,9 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kConvThreads); umma::mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kGrpThreads / 32); umma::mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEpiWarps); }
-        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kConvThreads); }
+        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kGrpThreads / 32); }
         umma::fence_barrier_init();
     }
     if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
@@ -418,63 +448,63 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
 
     if (warp < kConvWarps) {
         // ------------------------------------------------------------ converters: uint8 -> s2d bf16 image
-        const int tid = threadIdx.x;
+        // Two groups of four warps take alternate units (one channel of one sample each), so that one group's
+        // wait -> read -> convert -> fence -> arrive chain overlaps the other's (a single group of eight warps
+        // marching in lock-step was latency-bound at ~1200 cycles per unit).
+        const int grp = warp / (kConvWarps / kConvGroups);
+        const int tid = threadIdx.x - grp * kGrpThreads;
         const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
         const float4* s_rstd = s_mean + p.h * p.w / 4;
         const int groups = p.h * p.w / 4;
-        int stage = 0; uint32_t phase = 0;
-        int rslot = 0; uint32_t rphase = 0;
-        uint32_t px[kMaxGroups];
-        // where this thread's 4-pixel groups land in the s2d image never changes: computed once
-        uint32_t soff[kMaxGroups];
-        {
-            int y = tid / bwc, x4 = tid - y * bwc;
-            const int dy = kConvThreads / bwc, dx = kConvThreads - dy * bwc;
+        // Thread -> pixel-group map, fixed for the whole kernel (computed once): item i of a thread is the 4-pixel
+        // group g = tid + i*threads of the raw frame; soff = where it lands in the s2d image.
+        uint32_t soff[kGrpMaxGroups]; int gidx[kGrpMaxGroups];
 #pragma unroll
-            for (int i = 0; i < kMaxGroups; ++i) {
-                soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
-                y += dy; x4 += dx;
-                if (x4 >= bwc) { x4 -= bwc; ++y; }
-            }
+        for (int i = 0; i < kGrpMaxGroups; ++i) {
+            const int g = tid + i * kGrpThreads, y = g / bwc, x4 = g - y * bwc;
+            gidx[i] = g < groups ? g : -1;
+            soff[i] = (uint32_t)(((y >> 2) * bwc + x4) * RB + (y & 3) * 8);          // + 32*channel, then swizzled
         }
         const bool norm = p.mean && !(p.debug & 1);
-        int s = blockIdx.x, c = 0;
-        while (s < p.n) {
-            // this unit's raw pixels: staged by the loader warp several units ahead (HBM latency hidden)
-            umma::mbar_wait(rfull_bar(rslot), rphase);
-            {
+        // unit k (in this CTA's order: CPK channels of one sample) uses pipeline stage k % stages; its frames
+        // are k*CPK .. k*CPK+CPK-1 of the raw ring
+        const int my_samples = (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int my_units = my_samples * ups;
+        for (int k = grp; k < my_units; k += kConvGroups) {
+            const int stage = k % p.stages;
+            const uint32_t phase = (uint32_t)(k / p.stages) & 1u;
+            uint8_t* A = gen + st_off + stage * stage_bytes;
+#pragma unroll 1
+            for (int cc = 0; cc < CPK; ++cc) {
+                const int fr = k * CPK + cc, rslot = fr % p.raw_slots;
+                const uint32_t rphase = (uint32_t)(fr / p.raw_slots) & 1u;
+                // this frame's raw pixels: staged by the loader warp several frames ahead (HBM latency hidden)
+                umma::mbar_wait(rfull_bar(rslot), rphase);
+                if (cc == 0) umma::mbar_wait(empty_bar(stage), phase ^ 1u);
                 const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
 #pragma unroll
-                for (int i = 0; i < kMaxGroups; ++i) {
-                    const int g = tid + i * kConvThreads;
-                    px[i] = g < groups ? raw[g] : 0u;
-                }
-            }
-            umma::mbar_arrive(rempty_bar(rslot));
-            if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
-            umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-            uint8_t* A = gen + st_off + stage * kS2dStageBytes;
-#pragma unroll
-            for (int i = 0; i < kMaxGroups; ++i) {
-                const int g = tid + i * kConvThreads;
-                if (g < groups) {
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
-                    if (norm) {
-                        const float4 m = s_mean[g], r = s_rstd[g];
-                        v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
-                        v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
-                        v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
-                        v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                for (int i = 0; i < kGrpMaxGroups; ++i) {
+                    const int g = gidx[i];
+                    if (g >= 0) {
+                        const uint32_t px = raw[g];
+                        float v[4];
+                        u8x4_to_f32(px, v);
+                        if (norm) {
+                            const float4 m = s_mean[g], r = s_rstd[g];
+                            v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                            v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                            v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                            v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                        }
+                        *reinterpret_cast<uint2*>(A + PK::swz(soff[i] + cc * 32)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                     }
-                    *reinterpret_cast<uint2*>(A + soff[i]) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                 }
+                __syncwarp();                                 // one arrival per warp: 32 lanes arriving on the same
+                if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));   // mbarrier serialise (~4 cycles each)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            umma::mbar_arrive(full_bar(stage));
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            if (++c == p.cin) { c = 0; s += gridDim.x; }
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(full_bar(stage));
         }
     } else if (warp == kLoadWarp) {
         // ------------------------------------------------------------ raw-frame loader
@@ -490,32 +520,42 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
                 }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            const uint32_t idesc = N == 64 ? umma::make_idesc(128, 64, 0, 0) : umma::make_idesc(128, 32, 0, 0);
-            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
-                umma::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                for (int c = 0; c < p.cin; ++c) {
-                    umma::mbar_wait(full_bar(stage), phase);
-                    umma::fence_after_thread_sync();
-                    const uint64_t da0 = desc_sw32(smem_base + st_off + stage * kS2dStageBytes);
-                    const uint64_t db0 = desc_sw32(smem_base + c * 4 * N * 32);
-                    for (int mt = 0; mt < ((p.debug & 16) ? 1 : row_tiles); ++mt) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 4 + mt) * N);
+        // All 32 lanes run the loops (warp-uniform state); one elected lane issues the tcgen05 instructions.
+        const bool leader = umma::elect_one();
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t idesc = N == 64 ? umma::make_idesc(128, 64, 0, 0) : umma::make_idesc(128, 32, 0, 0);
+        for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
+            umma::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            for (int u = 0; u < ups; ++u) {
+                umma::mbar_wait(full_bar(stage), phase);
+                umma::fence_after_thread_sync();
+                const uint64_t da0 = desc_any(smem_base + st_off + stage * stage_bytes, 16, PK::SBO, PK::LAYOUT);
+                const uint64_t db0 = desc_any(smem_base + u * 4 * N * RB, 16, PK::SBO, PK::LAYOUT);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * N);
+                if (leader) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int shift = (t >> 1) * bwc + (t & 1);
-                            umma::mma_f16_ss(d_tmem, da0 + (uint64_t)((mt * 128 + shift) * 2), db0 + (uint64_t)(t * N * 2),
-                                             idesc, (c | t) ? 1u : 0u);
+                    for (int mt = 0; mt < 4; ++mt) {
+                        if (mt < row_tiles && !((p.debug & 16) && mt)) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int shift = (t >> 1) * bwc + (t & 1);
+#pragma unroll
+                                for (int kc = 0; kc < CPK; ++kc)     // one 16-pixel k-step per interleaved channel
+                                    umma::mma_f16_ss(d0 + (uint32_t)(mt * N),
+                                                     da0 + (uint64_t)((((mt * 128 + shift) * RB) >> 4) + kc * 2),
+                                                     db0 + (uint64_t)(((t * N * RB) >> 4) + kc * 2), idesc, (u | t | kc) ? 1u : 0u);
+                            }
                         }
                     }
                     umma::mma_commit(empty_bar(stage));
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                umma::mma_commit(tfull_bar(acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (leader) umma::mma_commit(tfull_bar(acc));
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ------------------------------------------------------------ epilogue
@@ -593,28 +633,40 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
     if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
-    const int N = 32 * p.nets;
-    const int raw_bytes = (p.h * p.w + 127) & ~127;
-    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256 + 512;
-    p.stages = (224 * 1024 - fixed - 4 * raw_bytes) / kS2dStageBytes;
-    if (p.stages > 4) p.stages = 4;
-    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1: does not fit shared memory");
-    p.raw_slots = (224 * 1024 - fixed - p.stages * kS2dStageBytes) / raw_bytes;
-    if (p.raw_slots > kMaxRaw) p.raw_slots = kMaxRaw;
-    const int smem = fixed + p.stages * kS2dStageBytes + p.raw_slots * raw_bytes;
+template <int CPK>
+int launch_s2d_fwd_t(Conv1Params& p, int smem, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel<CPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = p.n < sms ? p.n : sms;
-    umma_conv1s_fwd_kernel<<<grid, kThreadsS2d, smem, s>>>(p);
+    umma_conv1s_fwd_kernel<CPK><<<grid, kThreadsS2d, smem, s>>>(p);
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
+    const int N = 32 * p.nets;
+    const int raw_bytes = (p.h * p.w + 127) & ~127;
+    const int bwc = p.w / 4, row_tiles = ((p.h / 4) * bwc + 127) / 128;
+    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256 + 512;
+    // four channels interleaved per block row when they fit (128-byte rows feed the MMA far better than 32-byte ones)
+    int cpk = p.cin % 4 == 0 ? 4 : 1;
+    for (;; cpk = 1) {
+        p.s2d_stage_bytes = ((row_tiles * 128 + bwc + 2) * 32 * cpk + 1023) & ~1023;
+        p.stages = (224 * 1024 - fixed - (cpk + 2) * raw_bytes) / p.s2d_stage_bytes;
+        if (p.stages >= 2 || cpk == 1) break;
+    }
+    if (p.stages > 4) p.stages = 4;
+    CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1: does not fit shared memory");
+    p.raw_slots = (224 * 1024 - fixed - p.stages * p.s2d_stage_bytes) / raw_bytes;
+    if (p.raw_slots > kMaxRaw) p.raw_slots = kMaxRaw;
+    const int smem = fixed + p.stages * p.s2d_stage_bytes + p.raw_slots * raw_bytes;
+    return cpk == 4 ? launch_s2d_fwd_t<4>(p, smem, s) : launch_s2d_fwd_t<1>(p, smem, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -696,8 +748,8 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         umma::prefetch_tmap(&tmDy);
-        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kWgConvThreads + 1); umma::mbar_init(empty_bar(s), 1); }
-        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kWgConvThreads); }
+        for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kWgConvWarps + 1); umma::mbar_init(empty_bar(s), 1); }
+        for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kWgConvWarps); }
         umma::mbar_init(done_bar, 1);
         umma::fence_barrier_init();
     }
@@ -715,40 +767,27 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         const int groups = p.h * p.w / 4;
         int stage = 0; uint32_t phase = 0;
         int rslot = 0; uint32_t rphase = 0;
-        uint32_t soff[kMaxGroups];                         // fixed landing offsets of this thread's pixel groups
-        {
-            int y = tid / bwc, x4 = tid - y * bwc;
-            const int dy_ = kWgConvThreads / bwc, dx_ = kWgConvThreads - dy_ * bwc;
+        // thread -> pixel-group map, computed once (see the forward kernel)
+        uint32_t soff[kMaxGroups]; int gidx[kMaxGroups];
 #pragma unroll
-            for (int i = 0; i < kMaxGroups; ++i) {
-                soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
-                y += dy_; x4 += dx_;
-                if (x4 >= bwc) { x4 -= bwc; ++y; }
-            }
+        for (int i = 0; i < kMaxGroups; ++i) {
+            const int g = tid + i * kWgConvThreads, y = g / bwc, x4 = g - y * bwc;
+            gidx[i] = g < groups ? g : -1;
+            soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
         }
         for (int s = blockIdx.x; s < p.n; s += gridDim.x)
             for (int c = 0; c < p.cin; ++c) {
-                uint32_t px[kMaxGroups];
                 umma::mbar_wait(rfull_bar(rslot), rphase);
-                {
-                    const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
-#pragma unroll
-                    for (int i = 0; i < kMaxGroups; ++i) {
-                        const int g = tid + i * kWgConvThreads;
-                        px[i] = g < groups ? raw[g] : 0u;
-                    }
-                }
-                umma::mbar_arrive(rempty_bar(rslot));
-                if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
                 uint8_t* A = gen + stage * geo.stage_bytes + geo.dy_bytes;
 #pragma unroll
                 for (int i = 0; i < kMaxGroups; ++i) {
-                    const int g = tid + i * kWgConvThreads;
-                    if (g < groups) {
+                    const int g = gidx[i];
+                    if (g >= 0) {
+                        const uint32_t px = raw[g];
                         float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = (float)((px[i] >> (8 * j)) & 0xffu);
+                        u8x4_to_f32(px, v);
                         if (p.mean) {
                             const float4 m = s_mean[g], r = s_rstd[g];
                             v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
@@ -759,8 +798,12 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                         *reinterpret_cast<uint2*>(A + soff[i]) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                     }
                 }
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
+                if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                umma::mbar_arrive(full_bar(stage));
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(full_bar(stage));
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
     } else if (warp == kWgRawWarp) {
@@ -789,34 +832,33 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                 }
         }
     } else if (warp == kWgMmaWarp) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            bool seen[kMaxCin] = {false, false, false, false};
-            constexpr uint32_t idesc = umma::make_idesc(64, 32, 1, 1);
-            constexpr uint32_t idesc_b = umma::make_idesc(64, 16, 1, 1);
-            for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
-                for (int c = 0; c < p.cin; ++c) {
-                    umma::mbar_wait(full_bar(stage), phase);
-                    umma::fence_after_thread_sync();
-                    const uint32_t st = smem_base + stage * geo.stage_bytes;
-                    const uint64_t da0 = desc_mn(st, (uint32_t)(bwc * 64), 512, 4);              // SWIZZLE_64B, windows G rows apart
-                    const uint64_t db0 = desc_mn(st + geo.dy_bytes, 32, 256, 6);                 // SWIZZLE_32B, windows 1 row apart
+        // all 32 lanes run the loops (warp-uniform state, descriptors in uniform registers); one elected lane issues
+        const bool leader = umma::elect_one();
+        int stage = 0; uint32_t phase = 0;
+        uint32_t seen = 0;
+        constexpr uint32_t idesc = umma::make_idesc(64, 32, 1, 1);
+        for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
+            for (int c = 0; c < p.cin; ++c) {
+                umma::mbar_wait(full_bar(stage), phase);
+                umma::fence_after_thread_sync();
+                const uint32_t st = smem_base + stage * geo.stage_bytes;
+                const uint64_t da0 = desc_mn(st, (uint32_t)(bwc * 64), 512, 4);              // SWIZZLE_64B, windows G rows apart
+                const uint64_t db0 = desc_mn(st + geo.dy_bytes, 32, 256, 6);                 // SWIZZLE_32B, windows 1 row apart
+                const uint32_t first = (seen >> c) & 1u;
+                if (leader) {
+#pragma unroll 4
                     for (int k = 0; k < geo.ksteps; ++k)
                         umma::mma_f16_ss(tmem_base + (uint32_t)(c * 32), da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * 32), idesc,
-                                         (!seen[c] && k == 0) ? 0u : 1u);
-                    if (c == 0 && p.dbias) {     // column sums of dy: the same A windows times a block of ones
-                        const uint64_t d1 = desc_mn(smem_base + ones_off, 32, 256, 6);
-                        for (int k = 0; k < geo.ksteps; ++k)
-                            umma::mma_f16_ss(tmem_base + (uint32_t)(p.cin * 32), da0 + (uint64_t)(k * 64), d1, idesc_b,
-                                             (!seen[0] && k == 0) ? 0u : 1u);
-                    }
-                    seen[c] = true;
+                                         (first | (uint32_t)k) ? 1u : 0u);
                     umma::mma_commit(empty_bar(stage));
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                seen |= 1u << c;
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma::mma_commit(done_bar);
         }
+        if (leader) umma::mma_commit(done_bar);
+        __syncwarp();
     } else if (warp < kWgRawWarp && blockIdx.x < p.n) {
         // ------------------------------------------------------------ epilogue: TMEM -> atomics into dW
         // M = 64 accumulator: row i = (j, n) lives in TMEM lane (i/16)*32 + i%16
@@ -892,6 +934,7 @@ int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
 bool s2d_ok(const cb_conv_desc* d) {      // block grid must fit four M tiles plus the largest tap shift
     const int bwc = d->in_w / 4, brows = (d->in_h / 4) * bwc;
     return d->in_h % 4 == 0 && brows <= 512 && (brows + 127) / 128 * 128 + bwc + 1 <= kS2dStageBytes / 32 &&
+           (d->in_h * d->in_w / 4 + kGrpThreads - 1) / kGrpThreads <= kGrpMaxGroups &&
            (d->in_h * d->in_w) % 16 == 0 && d->in_stride_n % 16 == 0 && d->in_stride_c % 16 == 0;   // cp.async.bulk
 }
 

@@ -383,6 +383,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        // (One lane runs the loop here.  The window / weight-gradient / conv1 kernels instead keep the whole
+        // warp converged and elect a lane per instruction -- elect_one() -- which removes the per-MMA operand
+        // "waterfall" and is worth 10-35 % where many short MMAs are issued per stage; with 4-8 MMAs per
+        // k-block the extra 32-lane barrier polling costs more than it saves: measured 7 % slower.)
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;

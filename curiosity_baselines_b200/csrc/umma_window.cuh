@@ -113,17 +113,19 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            mbar_wait(w_bar, 0);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                mbar_wait(full_bar(stage), phase);
-                fence_after_thread_sync();
-                const uint64_t da0 = make_smem_desc(a_base + stage * p.stage_bytes, 16, 1024);
-                const uint64_t db0 = make_smem_desc(smem_base, 16, 1024);
+        // all lanes run the loops (warp-uniform state); one elected lane issues (see umma_gemm_kernel)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        mbar_wait(w_bar, 0);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            mbar_wait(full_bar(stage), phase);
+            fence_after_thread_sync();
+            const uint64_t da0 = make_smem_desc(a_base + stage * p.stage_bytes, 16, 1024);
+            const uint64_t db0 = make_smem_desc(smem_base, 16, 1024);
+            if (leader) {
                 for (int kb = 0; kb < p.kb_count; ++kb) {
                     const uint64_t da = da0 + (uint64_t)p.kb_off16[kb];
                     const uint64_t db = db0 + (uint64_t)(kb * BN * 8);
@@ -138,9 +140,10 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 }
                 mma_commit(empty_bar(stage));
                 mma_commit(tfull_bar(acc));
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= kEpiWarp0) {
         const int quarter = warp & 3;
@@ -282,29 +285,32 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-            int stage = 0; uint32_t phase = 0;
-            bool first = true;
-            for (int slab = split; slab < p.slabs_total; slab += p.splits) {
-                mbar_wait(full_bar(stage), phase);
-                fence_after_thread_sync();
-                const uint32_t st = smem_base + stage * p.stage_bytes;
-                const int ksteps = p.k_rows / 16;
+        const bool leader = elect_one();          // all lanes loop, one issues (see umma_gemm_kernel)
+        constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        uint32_t first = 1;
+        for (int slab = split; slab < p.slabs_total; slab += p.splits) {
+            mbar_wait(full_bar(stage), phase);
+            fence_after_thread_sync();
+            const uint32_t st = smem_base + stage * p.stage_bytes;
+            const int ksteps = p.k_rows / 16;
+            if (leader) {
                 for (int g = 0; g < p.n_acc; ++g) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(g * BN);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t da = make_smem_desc(st + p.acc_a_off[g] + k * 2048, (uint32_t)p.acc_a_lbo[g], 1024);
-                        const uint64_t db = make_smem_desc(st + p.b_offset + k * 2048, (uint32_t)p.b_box_stride, 1024);
-                        mma_f16_ss(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
-                    }
+                    const uint64_t da0 = make_smem_desc(st + p.acc_a_off[g], (uint32_t)p.acc_a_lbo[g], 1024);
+                    const uint64_t db0 = make_smem_desc(st + p.b_offset, (uint32_t)p.b_box_stride, 1024);
+                    for (int k = 0; k < ksteps; ++k)          // one k-step = 16 rows of 128 B = 2048 B
+                        mma_f16_ss(d_tmem, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc,
+                                   (first && k == 0) ? 0u : 1u);
                 }
-                first = false;
                 mma_commit(empty_bar(stage));
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            mma_commit(done_bar);
+            __syncwarp();
+            first = 0;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (leader) mma_commit(done_bar);
+        __syncwarp();
     } else {
         // epilogue: wait for the CTA's whole K range, then atomically add into dW
         const int quarter = warp & 3;

@@ -1,0 +1,3 @@
+#!/bin/bash
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python tools/layer_bench.py 2>&1 | tail -16
