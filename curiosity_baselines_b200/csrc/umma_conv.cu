@@ -128,7 +128,7 @@ int launch_epi(const Plan& pl, cudaStream_t s) {
     }
     int tiles = pl.p.m_tiles * pl.p.n_tiles;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::gemm_threads<EPI>(), Cfg::SMEM_BYTES, s>>>(
+    umma::umma_gemm_kernel<BN, MT, EPI><<<grid, umma::plain_gemm_threads<EPI>(), Cfg::SMEM_BYTES, s>>>(
         pl.tmA, pl.tmB, pl.p.side_kb ? pl.tmS : pl.tmA, pl.p);
     CB_LAUNCH_CHECK();
     return CB_OK;

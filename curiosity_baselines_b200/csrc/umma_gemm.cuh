@@ -22,8 +22,15 @@ namespace umma {
 // With one warp per scheduler every tcgen05.ld / global-load latency is exposed (ncu: issue slots 22 %
 // busy, tensor pipe 46 %); several warps per scheduler hide it.
 constexpr int kEpiWarp0 = 2;
-template <int EPI> struct EpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 2; };   // SIMPLE needs few registers
+// SIMPLE needs few registers: 16 warps.  The epilogues with global side operands run 12 warps (3 per quarter, 128
+// registers each) and fetch those operands on demand -- they were asked from L2 by the producer when the tile's
+// slab was loaded -- instead of 8 warps with a two-deep register prefetch (167 registers).
+template <int EPI> struct EpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 3; };
 template <int EPI> constexpr int gemm_threads() { return (kEpiWarp0 + 4 * EpiWarps<EPI>::GROUPS) * 32; }
+// The plain GEMM kernel has no such producer-side L2 prefetch (its tiles' side operands are strided blocks): its
+// full / dgrad epilogues keep 8 warps and the two-deep register prefetch.
+template <int EPI> struct GemmEpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 2; };
+template <int EPI> constexpr int plain_gemm_threads() { return (kEpiWarp0 + 4 * GemmEpiWarps<EPI>::GROUPS) * 32; }
 
 constexpr int kBiasSmemFloats = 4096;   // bias vectors up to this length are staged in shared memory
 
@@ -263,12 +270,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 // so their HBM latency overlaps the MMAs and the math.  (Copying a prefetch buffer would stall on the
 // pending loads -- the buffers are only ever consumed.)
 // row_fn(mt, valid, grow, base): output row of this lane in sub-tile mt, and its element offset (row_base).
-template <int BN, int MT, int EPI, class RowFn>
+template <int BN, int MT, int EPI, int G, bool PIPE, class RowFn>      // G warps per quarter: this warp handles items sub, sub + G, ...
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* bias, uint32_t tmem_acc, int quarter,
                                               int sub, int lane, int n_base, uint32_t tfull, uint32_t parity, RowFn row_fn) {
     constexpr int NCH = BN / 32;
     constexpr int ITEMS = MT * NCH;
-    constexpr int G = EpiWarps<EPI>::GROUPS;       // this warp handles items sub, sub + G, ...
     bool valid[MT]; long long grow[MT], base[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) row_fn(mt, valid[mt], grow[mt], base[mt]);
@@ -300,14 +306,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
         if (v_now && !(p.debug & 1))
             epilogue_chunk<EPI>(p, bias, raw, row_off(mt) + chunk_delta(p, n_base + cb * 32), n_base + cb * 32, sv, buf);
     };
-    AuxRegs b0, b1;
-    request(sub, b0);
+    AuxRegs b0;
+    request(sub, b0);                       // first item's side operands: in flight while the accumulator is awaited
     mbar_wait(tfull, parity);
     fence_after_thread_sync();
-    if (EPI == EPI_SIMPLE) {
+    if (EPI == EPI_SIMPLE || !PIPE) {
 #pragma unroll 1
-        for (int it = sub; it < ITEMS; it += G) process(it, b0);
-    } else {
+        for (int it = sub; it < ITEMS; it += G) {
+            if (EPI != EPI_SIMPLE && it != sub) request(it, b0);
+            process(it, b0);
+        }
+    } else {                                // two-deep software pipeline with alternating register buffers
+        AuxRegs b1;
 #pragma unroll 1
         for (int it = sub; it < ITEMS; it += 2 * G) {
             request(it + G, b1);
@@ -321,7 +331,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const float* 
 }
 
 template <int BN, int MT, int EPI>
-__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
+__global__ void __launch_bounds__(plain_gemm_threads<EPI>(), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmS, const GemmParams p) {
     using Cfg = GemmConfig<BN, MT>;
@@ -345,7 +355,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         prefetch_tmap(&tmB);
         if (p.side_kb) prefetch_tmap(&tmS);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EpiWarps<EPI>::GROUPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * GemmEpiWarps<EPI>::GROUPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -423,7 +433,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
-            epilogue_tile<BN, MT, EPI>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, tn * BN,
+            epilogue_tile<BN, MT, EPI, GemmEpiWarps<EPI>::GROUPS, true>(p, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, tn * BN,
                                   tfull_bar(acc), acc_phase,
                                   [&](int mt, bool& valid, long long& grow, long long& base) {
                                       const int r = mt * 128 + quarter * 32 + lane;

@@ -167,7 +167,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const long long tile_elems = p.epi.shuffle ? (long long)p.S * p.epi.sh_h * p.epi.sh_w * 32 : tile_rows * p.epi.n_total;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            epilogue_tile<BN, MT, EPI>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, 0, tfull_bar(acc),
+            epilogue_tile<BN, MT, EPI, EpiWarps<EPI>::GROUPS, false>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, 0, tfull_bar(acc),
                                   acc_phase, [&](int mt, bool& valid, long long& grow, long long& base) {
                                       const int m = MT == 1 ? 0 : (mt ? MT - 1 : 0);
                                       valid = ok[m] && tile * p.S + smp[m] < p.n_samples;
