@@ -377,10 +377,13 @@ __device__ __forceinline__ uint64_t desc_any(uint32_t saddr, uint32_t lbo, uint3
 constexpr int kEpiBar = 2;             // named barrier of the epilogue threads
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBar), "n"(kEpiWarps * 32) : "memory"); }
 
-template <int CPK>
+// CG converter groups of four warps (alternate units) and 16 - 4*CG epilogue warps: the twin-network pass is
+// epilogue-bound (CG = 1: 4 + 12 warps), the 4-channel single-network pass converter-bound (CG = 2: 8 + 8).
+template <int CPK, int CG>
 __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const Conv1Params p) {
     using PK = Pack<CPK>;
     constexpr int RB = PK::RB;
+    constexpr int kCW = 4 * CG, kEW = 16 - 4 * CG, kMma = kCW, kEpi0 = kCW + 1, kLoad = 17, kEG = kEW / 4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
@@ -435,23 +438,23 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { umma::mbar_init(full_bar(s), kGrpThreads / 32); umma::mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), kEW); }
         for (int r = 0; r < p.raw_slots; ++r) { umma::mbar_init(rfull_bar(r), 1); umma::mbar_init(rempty_bar(r), kGrpThreads / 32); }
         umma::fence_barrier_init();
     }
-    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == kMma) umma::tmem_alloc(tmem_slot, tmem_cols);
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int row_tiles = (brows + 127) / 128;
 
-    if (warp < kConvWarps) {
+    if (warp < kCW) {
         // ------------------------------------------------------------ converters: uint8 -> s2d bf16 image
         // Two groups of four warps take alternate units (one channel of one sample each), so that one group's
         // wait -> read -> convert -> fence -> arrive chain overlaps the other's (a single group of eight warps
         // marching in lock-step was latency-bound at ~1200 cycles per unit).
-        const int grp = warp / (kConvWarps / kConvGroups);
+        const int grp = warp >> 2;
         const int tid = threadIdx.x - grp * kGrpThreads;
         const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
         const float4* s_rstd = s_mean + p.h * p.w / 4;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
         // are k*CPK .. k*CPK+CPK-1 of the raw ring
         const int my_samples = (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int my_units = my_samples * ups;
-        for (int k = grp; k < my_units; k += kConvGroups) {
+        for (int k = grp; k < my_units; k += CG) {
             const int stage = k % p.stages;
             const uint32_t phase = (uint32_t)(k / p.stages) & 1u;
             uint8_t* A = gen + st_off + stage * stage_bytes;
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(full_bar(stage));
         }
-    } else if (warp == kLoadWarp) {
+    } else if (warp == kLoad) {
         // ------------------------------------------------------------ raw-frame loader
         if (lane == 0) {
             int rslot = 0; uint32_t rphase = 0;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
                     if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kMma) {
         // All 32 lanes run the loops (warp-uniform state); one elected lane issues the tcgen05 instructions.
         const bool leader = umma::elect_one();
         int stage = 0; uint32_t phase = 0;
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
         // TMEM reads run at 64 B/clk/SM (a 32x32 fp32 block takes 64 cycles), so each warp keeps the NEXT
         // block's tcgen05.ld in flight while it applies bias/activation to the current one and stores it.
         const int quarter = warp & 3;
-        const int half = (warp - kMmaWarp - 1) >> 2;
+        const int sub = (warp - kEpi0) >> 2;                   // which of the kEG warps sharing this TMEM lane quarter
         const float* s_bias = reinterpret_cast<const float*>(gen + b_off);
         // The block-grid row of this lane in each row tile (and whether it is stored) never changes: hoisted
         // out of the sample loop so the per-block work is tcgen05.ld + bias/activation + pack + two stores.
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
                 if (!tile_live[mt]) continue;
 #pragma unroll 1
                 for (int net = 0; net < p.nets; ++net) {
-                    if (((mt * p.nets + net) & 1) != half) continue;
+                    if ((mt * p.nets + net) % kEG != sub) continue;
                     uint32_t raw[32];
                     umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32), raw);
                     umma::tmem_ld_wait();
@@ -630,21 +633,21 @@ __global__ void __launch_bounds__(kThreadsS2d, 1) umma_conv1s_fwd_kernel(const C
     }
     umma::fence_before_thread_sync();
     __syncthreads();
-    if (warp == kMmaWarp) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
+    if (warp == kMma) { umma::fence_after_thread_sync(); umma::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-template <int CPK>
+template <int CPK, int CG>
 int launch_s2d_fwd_t(Conv1Params& p, int smem, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel<CPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_fwd_kernel<CPK, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = p.n < sms ? p.n : sms;
-    umma_conv1s_fwd_kernel<CPK><<<grid, kThreadsS2d, smem, s>>>(p);
+    umma_conv1s_fwd_kernel<CPK, CG><<<grid, kThreadsS2d, smem, s>>>(p);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -666,7 +669,8 @@ int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
     p.raw_slots = (224 * 1024 - fixed - p.stages * p.s2d_stage_bytes) / raw_bytes;
     if (p.raw_slots > kMaxRaw) p.raw_slots = kMaxRaw;
     const int smem = fixed + p.stages * p.s2d_stage_bytes + p.raw_slots * raw_bytes;
-    return cpk == 4 ? launch_s2d_fwd_t<4>(p, smem, s) : launch_s2d_fwd_t<1>(p, smem, s);
+    if (cpk == 4) return launch_s2d_fwd_t<4, 2>(p, smem, s);
+    return launch_s2d_fwd_t<1, 2>(p, smem, s);      // (4 converter + 12 epilogue warps, <1, 1>, measured slower for the twin pass)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -837,6 +841,7 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         int stage = 0; uint32_t phase = 0;
         uint32_t seen = 0;
         constexpr uint32_t idesc = umma::make_idesc(64, 32, 1, 1);
+        constexpr uint32_t idesc_b = umma::make_idesc(64, 16, 1, 1);
         for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
             for (int c = 0; c < p.cin; ++c) {
                 umma::mbar_wait(full_bar(stage), phase);
@@ -845,11 +850,18 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                 const uint64_t da0 = desc_mn(st, (uint32_t)(bwc * 64), 512, 4);              // SWIZZLE_64B, windows G rows apart
                 const uint64_t db0 = desc_mn(st + geo.dy_bytes, 32, 256, 6);                 // SWIZZLE_32B, windows 1 row apart
                 const uint32_t first = (seen >> c) & 1u;
+                const uint64_t d1 = desc_mn(smem_base + ones_off, 32, 256, 6);
                 if (leader) {
 #pragma unroll 4
                     for (int k = 0; k < geo.ksteps; ++k)
                         umma::mma_f16_ss(tmem_base + (uint32_t)(c * 32), da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * 32), idesc,
                                          (first | (uint32_t)k) ? 1u : 0u);
+                    if (c == 0 && p.dbias) {     // column sums of dy (bias gradient): the same A windows times a block of ones
+#pragma unroll 4
+                        for (int k = 0; k < geo.ksteps; ++k)
+                            umma::mma_f16_ss(tmem_base + (uint32_t)(p.cin * 32), da0 + (uint64_t)(k * 64), d1, idesc_b,
+                                             (first | (uint32_t)k) ? 1u : 0u);
+                    }
                     umma::mma_commit(empty_bar(stage));
                 }
                 __syncwarp();
@@ -1024,11 +1036,13 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
     static int im2col = -1;
     if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
     const bool s2d = !im2col && s2d_ok(d) && s2d_wgrad_ok(d) && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0;
-    // Bias gradient: a separate column-sum pass.  (Summing dy on the tensor cores with an extra N = 16 block of
-    // ones -- p.dbias -- works but the 29 extra M=64 MMAs per unit cost more than the pass: each tiny MN-major
-    // MMA takes ~70 cycles of operand fetch whatever its N.)
-    if (dbias) { rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s); if (rc) return rc; }
-    // the s2d kernel prefetches a sample's dy rows into 8 registers per converter thread
+    // Bias gradient: in the s2d kernel dy is summed on the tensor cores (the same A windows times an N = 16 block
+    // of ones, 29 more small MMAs per sample) instead of a second pass over the 25.6 KB/sample of dy.
+    if (dbias) {
+        if (s2d) { p.dbias = dbias; rc = scale_buffer(dbias, 32, beta, s); }
+        else rc = colsum_bf16(dy, (int64_t)d->n * p.rows, 32, dbias, beta, s);
+        if (rc) return rc;
+    }
     if (s2d)
         return launch_s2d_wgrad(p, s);
     return launch<true>(p, s);
