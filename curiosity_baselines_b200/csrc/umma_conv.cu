@@ -616,8 +616,55 @@ bool window_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
     return false;
 }
 
+// Stride-2 k4 c32 forward (Burda conv2) in flat mode: the tensor is viewed as [n*h/2][2][w/2][64] and a tile is
+// 25 consecutive grid rows of the flattened (sample, row) axis plus a two-row halo for the taps.
+int window_conv_fwd_s2_flat(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
+    const int gh = d->in_h / 2, gw = d->in_w / 2;
+    const int RT = 256 / gw, halo = 2;                     // grid rows per tile; taps reach one grid row + one column further
+    umma::WindowParams p{};
+    CUtensorMap tmA, tmW;
+    p.S = 1; p.gh = gh; p.gw = gw; p.vh = d->out_h; p.vw = d->out_w; p.n_samples = d->n;
+    p.flat_rows = RT;
+    p.tiles = (int)(((long long)d->n * gh + RT - 1) / RT);
+    p.plane_rows = (RT + halo) * gw;
+    p.plane_bytes = round_up(p.plane_rows * 128, 1024);
+    uint64_t dims[4] = {64, (uint64_t)gw, 2, (uint64_t)d->n * gh};
+    uint64_t strides[3] = {128, (uint64_t)d->in_w * 64, (uint64_t)d->in_w * 128};
+    uint32_t box[4] = {64, (uint32_t)gw, 1, (uint32_t)(RT + halo)};
+    int rc = encode_bf16(&tmA, x, 4, dims, strides, box); if (rc) return rc;
+    p.a_rank = 4; p.a_sample_dim = 3; p.nplanes = 2;
+    p.a_coord[1][2] = 1;                                   // second plane: odd rows
+    p.stage_bytes = p.nplanes * p.plane_bytes;
+    p.kb_count = 8;
+    int max_shift = 0;
+    for (int kh = 0; kh < 4; ++kh)
+        for (int j = 0; j < 2; ++j) {
+            const int i = kh * 2 + j, shift = (kh >> 1) * gw + j;
+            p.kb_plane[i] = kh & 1; p.kb_shift[i] = shift;
+            p.kb_off16[i] = ((kh & 1) * p.plane_bytes + shift * 128) >> 4;
+            if (shift > max_shift) max_shift = shift;
+        }
+    const int over = 256 + max_shift - p.plane_rows;       // rows a shifted M=256 window reads past a plane
+    p.slack_bytes = over > 0 ? round_up(over * 128, 1024) : 0;
+    rc = plan_weights(&tmW, w, d->out_c, (long long)d->k_h * d->k_w * d->in_c); if (rc) return rc;
+    p.epi.n_total = d->out_c;
+    p.epi.bias = e->bias; p.epi.act = d->act;
+    p.epi.residual = (const __nv_bfloat16*)e->residual;
+    p.epi.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.epi.out_f32 = e->out_f32;
+    return d->out_c == 64 ? launch_window<64>(tmA, tmW, p, s) : launch_window<128>(tmA, tmW, p, s);
+}
+
 int window_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
     CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
+    {
+        static int flat = -1;
+        if (flat < 0) { const char* ev = getenv("CB_NO_FLAT"); flat = (ev && ev[0] == '1') ? 0 : 1; }
+        const int gw = d->in_w / 2, gh = d->in_h / 2;
+        // worth it when whole samples leave many of the 256 tile rows empty
+        if (flat && d->stride == 2 && !e->residual && gw <= 128 && (256 / (gh * gw)) * gh * gw < (256 / gw) * gw - gw &&
+            (long long)d->n * gh < (1ll << 31))
+            return window_conv_fwd_s2_flat(d, x, w, e, s);
+    }
     WindowGeo g{};
     g.x = x; g.n = d->n; g.h = d->in_h; g.w = d->in_w; g.c = d->in_c;
     g.vh = d->out_h; g.vw = d->out_w;

@@ -32,6 +32,9 @@ struct WindowParams {
     int kb_off16[kMaxTaps];                // (plane*plane_bytes + shift*128) >> 4, filled by the host
     // pixel grid per sample and its valid (stored) part
     int gh, gw, vh, vw, n_samples, tiles;
+    // flat mode (flat_rows > 0): a tile is `flat_rows` consecutive rows of the (sample, grid row) axis instead of
+    // S whole samples, so the 256 MMA rows are filled whatever gh*gw is (10x10 grid: 250 of 256 instead of 200)
+    int flat_rows;
     GemmParams epi;                        // epilogue operands (n_total == BN, shuffle fields honoured)
 };
 
@@ -106,7 +109,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     int c[5];
 #pragma unroll
                     for (int i = 0; i < 5; ++i) c[i] = p.a_coord[pl][i];
-                    c[p.a_sample_dim] += tile * p.S;
+                    c[p.a_sample_dim] += tile * (p.flat_rows ? p.flat_rows : p.S);
                     tma_load(p.a_rank, a_base + stage * p.stage_bytes + pl * p.plane_bytes, &tmA, full_bar(stage), c);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -152,12 +155,14 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         // Which output pixel a lane's row of each sub-tile is never changes from tile to tile: the divisions
         // are done once here, per tile only the sample base is added.
         bool ok[MT]; int smp[MT]; long long rel_row[MT], rel_base[MT];
+        int fq[MT], fx[MT];                                // flat mode: grid row within the tile, grid column
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int r = mt * 128 + quarter * 32 + lane;
             const int s = r / grid_px, rem = r - s * grid_px;
             const int gy = rem / p.gw, gx = rem - gy * p.gw;
-            ok[mt] = s < p.S && gy < p.vh && gx < p.vw;
+            fq[mt] = r / p.gw; fx[mt] = r - fq[mt] * p.gw;
+            ok[mt] = p.flat_rows ? (fq[mt] < p.flat_rows && fx[mt] < p.vw) : (s < p.S && gy < p.vh && gx < p.vw);
             smp[mt] = s;
             rel_row[mt] = ((long long)s * p.vh + gy) * p.vw + gx;
             rel_base[mt] = p.epi.shuffle ? (((long long)s * p.epi.sh_h + 2 * gy) * p.epi.sh_w + 2 * gx) * 32
@@ -170,6 +175,14 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             epilogue_tile<BN, MT, EPI, EpiWarps<EPI>::GROUPS, false>(p.epi, bias, tmem_base + (uint32_t)(acc * MT * BN), quarter, sub, lane, 0, tfull_bar(acc),
                                   acc_phase, [&](int mt, bool& valid, long long& grow, long long& base) {
                                       const int m = MT == 1 ? 0 : (mt ? MT - 1 : 0);
+                                      if (p.flat_rows) {       // (sample, grid row) from the flattened row index
+                                          const int G = tile * p.flat_rows + fq[m];
+                                          const int sample = G / p.gh, gy = G - sample * p.gh;
+                                          valid = ok[m] && gy < p.vh && sample < p.n_samples;
+                                          grow = ((long long)sample * p.vh + gy) * p.vw + fx[m];
+                                          base = grow * p.epi.n_total;
+                                          return;
+                                      }
                                       valid = ok[m] && tile * p.S + smp[m] < p.n_samples;
                                       grow = tile * tile_rows + rel_row[m];
                                       base = tile * tile_elems + rel_base[m];
