@@ -145,7 +145,9 @@ int launch(const Plan& pl, cudaStream_t s) {
 
 int dispatch(const Plan& pl, cudaStream_t s) {
     switch (pl.bn * 10 + pl.mt) {
+        case 2562: return launch<256, 2>(pl, s);
         case 2561: return launch<256, 1>(pl, s);
+        case 2242: return launch<224, 2>(pl, s);
         case 2241: return launch<224, 1>(pl, s);
         case 1282: return launch<128, 2>(pl, s);
         case 642:  return launch<64, 2>(pl, s);
@@ -154,10 +156,18 @@ int dispatch(const Plan& pl, cudaStream_t s) {
     }
 }
 
-int pick_bn(int n_total, int* mt) {
-    if (n_total % 256 == 0) { *mt = 1; return 256; }
+// A 128x256 tile needs 48 KB of operands per 64-wide k-block -- 96 B/clk/SM at full MMA rate, more than L2 delivers
+// (~42 B/clk/SM): the plain GEMMs are L2-bound at ~45 % of peak.  A 256x256 tile (MT = 2) moves 64 KB for twice
+// the math.  Used when there are enough rows to keep every SM busy with the larger tiles.
+int pick_bn(int n_total, int* mt, long long rows = 0) {
+    if (n_total % 256 == 0) {
+        static int big = -1;
+        if (big < 0) { const char* e = getenv("CB_NO_BIG_TILE"); big = (e && e[0] == '1') ? 0 : 1; }
+        *mt = (big && rows >= 256LL * 2 * 148) ? 2 : 1;
+        return 256;
+    }
     if (n_total % 128 == 0) { *mt = 2; return 128; }
-    if (n_total % 224 == 0) { *mt = 1; return 224; }
+    if (n_total % 224 == 0) { *mt = 1; return 224; }   // (256x224 single-buffered tiles measured slower: fc dgrad has K = 512 only)
     if (n_total % 64 == 0)  { *mt = 2; return 64; }
     if (n_total % 32 == 0)  { *mt = 2; return 32; }
     return 0;
@@ -316,7 +326,7 @@ int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_
     if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
     if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
     Plan pl{};
-    pl.bn = pick_bn(d->out_c, &pl.mt);
+    pl.bn = pick_bn(d->out_c, &pl.mt, (d->k_h == d->in_h && d->k_w == d->in_w && d->pad == 0) ? d->n : 0);
     Geo g = fwd_geo(d);
     int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
     const long long K = (long long)d->k_h * d->k_w * d->in_c;
@@ -357,7 +367,7 @@ int umma_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, cons
     CB_REQUIRE(dy && w_t && dx, CB_E_ARG, "cb_conv_dgrad: null pointer");
     if (use_window() && window_supports_dgrad(d)) return window_conv_dgrad(d, dy, w_t, x_saved, x_act, dx_add, dx, s);
     Plan pl{};
-    pl.bn = pick_bn(d->in_c, &pl.mt);
+    pl.bn = pick_bn(d->in_c, &pl.mt, (d->k_h == 1 && d->k_w == 1 && d->in_h == 1 && d->in_w == 1) ? d->n : 0);
     umma::GemmParams& p = pl.p;
     int rc;
     if (d->k_h == 1 && d->k_w == 1 && d->in_h == 1 && d->in_w == 1) {
@@ -401,7 +411,7 @@ int umma_grouped_fwd(int n, int groups, int k, int f, int x_shared, const void* 
     CB_REQUIRE(umma_supports_grouped(groups, k, f) && e->side_dim <= 16 && !e->norm_mean, CB_E_ARG,
                "cb_grouped_linear_fwd: unsupported shape or device");
     Plan pl{};
-    pl.bn = pick_bn(f, &pl.mt);
+    pl.bn = pick_bn(f, &pl.mt, n);
     Geo g{n, 1, 1, x_shared ? k : groups * k, 1, 1, 1, 0, 1, 1};
     int rc = plan_a(pl, g, x, pl.mt); if (rc) return rc;
     umma::GemmParams& p = pl.p;
@@ -429,7 +439,7 @@ int umma_grouped_dgrad(int n, int groups, int k, int f, const void* dy, const vo
     CB_REQUIRE(dy && w_t_all && dx, CB_E_ARG, "cb_grouped_linear_dgrad: null pointer");
     CB_REQUIRE(umma_supports_grouped(groups, f, k), CB_E_ARG, "cb_grouped_linear_dgrad: unsupported shape or device");
     Plan pl{};
-    pl.bn = pick_bn(k, &pl.mt);
+    pl.bn = pick_bn(k, &pl.mt, n);
     Geo g{n, 1, 1, groups * f, 1, 1, 1, 0, 1, 1};
     int rc = plan_a(pl, g, dy, pl.mt); if (rc) return rc;
     rc = plan_b(pl, w_t_all, groups * k, f); if (rc) return rc;
@@ -799,19 +809,25 @@ int wgrad_rows(int n, int out_c, int K, int groups, int x_shared, const void* x,
     uint32_t box[2] = {64, 64};
     int rc = encode_bf16(&tmA, dy, 2, da, sa, box); if (rc) return rc;
     rc = encode_bf16(&tmB, x, 2, db, sb, box); if (rc) return rc;
-    p.na = 2; p.nb = 4; p.a_rank = p.b_rank = 2;
+    // MC = 128-row output chunks per CTA: two of them share each x slab (64 KB of operands per 256x256x64 MACs
+    // instead of 48 KB per 128x256x64 -- these GEMMs are L2-bandwidth-bound)
+    const int MC = (out_c % 256 == 0 && K >= 1024) ? 2 : 1;      // small K: the atomic epilogue would dominate
+    p.na = 2 * MC; p.nb = 4; p.a_rank = p.b_rank = 2;
     for (int i = 0; i < 4; ++i) { p.a_coord[i][0] = i * 64; p.b_coord[i][0] = i * 64; }
     p.a_step_dim = p.b_step_dim = 1; p.a_step = p.b_step = 64;
-    p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = 128; p.b_unit_step = 256;
+    p.a_unit_dim = p.b_unit_dim = 0; p.a_unit_step = 128 * MC; p.b_unit_step = 256;
     p.a_box_bytes = p.b_box_bytes = 8192; p.a_box_stride = p.b_box_stride = 8192;
-    p.b_offset = 2 * 8192; p.stage_bytes = 6 * 8192; p.stages = 4; p.slack_bytes = 0; p.k_rows = 64;
+    p.b_offset = 2 * MC * 8192; p.stage_bytes = (2 * MC + 4) * 8192; p.stages = MC == 2 ? 3 : 4; p.slack_bytes = 0; p.k_rows = 64;
     const int n_tiles = (K + 255) / 256;
-    p.units = (out_all / 128) * n_tiles; p.unit_div = n_tiles;
-    if (groups > 1) { p.group_units = out_c / 128; p.b_group_koff = x_shared ? 0 : K; }
+    p.units = (out_all / (128 * MC)) * n_tiles; p.unit_div = n_tiles;
+    if (groups > 1) { p.group_units = out_c / (128 * MC); p.b_group_koff = x_shared ? 0 : K; }
     p.slabs_total = (n + 63) / 64;
-    p.n_acc = 1; p.acc_a_off[0] = 0; p.acc_a_lbo[0] = 8192;
-    p.acc_base0[0] = 0; p.acc_base1[0] = 64LL * K;
-    p.m_stride = K; p.n_stride = 1; p.unit_m_off = 128LL * K; p.unit_n_off = 256;
+    p.n_acc = MC;
+    for (int g = 0; g < MC; ++g) {
+        p.acc_a_off[g] = g * 2 * 8192; p.acc_a_lbo[g] = 8192;
+        p.acc_base0[g] = (long long)g * 128 * K; p.acc_base1[g] = (long long)g * 128 * K + 64LL * K;
+    }
+    p.m_stride = K; p.n_stride = 1; p.unit_m_off = 128LL * MC * K; p.unit_n_off = 256;
     p.n_cols_total = K; p.n_unit_cols = 256;
     int splits = (2 * sm_count()) / p.units; if (splits < 1) splits = 1;
     if (splits > p.slabs_total) splits = p.slabs_total;

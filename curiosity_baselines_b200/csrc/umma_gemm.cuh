@@ -82,10 +82,13 @@ struct GemmConfig {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
     static constexpr int ACC_COLS = MT * BN;                       // one accumulator stage
-    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
-                                     : 2 * ACC_COLS <= 256 ? 256 : 512;   // allocation: power of two
+    // two accumulator stages (epilogue of tile i under the MMAs of tile i+1) when they fit; a 256x256 tile fills
+    // all 512 TMEM columns and runs single-buffered (its MMAs last ~50k cycles, the drain ~2k)
+    static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+    static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS <= 32 ? 32 : ACC_STAGES * ACC_COLS <= 64 ? 64
+                                     : ACC_STAGES * ACC_COLS <= 128 ? 128 : ACC_STAGES * ACC_COLS <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + kBiasSmemFloats * 4;
-    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-byte aligned for SWIZZLE_128B");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 };
@@ -423,7 +426,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 mma_commit(tfull_bar(acc));                   // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -444,7 +447,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
