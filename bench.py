@@ -354,13 +354,18 @@ def main():
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / reps
     kern_tflops = 2.0 * 512 * 64 * 81 * n / (kern_ms * 1e-3) / 1e12
+    # algorithmic bytes of this kernel: a1 read once (400 positions x 32 ch bf16) + a2 written once (81 x 64 bf16)
+    alg_bytes = float(n) * (400 * 64 + 81 * 128)
+    kern_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
     if os.path.exists(tpath) and n == 131072:      # dram__bytes_read+write of this kernel at this size (ncu --set full)
         traffic = json.load(open(tpath))["conv2_fwd_window_n131072"]["dram_bytes_per_launch"]
-    roofline = {"bound": "tensor", "kernel": "conv2 forward (32->64, k4 s2) window implicit GEMM (umma_window_conv_kernel<64>)",
-                "achieved": kern_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": kern_tflops / tf_burst,
-                "traffic": traffic, "peak_source": f"{src} bf16 burst", "kernel_ms": kern_ms,
+    # 148 FLOP/byte is below the ridge (~206): the binding roofline of this layer is HBM, not the tensor pipe
+    roofline = {"bound": "hbm", "kernel": "conv2 forward (32->64, k4 s2) window implicit GEMM (umma_window_conv_kernel<64>)",
+                "achieved": kern_gbs, "peak": hbm, "unit": "GB/s", "frac": kern_gbs / hbm,
+                "traffic": traffic, "peak_source": f"{src} HBM copy bandwidth", "kernel_ms": kern_ms,
+                "algorithmic_bytes": alg_bytes, "tensor_tflops": kern_tflops, "tensor_frac_of_burst": kern_tflops / tf_burst,
                 "step_tflops": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": FLOP_PER_SAMPLE * T * B / (ms_per_step * 1e-3) / 1e12 / tf_sust}
 

@@ -696,13 +696,13 @@ constexpr int kWgMaxStages = 4;
 
 struct WgGeo { int dy_rows, dy_bytes, img_bytes, stage_bytes, ksteps; };
 
-__host__ __device__ inline WgGeo wg_geo(int h, int w) {
+__host__ __device__ inline WgGeo wg_geo(int h, int w, int cpk = 1) {        // cpk: channels interleaved per block row
     WgGeo g;
     const int G = w / 4, brows = (h / 4) * G;
     g.ksteps = (brows + G + 15) / 16;
     g.dy_rows = G * (h / 4 + 3);
     g.dy_bytes = (g.dy_rows * 64 + 1023) & ~1023;
-    g.img_bytes = ((g.ksteps * 16 + 1) * 32 + 1023) & ~1023;
+    g.img_bytes = ((g.ksteps * 16 + 1) * 32 * cpk + 1023) & ~1023;
     g.stage_bytes = g.dy_bytes + g.img_bytes;
     return g;
 }
@@ -712,13 +712,19 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32
     return (d & ~((uint64_t)7 << 61)) | ((uint64_t)layout << 61);
 }
 
+// CPK = 4: the four channels of a stack interleaved in 128-byte block rows (SWIZZLE_128B); one N = 128 MMA per 16
+// block rows then covers all channels and both window columns, and a pipeline unit is a whole sample.
+template <int CPK>
 __global__ void __launch_bounds__(kWgThreads, 1)
 umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Params p) {
+    using PK = Pack<CPK>;
+    constexpr int RB = PK::RB;
+    const int ups = p.cin / CPK;                               // pipeline units per sample
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - umma::smem_u32(smem_raw));
     const int bwc = p.w / 4;
-    const WgGeo geo = wg_geo(p.h, p.w);
+    const WgGeo geo = wg_geo(p.h, p.w, CPK);
     // layout: [stages: dyP | image] [mean|rstd table] [raw ring] [barriers]
     const uint32_t t_off = (uint32_t)(p.stages * geo.stage_bytes);
     const uint32_t t_bytes = p.mean ? (uint32_t)((p.h * p.w * 8 + 1023) & ~1023) : 0u;
@@ -777,34 +783,37 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         for (int i = 0; i < kMaxGroups; ++i) {
             const int g = tid + i * kWgConvThreads, y = g / bwc, x4 = g - y * bwc;
             gidx[i] = g < groups ? g : -1;
-            soff[i] = swz32((uint32_t)(((y >> 2) * bwc + x4) * 32 + (y & 3) * 8));
+            soff[i] = (uint32_t)(((y >> 2) * bwc + x4) * RB + (y & 3) * 8);       // + 32*channel, then swizzled
         }
         for (int s = blockIdx.x; s < p.n; s += gridDim.x)
-            for (int c = 0; c < p.cin; ++c) {
-                umma::mbar_wait(rfull_bar(rslot), rphase);
-                umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
+            for (int u = 0; u < ups; ++u) {
                 uint8_t* A = gen + stage * geo.stage_bytes + geo.dy_bytes;
+#pragma unroll 1
+                for (int cc = 0; cc < CPK; ++cc) {
+                    umma::mbar_wait(rfull_bar(rslot), rphase);
+                    if (cc == 0) umma::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
 #pragma unroll
-                for (int i = 0; i < kMaxGroups; ++i) {
-                    const int g = gidx[i];
-                    if (g >= 0) {
-                        const uint32_t px = raw[g];
-                        float v[4];
-                        u8x4_to_f32(px, v);
-                        if (p.mean) {
-                            const float4 m = s_mean[g], r = s_rstd[g];
-                            v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
-                            v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
-                            v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
-                            v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                    for (int i = 0; i < kMaxGroups; ++i) {
+                        const int g = gidx[i];
+                        if (g >= 0) {
+                            const uint32_t px = raw[g];
+                            float v[4];
+                            u8x4_to_f32(px, v);
+                            if (p.mean) {
+                                const float4 m = s_mean[g], r = s_rstd[g];
+                                v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
+                                v[1] = fminf(fmaxf((v[1] - m.y) * r.y, -5.f), 5.f);
+                                v[2] = fminf(fmaxf((v[2] - m.z) * r.z, -5.f), 5.f);
+                                v[3] = fminf(fmaxf((v[3] - m.w) * r.w, -5.f), 5.f);
+                            }
+                            *reinterpret_cast<uint2*>(A + PK::swz(soff[i] + cc * 32)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                         }
-                        *reinterpret_cast<uint2*>(A + soff[i]) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                     }
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
+                    if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 }
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
-                if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(full_bar(stage));
@@ -828,7 +837,7 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int s = blockIdx.x; s < p.n; s += gridDim.x)
-                for (int c = 0; c < p.cin; ++c) {
+                for (int u = 0; u < ups; ++u) {
                     umma::mbar_wait(empty_bar(stage), phase ^ 1u);
                     umma::mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(geo.dy_rows * 64));
                     umma::tma_load_4d(smem_base + stage * geo.stage_bytes, &tmDy, full_bar(stage), 0, 0, -1, s);
@@ -840,23 +849,23 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         const bool leader = umma::elect_one();
         int stage = 0; uint32_t phase = 0;
         uint32_t seen = 0;
-        constexpr uint32_t idesc = umma::make_idesc(64, 32, 1, 1);
+        constexpr uint32_t idesc = umma::make_idesc(64, 32 * CPK, 1, 1);
         constexpr uint32_t idesc_b = umma::make_idesc(64, 16, 1, 1);
         for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
-            for (int c = 0; c < p.cin; ++c) {
+            for (int u = 0; u < ups; ++u) {
                 umma::mbar_wait(full_bar(stage), phase);
                 umma::fence_after_thread_sync();
                 const uint32_t st = smem_base + stage * geo.stage_bytes;
                 const uint64_t da0 = desc_mn(st, (uint32_t)(bwc * 64), 512, 4);              // SWIZZLE_64B, windows G rows apart
-                const uint64_t db0 = desc_mn(st + geo.dy_bytes, 32, 256, 6);                 // SWIZZLE_32B, windows 1 row apart
-                const uint32_t first = (seen >> c) & 1u;
+                const uint64_t db0 = desc_mn(st + geo.dy_bytes, RB, PK::SBO, PK::LAYOUT);     // windows 1 row apart
                 const uint64_t d1 = desc_mn(smem_base + ones_off, 32, 256, 6);
+                const uint32_t first = (seen >> u) & 1u;
                 if (leader) {
 #pragma unroll 4
                     for (int k = 0; k < geo.ksteps; ++k)
-                        umma::mma_f16_ss(tmem_base + (uint32_t)(c * 32), da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * 32), idesc,
+                        umma::mma_f16_ss(tmem_base + (uint32_t)(u * 32 * CPK), da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * RB), idesc,
                                          (first | (uint32_t)k) ? 1u : 0u);
-                    if (c == 0 && p.dbias) {     // column sums of dy (bias gradient): the same A windows times a block of ones
+                    if (u == 0 && p.dbias) {     // column sums of dy (bias gradient): the same A windows times a block of ones
 #pragma unroll 4
                         for (int k = 0; k < geo.ksteps; ++k)
                             umma::mma_f16_ss(tmem_base + (uint32_t)(p.cin * 32), da0 + (uint64_t)(k * 64), d1, idesc_b,
@@ -865,7 +874,7 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                     umma::mma_commit(empty_bar(stage));
                 }
                 __syncwarp();
-                seen |= 1u << c;
+                seen |= 1u << u;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -878,17 +887,18 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
         umma::mbar_wait(done_bar, 0);
         umma::fence_after_thread_sync();
         const int K = p.cin * 64;
-        for (int c = 0; c < p.cin; ++c) {
+        for (int cb = 0; cb < p.cin; ++cb) {               // 32 accumulator columns at a time: col = u*32*CPK + (i, cc, e)
             uint32_t raw[32];
-            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), raw);
+            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), raw);
             umma::tmem_ld_wait();
             if (lane < 16) {
                 const int i = quarter * 16 + lane, j = i >> 5, n = i & 31, bh = 1 - j;
 #pragma unroll
-                for (int col = 0; col < 32; ++col) {
-                    const int bw = col >> 4, e = col & 15;
-                    const int kh = 4 * bh + (e >> 2), kw = 4 * bw + (e & 3);
-                    atomicAdd(p.dw + (long long)n * K + c * 64 + kh * 8 + kw, __uint_as_float(raw[col]));
+                for (int q = 0; q < 32; ++q) {
+                    const int col = cb * 32 + q, u = col / (32 * CPK), rem = col - u * 32 * CPK;
+                    const int bw = rem / (16 * CPK), cc = (rem / 16) % CPK, e = rem & 15;
+                    const int c = u * CPK + cc, kh = 4 * bh + (e >> 2), kw = 4 * bw + (e & 3);
+                    atomicAdd(p.dw + (long long)n * K + c * 64 + kh * 8 + kw, __uint_as_float(raw[q]));
                 }
             }
         }
@@ -911,11 +921,32 @@ bool s2d_wgrad_ok(const cb_conv_desc* d) {
            d->out_h == d->in_h / 4 - 1 && d->out_w == G - 1;
 }
 
+template <int CPK>
+int launch_s2d_wgrad_t(const CUtensorMap& tmDy, Conv1Params& p, int smem, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_wgrad_kernel<CPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = p.n < sms ? p.n : sms;
+    umma_conv1s_wgrad_kernel<CPK><<<grid, kWgThreads, smem, s>>>(tmDy, p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
-    const WgGeo g = wg_geo(p.h, p.w);
     const int raw_bytes = (p.h * p.w + 127) & ~127;
     const int fixed = (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 1024 + 512 + 512;
-    p.stages = (224 * 1024 - fixed - 3 * raw_bytes) / g.stage_bytes;
+    int cpk = p.cin % 4 == 0 ? 4 : 1;
+    WgGeo g;
+    for (;; cpk = 1) {         // four channels per block row when two stages of them fit
+        g = wg_geo(p.h, p.w, cpk);
+        p.stages = (224 * 1024 - fixed - (cpk + 1) * raw_bytes) / g.stage_bytes;
+        if (p.stages >= 2 || cpk == 1) break;
+    }
     if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
     CB_REQUIRE(p.stages >= 2, CB_E_ARG, "conv1 wgrad: does not fit shared memory");
     p.raw_slots = (224 * 1024 - fixed - p.stages * g.stage_bytes) / raw_bytes;
@@ -929,18 +960,7 @@ int launch_s2d_wgrad(Conv1Params& p, cudaStream_t s) {
         uint32_t box[4] = {32, (uint32_t)(p.w / 4), (uint32_t)(p.h / 4 + 3), 1};
         int rc = cb::encode_tmap_bf16(&tmDy, p.dy, 4, dims, strides, box, 2); if (rc) return rc;
     }
-    static bool attr = false;
-    if (!attr) {
-        CB_CUDA(cudaFuncSetAttribute(umma_conv1s_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = p.n < sms ? p.n : sms;
-    umma_conv1s_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmDy, p);
-    CB_LAUNCH_CHECK();
-    return CB_OK;
+    return cpk == 4 ? launch_s2d_wgrad_t<4>(tmDy, p, smem, s) : launch_s2d_wgrad_t<1>(tmDy, p, smem, s);
 }
 
 bool s2d_ok(const cb_conv_desc* d) {      // block grid must fit four M tiles plus the largest tap shift

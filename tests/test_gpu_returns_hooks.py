@@ -98,3 +98,26 @@ def test_hooks_icm_index_actions():
     inv, fwd = hooks.curiosity_loss(agent, "icm", obs, nxt, idx, torch.ones(T, B))
     (inv + fwd).backward()
     assert inv.device.type == "cpu" and m.encoder.model[0].weight.grad is not None
+
+
+def test_frame_stager_double_buffering():
+    """agents/hooks.FrameStager: the newest frame of every pinned stack (and the batch's small tensors) arrive
+    on the device for successive batches, buffers alternating, while earlier batches are still in use."""
+    from curiosity_baselines_b200.agents.hooks import FrameStager
+    T, B = 5, 3
+    st = FrameStager("cuda")
+    batches = [torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    extras = [[torch.randn(T, B).pin_memory(), torch.randn(B).pin_memory()] for _ in range(4)]
+    st.prefetch(batches[0], extras[0])
+    kept = []
+    for i in range(4):
+        buf = st.get()
+        ex = st.get_extras()
+        kept.append((buf.clone(), [e.clone() for e in ex]))
+        st.done()
+        if i + 1 < 4:
+            st.prefetch(batches[i + 1], extras[i + 1])
+    torch.cuda.synchronize()
+    for i, (buf, ex) in enumerate(kept):
+        assert torch.equal(buf.cpu(), batches[i][:, :, -1:])
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(ex, extras[i]))
