@@ -47,19 +47,28 @@ __global__ void obs_moments_kernel(const uint8_t* __restrict__ frames, int64_t f
     uint32_t s[16], q[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { s[i] = 0; q[i] = 0; }
-    for (int64_t f = f0; f < f1; ++f) {
-        int t = (int)(f / B), b = (int)(f % B);
-        if (t >= __ldg(n_valid + b)) continue;             // block-uniform branch
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(frames + f * frame_stride) + col);
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // four frames per trip: their 16-byte loads are all in flight before the first is consumed
+    for (int64_t f = f0; f < f1; f += 4) {
+        uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int u = 0; u < 4; ++u) {
+            const int64_t ff = f + u;
+            bool live = ff < f1;
+            if (live) { const int t = (int)(ff / B), b = (int)(ff % B); live = t < __ldg(n_valid + b); }   // block-uniform
+            v[u] = live ? __ldg(reinterpret_cast<const uint4*>(frames + ff * frame_stride) + col) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t p = (w[j] >> (8 * k)) & 0xffu;
-                s[j * 4 + k] += p;
-                q[j * 4 + k] += p * p;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t p = (w[j] >> (8 * k)) & 0xffu;
+                    s[j * 4 + k] += p;
+                    q[j * 4 + k] += p * p;
+                }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
