@@ -206,6 +206,53 @@ def other_model(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def ndigo_model(args, rank, world, local):
+    """BASELINE configs[4]: NDIGO on PyColab-shaped 3x5x5 binary frames, A=5, horizon 3, 10 predictors -- the
+    small-tensor regime (0.8 MFLOP per sample): bonus (no grad) + loss forward/backward + Adam.  The GRU is
+    torch.nn.GRU (cuDNN) for now, so this line is a measurement, not a roofline claim."""
+    from curiosity_baselines_b200 import _lib as L
+    from curiosity_baselines_b200.curiosity.ndigo import NDIGO
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    T, B, A = args.T, args.B, args.A or 5
+    torch.manual_seed(0)
+    model = NDIGO(image_shape=(3, 5, 5), action_size=A, horizon=3, feature_encoding="idf_maze", num_predictors=10).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    obs = (torch.rand(T, B, 3, 5, 5, device=dev, generator=g) < 0.3).float()
+    one = lambda: torch.nn.functional.one_hot(torch.randint(0, A, (T, B), device=dev, generator=g), A).float()
+    prev, act, valid = one(), one(), torch.ones(T, B, device=dev)
+
+    def one_step():
+        r_int = model.compute_bonus(obs, prev, act)
+        opt.zero_grad(set_to_none=True)
+        loss = model.compute_loss(obs, prev, act, valid)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss, r_int
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    l0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss, r_int = one_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "intrinsic-reward samples/sec (bonus+update)", "value": T * B / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ndigo bonus+update, T={T}, B={B}, 3x5x5 binary frames, A={A}, horizon 3, 10 predictors",
+                       "note": "GRU = torch.nn.GRU (cuDNN); encoder / predictors / BCE in libcuriosity_b200"},
+            "gpu_launches": L.launch_count() - l0, "e2e": None, "roofline": None, "cpu_baseline": None, "loss": float(loss)}))
+
+
 # ------------------------------------------------------------------------------ B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -217,7 +264,7 @@ def main():
     ap.add_argument("--B", type=int, default=1024, help="env columns per GPU (weak scaling)")
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement"],
+    ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement", "ndigo"],
                     help="rnd = BASELINE configs[1] (the headline line); icm / disagreement: the same unit of work "
                          "for the other two conv curiosity models (device-resident inputs only)")
     ap.add_argument("--A", type=int, default=None, help="number of discrete actions (icm: 4, disagreement: 7)")
@@ -243,6 +290,8 @@ def main():
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    if args.model == "ndigo":
+        return ndigo_model(args, rank, world, local)
     if args.model != "rnd":
         return other_model(args, rank, world, local)
     import torch.distributed as dist

@@ -294,3 +294,31 @@ def test_linear_side_as_kblock(A, n, use_res):
     assert rel(yf, ref) < 2e-5
     _, y_epi = layer.forward(x.to(torch.bfloat16), n, side=side, residual=resb, out_f32=True)
     assert rel(yf, y_epi) < 5e-3
+
+
+@pytest.mark.parametrize("n,act", [(80001, "relu"), (131072 + 77, "none")])
+def test_linear_big_tiles(n, act):
+    """Above 2*148*256 rows the Linear layers switch to 256x256 tiles with a single-buffered TMEM accumulator
+    (umma_gemm_kernel<256, 2>); ragged last tile included.  Forward, fp32 output, dgrad and the two-accumulator
+    row weight gradient (K >= 1024) against fp32 matmuls on the same bf16 operands."""
+    torch.manual_seed(3)
+    lin = nn.Linear(512, 512).to(DEV)
+    layer = LY.linear_layer(lin, act)
+    x = bf(torch.randn(n, 512, device=DEV))
+    xb = x.to(torch.bfloat16)
+    yb, yf = layer.forward(xb, n, out_f32=True)
+    ref = x @ bf(lin.weight.detach()).t() + lin.bias
+    ref = F.relu(ref) if act == "relu" else ref
+    assert rel(yf, ref) < 2e-5
+    assert rel(yb, ref) < 5e-3
+    dy = bf(torch.randn(n, 512, device=DEV))
+    dx = layer.dgrad(dy.to(torch.bfloat16), n, x_saved=xb, x_act="lrelu")
+    ref_dx = (dy @ bf(lin.weight.detach())) * torch.where(x > 0, 1.0, 0.01)
+    assert rel(dx, ref_dx) < 5e-3
+    fc = nn.Linear(1024, 512).to(DEV)
+    lfc = LY.linear_layer(fc, "none")
+    x2 = bf(torch.randn(n, 1024, device=DEV))
+    lfc.wgrad(x2.to(torch.bfloat16), dy.to(torch.bfloat16), n)
+    torch.cuda.synchronize()
+    assert rel(fc.weight.grad, dy.t() @ x2) < 2e-4
+    assert rel(fc.bias.grad, dy.sum(0)) < 2e-4
