@@ -313,7 +313,7 @@ bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
     if (!device_ok() || !dense_nhwc(d) || e->norm_mean) return false;
     int mt;
     if (!pick_bn(d->out_c, &mt)) return false;
-    if (e->side_dim > 16) return false;
+    if (e->side_dim > 16 && !e->side_bf16) return false;      // the epilogue path keeps at most 16 side inputs in registers
     Geo g = fwd_geo(d);
     View v = classify(g);
     if (v == VIEW_NONE) return false;

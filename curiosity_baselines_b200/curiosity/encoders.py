@@ -6,7 +6,8 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from ..layers import Chain, conv_layer, linear_layer
+from .. import layers as LY
+from ..layers import Chain, DenseConvLayer, conv_layer, linear_layer
 
 
 class BurdaHead(nn.Module):
@@ -82,6 +83,13 @@ class MazeHead(nn.Module):
     def build_chain(self, trainable=True, last_act="relu"):
         c, h, w = self.image_shape
         m = self.model
+        if LY.get_engine() != L.ENGINE_SIMT and h * w * c <= 1024:
+            # tiny grid: both convolutions as dense (block-Toeplitz) Linear layers on the tcgen05 GEMM
+            l1 = DenseConvLayer(m[0], (h, w, c), "relu", trainable)
+            l2 = DenseConvLayer(m[2], (l1.conv_out_h, l1.conv_out_w, 16), "relu", trainable, in_features=l1.out_c)
+            assert l2.conv_out_h == l2.conv_out_w and l2.real_out == self.conv_output_size and l2.out_c == l2.real_out
+            fc = linear_layer(m[5], "relu", spatial=(l2.conv_out_h, 16), trainable=trainable)
+            return Chain([l1, l2, fc]), None
         l1 = conv_layer(m[0], (h, w, c), "relu", trainable)
         l2 = conv_layer(m[2], (l1.out_h, l1.out_w, 16), "relu", trainable)
         assert l2.out_h == l2.out_w and l2.out_h * l2.out_w * 16 == self.conv_output_size
@@ -106,8 +114,8 @@ def frame_input(obs):
         raise L.CuriosityLibError("observations must be on a CUDA device (no CPU fallback)")
     obs = obs.contiguous()
     n, c, h, w = obs.shape
-    if obs.dtype == torch.uint8:
+    if obs.dtype == torch.uint8 and c * h * w > 1024:
         return obs, obs.data_ptr(), L.U8, (c * h * w, w, 1, h * w)
-    # float observations (PyColab {0,1} masks): stage once as bf16 NHWC (exact for small integers)
+    # float observations (PyColab {0,1} masks) and tiny uint8 grids: stage once as bf16 NHWC (exact for integers <= 256)
     x = obs.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
     return x, x, L.BF16, None

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from ..layers import linear_layer
+from ..layers import linear_layer, pad_side
 from .encoders import make_encoder, frame_input
 
 
@@ -60,7 +60,7 @@ class _PredictorFn(torch.autograd.Function):
         n = belief.shape[0]
         xb = belief.to(torch.bfloat16).contiguous()
         window = window.contiguous()
-        h, _ = l1.forward(xb, n, side=window)
+        h, _ = l1.forward(xb, n, side=window, side_pad=pad_side(window) if window.shape[1] <= 64 else None)
         _, logits = l2.forward(h, n, out_bf16=False, out_f32=True)
         ctx.layers, ctx.saved, ctx.params = layers, (xb, window, h, n), params
         return logits

@@ -234,6 +234,94 @@ class GemmLayer:
             w.grad[:, : self.K].copy_(dw)
             w.grad[:, self.K:].copy_(dsw)
 
+class DenseConvLayer(GemmLayer):
+    """A convolution on a tiny fixed grid (PyColab 5x5 mazes, encoders.py:37-66) run as ONE dense Linear over the
+    flattened NHWC map: the conv weight is expanded into its block-Toeplitz matrix
+    [round_up(oh*ow*oc, 128), round_up(ih*iw*ic, 8)], so these 3- and 16-channel layers run on the tcgen05 GEMM
+    (2.8x redundant MACs on ~0.1 MFLOP per sample) instead of the SIMT engine.  Gradients of the expanded matrix
+    are folded back onto the conv weight with one index_add_."""
+
+    def __init__(self, module, in_shape, act="none", trainable=True, in_features=None):
+        h, w, c = in_shape
+        k, s, pd = module.kernel_size[0], module.stride[0], module.padding[0]
+        oc = module.out_channels
+        oh, ow = (h + 2 * pd - k) // s + 1, (w + 2 * pd - k) // s + 1
+        self.real_in, self.real_out = h * w * c, oh * ow * oc
+        k_in = in_features if in_features is not None else (self.real_in + 7) // 8 * 8
+        n_out = (self.real_out + 127) // 128 * 128
+        super().__init__(module, (1, 1, k_in), 1, 1, 0, n_out, act, 0, trainable)
+        self.conv_out_h, self.conv_out_w, self.conv_out_c = oh, ow, oc    # geometry seen by the next layer
+        rows, cols, src = [], [], []
+        for oy in range(oh):
+            for ox in range(ow):
+                for ky in range(k):
+                    for kx in range(k):
+                        iy, ix = oy * s + ky - pd, ox * s + kx - pd
+                        if 0 <= iy < h and 0 <= ix < w:
+                            for o in range(oc):
+                                for i in range(c):
+                                    rows.append((oy * ow + ox) * oc + o)
+                                    cols.append((iy * w + ix) * c + i)
+                                    src.append(((o * c + i) * k + ky) * k + kx)
+        self._flat = torch.tensor(rows, dtype=torch.int64) * k_in + torch.tensor(cols, dtype=torch.int64)
+        self._src = torch.tensor(src, dtype=torch.int64)
+        self._brow = torch.arange(self.real_out, dtype=torch.int64) % oc          # conv output channel of each dense row
+        self._dense_w = self._dense_b = None
+
+    def prepare(self, force=False):
+        w, b = self.module.weight, self.module.bias
+        ver = (w._version, w.data_ptr(), b._version)
+        if not force and ver == self._version:
+            return
+        dev = w.device
+        if self._flat.device != dev:
+            self._flat, self._src, self._brow = self._flat.to(dev), self._src.to(dev), self._brow.to(dev)
+        dense = torch.zeros(self.out_c * self.K, dtype=torch.float32, device=dev)
+        dense[self._flat] = w.detach().reshape(-1)[self._src]
+        dense = dense.view(self.out_c, self.K)
+        if self.w_fwd is None:
+            self.w_fwd = torch.empty(self.out_c, self.K, dtype=torch.bfloat16, device=dev)
+            self.w_t = torch.empty(self.K, self.out_c, dtype=torch.bfloat16, device=dev)
+        L.call("cb_prepare_conv_weight", L.ptr(dense), L.ptr(self.w_fwd), L.ptr(self.w_t), self.out_c, self.K, 1, 1,
+               L.stream())
+        bias = torch.zeros(self.out_c, dtype=torch.float32, device=dev)
+        bias[: self.real_out] = b.detach()[self._brow]
+        self.bias, self.side_w, self.w_ext = bias, None, None
+        self._dense_w = dense                      # keeps the fp32 source alive until the conversion kernel ran
+        self._version = ver
+
+    def _flat_input(self, x, n):
+        """bf16 NHWC map [n, h, w, c] (or already flat) -> [n, K] with zero padding columns."""
+        x = x.reshape(n, -1)
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        if x.shape[1] != self.K:
+            x = torch.nn.functional.pad(x, (0, self.K - x.shape[1]))
+        return x.contiguous()
+
+    def forward(self, x, n, in_dtype=L.BF16, strides=None, **kw):
+        kw.pop("norm", None)
+        return super().forward(self._flat_input(x, n), n, **kw)
+
+    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+        if not self.trainable:
+            return
+        self.prepare()
+        w, b = self.module.weight, self.module.bias
+        dev = dy.device
+        dw = torch.empty(self.out_c, self.K, dtype=torch.float32, device=dev)
+        db = torch.empty(self.out_c, dtype=torch.float32, device=dev)
+        d = self.desc(n)
+        L.call("cb_conv_wgrad", C.byref(d), L.ptr(self._flat_input(x, n)), L.ptr(dy), None, None, L.ptr(dw), L.ptr(db), 0.0,
+               L.stream())
+        if w.grad is None or not accumulate:
+            w.grad = torch.zeros_like(w) if w.grad is None else w.grad.zero_()
+        if b.grad is None or not accumulate:
+            b.grad = torch.zeros_like(b) if b.grad is None else b.grad.zero_()
+        w.grad.view(-1).index_add_(0, self._src, dw.view(-1)[self._flat])          # fold the Toeplitz entries
+        b.grad.index_add_(0, self._brow, db[: self.real_out])
+
+
 def pad_side(side):
     """fp32 [n, A] side input (one-hot action) -> bf16 [n, 64] zero padded: the extra k-block operand."""
     n, a = side.shape
