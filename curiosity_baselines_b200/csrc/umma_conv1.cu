@@ -458,13 +458,12 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
         const float4* s_mean = reinterpret_cast<const float4*>(gen + t_off);
         const float4* s_rstd = s_mean + p.h * p.w / 4;
         const int groups = p.h * p.w / 4;
-        // Thread -> pixel-group map, fixed for the whole kernel (computed once): item i of a thread is the 4-pixel
-        // group g = tid + i*threads of the raw frame; soff = where it lands in the s2d image.
-        uint32_t soff[kGrpMaxGroups]; int gidx[kGrpMaxGroups];
+        // Thread -> pixel-group map, fixed for the whole kernel: item i of a thread is the 4-pixel group
+        // g = tid + i*threads of the raw frame; soff = where it lands in the s2d image (computed once).
+        uint32_t soff[kGrpMaxGroups];
 #pragma unroll
         for (int i = 0; i < kGrpMaxGroups; ++i) {
             const int g = tid + i * kGrpThreads, y = g / bwc, x4 = g - y * bwc;
-            gidx[i] = g < groups ? g : -1;
             soff[i] = (uint32_t)(((y >> 2) * bwc + x4) * RB + (y & 3) * 8);          // + 32*channel, then swizzled
         }
         const bool norm = p.mean && !(p.debug & 1);
@@ -482,15 +481,26 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                 const uint32_t rphase = (uint32_t)(fr / p.raw_slots) & 1u;
                 // this frame's raw pixels: staged by the loader warp several frames ahead (HBM latency hidden)
                 umma::mbar_wait(rfull_bar(rslot), rphase);
+                // all of this thread's pixels first (14 independent shared-memory loads in flight), so the raw
+                // slot is released early and the conversion below never waits on a load
+                uint32_t px[kGrpMaxGroups];
+                {
+                    const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
+#pragma unroll
+                    for (int i = 0; i < kGrpMaxGroups; ++i) {
+                        const int g = tid + i * kGrpThreads;
+                        px[i] = g < groups ? raw[g] : 0u;
+                    }
+                }
+                __syncwarp();                                 // one arrival per warp
+                if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));
                 if (cc == 0) umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
 #pragma unroll
                 for (int i = 0; i < kGrpMaxGroups; ++i) {
-                    const int g = gidx[i];
-                    if (g >= 0) {
-                        const uint32_t px = raw[g];
+                    const int g = tid + i * kGrpThreads;
+                    if (g < groups) {
                         float v[4];
-                        u8x4_to_f32(px, v);
+                        u8x4_to_f32(px[i], v);
                         if (norm) {
                             const float4 m = s_mean[g], r = s_rstd[g];
                             v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
@@ -501,8 +511,6 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                         *reinterpret_cast<uint2*>(A + PK::swz(soff[i] + cc * 32)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                     }
                 }
-                __syncwarp();                                 // one arrival per warp: 32 lanes arriving on the same
-                if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));   // mbarrier serialise (~4 cycles each)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -791,15 +799,22 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
 #pragma unroll 1
                 for (int cc = 0; cc < CPK; ++cc) {
                     umma::mbar_wait(rfull_bar(rslot), rphase);
+                    uint32_t px[kMaxGroups];                   // all loads first: the slot is released early
+                    {
+                        const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
+#pragma unroll
+                        for (int i = 0; i < kMaxGroups; ++i) px[i] = gidx[i] >= 0 ? raw[gidx[i]] : 0u;
+                    }
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
+                    if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                     if (cc == 0) umma::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + raw_off + rslot * raw_bytes);
 #pragma unroll
                     for (int i = 0; i < kMaxGroups; ++i) {
                         const int g = gidx[i];
                         if (g >= 0) {
-                            const uint32_t px = raw[g];
                             float v[4];
-                            u8x4_to_f32(px, v);
+                            u8x4_to_f32(px[i], v);
                             if (p.mean) {
                                 const float4 m = s_mean[g], r = s_rstd[g];
                                 v[0] = fminf(fmaxf((v[0] - m.x) * r.x, -5.f), 5.f);
@@ -810,9 +825,6 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
                             *reinterpret_cast<uint2*>(A + PK::swz(soff[i] + cc * 32)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
-                    if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
