@@ -16,7 +16,6 @@
 #include <mutex>
 #include <string.h>
 #include <stdlib.h>
-#include <string.h>
 
 namespace cb {
 
@@ -324,7 +323,6 @@ bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
 int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
     CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
     if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
-    if (use_window() && window_supports_fwd(d, e)) return window_conv_fwd(d, x, w, e, s);
     Plan pl{};
     pl.bn = pick_bn(d->out_c, &pl.mt, (d->k_h == d->in_h && d->k_w == d->in_w && d->pad == 0) ? d->n : 0);
     Geo g = fwd_geo(d);
@@ -351,7 +349,6 @@ int umma_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_
 // which is a stride-1 forward over dy with the filter walked backwards; linear layers are the 1x1 case.
 bool umma_supports_dgrad(const cb_conv_desc* d) {
     if (!device_ok()) return false;
-    if (use_window() && window_supports_dgrad(d)) return true;
     if (use_window() && window_supports_dgrad(d)) return true;
     int mt;
     if (!pick_bn(d->in_c, &mt)) return false;

@@ -29,8 +29,6 @@ constexpr int kMmaWarp = kConvWarps;   // MMA issuer / TMEM owner
 constexpr int kStagePitch = 80;         // bytes per staged output row (64 + 16: conflict-free 16-byte stores)
 constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, splitting the (row tile, net) items
 constexpr int kThreads = (kConvWarps + 1 + kEpiWarps) * 32;
-constexpr int kLoadWarp = kConvWarps + 1 + kEpiWarps;   // s2d forward: raw-frame loader (cp.async.bulk ring)
-constexpr int kThreadsS2d = kThreads + 32;
 constexpr int kMaxRaw = 8;             // raw uint8 frames in flight per CTA
 constexpr int kMaxStages1 = 4;
 constexpr int kMaxCin = 4;
@@ -269,7 +267,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
         // ------------------------------------------------------------ epilogue (4 warps, one per TMEM lane quarter)
         const int quarter = warp & 3;
         const int half = (warp - kMmaWarp - 1) >> 2;          // which of the two warps sharing this quarter
-        uint8_t* stage_o = gen + o_off + (warp - kMmaWarp - 1) * (kStagePitch * 32);
         if (!WGRAD) {
             int acc = 0; uint32_t acc_phase = 0;
             for (int s = blockIdx.x; s < p.n; s += gridDim.x) {
@@ -354,11 +351,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv1_kernel(const Conv1Para
 constexpr int kS2dStageBytes = 18 * 1024;       // (4*128 + 22) rows x 32 B, rounded
 constexpr int kS2dMaxStages = 6;
 
-__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
-    uint64_t d = umma::make_smem_desc(saddr, 16, 256);
-    return (d & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);          // SWIZZLE_32B
-}
-__device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
 // Block rows may interleave CPK input channels (rows of 32*CPK bytes): SWIZZLE_32B for one channel,
 // SWIZZLE_128B for four.  Address-based XOR swizzle of such an image and the matching descriptor constants.
 template <int CPK> struct Pack {
@@ -373,9 +365,6 @@ __device__ __forceinline__ uint64_t desc_any(uint32_t saddr, uint32_t lbo, uint3
     uint64_t d = umma::make_smem_desc(saddr, lbo, sbo);
     return (d & ~((uint64_t)7 << 61)) | ((uint64_t)layout << 61);
 }
-
-constexpr int kEpiBar = 2;             // named barrier of the epilogue threads
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kEpiBar), "n"(kEpiWarps * 32) : "memory"); }
 
 // CG converter groups of four warps (alternate units) and kEW epilogue warps (a multiple of 4).
 template <int CPK, int CG, int kEW>
