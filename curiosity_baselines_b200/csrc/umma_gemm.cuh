@@ -23,12 +23,14 @@ namespace umma {
 // busy, tensor pipe 46 %); several warps per scheduler hide it.
 constexpr int kEpiWarp0 = 2;
 // SIMPLE needs few registers: 16 warps.  The epilogues with global side operands run 12 warps (3 per quarter, 128
-// registers each) and fetch those operands on demand -- they were asked from L2 by the producer when the tile's
-// slab was loaded -- instead of 8 warps with a two-deep register prefetch (167 registers).
+// registers each) and fetch those operands on demand instead of 8 warps with a two-deep register prefetch (167
+// registers): conv2 dgrad 2.41 -> 1.85 ms.  (A producer-side cp.async.bulk.prefetch.L2 of the tile's side
+// operands helped the 8-warp version but, with 12 warps, only added 2.4 GB of duplicate DRAM reads -- ncu: 7.07 GB
+// read for 4.7 GB algorithmic -- to a kernel that already runs at 80 % of HBM peak; removed.)
 template <int EPI> struct EpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 3; };
 template <int EPI> constexpr int gemm_threads() { return (kEpiWarp0 + 4 * EpiWarps<EPI>::GROUPS) * 32; }
-// The plain GEMM kernel has no such producer-side L2 prefetch (its tiles' side operands are strided blocks): its
-// full / dgrad epilogues keep 8 warps and the two-deep register prefetch.
+// The plain GEMM kernel's full / dgrad epilogues keep 8 warps and the two-deep register prefetch (its tiles' side
+// operands are strided blocks with longer exposed latency).
 template <int EPI> struct GemmEpiWarps { static constexpr int GROUPS = (EPI == 0) ? 4 : 2; };
 template <int EPI> constexpr int plain_gemm_threads() { return (kEpiWarp0 + 4 * GemmEpiWarps<EPI>::GROUPS) * 32; }
 

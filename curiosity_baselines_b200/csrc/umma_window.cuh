@@ -88,22 +88,8 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int kb = 0; kb < p.kb_count; ++kb)
                 tma_load_2d(smem_base + kb * BN * 128, &tmW, w_bar, kb * 64, 0);
             int stage = 0; uint32_t phase = 0;
-            // The epilogue's row-major side operands (saved activation, skip gradient, residual) of a tile are
-            // one contiguous range: ask L2 for it when the tile's slab is requested, `stages` tiles before the
-            // epilogue reads it, so those per-thread loads hit L2 instead of paying HBM latency.
-            const __nv_bfloat16* aux0 = p.epi.add_pre ? p.epi.add_pre : p.epi.residual;
-            const __nv_bfloat16* aux1 = p.epi.actgrad_src;
-            const long long per_sample = p.epi.shuffle ? (long long)p.epi.sh_h * p.epi.sh_w * 32
-                                                       : (long long)p.vh * p.vw * p.epi.n_total;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                if (EPI != EPI_SIMPLE && (aux0 || aux1)) {
-                    const int s0 = tile * p.S;
-                    const int ns = p.n_samples - s0 < p.S ? p.n_samples - s0 : p.S;
-                    const uint32_t bytes = (uint32_t)((ns * per_sample * 2) & ~15ll);
-                    if (aux0) prefetch_l2_bulk(aux0 + s0 * per_sample, bytes);
-                    if (aux1) prefetch_l2_bulk(aux1 + s0 * per_sample, bytes);
-                }
                 mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(p.nplanes * p.plane_rows * 128));
                 for (int pl = 0; pl < p.nplanes; ++pl) {
                     int c[5];
