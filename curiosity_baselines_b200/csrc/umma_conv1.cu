@@ -386,8 +386,12 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
     const uint32_t stage_bytes = (uint32_t)p.s2d_stage_bytes;
     const uint32_t raw_off = st_off + p.stages * stage_bytes;                 // ring of raw uint8 frames
     const uint32_t raw_bytes = (uint32_t)((p.h * p.w + 127) & ~127);
-    const uint32_t b_off = raw_off + p.raw_slots * raw_bytes;                  // biases: [net][32] fp32
-    const uint32_t bar_base = smem_base + b_off + 256u;
+    // The bias is added by the tensor cores: one more K = 16 MMA per row tile whose A block has ones in its first
+    // three elements of every row and whose B block holds bias[n] split into three bf16 terms (hi + mid + lo, exact
+    // to fp32 rounding) -- instead of 32 FADDs and 8 shared-memory loads per 32x32 block in the epilogue.
+    const uint32_t ones_off = (raw_off + p.raw_slots * raw_bytes + 1023u) & ~1023u;     // [128 rows][RB]
+    const uint32_t bblk_off = ones_off + 128u * RB;                                     // [N rows][RB]
+    const uint32_t bar_base = smem_base + bblk_off + 64u * RB;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kS2dMaxStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kS2dMaxStages + a); };
@@ -419,9 +423,23 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
             tm[g4 + i] = __ldg(reinterpret_cast<const float4*>(p.rstd) + i);
         }
     }
-    if (threadIdx.x < 64) {
-        const float* b = p.bias[threadIdx.x >> 5];
-        reinterpret_cast<float*>(gen + b_off)[threadIdx.x] = (b && (int)(threadIdx.x >> 5) < p.nets) ? __ldg(b + (threadIdx.x & 31)) : 0.f;
+    for (uint32_t i = threadIdx.x; i < (128u + 64u) * RB / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(gen + ones_off)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 128) {            // ones: elements 0..2 of every row
+        const uint32_t o = PK::swz((uint32_t)(threadIdx.x * RB));
+        *reinterpret_cast<uint2*>(gen + ones_off + o) = make_uint2(0x3f803f80u, 0x00003f80u);
+    }
+    if ((int)threadIdx.x < N && p.bias[threadIdx.x >> 5]) {
+        const float b = __ldg(p.bias[threadIdx.x >> 5] + (threadIdx.x & 31));
+        const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+        const float r1 = b - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        const uint32_t o = PK::swz((uint32_t)(threadIdx.x * RB));
+        *reinterpret_cast<uint2*>(gen + bblk_off + o) =
+            make_uint2((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                       (uint32_t)__bfloat16_as_ushort(lo));
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
@@ -532,10 +550,13 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                 const uint64_t da0 = desc_any(smem_base + st_off + stage * stage_bytes, 16, PK::SBO, PK::LAYOUT);
                 const uint64_t db0 = desc_any(smem_base + u * 4 * N * RB, 16, PK::SBO, PK::LAYOUT);
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 4 * N);
+                const uint64_t d_ones = desc_any(smem_base + ones_off, 16, PK::SBO, PK::LAYOUT);
+                const uint64_t d_bias = desc_any(smem_base + bblk_off, 16, PK::SBO, PK::LAYOUT);
                 if (leader) {
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
                         if (mt < row_tiles && !((p.debug & 16) && mt)) {
+                            if (u == 0) umma::mma_f16_ss(d0 + (uint32_t)(mt * N), d_ones, d_bias, idesc, 0u);   // D = bias
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const int shift = (t >> 1) * bwc + (t & 1);
@@ -543,7 +564,7 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                                 for (int kc = 0; kc < CPK; ++kc)     // one 16-pixel k-step per interleaved channel
                                     umma::mma_f16_ss(d0 + (uint32_t)(mt * N),
                                                      da0 + (uint64_t)((((mt * 128 + shift) * RB) >> 4) + kc * 2),
-                                                     db0 + (uint64_t)(((t * N * RB) >> 4) + kc * 2), idesc, (u | t | kc) ? 1u : 0u);
+                                                     db0 + (uint64_t)(((t * N * RB) >> 4) + kc * 2), idesc, 1u);
                             }
                         }
                     }
@@ -562,7 +583,6 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
         // block's tcgen05.ld in flight while it applies bias/activation to the current one and stores it.
         const int quarter = warp & 3;
         const int sub = (warp - kEpi0) >> 2;                   // which of the kEG warps sharing this TMEM lane quarter
-        const float* s_bias = reinterpret_cast<const float*>(gen + b_off);
         // The block-grid row of this lane in each row tile (and whether it is stored) never changes: hoisted
         // out of the sample loop so the per-block work is tcgen05.ld + bias/activation + pack + two stores.
         int out_row[4];                                  // by*ow + bx, or -1
@@ -592,23 +612,25 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                     umma::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 4 + mt) * N + net * 32), raw);
                     umma::tmem_ld_wait();
                     if (out_row[mt] < 0 || (p.debug & 2)) continue;
-                    float v[32];
-                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + net * 32);
+                    // accumulator = conv + bias already; LeakyReLU / ReLU on packed bf16 pairs (half the instructions of
+                    // the fp32 form; the negative branch is rounded twice, 2^-9 relative on values scaled by 0.01)
+                    uint32_t pk[16];
+                    if (act == CB_ACT_ELU) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = b4[q];
-                        v[q * 4] = __uint_as_float(raw[q * 4]) + b.x; v[q * 4 + 1] = __uint_as_float(raw[q * 4 + 1]) + b.y;
-                        v[q * 4 + 2] = __uint_as_float(raw[q * 4 + 2]) + b.z; v[q * 4 + 3] = __uint_as_float(raw[q * 4 + 3]) + b.w;
-                    }
-                    if (act == CB_ACT_LRELU) {
+                        for (int e = 0; e < 16; ++e) {
+                            float a = __uint_as_float(raw[2 * e]), b = __uint_as_float(raw[2 * e + 1]);
+                            a = a > 0.f ? a : expm1f(a); b = b > 0.f ? b : expm1f(b);
+                            pk[e] = pack2(a, b);
+                        }
+                    } else {
+                        const __nv_bfloat162 slope = __floats2bfloat162_rn(0.01f, 0.01f), zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.01f * v[j]);
-                    } else if (act == CB_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (act == CB_ACT_ELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                        for (int e = 0; e < 16; ++e) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]));
+                            if (act == CB_ACT_LRELU) h = __hmax2(h, __hmul2(h, slope));
+                            else if (act == CB_ACT_RELU) h = __hmax2(h, zero);
+                            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                        }
                     }
                     // this lane owns one 64-byte NHWC output row: two full-sector 32-byte stores
                     __nv_bfloat16* o = (net ? p.out[1] : p.out[0]) + (obase + out_row[mt]) * 32;
@@ -616,7 +638,7 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                     for (int q = 0; q < 2; ++q) {
                         umma::U256 u;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) u.w[e] = pack2(v[q * 16 + e * 2], v[q * 16 + e * 2 + 1]);
+                        for (int e = 0; e < 8; ++e) u.w[e] = pk[q * 8 + e];
                         umma::st_global_256(o + q * 16, u);
                     }
                 }
@@ -652,7 +674,7 @@ int launch_s2d_fwd(Conv1Params& p, cudaStream_t s) {
     const int N = 32 * p.nets;
     const int raw_bytes = (p.h * p.w + 127) & ~127;
     const int bwc = p.w / 4, row_tiles = ((p.h / 4) * bwc + 127) / 128;
-    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 256 + 512;
+    const int fixed = p.cin * 4 * N * 32 + (p.mean ? ((p.h * p.w * 8 + 1023) & ~1023) : 0) + 1024 + 1024 + 192 * 128 + 512;
     // four channels interleaved per block row when they fit (128-byte rows feed the MMA far better than 32-byte ones)
     int cpk = p.cin % 4 == 0 ? 4 : 1;
     for (;; cpk = 1) {
