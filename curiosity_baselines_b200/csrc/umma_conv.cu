@@ -561,11 +561,17 @@ template <int BN, int EPI>
 int launch_window_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CB_EPI_DEBUG"); dbg = e ? atoi(e) : 0; } p.epi.debug = dbg; }
     const int w_bytes = p.kb_count * BN * 128;
-    int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 1024;
+    // forward-simple epilogue: let the tensor cores add the bias when its operand blocks (4 KB + BN*32 B) fit
+    int extra = 0;
+    if (EPI == umma::EPI_SIMPLE && p.epi.bias && kSmemBudget - w_bytes - p.slack_bytes - 2048 - 4096 - BN * 32 >= 2 * p.stage_bytes) {
+        p.epi.bias_in_acc = 1;
+        extra = 4096 + BN * 32;
+    }
+    int avail = kSmemBudget - w_bytes - p.slack_bytes - 1024 - 1024 - extra;
     p.stages = avail / p.stage_bytes;
     if (p.stages > umma::kMaxStages) p.stages = umma::kMaxStages;
     CB_REQUIRE(p.stages >= 2, CB_E_ARG, "window conv: slab does not fit shared memory (stage %d B)", p.stage_bytes);
-    const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 1024;     // + barriers + bias[BN]
+    const int smem = w_bytes + p.stages * p.stage_bytes + p.slack_bytes + 1024 + 1024 + extra;   // + barriers + bias[BN] (+ bias blocks)
     static bool attr = false;
     if (!attr) {
         CB_CUDA(cudaFuncSetAttribute(umma::umma_window_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,

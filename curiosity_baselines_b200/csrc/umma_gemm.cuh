@@ -58,6 +58,9 @@ struct GemmParams {
     // torch.cat([x, action]) of icm.py:19-21 done by the tensor cores instead of 32*side_dim FMAs per
     // output chunk in the epilogue.
     int side_kb;
+    // forward-simple epilogue only: the bias was already added by the tensor cores (an extra K = 16 MMA of a ones
+    // block against a hi/mid/lo bf16 split of the bias), so the epilogue is activation + pack + store
+    int bias_in_acc;
     int rows_per_tile;     // valid rows of each tile (<= MT*128)
     long long m_total;     // total output rows
     int n_total;           // total output columns (row stride of all row-major operands below)
@@ -190,10 +193,31 @@ enum { EPI_SIMPLE = 0, EPI_FULL = 1, EPI_DGRAD = 2 };
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* bias, const uint32_t (&raw)[32],
                                                long long co, int n0, const float (&sv)[16], const AuxRegs& aux) {
+    if (EPI == EPI_SIMPLE && p.bias_in_acc && p.act != CB_ACT_ELU) {
+        // accumulator = conv + bias: activation on packed bf16 pairs (the negative LeakyReLU branch is rounded twice,
+        // 2^-9 relative on values scaled by 0.01), then two 32-byte stores
+        const __nv_bfloat162 slope = __floats2bfloat162_rn(0.01f, 0.01f), zero = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]));
+            if (p.act == CB_ACT_LRELU) h = __hmax2(h, __hmul2(h, slope));
+            else if (p.act == CB_ACT_RELU) h = __hmax2(h, zero);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            U256 u;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u.w[e] = pk[q * 8 + e];
+            st_global_256(p.out_bf16 + co + q * 16, u);
+        }
+        return;
+    }
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-    if (EPI != EPI_DGRAD && bias) {          // `bias` points at the shared-memory copy when it fits
+    if (EPI != EPI_DGRAD && bias && !(EPI == EPI_SIMPLE && p.bias_in_acc)) {   // `bias`: the shared-memory copy when it fits
         const float4* bsrc = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {

@@ -61,6 +61,28 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* bias = stage_bias(p.epi, gen_base + (bar_base + 256u - smem_base));
+    // bias-by-MMA operands (SWIZZLE_32B, rows of 32 B): ones [128 rows], bias split [BN rows]
+    const uint32_t ones_base = bar_base + 2048u;
+    const uint32_t bblk_base = ones_base + 4096u;
+    if (EPI == EPI_SIMPLE && p.epi.bias_in_acc) {
+        uint8_t* ob = gen_base + (ones_base - smem_base);
+        for (uint32_t i = threadIdx.x; i < (4096u + BN * 32u) / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(ob)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        auto swz32 = [](uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); };
+        if (threadIdx.x < 128)
+            *reinterpret_cast<uint2*>(ob + swz32(threadIdx.x * 32u)) = make_uint2(0x3f803f80u, 0x00003f80u);
+        if ((int)threadIdx.x < BN) {
+            const float b = __ldg(p.epi.bias + threadIdx.x);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const float r1 = b - __bfloat162float(hi);
+            const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+            *reinterpret_cast<uint2*>(ob + 4096u + swz32(threadIdx.x * 32u)) =
+                make_uint2((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                           (uint32_t)__bfloat16_as_ushort(lo));
+        }
+    }
     // one-time zero of the slab area: rows a shifted window reads past a slab are then always finite
     {
         uint4* z = reinterpret_cast<uint4*>(gen_base + w_bytes);
@@ -114,7 +136,16 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             fence_after_thread_sync();
             const uint64_t da0 = make_smem_desc(a_base + stage * p.stage_bytes, 16, 1024);
             const uint64_t db0 = make_smem_desc(smem_base, 16, 1024);
+            const bool bias_mma = EPI == EPI_SIMPLE && p.epi.bias_in_acc;
+            // SWIZZLE_32B descriptors (layout code 6) of the ones / bias blocks
+            const uint64_t d_ones = (make_smem_desc(ones_base, 16, 256) & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);
+            const uint64_t d_bias = (make_smem_desc(bblk_base, 16, 256) & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);
             if (leader) {
+                if (bias_mma) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        mma_f16_ss(tmem_base + (uint32_t)((acc * MT + mt) * BN), d_ones, d_bias, idesc, 0u);     // D = bias
+                }
                 for (int kb = 0; kb < p.kb_count; ++kb) {
                     const uint64_t da = da0 + (uint64_t)p.kb_off16[kb];
                     const uint64_t db = db0 + (uint64_t)(kb * BN * 8);
@@ -124,7 +155,7 @@ umma_window_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             mma_f16_ss(d_tmem, da + (uint64_t)(mt * 1024 + k * 2), db + (uint64_t)(k * 2), idesc,
-                                       (kb | k) ? 1u : 0u);
+                                       (bias_mma || (kb | k)) ? 1u : 0u);
                     }
                 }
                 mma_commit(empty_bar(stage));
