@@ -230,6 +230,42 @@ __global__ void side_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const fl
     }
 }
 
+// Same product with each thread owning 8 consecutive output columns (one 16-byte load per row) and 8 side columns
+// at a time in registers: dy is read once per 8 side inputs instead of once per side input, with 2-byte loads.
+// block = (cgs column groups) x (256 / cgs row lanes); grid = (row blocks, column-group blocks, side chunks of 8).
+__global__ void side_wgrad_vec_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ side,
+                                      float* __restrict__ dsw, int64_t m, int out_c, int side_dim, int64_t rows_per_block) {
+    const int cg = blockIdx.y * blockDim.x + threadIdx.x;             // 8-column group
+    if (cg * 8 >= out_c) return;
+    const int s0 = blockIdx.z * 8;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(m, r0 + rows_per_block);
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + r * out_c) + cg);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); x[2 * e] = f.x; x[2 * e + 1] = f.y; }
+        float sv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sv[k] = (s0 + k < side_dim) ? __ldg(side + r * side_dim + s0 + k) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(x[j], sv[k], acc[j][k]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (s0 + k < side_dim && acc[j][k] != 0.f)
+                atomicAdd(dsw + (int64_t)(cg * 8 + j) * side_dim + s0 + k, acc[j][k]);
+}
+
 int check_desc(const cb_conv_desc* d, const char* who) {
     CB_REQUIRE(d, CB_E_ARG, "%s: null descriptor", who);
     CB_REQUIRE(d->n >= 1 && d->in_h >= 1 && d->in_w >= 1 && d->in_c >= 1 && d->k_h >= 1 && d->k_w >= 1 &&
@@ -330,6 +366,18 @@ extern "C" int cb_side_wgrad(const void* dy, const float* side, float* dsw, int6
     int64_t nw = (int64_t)out_c * side_dim;
     scale_kernel<<<(unsigned)cb::ceil_div<int64_t>(nw, 256), 256, 0, s>>>(dsw, nw, beta);
     CB_LAUNCH_CHECK();
+    if (out_c % 8 == 0 && (((uintptr_t)dy) & 15) == 0) {
+        const int cgs_total = out_c / 8;
+        const int bx = cgs_total < 256 ? cgs_total : 256;                  // column groups per block
+        int by = 256 / bx; if (by < 1) by = 1;                             // row lanes per block
+        const int col_blocks = cb::ceil_div(cgs_total, bx), side_chunks = cb::ceil_div(side_dim, 8);
+        int64_t row_blocks = std::max<int64_t>(1, (148 * 4) / ((int64_t)col_blocks * side_chunks));
+        int64_t rpb = std::max<int64_t>(64, cb::ceil_div<int64_t>(m, row_blocks));
+        dim3 grid((unsigned)cb::ceil_div<int64_t>(m, rpb), (unsigned)col_blocks, (unsigned)side_chunks);
+        side_wgrad_vec_kernel<<<grid, dim3(bx, by), 0, s>>>((const __nv_bfloat16*)dy, side, dsw, m, out_c, side_dim, rpb);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
     int64_t rpb = std::max<int64_t>(64, cb::ceil_div<int64_t>(m, 148 * 2));
     dim3 grid((unsigned)cb::ceil_div<int64_t>(m, rpb), (unsigned)cb::ceil_div(out_c, 128));
     side_wgrad_kernel<<<grid, 128, 0, s>>>((const __nv_bfloat16*)dy, side, dsw, m, out_c, side_dim, rpb);
