@@ -814,7 +814,8 @@ int wgrad_rows(int n, int out_c, int K, int groups, int x_shared, const void* x,
     rc = encode_bf16(&tmB, x, 2, db, sb, box); if (rc) return rc;
     // MC = 128-row output chunks per CTA: two of them share each x slab (64 KB of operands per 256x256x64 MACs
     // instead of 48 KB per 128x256x64 -- these GEMMs are L2-bandwidth-bound)
-    const int MC = (out_c % 256 == 0 && K >= 1024) ? 2 : 1;      // small K: the atomic epilogue would dominate
+    // small problems (512 x 512): the atomic epilogue of the doubled tile would dominate -- measured slower
+    const int MC = (out_c % 256 == 0 && (K >= 1024 || out_all >= 2048)) ? 2 : 1;
     p.na = 2 * MC; p.nb = 4; p.a_rank = p.b_rank = 2;
     for (int i = 0; i < 4; ++i) { p.a_coord[i][0] = i * 64; p.b_coord[i][0] = i * 64; }
     p.a_step_dim = p.b_step_dim = 1; p.a_step = p.b_step = 64;
