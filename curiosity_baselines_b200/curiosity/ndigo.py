@@ -11,7 +11,8 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from ..layers import linear_layer, pad_side
+from .. import layers as LY
+from ..layers import linear_layer, pad_side, PaddedLinearLayer
 from .encoders import make_encoder, frame_input
 
 
@@ -63,7 +64,8 @@ class _PredictorFn(torch.autograd.Function):
         h, _ = l1.forward(xb, n, side=window, side_pad=pad_side(window) if window.shape[1] <= 64 else None)
         _, logits = l2.forward(h, n, out_bf16=False, out_f32=True)
         ctx.layers, ctx.saved, ctx.params = layers, (xb, window, h, n), params
-        return logits
+        real = getattr(l2, "real_out", l2.out_c)
+        return logits if real == l2.out_c else logits[:, :real].contiguous()      # padded layers: drop the zero columns
 
     @staticmethod
     def backward(ctx, dlogits):
@@ -73,6 +75,8 @@ class _PredictorFn(torch.autograd.Function):
         for p in ctx.params:
             p.grad = None
         dy = dlogits.to(torch.bfloat16).contiguous()
+        if getattr(l2, "real_out", l2.out_c) != l2.out_c:
+            dy = torch.nn.functional.pad(dy, (0, l2.out_c - dy.shape[1])).contiguous()
         l2.wgrad(h, dy, n)
         dh = l2.dgrad(dy, n, x_saved=h, x_act="relu")
         l1.wgrad(xb, dh, n, side=window)
@@ -136,7 +140,12 @@ class NDIGO(nn.Module):
             preds = {}
             for k in range(1, 11):
                 seq = getattr(self, f"forward_model_{k}").model
-                preds[k] = (linear_layer(seq[0], "relu", side_dim=k * self.action_size), linear_layer(seq[2], "none"))
+                if LY.get_engine() != L.ENGINE_SIMT and self.gru_size % 64 == 0:
+                    # 128+kA -> 64 -> obs_dim on the tcgen05 kernels with zero-padded widths (64 -> 128, obs_dim -> 128k)
+                    l1 = PaddedLinearLayer(seq[0], "relu", side_dim=k * self.action_size)
+                    preds[k] = (l1, PaddedLinearLayer(seq[2], "none", in_features=l1.out_c))
+                else:
+                    preds[k] = (linear_layer(seq[0], "relu", side_dim=k * self.action_size), linear_layer(seq[2], "none"))
             self._exec = dict(dev=dev, chain=chain, perm=None if perm is None else perm.to(dev), preds=preds)
         return self._exec
 

@@ -322,6 +322,69 @@ class DenseConvLayer(GemmLayer):
         b.grad.index_add_(0, self._brow, db[: self.real_out])
 
 
+class PaddedLinearLayer(GemmLayer):
+    """A Linear layer whose sizes the tcgen05 kernels do not tile (NDIGO's 128+kA -> 64 -> 75 predictors,
+    ndigo.py:19-34) run with zero-padded weights: outputs padded to a multiple of 128 (zero rows -> exact zeros
+    after ReLU), inputs to ``in_features``.  Callers see the padded width; ``real_out`` columns are meaningful.
+    Gradients are sliced back onto the holder's parameters."""
+
+    def __init__(self, module, act="none", side_dim=0, trainable=True, in_features=None):
+        self.real_out = module.out_features
+        self.real_K = module.in_features - side_dim
+        k_in = in_features if in_features is not None else self.real_K
+        out_pad = (self.real_out + 127) // 128 * 128
+        super().__init__(module, (1, 1, k_in), 1, 1, 0, out_pad, act, side_dim, trainable)
+
+    def prepare(self, force=False):
+        w, b = self.module.weight, self.module.bias
+        ver = (w._version, w.data_ptr(), b._version)
+        if not force and ver == self._version:
+            return
+        dev = w.device
+        dense = torch.zeros(self.out_c, self.K, dtype=torch.float32, device=dev)
+        dense[: self.real_out, : self.real_K] = w.detach()[:, : self.real_K]
+        if self.w_fwd is None:
+            self.w_fwd = torch.empty(self.out_c, self.K, dtype=torch.bfloat16, device=dev)
+            self.w_t = torch.empty(self.K, self.out_c, dtype=torch.bfloat16, device=dev)
+        L.call("cb_prepare_conv_weight", L.ptr(dense), L.ptr(self.w_fwd), L.ptr(self.w_t), self.out_c, self.K, 1, 1,
+               L.stream())
+        self._dense_w = dense
+        bias = torch.zeros(self.out_c, dtype=torch.float32, device=dev)
+        bias[: self.real_out] = b.detach()
+        self.bias = bias
+        self.side_w = self.w_ext = None
+        if self.side_dim:
+            sw = torch.zeros(self.out_c, self.side_dim, dtype=torch.float32, device=dev)
+            sw[: self.real_out] = w.detach()[:, self.real_K:]
+            self.side_w = sw
+            if self.K % 64 == 0 and self.side_dim <= 64:
+                self.w_ext = torch.zeros(self.out_c, self.K + 64, dtype=torch.bfloat16, device=dev)
+                self.w_ext[:, : self.K] = self.w_fwd
+                self.w_ext[:, self.K: self.K + self.side_dim] = sw.to(torch.bfloat16)
+        self._version = ver
+
+    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+        if not self.trainable:
+            return
+        self.prepare()
+        w, b = self.module.weight, self.module.bias
+        dev = dy.device
+        dw = torch.empty(self.out_c, self.K, dtype=torch.float32, device=dev)
+        db = torch.empty(self.out_c, dtype=torch.float32, device=dev)
+        d = self.desc(n)
+        L.call("cb_conv_wgrad", C.byref(d), L.ptr(x), L.ptr(dy), None, None, L.ptr(dw), L.ptr(db), 0.0, L.stream())
+        if w.grad is None or not accumulate:
+            w.grad = torch.zeros_like(w) if w.grad is None else w.grad.zero_()
+        if b.grad is None or not accumulate:
+            b.grad = torch.zeros_like(b) if b.grad is None else b.grad.zero_()
+        w.grad[:, : self.real_K].add_(dw[: self.real_out, : self.real_K])
+        b.grad.add_(db[: self.real_out])
+        if self.side_dim:
+            dsw = torch.empty(self.out_c, self.side_dim, dtype=torch.float32, device=dev)
+            L.call("cb_side_wgrad", L.ptr(dy), L.ptr(side), L.ptr(dsw), n, self.out_c, self.side_dim, 0.0, L.stream())
+            w.grad[:, self.real_K:].add_(dsw[: self.real_out])
+
+
 def pad_side(side):
     """fp32 [n, A] side input (one-hot action) -> bf16 [n, 64] zero padded: the extra k-block operand."""
     n, a = side.shape
