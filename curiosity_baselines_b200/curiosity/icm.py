@@ -373,6 +373,8 @@ class _IcmBase(nn.Module):
             layers += [ly["first"], ly["last"]] + ly["a"] + ly["b"]
         for layer in layers:
             layer._version = None
+        if getattr(self, "_grouped", None) is not None:
+            self._grouped._key = None          # the stacked ensemble weights must be rebuilt as well
 
     def compute_loss(self, observations, next_observations, actions, valid, dropout_masks="default"):
         """icm.py:136-145 / disagreement.py:142-167 -> (inverse_loss_wt*inv, forward_loss_wt*fwd)."""

@@ -76,3 +76,45 @@ def test_host_staging_of_newest_frame():
     out = newest_frame_to_device(frames, torch.device(DEV))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), frames[:, :, -1:])
+
+
+def test_disagreement_step_against_oracle_two_iterations():
+    """IcmStep (bonus -> returns -> loss/grad -> clip -> Adam) on Disagreement, grouped ensemble GEMMs included,
+    against the CPU oracle trained with torch.optim.Adam for two iterations: the second iteration only matches if
+    the stacked / prepared bf16 weights were refreshed after the first update."""
+    from curiosity_baselines_b200.curiosity.icm import Disagreement
+    from curiosity_baselines_b200.trainer import IcmStep
+    T, B, A, seed = 10, 6, 7, 91
+    params = R.make_params(R.disagreement_shapes(A, "idf_burda"), seed)
+    model = Disagreement(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+    model.load_state_dict(params)
+    step = IcmStep(model, lr=1e-3)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(p.values()), lr=1e-3)
+    losses = []
+    for it in range(2):
+        obs, nxt = R.make_frames(seed + it, T, B), R.make_frames(seed + 5 + it, T, B)
+        act = R.onehot(R.make_actions(seed + 10 + it, T, B, A), A)
+        done = R.make_suffix_done(seed + 15 + it, T, B, frac=0.4)
+        value, boot = R.make_normal(seed + 20 + it, T, B), R.make_normal(seed + 30 + it, B)
+        loss, r_int, adv, ret = step(obs.to(DEV), nxt.to(DEV), act.to(DEV), done.to(DEV), torch.zeros(T, B, device=DEV),
+                                     value.to(DEV), boot.to(DEV), dropout_masks=None)
+        r_ref = O.disagreement_bonus(p, obs, nxt, act, "idf_burda", 1.0)
+        valid = O.valid_from_done(done)
+        opt.zero_grad()
+        inv_r, fwd_r = O.disagreement_loss(p, obs, nxt, act, valid, "idf_burda", 0.2, None)
+        (inv_r + fwd_r).backward()
+        gn_ref = float(torch.nn.utils.clip_grad_norm_(list(p.values()), 1.0))
+        opt.step()
+        l_ref = float(inv_r + fwd_r)
+        losses.append((float(loss), l_ref))
+        assert abs(float(loss) - l_ref) / l_ref < 2e-2, (it, losses)
+        assert abs(step.opt.grad_norm() - gn_ref) / gn_ref < 5e-2, (it, step.opt.grad_norm(), gn_ref)
+    # the loss moved between the iterations (different batch + updated weights) and both sides agree on it
+    assert abs(losses[1][0] - losses[0][0]) > 0
+    for k, prm in model.named_parameters():
+        d = (prm.detach().cpu() - params[k]).flatten()
+        d_ref = (p[k].detach() - params[k]).flatten()
+        if float(d_ref.norm()) > 0:
+            cos = float(d @ d_ref / (d.norm() * d_ref.norm()).clamp_min(1e-30))
+            assert cos > 0.9, (k, cos)
