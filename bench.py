@@ -389,6 +389,35 @@ def main():
     h2d = T * B * 84 * 84 + sum(t.numel() * 4 for t in h_small)
     d2h = 3 * T * B * 4 + 4
 
+    # ---- the same step with RND.reuse_features (NOT the headline value): the reference passes the same
+    # next_observation to compute_bonus and compute_loss (base.py:72-73, ppo.py:107-110), so the loss pass can reuse
+    # the bonus pass's features after a device-side equality check of the frames.  Reported separately; `value`
+    # above recomputes everything.
+    reuse = None
+    try:
+        model.reuse_features = True
+        for _ in range(3):
+            one_step()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hits0 = dict(model.reuse_hits)
+        r0.record()
+        for _ in range(args.steps):
+            one_step()
+        r1.record()
+        barrier()
+        rms = torch.tensor([r0.elapsed_time(r1)], device=dev)
+        if world > 1:
+            dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+        rms_step = float(rms) / args.steps
+        reuse = {"ms_per_step": rms_step, "value": world * T * B / (rms_step * 1e-3), "unit": "samples/s",
+                 "full_hits": model.reuse_hits["full"] - hits0["full"], "steps": args.steps,
+                 "note": "loss pass reuses the bonus pass's target+predictor features of the same frames "
+                         "(exact; guarded by cb_frames_differ); not the headline value"}
+    finally:
+        model.reuse_features = False
+        model._cache = None
+
     # ---- roofline of the dominant kernel: predictor conv2 forward (implicit GEMM 512x64 per position)
     hbm, tf_burst, tf_sust, src = peaks()
     layer = model._chains[0].layers[1]
@@ -439,7 +468,7 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": world * T * B / (float(e2e_ms) * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_ms)},
-        "roofline": roofline, "cpu_baseline": cpu, "loss": float(loss)}))
+        "roofline": roofline, "cpu_baseline": cpu, "with_feature_reuse": reuse, "loss": float(loss)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -45,6 +45,7 @@ _SIGS = {
     "cb_valid_lengths": [_P, _P, _P, _I, _I, _P],
     "cb_obs_moments_u8": [_P, _L, _I, _P, _I, _I, _P, _P, _P],
     "cb_rms_merge_from_sums": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cb_frames_differ": [_P, _L, _P, _L, _I, _L, _P, _P],
     "cb_reward_filter": [_P, _P, _F, _P, _P, _P, _I, _I, _P],
     "cb_moments_partial": [_P, _L, _P, _P, _P],
     "cb_rms_merge_moments": [_P, _P, C.c_double, _P, _P, _P, _P],

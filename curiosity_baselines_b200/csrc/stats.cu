@@ -78,6 +78,25 @@ __global__ void obs_moments_kernel(const uint8_t* __restrict__ frames, int64_t f
     }
 }
 
+// differ[0] += number of 16-byte words in which frame f of a differs from frame f of b (both uint8, `pixels` bytes
+// per frame, frame strides in bytes).  Guard for reusing features computed on "the same" batch (rnd.py call sites:
+// compute_bonus and compute_loss both receive samples.env.next_observation, algos/pg/base.py:72, ppo.py:107-110).
+__global__ void frames_differ_kernel(const uint8_t* __restrict__ a, int64_t a_stride, const uint8_t* __restrict__ b,
+                                     int64_t b_stride, int pixels, int64_t frames, unsigned int* __restrict__ differ) {
+    const int words = pixels / 16;
+    const int64_t total = frames * words;
+    unsigned int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / words;
+        const int w = (int)(i - f * words);
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(a + f * a_stride) + w);
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(b + f * b_stride) + w);
+        bad += (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(differ, bad);
+}
+
 // ---- Chan merge (averages.py:54-68) --------------------------------------------------------
 __device__ __forceinline__ void chan_merge(double& mean, double& var, double count, double b_mean,
                                            double b_var, double b_count) {
@@ -266,6 +285,17 @@ extern "C" int cb_obs_moments_u8(const uint8_t* frames, int64_t frame_stride, in
               (unsigned)cb::ceil_div(cols, threads));
     obs_moments_kernel<<<grid, threads, 0, cb::as_stream(stream)>>>(frames, frame_stride, pixels,
                                                                     n_valid, T, B, sum, sumsq);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_frames_differ(const void* a, int64_t a_stride, const void* b, int64_t b_stride, int32_t pixels,
+                                int64_t frames, uint32_t* differ, void* stream) {
+    CB_REQUIRE(a && b && differ && pixels >= 16 && pixels % 16 == 0 && frames >= 1, CB_E_ARG, "cb_frames_differ: bad argument");
+    CB_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)a_stride | (uintptr_t)b_stride) & 15) == 0, CB_E_ALIGN,
+               "cb_frames_differ: frames must be 16-byte aligned");
+    frames_differ_kernel<<<148 * 8, 256, 0, cb::as_stream(stream)>>>((const uint8_t*)a, a_stride, (const uint8_t*)b, b_stride,
+                                                                   pixels, frames, differ);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -78,6 +78,11 @@ class RND(nn.Module):
         self.rew_rff = RewardForwardFilter(gamma)
         self._chains = None
         self._norm = None
+        # Opt-in exact reuse of a batch's features between compute_bonus and compute_loss (see _reusable).
+        self.reuse_features = False
+        self._cache = None
+        self._wver = 0            # bumped whenever the predictor's master weights change outside torch's tracking
+        self.reuse_hits = {"full": 0, "target": 0, "miss": 0}
 
     # ------------------------------------------------------------------ plumbing
     def _build(self):
@@ -107,10 +112,12 @@ class RND(nn.Module):
         self._mean_len = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm = (torch.zeros(px, dtype=torch.float32, device=dev),
                       torch.ones(px, dtype=torch.float32, device=dev))
+        self._norm_ver = 0
         self._refresh_norm()
 
     def _refresh_norm(self):
         """fp32 mean and 1/sqrt(var) of the current obs_rms (rnd.py:162-169)."""
+        self._norm_ver = getattr(self, "_norm_ver", 0) + 1
         self._norm[0].copy_(self.obs_rms._mean)
         self._norm[1].copy_(self.obs_rms._var.rsqrt())
 
@@ -138,6 +145,43 @@ class RND(nn.Module):
         acts, phi_hat = pred.forward(base, n, first_out=a1_p)
         return obs, T, B, base, strides, phi, phi_hat, (acts if keep_acts else None)
 
+    def _forward_predictor(self, obs):
+        """Predictor alone (target features reused): single-network first conv."""
+        obs, T, B, base, strides = self._frame_view(obs)
+        acts, phi_hat = self._chains[0].forward(base, T * B, in_dtype=L.U8, strides=strides, norm=self._norm)
+        return acts, phi_hat
+
+    # ------------------------------------------------------------------ feature reuse
+    # The reference hands the SAME frames to both calls of a training iteration: process_returns passes
+    # samples.env.next_observation to compute_bonus (algos/pg/base.py:72-73) and optimize_agent passes it again
+    # to compute_loss (ppo.py:107-110, 235-237); compute_loss does not touch the observation statistics.  The
+    # target network is frozen, so its features of that batch are valid for every epoch / minibatch over it; the
+    # predictor's forward is valid until its weights change, i.e. for the first update after the bonus.  Reuse is
+    # exact (identical kernels on identical operands) and guarded by a device-side comparison of the frames.
+    def _weights_version(self):
+        return (self._wver,) + tuple(p._version for p in self.forward_model.parameters())
+
+    def _remember(self, obs, T, B, phi, phi_hat, acts):
+        self._cache = dict(obs=obs, shape=(T, B), phi=phi, phi_hat=phi_hat, acts=acts,
+                           norm_ver=self._norm_ver, wver=self._weights_version())
+
+    def _reusable(self, obs, T, B, base, strides):
+        """None, or the cached entry whose frames equal `obs` under the current observation statistics."""
+        c = self._cache
+        if not self.reuse_features or c is None or c["shape"] != (T, B) or c["norm_ver"] != self._norm_ver:
+            return None
+        co = c["obs"]
+        if co.data_ptr() != obs.data_ptr() or co._version != obs._version or co.shape != obs.shape:
+            cobs, _, _, cbase, cstrides = self._frame_view(co)
+            if not ((base | cbase | strides[0] | cstrides[0]) & 15 == 0):
+                return None
+            flag = torch.zeros(1, dtype=torch.int32, device=self._dev)
+            L.call("cb_frames_differ", base, strides[0], cbase, cstrides[0], self.image_hw[0] * self.image_hw[1], T * B,
+                   L.ptr(flag), L.stream())
+            if int(flag.item()) != 0:           # host sync: the price of the guard (one scalar)
+                return None
+        return c
+
     # ------------------------------------------------------------------ bonus
     @torch.no_grad()
     def compute_bonus(self, next_observation, done):
@@ -159,8 +203,11 @@ class RND(nn.Module):
         L.call("cb_rms_merge_from_sums", L.ptr(self._sum[0]), L.ptr(self._sum[1]),
                L.ptr(self._n_total), L.ptr(rms._mean), L.ptr(rms._var), L.ptr(rms._count),
                L.ptr(self._norm[0]), L.ptr(self._norm[1]), px, st)
+        self._norm_ver += 1                       # the statistics the forward passes normalise with have changed
         # target / predictor features and per-sample error (rnd.py:174-183)
-        _, _, _, _, _, phi, phi_hat, _ = self._forward_nets(obs, False)
+        _, _, _, _, _, phi, phi_hat, acts = self._forward_nets(obs, self.reuse_features)
+        if self.reuse_features:
+            self._remember(obs, T, B, phi, phi_hat, acts)
         err = torch.empty(T, B, dtype=torch.float32, device=self._dev)
         L.call("cb_rowwise_sqerr", L.ptr(phi_hat), L.ptr(phi), 1.0 / self.feature_size, L.ptr(err),
                T * B, self.feature_size, st)
@@ -177,7 +224,18 @@ class RND(nn.Module):
     # ------------------------------------------------------------------ loss
     def _loss_and_grads(self, observations, valid, mask, need_grad, inplace=False):
         self._build()
-        obs, T, B, base, strides, phi, phi_hat, acts = self._forward_nets(observations, need_grad)
+        obs, T, B, base, strides = self._frame_view(observations)
+        hit = self._reusable(obs, T, B, base, strides)
+        if hit is not None and hit["wver"] == self._weights_version() and (hit["acts"] is not None or not need_grad):
+            phi, phi_hat, acts = hit["phi"], hit["phi_hat"], hit["acts"]          # same frames, statistics and weights
+            self.reuse_hits["full"] += 1
+        elif hit is not None:
+            phi = hit["phi"]                                                     # frozen target: still valid
+            acts, phi_hat = self._forward_predictor(obs)
+            self.reuse_hits["target"] += 1
+        else:
+            obs, T, B, base, strides, phi, phi_hat, acts = self._forward_nets(observations, need_grad)
+            self.reuse_hits["miss"] += 1
         n, F = T * B, self.feature_size
         st = L.stream()
         valid = valid.to(self._dev, torch.float32).reshape(n).contiguous()
@@ -219,6 +277,7 @@ class RND(nn.Module):
 
     def invalidate_weights(self):
         """Call after the fp32 master weights were updated outside torch's version tracking."""
+        self._wver += 1
         if self._chains is not None:
             for layer in self._chains[0].layers:
                 layer._version = None

@@ -93,6 +93,11 @@ int cb_obs_moments_u8(const uint8_t* frames, int64_t frame_stride, int pixels,
 int cb_rms_merge_from_sums(const unsigned long long* sum, const unsigned long long* sumsq,
                            const int64_t* n_total, double* mean, double* var, double* count,
                            float* mean_f32, float* rstd_f32, int pixels, void* stream);
+/* differ[0] += number of 16-byte words in which the uint8 frames a[f] and b[f] differ (f < frames; strides in bytes,
+ * pixels % 16 == 0).  Guard for reusing features of a batch: the reference hands the SAME next_observation to
+ * RND.compute_bonus and RND.compute_loss (algos/pg/base.py:72-73, ppo.py:107-110). */
+int cb_frames_differ(const void* a, int64_t a_stride, const void* b, int64_t b_stride, int32_t pixels,
+                     int64_t frames, uint32_t* differ, void* stream);
 /* averages.py:75-89 driven as rnd.py:186-189: per-env discounted running sum over T with
  * the not-done mask |done-1|; rewems[B] persists across calls; *initialized is 0 before the first
  * call (first row seeds all envs unmasked) and set to 1.  total[T,B] receives the copy

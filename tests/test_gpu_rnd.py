@@ -109,3 +109,47 @@ def test_upstream_gradient_scaling():
     m.zero_grad()
     (3.0 * m.compute_loss(frames, valid)).backward()
     assert torch.allclose(m.forward_model[11].weight.grad, 3 * g1, rtol=1e-5, atol=1e-8)
+
+
+def test_feature_reuse_is_exact_and_guarded():
+    """RND.reuse_features: compute_loss on the frames compute_bonus just saw (what the reference passes,
+    base.py:72-73 / ppo.py:107-110) reuses the cached features -- bit-identical bonus and loss, gradients equal up to atomic summation order -- while any other
+    batch, a weight update or new observation statistics fall back to (partial) recomputation."""
+    import recipes as R
+    T, B, seed = 6, 5, 11
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    frames = R.make_frames(seed, T, B).to(DEV)
+    done = R.make_suffix_done(seed + 1, T, B, frac=0.4).to(DEV)
+    valid = torch.ones(T, B, device=DEV)
+    mask = torch.ones(T, B, device=DEV)
+
+    def run(reuse, loss_frames):
+        m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+        m.load_state_dict(params)
+        m.reuse_features = reuse
+        bonus = m.compute_bonus(frames, done)
+        loss = m.compute_loss(loss_frames, valid, mask)
+        loss.backward()
+        return m, bonus, loss.detach(), [p.grad.clone() for p in m.forward_model.parameters()]
+
+    _, b0, l0, g0 = run(False, frames)
+    m1, b1, l1, g1 = run(True, frames.clone())            # a different tensor with equal content: guard compares
+    assert m1.reuse_hits == {"full": 1, "target": 0, "miss": 0}
+    assert torch.equal(b0, b1) and torch.equal(l0, l1)
+    # (weight gradients are summed with fp32 atomics: equal up to summation order)
+    assert all(float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12 for a, b in zip(g0, g1))
+    # after a weight update only the frozen target's features are reused
+    with torch.no_grad():
+        for p in m1.forward_model.parameters():
+            p.add_(0.01)
+    m1.invalidate_weights()
+    l2 = m1.compute_loss(frames, valid, mask)
+    assert m1.reuse_hits["target"] == 1 and float(l2) != float(l1)
+    m_ref = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m_ref.load_state_dict(m1.state_dict())
+    m_ref.compute_bonus(frames, done)
+    assert abs(float(m_ref.compute_loss(frames, valid, mask)) - float(l2)) <= 1e-6 * abs(float(l2))
+    # different frames: no reuse
+    other = frames.clone(); other[0, 0, -1, 0, 0] ^= 1
+    m1.compute_loss(other, valid, mask)
+    assert m1.reuse_hits["miss"] == 1
