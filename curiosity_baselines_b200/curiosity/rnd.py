@@ -43,6 +43,8 @@ class _RndLoss(torch.autograd.Function):
 class RND(nn.Module):
     """rnd.py:15-124."""
 
+    default_reuse_features = False     # integration.install() switches this on for models built under rlpyt
+
     def __init__(self, image_shape, prediction_beta=1.0, drop_probability=1.0, gamma=0.99,
                  device="cpu"):
         super().__init__()
@@ -79,7 +81,7 @@ class RND(nn.Module):
         self._chains = None
         self._norm = None
         # Opt-in exact reuse of a batch's features between compute_bonus and compute_loss (see _reusable).
-        self.reuse_features = False
+        self.reuse_features = self.default_reuse_features
         self._cache = None
         self._wver = 0            # bumped whenever the predictor's master weights change outside torch's tracking
         self.reuse_hits = {"full": 0, "target": 0, "miss": 0}
