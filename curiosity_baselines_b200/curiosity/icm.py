@@ -224,6 +224,7 @@ class _IcmLoss(torch.autograd.Function):
 
 class _IcmBase(nn.Module):
     n_forward_models = 1
+    default_reuse_features = False     # integration.install() switches this on for models built under rlpyt
 
     def _init_common(self, image_shape, action_size, feature_encoding, batch_norm, prediction_beta, obs_stats,
                      forward_loss_wt):
@@ -239,6 +240,11 @@ class _IcmBase(nn.Module):
         self.inverse_model = nn.Sequential(nn.Linear(self.feature_size * 2, self.feature_size), nn.ReLU(),
                                            nn.Linear(self.feature_size, action_size))
         self._exec = None
+        # opt-in exact reuse of a batch's forward pass between compute_bonus and compute_loss (see _cached_forward)
+        self.reuse_features = self.default_reuse_features
+        self._cache = None
+        self._wver = 0
+        self.reuse_hits = {"full": 0, "miss": 0}
 
     # ------------------------------------------------------------------ executors
     def _forward_models(self):
@@ -290,12 +296,58 @@ class _IcmBase(nn.Module):
         action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
         return T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action
 
+    # ------------------------------------------------------------------ forward pass shared by bonus and loss
+    # The reference hands the same (observation, next_observation, action) to curiosity_step and curiosity_loss
+    # (algos/pg/base.py:64-66, ppo.py:93-98, 226-229).  Until the first optimiser step the loss's forward pass --
+    # both encoder passes and the forward models -- is the bonus's: it is reused after a device-side equality
+    # check of the three inputs (exact: identical kernels on identical operands).
+    def _weights_version(self):
+        return (self._wver,) + tuple(p._version for p in self.parameters())
+
+    def _same_batch(self, c, observations, next_observations, actions):
+        if c["shapes"] != (tuple(observations.shape), tuple(next_observations.shape), tuple(actions.shape)):
+            return False
+        dev = self._exec["dev"]
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        for a, b in ((observations, c["obs"]), (next_observations, c["next"])):
+            if a.dtype != torch.uint8 or not a.is_cuda:
+                return False
+            a, b = a.contiguous(), b.contiguous()
+            if a.data_ptr() == b.data_ptr() and a._version == b._version:
+                continue
+            per = a[0, 0].numel()
+            if per % 16 or (a.data_ptr() | b.data_ptr()) & 15:
+                return False
+            L.call("cb_frames_differ", a.data_ptr(), per, b.data_ptr(), per, per, a.shape[0] * a.shape[1], L.ptr(flag), L.stream())
+        same_act = torch.equal(actions.to(dev, torch.float32).reshape(c["act"].shape), c["act"])     # tiny; host sync
+        return same_act and int(flag.item()) == 0
+
+    def _cached_forward(self, observations, next_observations, actions, remember):
+        """(T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action, saved, pred): features + forward-model outputs."""
+        self._build()
+        c = self._cache
+        if (self.reuse_features and not remember and c is not None and c["wver"] == self._weights_version()
+                and self._same_batch(c, observations, next_observations, actions)):
+            self.reuse_hits["full"] += 1
+            return c["out"]
+        feats = self._features(observations, next_observations, actions)
+        T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action = feats
+        saved, pred = self._forward_exec().run_forward(phi1_b, action, n)            # pred fp32, packed [n, E*F]
+        out = feats + (saved, pred)
+        if self.reuse_features and remember:
+            self._cache = dict(obs=observations, next=next_observations, act=action.clone(), wver=self._weights_version(),
+                               shapes=(tuple(observations.shape), tuple(next_observations.shape), tuple(actions.shape)),
+                               out=out)
+        elif not remember:
+            self.reuse_hits["miss"] += 1
+        return out
+
     # ------------------------------------------------------------------ loss
     def _loss_and_grads(self, observations, next_observations, actions, valid, masks, need_grad, inplace=False):
         if actions.dim() == 2:
             actions = actions.unsqueeze(1)                  # icm.py:138
-        T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action = self._features(observations, next_observations,
-                                                                              actions)
+        T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action, saved, pred = self._cached_forward(
+            observations, next_observations, actions, remember=False)
         ex, st, dev, F = self._exec, L.stream(), self._exec["dev"], self.feature_size
         valid = valid.to(dev, torch.float32).reshape(n).contiguous()
         denom = dist.all_reduce_sum_(valid.sum().reshape(1)) if dist.world_size() > 1 else None
@@ -317,7 +369,6 @@ class _IcmBase(nn.Module):
         E = self.n_forward_models
         fwd_terms = torch.empty(E, dtype=torch.float32, device=dev)
         fmx = self._forward_exec()
-        saved, pred = fmx.run_forward(phi1_b, action, n)                 # pred fp32, packed [n, E*F]
         mask = None
         if masks is not None:
             mask = torch.stack([m.to(dev, torch.float32).reshape(n, F) for m in masks]).contiguous()
@@ -365,6 +416,7 @@ class _IcmBase(nn.Module):
 
     def invalidate_weights(self):
         """Call after the fp32 master weights were updated outside torch's version tracking (FlatAdam)."""
+        self._wver += 1
         if self._exec is None:
             return
         layers = list(self._exec["chain"].layers) + [self._exec["inv0"], self._exec["inv2"]]
@@ -407,8 +459,8 @@ class ICM(_IcmBase):
     @torch.no_grad()
     def compute_bonus(self, observations, next_observations, actions):
         """icm.py:131-134: beta * sum_f (pred_phi2 - phi2)^2 / F -> fp32 [T,B]."""
-        T, B, n, _, _, phi1_b, phi2_f, _, action = self._features(observations, next_observations, actions)
-        _, pred = self.forward_model.run_forward(phi1_b, action, n)
+        T, B, n, _, _, phi1_b, phi2_f, _, action, _, pred = self._cached_forward(observations, next_observations,
+                                                                                 actions, remember=True)
         out = torch.empty(T, B, dtype=torch.float32, device=self._exec["dev"])
         L.call("cb_rowwise_sqerr", L.ptr(pred), L.ptr(phi2_f), float(self.prediction_beta) / self.feature_size,
                L.ptr(out), n, self.feature_size, L.stream())
@@ -446,8 +498,8 @@ class Disagreement(_IcmBase):
     @torch.no_grad()
     def compute_bonus(self, observations, next_observations, actions):
         """disagreement.py:136-140: beta * mean_f var_e(pred_e) with the unbiased variance."""
-        T, B, n, _, _, phi1_b, _, _, action = self._features(observations, next_observations, actions)
-        _, pred = self._forward_exec().run_forward(phi1_b, action, n)       # packed [n, 4*F]
+        T, B, n, _, _, phi1_b, _, _, action, _, pred = self._cached_forward(observations, next_observations, actions,
+                                                                             remember=True)         # pred packed [n, 4*F]
         out = torch.empty(T, B, dtype=torch.float32, device=self._exec["dev"])
         L.call("cb_ensemble_variance_packed", L.ptr(pred), self.n_forward_models, float(self.prediction_beta),
                L.ptr(out), n, self.feature_size, L.stream())

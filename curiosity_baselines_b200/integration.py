@@ -31,6 +31,7 @@ def install(strict=True, reuse_features=True):
 
     patched = []
     RND.default_reuse_features = bool(reuse_features)
+    ICM.default_reuse_features = Disagreement.default_reuse_features = bool(reuse_features)
 
     def patch(modname, **attrs):
         try:

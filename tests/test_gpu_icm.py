@@ -110,3 +110,40 @@ def test_icm_oracle_parity(enc, A, T, B):
         # bias gradients are signed sums of bf16-rounded dy rows (cancellation): allow 8% on their norm
         tol = 8e-2 if gg.numel() <= 64 else 3e-2
         assert cos > 0.99 and abs(float(gg.norm() / gref.norm()) - 1) < tol, (k, cos, float(gg.norm() / gref.norm()))
+
+
+@pytest.mark.parametrize("cls_name", ["icm", "disagreement"])
+def test_forward_reuse_between_bonus_and_loss(cls_name):
+    """reuse_features: compute_loss on the batch compute_bonus just saw (what the reference passes) reuses the whole
+    forward pass after an equality check of observations, next observations and actions -- identical losses -- and
+    recomputes for any other batch or after a weight update."""
+    T, B, A, seed = 5, 4, 7, 23
+    cls = ICM if cls_name == "icm" else Disagreement
+    shapes = R.icm_shapes(A, "idf_burda") if cls_name == "icm" else R.disagreement_shapes(A, "idf_burda")
+    params = R.make_params(shapes, seed)
+    obs, nxt = R.make_frames(seed + 1, T, B).to(DEV), R.make_frames(seed + 2, T, B).to(DEV)
+    act = R.onehot(R.make_actions(seed + 3, T, B, A), A).to(DEV)
+    valid = torch.ones(T, B, device=DEV)
+
+    def run(reuse):
+        m = cls(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+        m.load_state_dict(params)
+        m.reuse_features = reuse
+        bonus = m.compute_bonus(obs, nxt, act)
+        inv, fwd = m.compute_loss(obs.clone(), nxt.clone(), act.clone(), valid, dropout_masks=None)
+        (inv + fwd).backward()
+        return m, bonus, inv.detach(), fwd.detach(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    _, b0, i0, f0, g0 = run(False)
+    m1, b1, i1, f1, g1 = run(True)
+    assert m1.reuse_hits == {"full": 1, "miss": 0}
+    assert torch.equal(b0, b1) and torch.equal(i0, i1) and torch.equal(f0, f1)
+    for k in g0:      # weight gradients are summed with fp32 atomics: equal up to summation order
+        assert float((g0[k] - g1[k]).abs().max()) <= 1e-4 * float(g0[k].abs().max()) + 1e-12, k
+    other = nxt.clone(); other[0, 0, 0, 0, 0] ^= 1
+    m1.compute_loss(obs, other, act, valid, dropout_masks=None)
+    assert m1.reuse_hits["miss"] == 1
+    with torch.no_grad():
+        next(m1.parameters()).add_(0.0)          # bumps the parameter's version: weights may have changed
+    m1.compute_loss(obs, nxt, act, valid, dropout_masks=None)
+    assert m1.reuse_hits["miss"] == 2
