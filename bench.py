@@ -327,7 +327,10 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        from curiosity_baselines_b200.dist import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)    # host staging buffers local to the GPU's socket
         dist.init_process_group("nccl", device_id=dev)
     LY.set_engine(args.engine)
 
@@ -488,7 +491,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_B": B * world, "l2": "inputs (3.7 GB frames/GPU) larger than L2",
-                   "engine": args.engine, "parallelism": f"dp{world} over B"},
+                   "engine": args.engine, "parallelism": f"dp{world} over B", "numa_node_rank0": numa},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": world * T * B / (float(e2e_ms) * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e2e_ms)},

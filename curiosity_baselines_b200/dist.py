@@ -36,3 +36,31 @@ def shard_columns(B, r=None, w=None):
     if per * w != B:
         raise ValueError(f"B={B} is not divisible by world size {w}")
     return r * per, (r + 1) * per
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards: first touch) to the CPUs of
+    the NUMA node the GPU hangs off.  With one process per GPU the newest-frame uploads of 8 ranks (8 x 0.93 GB per
+    step) otherwise cross the inter-socket link for half the ranks.  Returns the node, or None when the platform
+    does not expose the topology (then nothing is changed)."""
+    import os
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, AttributeError, ValueError):
+        return None
