@@ -30,6 +30,16 @@ FLOP_PER_SAMPLE = 2 * (2 * (FWD_MAC_TARGET + FWD_MAC_PRED)                      
                        + 2 * FWD_MAC_PRED - 64 * 32 * 400)                       # bwd: wgrad all + dgrad (no conv1 dgrad)
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,7 +320,8 @@ def main():
             "unit": "samples/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "cpu_model": cpu_model(),
+                             "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -484,7 +495,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         v, ms_cpu, k = cpu_reference(T, args.cpu_B, 6, 1, seconds_cap=25.0)
-        cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
                "sample": f"T={T}, B={args.cpu_B} ({T * args.cpu_B} samples/step), {k} steps, {ms_cpu:.0f} ms/step"}
     print(json.dumps({
         "metric": "intrinsic-reward samples/sec (bonus+update)", "value": value_sps, "unit": "samples/s",
