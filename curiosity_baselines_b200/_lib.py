@@ -76,6 +76,12 @@ _SIGS = {
     "cb_weighted_mean": [_P, _P, _P, _L, _P],
     "cb_loss_coef": [_P, _P, _F, _P, _P, _L, _P],
     "cb_dot": [_P, _P, _P, _L, _P],
+    "cb_lstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cb_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cb_softmax_fwd": [_P, _P, _L, _I, _P],
+    "cb_softmax_bwd": [_P, _P, _P, _L, _I, _P],
+    "cb_ppo_loss": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _L, _I, _P],
+    "cb_add_to_bf16": [_P, _P, _P, _L, _P],
     "cb_sumsq": [_P, _L, _P, _P],
     "cb_adam_clip_step": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P],
     "cb_h2d_2d": [_P, _L, _P, _L, _L, _L, _P],

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcuriosity_b200.so")
-SOURCES = ["api.cu", "returns.cu", "stats.cu", "rowwise.cu", "simt_gemm.cu", "umma_conv.cu", "umma_conv1.cu", "umma_probe.cu"]  # headers: common.cuh umma_common.cuh umma_gemm.cuh
+SOURCES = ["api.cu", "returns.cu", "stats.cu", "rowwise.cu", "policy.cu", "simt_gemm.cu", "umma_conv.cu", "umma_conv1.cu", "umma_probe.cu"]  # headers: common.cuh umma_common.cuh umma_gemm.cuh
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

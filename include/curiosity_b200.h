@@ -252,6 +252,37 @@ int cb_loss_coef(const float* valid, const float* mask, float upstream, const fl
                  float* coef, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Policy network + PPO loss.   models/pg/atari_lstm_model.py:114-154, algos/pg/ppo.py:192-225,
+ * distributions/categorical.py:33-46.  The LSTM's two GEMMs per timestep (x W_ih^T for all T at once,
+ * h W_hh^T per step) run through cb_conv_fwd / cb_conv_dgrad / cb_conv_wgrad as Linear layers.
+ * ---------------------------------------------------------------------------------- */
+/* torch.nn.LSTM cell (gate order i,f,g,o): a = gx + gh (fp32 [B,4H] each, biases already added by the GEMM
+ * epilogues); gates <- (sigmoid(a_i), sigmoid(a_f), tanh(a_g), sigmoid(a_o)) (fp32 [B,4H], may alias gx);
+ * c_out = f*c_prev + i*g (fp32 [B,H]); h = o*tanh(c_out) as bf16 [B,H] (next GEMM operand) and, when h_f32 is
+ * given, fp32.  H % 4 == 0, rows 16-byte aligned. */
+int cb_lstm_cell_fwd(const float* gx, const float* gh, const float* c_prev, float* gates, float* c_out,
+                     void* h_bf16, float* h_f32, int32_t B, int32_t H, void* stream);
+/* backward of the cell: dh bf16 [B,H] (all gradient arriving at h_t), dc_next fp32 [B,H] or NULL;
+ * dgates bf16 [B,4H] = gradient w.r.t. the pre-activations a; dc_prev fp32 [B,H]. */
+int cb_lstm_cell_bwd(const void* dh_bf16, const float* dc_next, const float* gates, const float* c_prev,
+                     const float* c, void* dgates_bf16, float* dc_prev, int32_t B, int32_t H, void* stream);
+/* atari_lstm_model.py:144: F.softmax over the last dimension, fp32 [n,a]; and its backward */
+int cb_softmax_fwd(const float* logits, float* prob, int64_t n, int32_t a, void* stream);
+int cb_softmax_bwd(const float* prob, const float* dprob, float* dlogits, int64_t n, int32_t a, void* stream);
+/* ppo.py:209-223 per sample m (a <= 64): p = softmax(logits[m]); ratio = (p[act]+1e-8)/(old_prob[m,act]+1e-8);
+ * terms[0*n+m] = min(ratio*adv, clamp(ratio, 1-clip, 1+clip)*adv); terms[1*n+m] = 0.5*(value-return)^2;
+ * terms[2*n+m] = -sum p log(p+1e-8); terms[3*n+m] = exp(entropy).  prob_out [n,a] optional.
+ * When dlogits is given: gradients of  -sum_m coef*surr + value_coeff*sum_m coef*verr - entropy_coeff*sum_m coef*ent
+ * w.r.t. logits (fp32 [n,a]) and value (fp32 [n]); coef[m] = valid[m]/sum(valid) (cb_loss_coef).
+ * torch.min's tie rule and clamp's inclusive bounds are reproduced. */
+int cb_ppo_loss(const float* logits, const float* value, const int64_t* action, const float* old_prob,
+                const float* advantage, const float* return_, const float* coef, float ratio_clip,
+                float value_coeff, float entropy_coeff, float* prob_out, float* terms, float* dlogits,
+                float* dvalue, int64_t n, int32_t a, void* stream);
+/* out (bf16) = a + b (fp32, b may be NULL): gradient hand-over between fp32 loss heads and bf16 GEMM operands */
+int cb_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Optimiser.   ppo.py:147-150 (clip_grad_norm_ over all params, then Adam.step)
  * ---------------------------------------------------------------------------------- */
 /* out[0] += sum g^2 over n elements (caller zeroes out; call once per flat buffer) */

@@ -26,6 +26,8 @@ Reference lines restated (all under rlpyt/):
   discount_return / gae / valid_from_done algos/utils.py:8-40,104-112
   process_returns ....................... algos/pg/base.py:53-108
   valid_mean ............................ utils/tensor.py:39-46
+  lstm_sequence / policy_forward ........ models/pg/atari_lstm_model.py:114-154
+  ppo_loss .............................. algos/pg/ppo.py:192-242, distributions/categorical.py:33-46
 """
 import math
 
@@ -457,3 +459,63 @@ class ReturnsOracle:
             sel = adv[valid > 0] if valid is not None else adv
             adv = (adv - sel.mean()) / max(sel.std(), 1e-6)
         return ret, adv, valid
+
+
+# --------------------------------------------------------------------------- policy net + PPO loss
+def lstm_sequence(x, p, h0, c0):
+    """torch.nn.LSTM, single layer (atari_lstm_model.py:112,142), gate order i,f,g,o.
+    x [T,B,I]; h0, c0 [B,H] -> (outputs [T,B,H], h_T, c_T)."""
+    w_ih, w_hh, b_ih, b_hh = (p["lstm.weight_ih_l0"], p["lstm.weight_hh_l0"],
+                              p["lstm.bias_ih_l0"], p["lstm.bias_hh_l0"])
+    h, c = h0, c0
+    outs = []
+    for t in range(x.shape[0]):
+        a = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        a_i, a_f, a_g, a_o = a.chunk(4, 1)
+        c = torch.sigmoid(a_f) * c + torch.sigmoid(a_i) * torch.tanh(a_g)
+        h = torch.sigmoid(a_o) * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs), h, c
+
+
+def policy_forward(p, image, prev_action, init_rnn_state=None, feature_encoding="idf_burda"):
+    """AtariLstmModel.forward (atari_lstm_model.py:117-154) for the curiosity configurations whose
+    policy encoder is one of the curiosity heads (``self.conv = BurdaHead/UniverseHead/MazeHead``,
+    :80-94): raw float pixels (no /255, :130-133) -> conv -> cat one-hot prev_action -> LSTM ->
+    softmax(pi), value.  image [T,B,C,H,W]; prev_action one-hot float [T,B,A];
+    init_rnn_state (h, c) each [1,B,H] or None.  Returns pi [T,B,A], v [T,B], (h_n, c_n) [1,B,H]."""
+    T, B = image.shape[:2]
+    fn, _ = ENCODERS[feature_encoding]
+    x = image.to(torch.float32).reshape(T * B, *image.shape[2:])
+    fc_out = fn(x, _sub(p, "conv."))
+    lstm_in = torch.cat([fc_out.view(T, B, -1), prev_action.view(T, B, -1)], dim=2)
+    H = p["lstm.weight_hh_l0"].shape[1]
+    if init_rnn_state is None:
+        h0, c0 = torch.zeros(B, H), torch.zeros(B, H)
+    else:
+        h0, c0 = init_rnn_state[0][0], init_rnn_state[1][0]
+    out, hn, cn = lstm_sequence(lstm_in, p, h0, c0)
+    flat = out.view(T * B, -1)
+    pi = F.softmax(F.linear(flat, p["pi.weight"], p["pi.bias"]), dim=-1)
+    v = F.linear(flat, p["value.weight"], p["value.bias"]).squeeze(-1)
+    return pi.view(T, B, -1), v.view(T, B), (hn.unsqueeze(0), cn.unsqueeze(0))
+
+
+def ppo_loss(pi, value, action, old_prob, return_, advantage, valid, ratio_clip=0.1,
+             value_loss_coeff=1.0, entropy_loss_coeff=0.01):
+    """PPO.loss without the curiosity terms (ppo.py:209-223) on the Categorical distribution
+    (categorical.py:33-46, EPS=1e-8).  action int64 [T,B].  Returns
+    (loss, pi_loss, value_loss, entropy_loss, entropy, perplexity)."""
+    eps = 1e-8
+    num = pi.gather(-1, action.unsqueeze(-1)).squeeze(-1)
+    den = old_prob.gather(-1, action.unsqueeze(-1)).squeeze(-1)
+    ratio = (num + eps) / (den + eps)
+    surr_1 = ratio * advantage
+    surr_2 = torch.clamp(ratio, 1.0 - ratio_clip, 1.0 + ratio_clip) * advantage
+    pi_loss = -valid_mean(torch.min(surr_1, surr_2), valid)
+    value_loss = value_loss_coeff * valid_mean(0.5 * (value - return_) ** 2, valid)
+    ent = -torch.sum(pi * torch.log(pi + eps), dim=-1)
+    entropy = valid_mean(ent, valid)
+    perplexity = valid_mean(torch.exp(ent), valid)
+    entropy_loss = -entropy_loss_coeff * entropy
+    return pi_loss + value_loss + entropy_loss, pi_loss, value_loss, entropy_loss, entropy, perplexity

@@ -258,9 +258,67 @@ def gen_stats():
     save("stats", seed=seed, **outs)
 
 
+def gen_policy():
+    """AtariLstmModel.forward + PPO.loss (policy + ICM terms) through the reference's own agent
+    (agents/pg/atari.py, agents/pg/categorical.py:36-56,106-130; algos/pg/ppo.py:192-242)."""
+    from rlpyt.agents.pg.atari import AtariLstmAgent
+    from rlpyt.agents.base import AgentInputs
+    from rlpyt.algos.pg.ppo import PPO, IcmAgentCuriosityInputs
+    from rlpyt.distributions.categorical import DistInfo
+    from rlpyt.envs.base import EnvSpaces
+    from rlpyt.models.pg.atari_lstm_model import RnnState
+    from rlpyt.spaces.int_box import IntBox
+    A, T, B, seed = 4, 6, 3, 81
+    agent = AtariLstmAgent(model_kwargs=dict(curiosity_kwargs=dict(
+        curiosity_alg="icm", feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
+        forward_loss_wt=0.2)), no_extrinsic=True)
+    agent.initialize(EnvSpaces(observation=IntBox(0, 255, shape=(4, 84, 84), dtype="uint8"), action=IntBox(0, A)),
+                     share_memory=False, global_B=B, obs_stats=None, env_ranks=list(range(B)))
+    params = R.make_policy_params(A, seed)
+    params.update({"curiosity_model." + k: v for k, v in R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2).items()})
+    load_into(agent.model, params)
+    obs = R.make_frames(seed + 3, T, B)
+    nxt = R.make_frames(seed + 4, T, B)
+    prev_action = R.make_actions(seed + 5, T, B, A)
+    action = R.make_actions(seed + 6, T, B, A)
+    old_prob = R.make_probs(seed + 7, T, B, A)
+    ret = R.make_normal(seed + 8, T, B)
+    adv = R.make_normal(seed + 9, T, B)
+    valid = 1 - R.make_suffix_done(seed + 10, T, B, frac=0.5)
+    h0 = R.make_normal(seed + 11, B, 1, 512) * 0.5          # [B,N,H] as ppo.py:124-126 slices it
+    c0 = R.make_normal(seed + 12, B, 1, 512) * 0.5
+    algo = PPO(curiosity_type="icm")
+    algo.agent = agent
+    outs = {}
+    with torch.no_grad():
+        fc = agent.model.conv(obs.float().view(T * B, 4, 84, 84))
+        print("policy fc_out std", float(fc.std()), "abs max", float(fc.abs().max()))
+        pi, v, (hn, cn) = agent.model(obs, R.onehot(prev_action, A), torch.zeros(T, B),
+                                      (h0.transpose(0, 1).contiguous(), c0.transpose(0, 1).contiguous()))
+    outs.update(pi=pi, value=v, hn=hn, cn=cn)
+    agent_inputs = AgentInputs(observation=obs, prev_action=prev_action, prev_reward=torch.zeros(T, B))
+    cur = IcmAgentCuriosityInputs(observation=obs.clone(), next_observation=nxt.clone(), action=action.clone(),
+                                  valid=valid)
+    loss, pi_loss, value_loss, entropy_loss, entropy, perplexity, (inv, fwd) = algo.loss(
+        agent_inputs, cur, action, ret, adv, valid, DistInfo(prob=old_prob), RnnState(h=h0, c=c0))
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(agent.model.parameters(), 1e9)
+    outs.update(loss=loss.double(), pi_loss=pi_loss.double(), value_loss=value_loss.double(),
+                entropy_loss=entropy_loss.double(), entropy=entropy.double(), perplexity=perplexity.double(),
+                inv_loss=inv.double(), fwd_loss=fwd.double(), grad_norm=gn.double(),
+                ratio_clip=algo.ratio_clip, value_loss_coeff=algo.value_loss_coeff,
+                entropy_loss_coeff=algo.entropy_loss_coeff)
+    outs.update(grad_summary(agent.model))
+    save("policy_ppo_icm", T=T, B=B, A=A, seed=seed, **outs)
+
+
 if __name__ == "__main__":
     import_reference()
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_returns()
     gen_stats()
     gen_process_returns()

@@ -91,6 +91,31 @@ def ndigo_shapes(action_size, c_in=3, hw=5, gru=128, num_predictors=10):
     return out
 
 
+def policy_shapes(action_size, feature_encoding="idf_burda", c_in=4, lstm=512):
+    """AtariLstmModel minus its curiosity_model (atari_lstm_model.py:80-114)."""
+    enc, feat = encoder_shapes(feature_encoding, c_in)
+    enc = [(k.replace("encoder.", "conv.", 1), s) for k, s in enc]
+    return enc + [("lstm.weight_ih_l0", (4 * lstm, feat + action_size)), ("lstm.weight_hh_l0", (4 * lstm, lstm)),
+                  ("lstm.bias_ih_l0", (4 * lstm,)), ("lstm.bias_hh_l0", (4 * lstm,)),
+                  ("pi.weight", (action_size, lstm)), ("pi.bias", (action_size,)),
+                  ("value.weight", (1, lstm)), ("value.bias", (1,))]
+
+
+def make_policy_params(action_size, seed, feature_encoding="idf_burda", conv_gain=0.65):
+    """Policy weights whose encoder is damped (gain < 1 per layer) so that raw 0..255 pixels give O(1)
+    features: the LSTM gates then work in their non-saturated range and parity is informative."""
+    shapes = policy_shapes(action_size, feature_encoding)
+    conv = [s for s in shapes if s[0].startswith("conv.")]
+    rest = [s for s in shapes if not s[0].startswith("conv.")]
+    out = make_params(conv, seed, gain=conv_gain, bias_scale=conv_gain)
+    out.update(make_params(rest, seed + 1, gain=1.0))
+    return out
+
+
+def make_probs(seed, T, B, A):
+    return torch.softmax(make_normal(seed, T, B, A), dim=-1)
+
+
 def make_params(shapes, seed, gain=1.0, bias_scale=1.0):
     """U(-b, b) with b = gain / sqrt(fan_in) (torch's default Linear/Conv bound).
     Biases get the same bound so they are exercised (RND's own init zeroes them)."""

@@ -146,3 +146,45 @@ def test_ndigo():
         loss.backward()
         assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < TOL
         assert not check_grads({k: v.grad for k, v in p.items() if v.grad is not None}, g, 0.9999, 1e-3)
+
+
+def policy_case(g):
+    """Inputs of tests/golden/make_golden.py::gen_policy rebuilt from the seed."""
+    T, B, A, seed = int(g["T"]), int(g["B"]), int(g["A"]), int(g["seed"])
+    return dict(T=T, B=B, A=A, params=R.make_policy_params(A, seed),
+                icm_params=R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2),
+                obs=R.make_frames(seed + 3, T, B), nxt=R.make_frames(seed + 4, T, B),
+                prev_action=R.make_actions(seed + 5, T, B, A), action=R.make_actions(seed + 6, T, B, A),
+                old_prob=R.make_probs(seed + 7, T, B, A), ret=R.make_normal(seed + 8, T, B),
+                adv=R.make_normal(seed + 9, T, B), valid=1 - R.make_suffix_done(seed + 10, T, B, frac=0.5),
+                h0=(R.make_normal(seed + 11, B, 1, 512) * 0.5).transpose(0, 1).contiguous(),
+                c0=(R.make_normal(seed + 12, B, 1, 512) * 0.5).transpose(0, 1).contiguous())
+
+
+def test_policy_ppo_icm():
+    """AtariLstmModel.forward + PPO.loss with the ICM terms, through the reference's own agent."""
+    g = golden("policy_ppo_icm")
+    c = policy_case(g)
+    A = c["A"]
+    with torch.no_grad():
+        pi, v, (hn, cn) = O.policy_forward(c["params"], c["obs"], R.onehot(c["prev_action"], A), (c["h0"], c["c0"]))
+    assert rel_err(pi, g["pi"]) < TOL and rel_err(v, g["value"]) < TOL
+    assert rel_err(hn, g["hn"]) < TOL and rel_err(cn, g["cn"]) < TOL
+    p = _leaf(c["params"])
+    q = _leaf(c["icm_params"])
+    pi, v, _ = O.policy_forward(p, c["obs"], R.onehot(c["prev_action"], A), (c["h0"], c["c0"]))
+    loss, pi_loss, value_loss, entropy_loss, entropy, perplexity = O.ppo_loss(
+        pi, v, c["action"], c["old_prob"], c["ret"], c["adv"], c["valid"], float(g["ratio_clip"]),
+        float(g["value_loss_coeff"]), float(g["entropy_loss_coeff"]))
+    inv, fwd = O.icm_loss(q, c["obs"], c["nxt"], R.onehot(c["action"], A), c["valid"], "idf_burda", 0.2)
+    total = loss + inv + fwd
+    for name, val in [("pi_loss", pi_loss), ("value_loss", value_loss), ("entropy_loss", entropy_loss),
+                      ("entropy", entropy), ("perplexity", perplexity), ("inv_loss", inv), ("fwd_loss", fwd),
+                      ("loss", total)]:
+        assert abs(float(val) - float(g[name])) <= TOL * max(abs(float(g[name])), 1e-3), name
+    total.backward()
+    grads = {k: t.grad for k, t in p.items()}
+    grads.update({"curiosity_model." + k: t.grad for k, t in q.items()})
+    assert not check_grads(grads, g, 0.9999, 1e-3)
+    gn = torch.sqrt(sum((t.grad.double() ** 2).sum() for t in list(p.values()) + list(q.values())))
+    assert abs(float(gn) - float(g["grad_norm"])) / float(g["grad_norm"]) < 1e-3
