@@ -288,6 +288,130 @@ def ndigo_model(args, rank, world, local):
 
 
 # ------------------------------------------------------------------------------ B200 arm
+# ------------------------------------------------------------------------------ ICM + LSTM PPO (BASELINE configs[3])
+def ppo_flops(A, epochs):
+    """Algorithmic FLOP per sample of one PPO iteration (SURVEY 8d ii): ICM bonus forward + ``epochs`` x (policy
+    forward/backward + ICM forward/backward).  Policy: Burda encoder + LSTM(512+A -> 512) + pi/value heads."""
+    F, H = 512, 512
+    lstm = (F + A) * 4 * H + H * 4 * H
+    heads = H * (A + 1)
+    pol_fwd = ENC_MAC + lstm + heads
+    # backward: encoder wgrad + dgrad (no conv1 dgrad); LSTM: wgrad of both matrices, dgrad to the features and to h
+    pol_bwd = (2 * ENC_MAC - 256 * 32 * 400) + 2 * lstm - A * 4 * H + 2 * heads
+    icm_unit = icm_flops(A, 1) // 2                    # MAC of 2*fwd + bwd
+    resf = 10 * (F + A) * F
+    inv = 2 * F * F + F * A
+    icm_fwd = 2 * ENC_MAC + inv + resf
+    icm_bwd = icm_unit - 2 * icm_fwd
+    return 2 * (icm_fwd + epochs * (pol_fwd + pol_bwd + icm_fwd + icm_bwd))
+
+
+def ppo_model(args, rank, world, local):
+    import numpy as np
+    import torch.distributed as dist
+    from curiosity_baselines_b200 import _lib as L
+    from curiosity_baselines_b200 import layers as LY
+    from curiosity_baselines_b200.algos.ppo import PPO, PpoBatch
+    from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    LY.set_engine(args.engine)
+    T, B = args.T, args.B
+    A = args.A or 4
+    epochs, minibatches = args.epochs, args.minibatches
+    torch.manual_seed(0)
+    model = AtariLstmModel((4, 84, 84), A, curiosity_kwargs=dict(
+        curiosity_alg="icm", feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
+        forward_loss_wt=0.2)).to(dev)
+    with torch.no_grad():       # damp the policy encoder so raw 0..255 pixels give O(1) features (non-saturated gates)
+        for name, prm in model.conv.named_parameters():
+            prm.mul_(0.65)
+    algo = PPO(discount=0.99, learning_rate=1e-4, gae_lambda=0.95, minibatches=minibatches, epochs=epochs,
+               curiosity_type="icm", linear_lr_schedule=False)
+    algo.initialize(model, n_itr=10 ** 6, rng=np.random.RandomState(rank))
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    obs = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    nxt = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g)
+    act = torch.randint(0, A, (T, B), device=dev, generator=g)
+    prev = torch.randint(0, A, (T, B), device=dev, generator=g)
+    old_prob = torch.softmax(torch.randn(T, B, A, device=dev, generator=g), -1)
+    first = torch.randint(1, T + 1, (B,), device=dev, generator=g)
+    has = torch.rand(B, device=dev, generator=g) < 0.01
+    first = torch.where(has, first, torch.full_like(first, T))
+    done = (torch.arange(T, device=dev).unsqueeze(1) >= first.unsqueeze(0)).float()
+    value = torch.randn(T, B, device=dev, generator=g)
+    boot = torch.randn(B, device=dev, generator=g)
+    h0 = torch.randn(B, 1, 512, device=dev, generator=g) * 0.1
+    c0 = torch.randn(B, 1, 512, device=dev, generator=g) * 0.1
+
+    def one_step():
+        batch = PpoBatch(obs, nxt, prev, act, old_prob, torch.zeros(T, B, device=dev), done, value, boot, (h0, c0))
+        return algo.optimize_agent(0, batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    l0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        infos = one_step()
+    ev1.record()
+    barrier()
+    launches = L.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    # the policy pass alone (forward + PPO loss + backward), for the breakdown
+    ret, adv, valid = algo.process_returns(PpoBatch(obs, nxt, prev, act, old_prob, torch.zeros(T, B, device=dev), done,
+                                                    value, boot, (h0, c0)))
+    algo_p = PPO(curiosity_type="none")
+    algo_p.model = model
+    for _ in range(2):
+        algo_p.loss_and_grads_(obs, prev, act, ret, adv, valid, old_prob, (h0, c0))
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        algo_p.loss_and_grads_(obs, prev, act, ret, adv, valid, old_prob, (h0, c0))
+    p1.record()
+    barrier()
+    policy_ms = p0.elapsed_time(p1) / 3
+    hbm, tf_burst, tf_sust, src = peaks()
+    flop = ppo_flops(A, epochs)
+    if rank == 0:
+        tfl = flop * T * B / (ms_per_step * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "intrinsic-reward samples/sec (bonus+update)", "value": world * T * B / (ms_per_step * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ICM + LSTM PPO full iteration (BASELINE configs[3]): bonus + returns + {epochs} epochs x "
+                                   f"{minibatches} minibatches of policy+ICM loss/backward/clip/Adam, T={T}, B={B}/GPU, "
+                                   f"4x84x84 uint8, A={A}",
+                       "global_B": B * world, "l2": "inputs (14.8 GB frames/GPU) larger than L2", "engine": args.engine,
+                       "parallelism": f"dp{world} over B"},
+            "clocks": clocks, "gpu_launches": launches, "e2e": None,
+            "roofline": {"bound": "tensor", "kernel": "whole iteration", "achieved": tfl, "peak": tf_sust,
+                         "unit": "TFLOP/s", "frac": tfl / tf_sust, "traffic": None,
+                         "peak_source": f"{src} bf16 sustained", "mflop_per_sample": flop / 1e6},
+            "cpu_baseline": None, "policy_fwd_loss_bwd_ms": policy_ms,
+            "loss": float(infos[-1].loss), "grad_norm": float(infos[-1].gradNorm)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,10 +419,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--T", type=int, default=128)
-    ap.add_argument("--B", type=int, default=1024, help="env columns per GPU (weak scaling)")
+    ap.add_argument("--B", type=int, default=None, help="env columns per GPU (weak scaling); default 1024 "
+                                                       "(2048 for ppo_icm, BASELINE configs[3])")
+    ap.add_argument("--epochs", type=int, default=3, help="ppo_icm: PPO epochs per iteration (launcher default 3)")
+    ap.add_argument("--minibatches", type=int, default=1, help="ppo_icm: minibatches per epoch (launcher default 1)")
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement", "ndigo"],
+    ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement", "ndigo", "ppo_icm"],
                     help="rnd = BASELINE configs[1] (the headline line); icm / disagreement: the same unit of work "
                          "for the other two conv curiosity models (device-resident inputs only)")
     ap.add_argument("--A", type=int, default=None, help="number of discrete actions (icm: 4, disagreement: 7)")
@@ -307,6 +434,8 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.B is None:
+        args.B = 2048 if args.model == "ppo_icm" else 1024
     T, B = args.T, args.B
     workload = f"RND bonus+update, T={T}, B={B}/GPU, 4x84x84 uint8 (BASELINE configs[1])"
 
@@ -327,6 +456,8 @@ def main():
 
     if args.model == "ndigo":
         return ndigo_model(args, rank, world, local)
+    if args.model == "ppo_icm":
+        return ppo_model(args, rank, world, local)
     if args.model != "rnd":
         return other_model(args, rank, world, local)
     import torch.distributed as dist

@@ -1,0 +1,171 @@
+"""PPO on B200: the reference's ``PPO.optimize_agent`` / ``PPO.loss``
+(rlpyt/algos/pg/ppo.py:72-242) for the recurrent categorical agent, with the policy network, the curiosity
+model, the loss and the optimiser all running in libcuriosity_b200.so.
+
+Per iteration (``optimize_agent``):  curiosity bonus -> reward += r_int -> GAE / returns / valid
+(``algos.pg_base.returns_on_device``) -> ``epochs`` x ``minibatches`` gradient steps, each over all T and a
+shuffled slice of B (recurrent minibatching, ppo.py:133-140):  policy forward -> ``cb_ppo_loss`` (clipped
+surrogate + value + entropy and their gradient) -> policy backward -> curiosity ``loss_and_grads_`` ->
+ONE global-norm clip + Adam over policy U curiosity parameters (``FlatAdam``; ppo.py:147-150) -> linear
+learning-rate and ratio-clip decay (:184-186).  Data-parallel: every normaliser ``sum(valid)`` is all-reduced
+so the sharded loss equals the single-process one; gradients are summed by one all-reduce in ``FlatAdam``.
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .. import dist
+from ..trainer import FlatAdam
+from .pg_base import returns_on_device
+
+PpoBatch = namedtuple("PpoBatch", ["observation", "next_observation", "prev_action", "action", "old_prob", "reward",
+                                   "done", "value", "bootstrap_value", "init_rnn_state"])
+PpoBatch.__doc__ = """One sampled rollout batch on the device (the fields of rlpyt's ``Samples`` that ppo.py reads):
+observation / next_observation uint8 [T,B,C,H,W]; prev_action / action int64 [T,B]; old_prob fp32 [T,B,A]
+(``samples.agent.agent_info.dist_info.prob``); reward / done / value fp32 [T,B]; bootstrap_value [B];
+init_rnn_state (h, c) each [B,1,H] (``prev_rnn_state[0]``, ppo.py:124-126) or None."""
+
+OptInfo = namedtuple("OptInfo", ["loss", "pi_loss", "value_loss", "entropy_loss", "inv_loss", "forward_loss",
+                                 "entropy", "perplexity", "gradNorm"])
+
+
+def _onehot(idx, A):
+    return torch.zeros(idx.shape + (A,), dtype=torch.float32, device=idx.device).scatter_(-1, idx.unsqueeze(-1), 1)
+
+
+class PPO:
+    """ppo.py:20-70 constructor arguments (same names and defaults)."""
+
+    def __init__(self, discount=0.99, learning_rate=0.001, value_loss_coeff=1., entropy_loss_coeff=0.01,
+                 clip_grad_norm=1., gae_lambda=1, minibatches=4, epochs=4, ratio_clip=0.1, linear_lr_schedule=True,
+                 normalize_advantage=False, normalize_reward=False, curiosity_type="none"):
+        self.discount, self.learning_rate = discount, learning_rate
+        self.value_loss_coeff, self.entropy_loss_coeff = value_loss_coeff, entropy_loss_coeff
+        self.clip_grad_norm, self.gae_lambda = clip_grad_norm, gae_lambda
+        self.minibatches, self.epochs = minibatches, epochs
+        self.ratio_clip = self._ratio_clip = ratio_clip
+        self.linear_lr_schedule = linear_lr_schedule
+        self.normalize_advantage, self.normalize_reward = normalize_advantage, normalize_reward
+        self.curiosity_type = curiosity_type
+        self.intrinsic_rewards = None
+        self.update_counter = 0
+        self._returns_state = None
+
+    def initialize(self, model, n_itr, rng=None):
+        """``model``: a ``pg.atari_lstm_model.AtariLstmModel`` on the device.  One optimiser over ALL of its parameters
+        (policy + curiosity, algos/pg/base.py:44)."""
+        self.model, self.n_itr = model, n_itr
+        self.opt = FlatAdam(model.parameters(), lr=self.learning_rate, max_norm=self.clip_grad_norm)
+        self.rng = rng or np.random
+        if self.normalize_reward:
+            from .pg_base import ReturnsState
+            self._returns_state = ReturnsState(self.discount)
+
+    # ------------------------------------------------------------------ loss + gradients of one minibatch
+    def loss_and_grads_(self, observation, prev_action, action, return_, advantage, valid, old_prob, init_rnn_state,
+                        curiosity_inputs=None, dropout_masks="default"):
+        """ppo.py:192-242 with gradients left in ``.grad`` of every parameter (no autograd graph).  Tensors on the
+        device, time-major; init_rnn_state (h, c) each [B,1,H] as ppo.py slices it (transposed here like :203-205)
+        or None.  ``curiosity_inputs``: the positional inputs of the curiosity model's ``loss_and_grads_`` after
+        which ``valid`` is appended.  Returns an ``OptInfo`` of device scalars (gradNorm filled by ``step``)."""
+        m = self.model
+        dev = m.pi.weight.device
+        T, B = action.shape
+        n, A = T * B, m.action_size
+        st = L.stream()
+        if init_rnn_state is not None:
+            init_rnn_state = tuple(s.transpose(0, 1).contiguous() for s in init_rnn_state)
+        s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True)
+        validf = (torch.ones(n, device=dev) if valid is None else valid.to(dev, torch.float32).reshape(n)).contiguous()
+        denom = dist.all_reduce_sum_(validf.sum().reshape(1)) if dist.world_size() > 1 else None
+        coef = torch.empty(n, dtype=torch.float32, device=dev)
+        L.call("cb_loss_coef", L.ptr(validf), None, 1.0, L.ptr(denom), L.ptr(coef), n, st)
+        terms = torch.empty(4, n, dtype=torch.float32, device=dev)
+        dlogits = torch.empty(n, A, dtype=torch.float32, device=dev)
+        dvalue = torch.empty(n, dtype=torch.float32, device=dev)
+        L.call("cb_ppo_loss", L.ptr(s["logits"]), L.ptr(s["value"]), L.ptr(action.reshape(n).contiguous()),
+               L.ptr(old_prob.reshape(n, A).float().contiguous()), L.ptr(advantage.reshape(n).contiguous()),
+               L.ptr(return_.reshape(n).contiguous()), L.ptr(coef), float(self.ratio_clip), float(self.value_loss_coeff),
+               float(self.entropy_loss_coeff), None, L.ptr(terms), L.ptr(dlogits), L.ptr(dvalue), n, A, st)
+        means = torch.empty(4, dtype=torch.float32, device=dev)
+        for i in range(4):
+            L.call("cb_dot", L.ptr(terms[i]), L.ptr(coef), L.ptr(means[i:i + 1]), n, st)
+        m._run_backward(s, dlogits, dvalue)
+        pi_loss = -means[0]
+        value_loss = self.value_loss_coeff * means[1]
+        entropy_loss = -self.entropy_loss_coeff * means[2]
+        loss = pi_loss + value_loss + entropy_loss
+        zero = torch.zeros((), device=dev)
+        inv = fwd = zero
+        if self.curiosity_type in ("icm", "disagreement"):
+            inv, fwd = m.curiosity_model.loss_and_grads_(*curiosity_inputs, valid, dropout_masks)
+        elif self.curiosity_type == "rnd":
+            fwd = m.curiosity_model.loss_and_grads_(*curiosity_inputs, valid)
+        elif self.curiosity_type == "ndigo":
+            raise NotImplementedError("fused PPO step for NDIGO: use the autograd path (compute_loss)")
+        loss = loss + inv + fwd
+        return OptInfo(loss, pi_loss, value_loss, entropy_loss, inv, fwd, means[2], means[3], None)
+
+    def step(self):
+        """clip_grad_norm_ over all parameters + Adam.step (ppo.py:147-150); weights changed -> prepared copies stale."""
+        self.opt.step()
+        self.model.invalidate_weights()
+        self.update_counter += 1
+
+    # ------------------------------------------------------------------ one iteration
+    def process_returns(self, batch):
+        """algos/pg/base.py:53-108 on device tensors: bonus, in-place reward add, returns / advantages / valid."""
+        cm = getattr(self.model, "curiosity_model", None)
+        A = self.model.action_size
+        r_int = None
+        with torch.no_grad():
+            if self.curiosity_type in ("icm", "disagreement"):
+                r_int = cm.compute_bonus(batch.observation, batch.next_observation, _onehot(batch.action, A))
+            elif self.curiosity_type == "rnd":
+                r_int = cm.compute_bonus(batch.next_observation, batch.done)
+            elif self.curiosity_type == "ndigo":
+                r_int = cm.compute_bonus(batch.observation, _onehot(batch.prev_action, A), _onehot(batch.action, A))
+        if r_int is not None:
+            batch.reward.add_(r_int)                       # in place (base.py:66)
+            self.intrinsic_rewards = r_int
+        ret, adv, valid, _ = returns_on_device(batch.reward, batch.done, batch.value, batch.bootstrap_value,
+                                               self.discount, self.gae_lambda, self.normalize_reward,
+                                               self.normalize_advantage, True, self._returns_state)
+        return ret, adv, valid
+
+    def minibatch_indices(self, B):
+        """utils/misc.py:17-26 (iterate_mb_idxs with shuffle) over the B dimension (recurrent agents)."""
+        mb = B // self.minibatches
+        idx = np.arange(B)
+        self.rng.shuffle(idx)
+        return [idx[s:s + mb] for s in range(0, B - mb + 1, mb)]
+
+    def optimize_agent(self, itr, batch, dropout_masks="default"):
+        """ppo.py:72-190 for one ``PpoBatch``; returns a list of ``OptInfo`` (one per gradient step)."""
+        ret, adv, valid = self.process_returns(batch)
+        T, B = batch.reward.shape
+        infos = []
+        for _ in range(self.epochs):
+            for idxs in self.minibatch_indices(B):
+                whole = len(idxs) == B and self.minibatches == 1
+                sl = (lambda t: t) if whole else (lambda t, i=torch.as_tensor(idxs, device=batch.reward.device):
+                                                  t.index_select(1, i).contiguous())
+                rnn = None if batch.init_rnn_state is None else tuple(
+                    s if whole else s.index_select(0, torch.as_tensor(idxs, device=s.device)) for s in batch.init_rnn_state)
+                obs, act = sl(batch.observation), sl(batch.action)
+                cur = None
+                if self.curiosity_type in ("icm", "disagreement"):
+                    cur = (obs, sl(batch.next_observation), _onehot(act, self.model.action_size))
+                elif self.curiosity_type == "rnd":
+                    cur = (sl(batch.next_observation),)
+                info = self.loss_and_grads_(obs, sl(batch.prev_action), act, sl(ret), sl(adv), sl(valid),
+                                            sl(batch.old_prob), rnn, cur, dropout_masks)
+                self.step()
+                infos.append(info._replace(gradNorm=self.opt.sumsq.sqrt().float()))
+        if self.linear_lr_schedule:                        # ppo.py:184-186 (LambdaLR stepped once per iteration)
+            frac = (self.n_itr - (itr + 1)) / self.n_itr
+            self.opt.lr = self.learning_rate * frac
+            self.ratio_clip = self._ratio_clip * (self.n_itr - itr) / self.n_itr
+        return infos

@@ -13,8 +13,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 // gates layout per env row: [i | f | g | o], each H wide (torch.nn.LSTM chunk order).
 // One thread handles 4 consecutive hidden units of one env.
-__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ gh,
-                                     const float* __restrict__ c_prev, float* __restrict__ gates,
+// gx and gates may alias (in-place activation): neither is __restrict__.
+__global__ void lstm_cell_fwd_kernel(const float* gx, const float* __restrict__ gh,
+                                     const float* __restrict__ c_prev, float* gates,
                                      float* __restrict__ c_out, __nv_bfloat16* __restrict__ h_bf16,
                                      float* __restrict__ h_f32, int B, int H) {
     const int q = H >> 2;

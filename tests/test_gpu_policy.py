@@ -1,0 +1,285 @@
+"""The policy network (AtariLstmModel) and the PPO loss / update on the GPU vs the reference's golden vectors
+(tests/golden/policy_ppo_icm.npz, produced by the reference's own agent + PPO.loss) and the CPU oracle.
+Tolerances (north_star): outputs and losses within 1e-2 relative (bf16 operands, fp32 accumulation); the
+elementwise fp32 kernels (LSTM cell, PPO loss) within 1e-5 of the same formula in torch fp32."""
+import numpy as np
+import pytest
+import torch
+
+import recipes as R
+from helpers import golden, check_grads, rel_err, cosine
+from oracle import curiosity_oracle as O
+from test_oracle_golden import policy_case
+from curiosity_baselines_b200 import _lib as L
+from curiosity_baselines_b200 import layers as LY
+from curiosity_baselines_b200.algos.ppo import PPO, PpoBatch
+from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ICM_KW = dict(curiosity_alg="icm", feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
+              forward_loss_wt=0.2)
+
+
+def make_model(A, params, icm_params):
+    m = AtariLstmModel((4, 84, 84), A, curiosity_kwargs=ICM_KW).to(DEV)
+    sd = dict(params)
+    sd.update({"curiosity_model." + k: v for k, v in icm_params.items()})
+    assert set(sd) == set(m.state_dict())
+    m.load_state_dict(sd)
+    return m
+
+
+def test_state_dict_keys_match_reference():
+    m = AtariLstmModel((4, 84, 84), 4, curiosity_kwargs=ICM_KW)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("curiosity_model.")}
+    assert got == dict(R.policy_shapes(4, "idf_burda"))
+
+
+def test_lstm_cell_kernels_match_torch_fp32():
+    B, H = 37, 512
+    g = torch.Generator(device="cpu").manual_seed(5)
+    gx, gh = torch.randn(B, 4 * H, generator=g).to(DEV), torch.randn(B, 4 * H, generator=g).to(DEV)
+    c_prev = torch.randn(B, H, generator=g).to(DEV).requires_grad_(True)
+    a = (gx + gh).requires_grad_(True)
+    ai, af, ag, ao = a.chunk(4, 1)
+    c_ref = torch.sigmoid(af) * c_prev + torch.sigmoid(ai) * torch.tanh(ag)
+    h_ref = torch.sigmoid(ao) * torch.tanh(c_ref)
+    gates, c = torch.empty(B, 4 * H, device=DEV), torch.empty(B, H, device=DEV)
+    hb, hf = torch.empty(B, H, dtype=torch.bfloat16, device=DEV), torch.empty(B, H, device=DEV)
+    L.call("cb_lstm_cell_fwd", L.ptr(gx), L.ptr(gh), L.ptr(c_prev.detach()), L.ptr(gates), L.ptr(c), L.ptr(hb), L.ptr(hf),
+           B, H, L.stream())
+    assert torch.allclose(c, c_ref, rtol=1e-5, atol=1e-6) and torch.allclose(hf, h_ref, rtol=1e-5, atol=1e-6)
+    assert torch.equal(hb, hf.to(torch.bfloat16))
+    ref_gates = torch.cat([torch.sigmoid(ai), torch.sigmoid(af), torch.tanh(ag), torch.sigmoid(ao)], 1)
+    assert torch.allclose(gates, ref_gates, rtol=1e-5, atol=1e-6)
+    # in-place form (gates aliasing gx) gives the same result
+    gx2 = gx.clone()
+    L.call("cb_lstm_cell_fwd", L.ptr(gx2), L.ptr(gh), L.ptr(c_prev.detach()), L.ptr(gx2), L.ptr(c), L.ptr(hb), None, B, H,
+           L.stream())
+    assert torch.equal(gx2, gates)
+    # backward
+    dh = torch.randn(B, H, generator=g).to(DEV).to(torch.bfloat16)
+    dc_next = torch.randn(B, H, generator=g).to(DEV)
+    (h_ref * dh.float()).sum().backward(retain_graph=True)
+    (c_ref * dc_next).sum().backward()
+    dg, dcp = torch.empty(B, 4 * H, dtype=torch.bfloat16, device=DEV), torch.empty(B, H, device=DEV)
+    L.call("cb_lstm_cell_bwd", L.ptr(dh), L.ptr(dc_next), L.ptr(gates), L.ptr(c_prev.detach()), L.ptr(c), L.ptr(dg), L.ptr(dcp),
+           B, H, L.stream())
+    assert torch.allclose(dcp, c_prev.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dg.float(), a.grad, rtol=1e-2, atol=1e-4)          # bf16 output
+
+
+def test_ppo_loss_kernel_matches_oracle():
+    n, A = 1000, 7
+    g = torch.Generator(device="cpu").manual_seed(9)
+    logits = (torch.randn(n, A, generator=g) * 2).requires_grad_(True)
+    value = torch.randn(n, generator=g).requires_grad_(True)
+    action = torch.randint(0, A, (n,), generator=g)
+    old = torch.softmax(logits.detach() + 0.3 * torch.randn(n, A, generator=g), -1)    # ratios on both sides of the clip
+    adv, ret = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    valid = (torch.rand(n, generator=g) > 0.2).float()
+    pi = torch.softmax(logits, -1)
+    ref = O.ppo_loss(pi.view(n, 1, A), value.view(n, 1), action.view(n, 1), old.view(n, 1, A), ret.view(n, 1),
+                     adv.view(n, 1), valid.view(n, 1), 0.1, 0.5, 0.01)
+    ref[0].backward()
+    d = lambda t: t.detach().to(DEV).contiguous()
+    coef = d(valid / valid.sum())
+    terms = torch.empty(4, n, device=DEV)
+    prob, dl, dv = torch.empty(n, A, device=DEV), torch.empty(n, A, device=DEV), torch.empty(n, device=DEV)
+    L.call("cb_ppo_loss", L.ptr(d(logits)), L.ptr(d(value)), L.ptr(d(action)), L.ptr(d(old)), L.ptr(d(adv)), L.ptr(d(ret)),
+           L.ptr(coef), 0.1, 0.5, 0.01, L.ptr(prob), L.ptr(terms), L.ptr(dl), L.ptr(dv), n, A, L.stream())
+    means = (terms * coef).sum(1).cpu()
+    loss = -means[0] + 0.5 * means[1] - 0.01 * means[2]
+    assert abs(float(loss) - float(ref[0])) < 1e-5 * max(1.0, abs(float(ref[0])))
+    assert abs(float(means[2]) - float(ref[4])) < 1e-5 and abs(float(means[3]) - float(ref[5])) < 1e-4
+    assert torch.allclose(prob.cpu(), pi.detach(), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(dl.cpu(), logits.grad, rtol=1e-4, atol=1e-8)
+    assert torch.allclose(dv.cpu(), value.grad, rtol=1e-5, atol=1e-9)
+    # softmax forward / backward pair used by the autograd drop-in
+    p2, dp = torch.empty(n, A, device=DEV), torch.randn(n, A, device=DEV)
+    L.call("cb_softmax_fwd", L.ptr(d(logits)), L.ptr(p2), n, A, L.stream())
+    assert torch.allclose(p2.cpu(), pi.detach(), rtol=1e-5, atol=1e-7)
+    lg = d(logits).requires_grad_(True)
+    (torch.softmax(lg, -1) * dp).sum().backward()
+    dl2 = torch.empty(n, A, device=DEV)
+    L.call("cb_softmax_bwd", L.ptr(p2), L.ptr(dp), L.ptr(dl2), n, A, L.stream())
+    assert torch.allclose(dl2, lg.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_lstm_gemms_run_on_tcgen05():
+    """The three GEMM shapes of the LSTM (x W_ih^T with the one-hot k-block, h W_hh^T, their dgrad / wgrad) have
+    tcgen05 specialisations: forcing the engine must not raise."""
+    m = AtariLstmModel((4, 84, 84), 4, curiosity_kwargs=ICM_KW).to(DEV)
+    ex = m._build()
+    n, B, H = 256, 32, 512
+    feat = torch.randn(n, 512, device=DEV).to(torch.bfloat16)
+    side = R.onehot(R.make_actions(1, n, 1, 4), 4).reshape(n, 4).to(DEV)
+    LY.set_engine("umma")
+    try:
+        _, gx = ex["ih"].forward(feat, n, side=side, side_pad=LY.pad_side(side), out_bf16=False, out_f32=True)
+        _, gh = ex["hh"].forward(feat[:B].contiguous(), B, out_bf16=False, out_f32=True)
+        dg = torch.randn(n, 4 * H, device=DEV).to(torch.bfloat16)
+        ex["hh"].dgrad(dg[:B].contiguous(), B, dx_add=feat[:B].contiguous())
+        ex["ih"].dgrad(dg, n)
+        ex["hh"].wgrad(feat, dg, n)
+        ex["ih"].wgrad(feat, dg, n, side=side)
+    finally:
+        LY.set_engine("auto")
+    ls = m.lstm
+    ref = feat.float() @ ls.weight_ih_l0[:, :512].t().to(torch.bfloat16).float() + side @ ls.weight_ih_l0[:, 512:].t() + ls.bias_ih_l0
+    assert rel_err(gx.cpu(), ref.detach().cpu()) < 1e-2
+    ref_dw = dg.float().t() @ feat.float()
+    assert rel_err(ls.weight_hh_l0.grad.cpu(), ref_dw.cpu()) < 1e-2
+    assert rel_err(ls.bias_hh_l0.grad.cpu(), dg.float().sum(0).cpu()) < 1e-2
+
+
+def test_policy_and_ppo_loss_golden():
+    g = golden("policy_ppo_icm")
+    c = policy_case(g)
+    T, B, A = c["T"], c["B"], c["A"]
+    m = make_model(A, c["params"], c["icm_params"])
+    dv = lambda t: t.to(DEV)
+    with torch.no_grad():
+        pi, v, rnn = m(dv(c["obs"]), dv(R.onehot(c["prev_action"], A)), torch.zeros(T, B), (dv(c["h0"]), dv(c["c0"])))
+    assert rel_err(pi.cpu(), g["pi"]) < 1e-2 and rel_err(v.cpu(), g["value"]) < 1e-2
+    assert rel_err(rnn.h.cpu(), g["hn"]) < 1e-2 and rel_err(rnn.c.cpu(), g["cn"]) < 1e-2
+    algo = PPO(curiosity_type="icm", ratio_clip=float(g["ratio_clip"]), value_loss_coeff=float(g["value_loss_coeff"]),
+               entropy_loss_coeff=float(g["entropy_loss_coeff"]), clip_grad_norm=1e9)
+    algo.initialize(m, n_itr=10)
+    h0b, c0b = dv(c["h0"].transpose(0, 1).contiguous()), dv(c["c0"].transpose(0, 1).contiguous())     # [B,1,H]
+    cur = (dv(c["obs"]), dv(c["nxt"]), dv(R.onehot(c["action"], A)))
+    info = algo.loss_and_grads_(dv(c["obs"]), dv(c["prev_action"]), dv(c["action"]), dv(c["ret"]), dv(c["adv"]),
+                                dv(c["valid"]), dv(c["old_prob"]), (h0b, c0b), cur, None)
+    for name, val in [("pi_loss", info.pi_loss), ("value_loss", info.value_loss), ("entropy_loss", info.entropy_loss),
+                      ("entropy", info.entropy), ("perplexity", info.perplexity), ("inv_loss", info.inv_loss),
+                      ("fwd_loss", info.forward_loss), ("loss", info.loss)]:
+        ref = float(g[name])
+        assert abs(float(val) - ref) <= 1e-2 * max(abs(ref), 1e-2), (name, float(val), ref)
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    assert all(v is not None for v in grads.values())
+    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)      # 18 samples: same allowance as the ICM golden case
+    assert not bad, bad
+    gn = float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())))
+    assert abs(gn - float(g["grad_norm"])) / float(g["grad_norm"]) < 5e-2
+
+
+def test_policy_gradients_vs_oracle_larger_batch():
+    """T=12, B=16 (192 samples): per-parameter cosine >= 0.999 and norm within 1e-2 of the oracle's autograd
+    (SURVEY 8d parity gate) for the policy parameters under the PPO loss alone."""
+    T, B, A, seed = 12, 16, 4, 123
+    params = R.make_policy_params(A, seed)
+    icm_params = R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2)
+    m = make_model(A, params, icm_params)
+    obs = R.make_frames(seed + 3, T, B)
+    prev_action, action = R.make_actions(seed + 5, T, B, A), R.make_actions(seed + 6, T, B, A)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A), R.make_normal(seed + 8, T, B), R.make_normal(seed + 9, T, B)
+    valid = 1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    pi, v, _ = O.policy_forward(p, obs, R.onehot(prev_action, A), None)
+    ref = O.ppo_loss(pi, v, action, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)
+    ref[0].backward()
+    algo = PPO(curiosity_type="none", clip_grad_norm=1e9)
+    algo.initialize(m, n_itr=10)
+    dv = lambda t: t.to(DEV)
+    info = algo.loss_and_grads_(dv(obs), dv(prev_action), dv(action), dv(ret), dv(adv), dv(valid), dv(old_prob), None)
+    assert abs(float(info.loss) - float(ref[0])) <= 1e-2 * abs(float(ref[0]))
+    bad = []
+    for k, t in p.items():
+        gq = dict(m.named_parameters())[k].grad.cpu()
+        cs = cosine(gq, t.grad)
+        nr = abs(float(gq.norm()) - float(t.grad.norm())) / float(t.grad.norm())
+        if cs < 0.999 or nr > 1e-2:
+            bad.append((k, cs, nr))
+    assert not bad, bad
+
+
+def test_autograd_dropin_matches_fused_path():
+    """model.forward under autograd + the reference's loss written in torch ops (what rlpyt's PPO.loss does after
+    integration.install()) gives the same gradients as the fused cb_ppo_loss path."""
+    T, B, A, seed = 5, 4, 4, 321
+    params = R.make_policy_params(A, seed)
+    icm_params = R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2)
+    obs = R.make_frames(seed + 3, T, B).to(DEV)
+    prev_action, action = R.make_actions(seed + 5, T, B, A).to(DEV), R.make_actions(seed + 6, T, B, A).to(DEV)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A).to(DEV), R.make_normal(seed + 8, T, B).to(DEV), R.make_normal(seed + 9, T, B).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)).to(DEV)
+    m1 = make_model(A, params, icm_params)
+    pi, v, _ = m1(obs, R.onehot(prev_action.cpu(), A).to(DEV), None, None)
+    loss = O.ppo_loss(pi, v, action, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)[0]      # torch ops on CUDA tensors
+    loss.backward()
+    m2 = make_model(A, params, icm_params)
+    algo = PPO(curiosity_type="none", clip_grad_norm=1e9)
+    algo.initialize(m2, n_itr=10)
+    info = algo.loss_and_grads_(obs, prev_action, action, ret, adv, valid, old_prob, None)
+    assert abs(float(info.loss) - float(loss)) <= 1e-4 * abs(float(loss))
+    g2 = dict(m2.named_parameters())
+    for k, prm in m1.named_parameters():
+        if k.startswith("curiosity_model."):
+            continue
+        assert cosine(prm.grad.cpu(), g2[k].grad.cpu()) > 0.9999, k
+
+
+def test_ppo_optimize_agent_two_iterations_vs_oracle():
+    """Full iteration (ICM bonus -> returns -> epochs x minibatches of policy + ICM loss -> one clip + Adam over
+    all parameters -> LR / ratio-clip decay) against the oracle trained with torch.optim.Adam on the same
+    minibatch order."""
+    T, B, A, seed = 8, 8, 4, 555
+    params = R.make_policy_params(A, seed)
+    icm_params = R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2)
+    m = make_model(A, params, icm_params)
+    algo = PPO(curiosity_type="icm", learning_rate=1e-3, gae_lambda=0.95, minibatches=2, epochs=2)
+    algo.initialize(m, n_itr=4, rng=np.random.RandomState(3))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    q = {k: v.clone().requires_grad_(True) for k, v in icm_params.items()}
+    allp = list(p.values()) + list(q.values())
+    opt = torch.optim.Adam(allp, lr=1e-3)
+    rng = np.random.RandomState(3)
+    ratio_clip, lr = 0.1, 1e-3
+    dv = lambda t: t.to(DEV)
+    for itr in range(2):
+        s = seed + 100 * itr
+        obs, nxt = R.make_frames(s + 3, T, B), R.make_frames(s + 4, T, B)
+        prev_action, action = R.make_actions(s + 5, T, B, A), R.make_actions(s + 6, T, B, A)
+        old_prob = R.make_probs(s + 7, T, B, A)
+        done = R.make_suffix_done(s + 10, T, B, frac=0.3)
+        value, boot = R.make_normal(s + 11, T, B), R.make_normal(s + 12, B)
+        h0, c0 = R.make_normal(s + 13, B, 1, 512) * 0.5, R.make_normal(s + 14, B, 1, 512) * 0.5
+        batch = PpoBatch(dv(obs), dv(nxt), dv(prev_action), dv(action), dv(old_prob), torch.zeros(T, B, device=DEV),
+                         dv(done), dv(value), dv(boot), (dv(h0), dv(c0)))
+        infos = algo.optimize_agent(itr, batch, dropout_masks=None)
+        # ---- oracle
+        with torch.no_grad():
+            r_int = O.icm_bonus(q, obs, nxt, R.onehot(action, A), "idf_burda", 1.0)
+        adv, ret = O.generalized_advantage_estimation(r_int.clone(), value, done, boot, 0.99, 0.95)
+        valid = O.valid_from_done(done)
+        for g_ in opt.param_groups:
+            g_["lr"] = lr
+        k = 0
+        for _ in range(2):
+            idx = np.arange(B)
+            rng.shuffle(idx)
+            for start in range(0, B - B // 2 + 1, B // 2):
+                i = torch.as_tensor(idx[start:start + B // 2])
+                opt.zero_grad()
+                pi, v, _ = O.policy_forward(p, obs[:, i], R.onehot(prev_action[:, i], A),
+                                            (h0[i].transpose(0, 1), c0[i].transpose(0, 1)))
+                pl = O.ppo_loss(pi, v, action[:, i], old_prob[:, i], ret[:, i], adv[:, i], valid[:, i], ratio_clip, 1.0, 0.01)
+                inv, fwd = O.icm_loss(q, obs[:, i], nxt[:, i], R.onehot(action[:, i], A), valid[:, i], "idf_burda", 0.2)
+                total = pl[0] + inv + fwd
+                total.backward()
+                gn = float(torch.nn.utils.clip_grad_norm_(allp, 1.0))
+                opt.step()
+                assert abs(float(infos[k].loss) - float(total)) <= 3e-2 * max(abs(float(total)), 1e-2), (itr, k, float(infos[k].loss), float(total))
+                assert abs(float(infos[k].gradNorm) - gn) / gn < 1e-1, (itr, k, float(infos[k].gradNorm), gn)
+                k += 1
+        assert k == len(infos) == 4
+        lr = 1e-3 * (4 - (itr + 1)) / 4
+        ratio_clip = 0.1 * (4 - itr) / 4
+        assert abs(algo.opt.lr - lr) < 1e-12 and abs(algo.ratio_clip - ratio_clip) < 1e-12
+    named = dict(m.named_parameters())
+    for k_, t in list(p.items()) + [("curiosity_model." + a, b) for a, b in q.items()]:
+        init = params[k_] if k_ in params else icm_params[k_[len("curiosity_model."):]]
+        d_ours = (named[k_].detach().cpu() - init).flatten()
+        d_ref = (t.detach() - init).flatten()
+        assert cosine(d_ours, d_ref) > 0.8, (k_, cosine(d_ours, d_ref))
