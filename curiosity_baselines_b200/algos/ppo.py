@@ -85,9 +85,13 @@ class PPO:
         terms = torch.empty(4, n, dtype=torch.float32, device=dev)
         dlogits = torch.empty(n, A, dtype=torch.float32, device=dev)
         dvalue = torch.empty(n, dtype=torch.float32, device=dev)
-        L.call("cb_ppo_loss", L.ptr(s["logits"]), L.ptr(s["value"]), L.ptr(action.reshape(n).contiguous()),
-               L.ptr(old_prob.reshape(n, A).float().contiguous()), L.ptr(advantage.reshape(n).contiguous()),
-               L.ptr(return_.reshape(n).contiguous()), L.ptr(coef), float(self.ratio_clip), float(self.value_loss_coeff),
+        # (named so that the operands outlive the asynchronous launch)
+        act_i = action.to(dev, torch.int64).reshape(n).contiguous()
+        old_p = old_prob.to(dev, torch.float32).reshape(n, A).contiguous()
+        adv_f = advantage.to(dev, torch.float32).reshape(n).contiguous()
+        ret_f = return_.to(dev, torch.float32).reshape(n).contiguous()
+        L.call("cb_ppo_loss", L.ptr(s["logits"]), L.ptr(s["value"]), L.ptr(act_i), L.ptr(old_p), L.ptr(adv_f),
+               L.ptr(ret_f), L.ptr(coef), float(self.ratio_clip), float(self.value_loss_coeff),
                float(self.entropy_loss_coeff), None, L.ptr(terms), L.ptr(dlogits), L.ptr(dvalue), n, A, st)
         means = torch.empty(4, dtype=torch.float32, device=dev)
         for i in range(4):

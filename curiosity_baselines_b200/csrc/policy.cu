@@ -147,7 +147,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, const float* _
         ent -= p[a] * logf(p[a] + EPS);
         if (prob_out) prob_out[m * A + a] = p[a];
     }
-    const int act = (int)action[m];
+    const int act = min(max((int)action[m], 0), A - 1);     // an out-of-range index must not fault the context
     const float den = old_prob[m * A + act] + EPS;
     const float ratio = (p[act] + EPS) / den;
     const float adv = advantage[m];
