@@ -82,6 +82,9 @@ _SIGS = {
     "cb_softmax_bwd": [_P, _P, _P, _L, _I, _P],
     "cb_ppo_loss": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _L, _I, _P],
     "cb_add_to_bf16": [_P, _P, _P, _L, _P],
+    "cb_policy_heads_supported": [_I, _I],
+    "cb_policy_heads_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "cb_policy_heads_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "cb_sumsq": [_P, _L, _P, _P],
     "cb_adam_clip_step": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P],
     "cb_h2d_2d": [_P, _L, _P, _L, _L, _L, _P],

@@ -188,6 +188,191 @@ __global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __r
     out[i] = cb::f2bf(a[i] + (b ? b[i] : 0.f));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// pi / value heads (atari_lstm_model.py:144-145): N = A and N = 1 Linear layers over the same [n,H] LSTM output.
+// As GEMMs they are 5..8 columns wide -- HBM-bound on reading h -- so they run fused on CUDA cores: one warp per
+// row, bf16 weights (the rounding the GEMM engines apply) in shared memory, fp32 accumulation, softmax in the
+// same pass.  Algorithmic bytes: forward n*H*2 read; backward n*H*2 read + n*H*2 written.
+constexpr int kHeadsMaxO = 8;       // A + 1 <= 8 outputs (larger action sets use the generic Linear path)
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+__device__ __forceinline__ void stage_head_weights(__nv_bfloat16* sw, const float* w_pi, const float* w_v, int H, int A) {
+    for (int i = threadIdx.x; i < (A + (w_v ? 1 : 0)) * H; i += blockDim.x) {
+        int o = i / H, j = i - o * H;
+        sw[i] = cb::f2bf(o < A ? w_pi[(size_t)o * H + j] : w_v[j]);
+    }
+}
+
+__global__ void __launch_bounds__(512) policy_heads_fwd_kernel(
+        const __nv_bfloat16* __restrict__ h, const float* __restrict__ w_pi, const float* __restrict__ b_pi,
+        const float* __restrict__ w_v, const float* __restrict__ b_v, float* __restrict__ logits,
+        float* __restrict__ value, float* __restrict__ prob, int64_t n, int H, int A) {
+    extern __shared__ __align__(16) unsigned char heads_smem[];
+    __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(heads_smem);
+    stage_head_weights(sw, w_pi, w_v, H, A);
+    __syncthreads();
+    const int AO = A + (w_v ? 1 : 0), lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float bias = lane < A ? b_pi[lane] : ((lane == A && w_v) ? b_v[0] : 0.f);
+    constexpr int R = 2;            // rows in flight per warp
+    for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n; row0 += warps * R) {
+        float acc[R][kHeadsMaxO];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int o = 0; o < kHeadsMaxO; ++o) acc[r][o] = 0.f;
+        for (int j0 = lane * 8; j0 < H; j0 += 256) {
+            uint4 hv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                hv[r] = (row0 + r < n) ? __ldg(reinterpret_cast<const uint4*>(h + (size_t)(row0 + r) * H + j0))
+                                       : make_uint4(0, 0, 0, 0);
+            float hf[R][8];
+#pragma unroll
+            for (int r = 0; r < R; ++r) bf16x8_to_f32(hv[r], hf[r]);
+#pragma unroll
+            for (int o = 0; o < kHeadsMaxO; ++o) {
+                if (o < AO) {
+                    float wf[8];
+                    bf16x8_to_f32(*reinterpret_cast<const uint4*>(sw + (size_t)o * H + j0), wf);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[r][o] = fmaf(hf[r][k], wf[k], acc[r][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float mine = 0.f;
+#pragma unroll
+            for (int o = 0; o < kHeadsMaxO; ++o) {
+                float s = cb::warp_sum(acc[r][o]);
+                if (lane == o) mine = s;
+            }
+            mine += bias;
+            // softmax over lanes 0..A-1
+            float mx = lane < A ? mine : -INFINITY;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float e = lane < A ? expf(mine - mx) : 0.f;
+            float se = cb::warp_sum(e);
+            const int64_t row = row0 + r;
+            if (row < n) {
+                if (lane < A) {
+                    logits[row * A + lane] = mine;
+                    if (prob) prob[row * A + lane] = e / se;
+                } else if (lane == A && w_v) {
+                    value[row] = mine;
+                }
+            }
+        }
+    }
+}
+
+// dh = dlogits W_pi + dvalue w_v (bf16);  dW_pi += dlogits^T h, dw_v += dvalue^T h, db likewise.
+// A warp owns one 256-column segment of the rows it visits, so its slice of dW stays in registers.
+__global__ void __launch_bounds__(256, 2) policy_heads_bwd_kernel(
+        const __nv_bfloat16* __restrict__ h, const float* __restrict__ dlogits, const float* __restrict__ dvalue,
+        const float* __restrict__ w_pi, const float* __restrict__ w_v, __nv_bfloat16* __restrict__ dh,
+        float* __restrict__ dw_pi, float* __restrict__ db_pi, float* __restrict__ dw_v, float* __restrict__ db_v,
+        int64_t n, int H, int A, int h_relu) {
+    extern __shared__ __align__(16) unsigned char heads_smem[];
+    const int AO = A + (w_v ? 1 : 0), lane = threadIdx.x & 31;
+    __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(heads_smem);
+    float* sdw = reinterpret_cast<float*>(heads_smem + (((size_t)AO * H * 2 + 15) & ~(size_t)15));
+    float* sdb = sdw + (size_t)AO * H;
+    stage_head_weights(sw, w_pi, w_v, H, A);
+    for (int i = threadIdx.x; i < AO * H; i += blockDim.x) sdw[i] = 0.f;
+    if (threadIdx.x < kHeadsMaxO) sdb[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int nseg = H >> 8;
+    const int64_t gwarp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);      // a multiple of nseg (host guarantees)
+    const int seg = (int)(gwarp % nseg);
+    const int j0 = seg * 256 + lane * 8;
+    float accw[kHeadsMaxO][8], accb[kHeadsMaxO];
+#pragma unroll
+    for (int o = 0; o < kHeadsMaxO; ++o) {
+        accb[o] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accw[o][k] = 0.f;
+    }
+    constexpr int R = 2;
+    for (int64_t row0 = (gwarp / nseg) * R; row0 < n; row0 += (warps / nseg) * R) {
+        uint4 hv[R];
+        float d[R][kHeadsMaxO];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            const bool ok = row < n;
+            hv[r] = ok ? __ldg(reinterpret_cast<const uint4*>(h + (size_t)row * H + j0)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int o = 0; o < kHeadsMaxO; ++o)
+                d[r][o] = !ok ? 0.f : (o < A ? __ldg(dlogits + row * A + o) : ((o == A && w_v) ? __ldg(dvalue + row) : 0.f));
+        }
+        float hf[R][8], g[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            bf16x8_to_f32(hv[r], hf[r]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[r][k] = 0.f;
+        }
+#pragma unroll
+        for (int o = 0; o < kHeadsMaxO; ++o) {
+            if (o < AO) {                    // weights of my 8 columns: conflict-free 16-byte shared loads
+                float wf[8];
+                bf16x8_to_f32(*reinterpret_cast<const uint4*>(sw + (size_t)o * H + j0), wf);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    accb[o] += d[r][o];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        g[r][k] = fmaf(d[r][o], wf[k], g[r][k]);
+                        accw[o][k] = fmaf(d[r][o], hf[r][k], accw[o][k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            if (row < n) {
+                if (h_relu) {            // h is a ReLU output: the gradient passes only where it was positive
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[r][k] = hf[r][k] > 0.f ? g[r][k] : 0.f;
+                }
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(g[r][0], g[r][1]), p1 = __floats2bfloat162_rn(g[r][2], g[r][3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(g[r][4], g[r][5]), p3 = __floats2bfloat162_rn(g[r][6], g[r][7]);
+                uint4 out;
+                out.x = *reinterpret_cast<uint32_t*>(&p0); out.y = *reinterpret_cast<uint32_t*>(&p1);
+                out.z = *reinterpret_cast<uint32_t*>(&p2); out.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(dh + (size_t)row * H + j0) = out;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kHeadsMaxO; ++o) {
+        if (o < AO) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(sdw + (size_t)o * H + j0 + k, accw[o][k]);
+            if (seg == 0 && lane == 0) atomicAdd(sdb + o, accb[o]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < AO * H; i += blockDim.x) {
+        int o = i / H, j = i - o * H;
+        atomicAdd(o < A ? dw_pi + (size_t)o * H + j : dw_v + j, sdw[i]);
+    }
+    if (threadIdx.x < AO) atomicAdd(threadIdx.x < A ? db_pi + threadIdx.x : db_v, sdb[threadIdx.x]);
+}
+
 }  // namespace
 
 extern "C" int cb_lstm_cell_fwd(const float* gx, const float* gh, const float* c_prev, float* gates, float* c_out,
@@ -246,6 +431,63 @@ extern "C" int cb_add_to_bf16(const float* a, const float* b, void* out_bf16, in
     CB_REQUIRE(a && out_bf16 && n >= 1, CB_E_ARG, "cb_add_to_bf16: bad argument");
     add_to_bf16_kernel<<<(unsigned)cb::ceil_div<int64_t>(n, 256), 256, 0, cb::as_stream(stream)>>>(
         a, b, (__nv_bfloat16*)out_bf16, n);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// `outputs` = all output columns (A logits + 1 value, or A when there is no value head)
+extern "C" int cb_policy_heads_supported(int32_t H, int32_t outputs) {
+    return (outputs >= 1 && outputs <= kHeadsMaxO && H >= 256 && H % 256 == 0 && H <= 2048) ? 1 : 0;
+}
+
+extern "C" int cb_policy_heads_fwd(const void* h_bf16, const float* w_pi, const float* b_pi, const float* w_v,
+                                   const float* b_v, float* logits, float* value, float* prob, int64_t n, int32_t H,
+                                   int32_t A, void* stream) {
+    CB_REQUIRE(h_bf16 && w_pi && b_pi && logits && n >= 1 && A >= 1, CB_E_ARG, "cb_policy_heads_fwd: bad argument");
+    CB_REQUIRE(!w_v || (b_v && value), CB_E_ARG, "cb_policy_heads_fwd: the value head needs b_v and value");
+    CB_REQUIRE(cb_policy_heads_supported(H, A + (w_v ? 1 : 0)), CB_E_ARG,
+               "cb_policy_heads_fwd: needs <= 8 output columns and H a multiple of 256");
+    CB_REQUIRE((((uintptr_t)h_bf16) & 15) == 0, CB_E_ALIGN, "cb_policy_heads_fwd: h must be 16-byte aligned");
+    size_t smem = (size_t)(A + (w_v ? 1 : 0)) * H * 2;
+    int blocks = (int)std::min<int64_t>(148 * 2, cb::ceil_div<int64_t>(n, 16 * 2));
+    policy_heads_fwd_kernel<<<blocks, 512, smem, cb::as_stream(stream)>>>(
+        (const __nv_bfloat16*)h_bf16, w_pi, b_pi, w_v, b_v, logits, value, prob, n, H, A);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_policy_heads_bwd(const void* h_bf16, const float* dlogits, const float* dvalue, const float* w_pi,
+                                   const float* w_v, void* dh_bf16, float* dw_pi, float* db_pi, float* dw_v,
+                                   float* db_v, int64_t n, int32_t H, int32_t A, int32_t h_act, void* stream) {
+    CB_REQUIRE(h_bf16 && dlogits && w_pi && dh_bf16 && dw_pi && db_pi && n >= 1 && A >= 1, CB_E_ARG,
+               "cb_policy_heads_bwd: bad argument");
+    CB_REQUIRE(!w_v || (dvalue && dw_v && db_v), CB_E_ARG, "cb_policy_heads_bwd: the value head needs dvalue, dw_v, db_v");
+    CB_REQUIRE(h_act == CB_ACT_NONE || h_act == CB_ACT_RELU, CB_E_ARG, "cb_policy_heads_bwd: h_act must be none or relu");
+    CB_REQUIRE(cb_policy_heads_supported(H, A + (w_v ? 1 : 0)), CB_E_ARG,
+               "cb_policy_heads_bwd: needs <= 8 output columns and H a multiple of 256");
+    CB_REQUIRE(((((uintptr_t)h_bf16) | ((uintptr_t)dh_bf16)) & 15) == 0, CB_E_ALIGN,
+               "cb_policy_heads_bwd: h / dh must be 16-byte aligned");
+    cudaStream_t s = cb::as_stream(stream);
+    CB_CUDA(cudaMemsetAsync(dw_pi, 0, sizeof(float) * (size_t)A * H, s));
+    CB_CUDA(cudaMemsetAsync(db_pi, 0, sizeof(float) * (size_t)A, s));
+    if (w_v) {
+        CB_CUDA(cudaMemsetAsync(dw_v, 0, sizeof(float) * (size_t)H, s));
+        CB_CUDA(cudaMemsetAsync(db_v, 0, sizeof(float), s));
+    }
+    const int AO = A + (w_v ? 1 : 0), nseg = H / 256;
+    size_t smem = (((size_t)AO * H * 2 + 15) & ~(size_t)15) + sizeof(float) * ((size_t)AO * H + kHeadsMaxO);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CB_CUDA(cudaFuncSetAttribute(policy_heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    CB_REQUIRE(smem <= 100 * 1024, CB_E_ARG, "cb_policy_heads_bwd: H too large");
+    // 8 warps per block; 8 % nseg == 0 for nseg in {1,2,4,8} so every block covers whole rows
+    CB_REQUIRE(8 % nseg == 0, CB_E_ARG, "cb_policy_heads_bwd: H/256 must divide 8");
+    int blocks = (int)std::min<int64_t>(148 * 2, cb::ceil_div<int64_t>(n * nseg, 8 * 2));
+    policy_heads_bwd_kernel<<<blocks, 256, smem, s>>>((const __nv_bfloat16*)h_bf16, dlogits, dvalue, w_pi, w_v,
+                                                      (__nv_bfloat16*)dh_bf16, dw_pi, db_pi, dw_v, db_v, n, H, A,
+                                                      h_act == CB_ACT_RELU ? 1 : 0);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -354,7 +354,15 @@ class _IcmBase(nn.Module):
         # inverse model (icm.py:88-92, 125)
         cat = torch.cat([phi1_b, phi2_b], 1)
         h, _ = ex["inv0"].forward(cat, n)
-        _, logits = ex["inv2"].forward(h, n, out_bf16=False, out_f32=True)
+        inv2 = self.inverse_model[2]
+        # Linear(F -> A) is A <= 8 columns wide: HBM-bound on reading h, so it runs as one fused CUDA-core pass
+        fused_head = bool(L.load().cb_policy_heads_supported(F, self.action_size))
+        if fused_head:
+            logits = torch.empty(n, self.action_size, dtype=torch.float32, device=dev)
+            L.call("cb_policy_heads_fwd", L.ptr(h), L.ptr(inv2.weight), L.ptr(inv2.bias), None, None, L.ptr(logits),
+                   None, None, n, F, self.action_size, st)
+        else:
+            _, logits = ex["inv2"].forward(h, n, out_bf16=False, out_f32=True)
         ce = torch.empty(n, dtype=torch.float32, device=dev)
         coef_inv = torch.empty(n, dtype=torch.float32, device=dev)
         L.call("cb_loss_coef", L.ptr(valid), None, float(self.inverse_loss_wt), L.ptr(denom), L.ptr(coef_inv), n, st)
@@ -391,9 +399,17 @@ class _IcmBase(nn.Module):
                self._mask_scale if mask is not None else 1.0, L.ptr(dpred), n, F, E, st)
         fmx.run_backward(phi1_b, action, saved, dpred, n)
         # ---- backward: inverse model -> both encoder passes
-        dlog_b = dlogits.to(torch.bfloat16)
-        ex["inv2"].wgrad(h, dlog_b, n)
-        dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
+        if fused_head:
+            for prm in (inv2.weight, inv2.bias):
+                if prm.grad is None:
+                    prm.grad = torch.zeros_like(prm)
+            dh = torch.empty(n, F, dtype=torch.bfloat16, device=dev)
+            L.call("cb_policy_heads_bwd", L.ptr(h), L.ptr(dlogits), None, L.ptr(inv2.weight), None, L.ptr(dh),
+                   L.ptr(inv2.weight.grad), L.ptr(inv2.bias.grad), None, None, n, F, self.action_size, L.ACT_RELU, st)
+        else:
+            dlog_b = dlogits.to(torch.bfloat16)
+            ex["inv2"].wgrad(h, dlog_b, n)
+            dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
         ex["inv0"].wgrad(cat, dh, n)
         dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
         self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False)

@@ -11,13 +11,17 @@ What gets replaced (reference file:line -> ours):
   PolicyGradientAlgo.process_returns  (algos/pg/base.py:53-108)       -> algos.pg_base.process_returns
   RecurrentCategoricalPgAgentBase.curiosity_step / curiosity_loss
                                       (agents/pg/categorical.py:83-130) -> agents.hooks
-The policy network itself (AtariLstmModel conv + LSTM heads) stays the reference's torch code: it is
-SURVEY 8(f) rank 1, the next row after the hot path.
+With ``policy=True`` the policy network is replaced as well:
+  rlpyt/models/pg/atari_lstm_model.py:19-154 AtariLstmModel           -> pg.atari_lstm_model.AtariLstmModel
+  (also the ``ModelCls`` defaults of AtariLstmAgent / AlternatingAtariLstmAgent, agents/pg/atari.py:26-36)
+The reference's ``PPO.loss`` then back-propagates through our kernels via the model's autograd boundary.  It is
+opt-in because the library has no CPU path: use it with samplers that evaluate the agent on the GPU
+(``GpuSampler``); ``CpuSampler`` workers evaluate a CPU copy of the model and need the reference class.
 """
 import importlib
 
 
-def install(strict=True, reuse_features=True):
+def install(strict=True, reuse_features=True, policy=False):
     """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
     that fail to import (e.g. optional dependencies missing).  ``reuse_features``: RND models built afterwards reuse
     a batch's features between compute_bonus and compute_loss when the frames are verified equal (the reference
@@ -61,4 +65,22 @@ def install(strict=True, reuse_features=True):
     patch("rlpyt.agents.pg.categorical",
           **{"RecurrentCategoricalPgAgentBase.curiosity_step": hooks.curiosity_step,
              "RecurrentCategoricalPgAgentBase.curiosity_loss": hooks.curiosity_loss})
+    if policy:
+        from .pg import atari_lstm_model as ours
+        try:
+            ref = importlib.import_module("rlpyt.models.pg.atari_lstm_model")
+            ours.AtariLstmModel.rnn_state_cls = ref.RnnState       # a namedarraytuple: the agents slice / transpose it
+        except Exception:
+            if strict:
+                raise
+        patch("rlpyt.models.pg.atari_lstm_model", AtariLstmModel=ours.AtariLstmModel)
+        patch("rlpyt.agents.pg.atari", AtariLstmModel=ours.AtariLstmModel)
+        try:
+            atari = importlib.import_module("rlpyt.agents.pg.atari")
+            for cls in (atari.AtariLstmAgent, atari.AlternatingAtariLstmAgent):
+                cls.__init__.__defaults__ = (ours.AtariLstmModel,)
+                patched.append(f"rlpyt.agents.pg.atari.{cls.__name__}.__init__ (ModelCls default)")
+        except Exception:
+            if strict:
+                raise
     return patched

@@ -10,7 +10,8 @@ holders; everything runs in libcuriosity_b200.so:
                         k-block, like ``torch.cat`` at :136-139); per timestep h W_hh^T on the same GEMM kernel
                         + ``cb_lstm_cell_fwd``; backward through time = ``cb_lstm_cell_bwd`` + the recurrent
                         dgrad GEMM per step, then both weight gradients as single GEMMs over all T*B rows
-  pi / value heads .... N = A and N = 1 Linear layers (generic engine) + ``cb_softmax_fwd``
+  pi / value heads .... ``cb_policy_heads_fwd/_bwd``: both heads + softmax in one HBM-bound pass over the LSTM
+                        output (A + 1 <= 8; larger action sets: generic Linear layers + ``cb_softmax_fwd``)
 
 There is no CPU fallback.
 """
@@ -86,6 +87,8 @@ class _PolicyFn(torch.autograd.Function):
 
 class AtariLstmModel(nn.Module):
     """atari_lstm_model.py:19-154."""
+
+    rnn_state_cls = RnnState        # integration.install(policy=True) swaps in rlpyt's namedarraytuple of the same name
 
     def __init__(self, image_shape, output_size, fc_sizes=512, lstm_size=512, use_maxpool=False, channels=None,
                  kernel_sizes=None, strides=None, paddings=None, curiosity_kwargs=dict(curiosity_alg="none"),
@@ -202,21 +205,73 @@ class AtariLstmModel(nn.Module):
             h_all[0].copy_(h0.to(dev).reshape(B, H))
             c_all[0].copy_(c0.to(dev).reshape(B, H))
         hn = torch.empty(1, B, H, dtype=torch.float32, device=dev)
-        for t in range(T):
-            _, gh = ex["hh"].forward(h_all[t], B, out_bf16=False, out_f32=True)
-            L.call("cb_lstm_cell_fwd", L.ptr(gates[t]), L.ptr(gh), L.ptr(c_all[t]), L.ptr(gates[t]), L.ptr(c_all[t + 1]),
-                   L.ptr(h_all[t + 1]), L.ptr(hn) if t == T - 1 else None, B, H, st)
+        self._lstm_forward(gates, h_all, c_all, hn)
         h_out = h_all[1:].reshape(n, H)
-        _, logits = ex["pi"].forward(h_out, n, out_bf16=False, out_f32=True)
-        _, value = ex["value"].forward(h_out, n, out_bf16=False, out_f32=True)
         prob = torch.empty(n, A, dtype=torch.float32, device=dev)
-        L.call("cb_softmax_fwd", L.ptr(logits), L.ptr(prob), n, A, st)
+        if self._fused_heads():
+            logits = torch.empty(n, A, dtype=torch.float32, device=dev)
+            value = torch.empty(n, dtype=torch.float32, device=dev)
+            L.call("cb_policy_heads_fwd", L.ptr(h_out), L.ptr(self.pi.weight), L.ptr(self.pi.bias),
+                   L.ptr(self.value.weight), L.ptr(self.value.bias), L.ptr(logits), L.ptr(value), L.ptr(prob), n, H, A, st)
+        else:
+            _, logits = ex["pi"].forward(h_out, n, out_bf16=False, out_f32=True)
+            _, value = ex["value"].forward(h_out, n, out_bf16=False, out_f32=True)
+            L.call("cb_softmax_fwd", L.ptr(logits), L.ptr(prob), n, A, st)
         out = dict(T=T, B=B, n=n, logits=logits, prob=prob, value=value.reshape(n), hn=hn,
                    cn=c_all[T].clone().unsqueeze(0))
         if save:
             out.update(keep=keep, x=x, dtype=dtype, strides=strides, acts=acts, feat=feat, side=side, gates=gates,
                        h_all=h_all, c_all=c_all)
         return out
+
+    def _fused_heads(self):
+        return bool(L.load().cb_policy_heads_supported(self.lstm_size, self.action_size + 1))
+
+    def _heads_backward(self, h_out, dlogits, dvalue, n):
+        """Gradients of the pi / value heads (into ``.grad``) and the gradient arriving at the LSTM output (bf16)."""
+        ex, st = self._exec, L.stream()
+        dev, H, A = ex["dev"], self.lstm_size, self.action_size
+        if self._fused_heads():
+            for prm in (self.pi.weight, self.pi.bias, self.value.weight, self.value.bias):
+                if prm.grad is None:
+                    prm.grad = torch.zeros_like(prm)
+            dh = torch.empty(n, H, dtype=torch.bfloat16, device=dev)
+            dlogits, dvalue = dlogits.contiguous(), dvalue.contiguous()
+            L.call("cb_policy_heads_bwd", L.ptr(h_out), L.ptr(dlogits), L.ptr(dvalue), L.ptr(self.pi.weight),
+                   L.ptr(self.value.weight), L.ptr(dh), L.ptr(self.pi.weight.grad), L.ptr(self.pi.bias.grad),
+                   L.ptr(self.value.weight.grad), L.ptr(self.value.bias.grad), n, H, A, L.ACT_NONE, st)
+            return dh
+        dlog_b = torch.empty(n, A, dtype=torch.bfloat16, device=dev)
+        dval_b = torch.empty(n, 1, dtype=torch.bfloat16, device=dev)
+        L.call("cb_add_to_bf16", L.ptr(dlogits), None, L.ptr(dlog_b), n * A, st)
+        L.call("cb_add_to_bf16", L.ptr(dvalue), None, L.ptr(dval_b), n, st)
+        ex["pi"].wgrad(h_out, dlog_b, n)
+        ex["value"].wgrad(h_out, dval_b, n)
+        dh = ex["pi"].dgrad(dlog_b, n)
+        return ex["value"].dgrad(dval_b, n, dx_add=dh)
+
+    def _lstm_forward(self, gates, h_all, c_all, hn):
+        """The recurrence over T.  gates fp32 [T,B,4H] holds x W_ih^T + b_ih on entry and the activated gates on
+        exit; h_all bf16 / c_all fp32 [T+1,B,H] with row 0 = the initial state; hn fp32 [1,B,H] or None."""
+        ex, st = self._exec, L.stream()
+        T, B, H = gates.shape[0], gates.shape[1], self.lstm_size
+        for t in range(T):
+            _, gh = ex["hh"].forward(h_all[t], B, out_bf16=False, out_f32=True)
+            L.call("cb_lstm_cell_fwd", L.ptr(gates[t]), L.ptr(gh), L.ptr(c_all[t]), L.ptr(gates[t]), L.ptr(c_all[t + 1]),
+                   L.ptr(h_all[t + 1]), L.ptr(hn) if (hn is not None and t == T - 1) else None, B, H, st)
+
+    def _lstm_backward(self, gates, h_all, c_all, dh_out, dgates):
+        """Back-propagation through time.  dh_out bf16 [T,B,H]: gradient arriving at every h_t from the heads;
+        dgates bf16 [T,B,4H] receives the gradient w.r.t. the gate pre-activations."""
+        ex, st = self._exec, L.stream()
+        T, B, H = gates.shape[0], gates.shape[1], self.lstm_size
+        dc = [torch.empty(B, H, dtype=torch.float32, device=gates.device) for _ in range(2)]
+        dh = dh_out[T - 1]
+        for t in range(T - 1, -1, -1):
+            L.call("cb_lstm_cell_bwd", L.ptr(dh), L.ptr(dc[(t + 1) & 1]) if t < T - 1 else None, L.ptr(gates[t]),
+                   L.ptr(c_all[t]), L.ptr(c_all[t + 1]), L.ptr(dgates[t]), L.ptr(dc[t & 1]), B, H, st)
+            if t > 0:
+                dh = ex["hh"].dgrad(dgates[t], B, dx_add=dh_out[t - 1])              # dL/dh_{t-1}, all paths
 
     def _run_backward(self, s, dlogits, dvalue):
         """dlogits fp32 [n,A], dvalue fp32 [n]: gradients of the loss w.r.t. the pi logits and the value.
@@ -227,23 +282,10 @@ class AtariLstmModel(nn.Module):
         st = L.stream()
         h_all, c_all, gates = s["h_all"], s["c_all"], s["gates"]
         h_out = h_all[1:].reshape(n, H)
-        dlog_b = torch.empty(n, A, dtype=torch.bfloat16, device=dev)
-        dval_b = torch.empty(n, 1, dtype=torch.bfloat16, device=dev)
-        L.call("cb_add_to_bf16", L.ptr(dlogits), None, L.ptr(dlog_b), n * A, st)
-        L.call("cb_add_to_bf16", L.ptr(dvalue), None, L.ptr(dval_b), n, st)
-        ex["pi"].wgrad(h_out, dlog_b, n)
-        ex["value"].wgrad(h_out, dval_b, n)
-        dh_out = ex["pi"].dgrad(dlog_b, n)
-        dh_out = ex["value"].dgrad(dval_b, n, dx_add=dh_out).view(T, B, H)          # bf16 [T,B,H]
+        dh_out = self._heads_backward(h_out, dlogits, dvalue, n).view(T, B, H)      # bf16 [T,B,H]
         # ---- back through time
         dgates = torch.empty(T, B, 4 * H, dtype=torch.bfloat16, device=dev)
-        dc = [torch.empty(B, H, dtype=torch.float32, device=dev) for _ in range(2)]
-        dh = dh_out[T - 1]
-        for t in range(T - 1, -1, -1):
-            L.call("cb_lstm_cell_bwd", L.ptr(dh), L.ptr(dc[(t + 1) & 1]) if t < T - 1 else None, L.ptr(gates[t]),
-                   L.ptr(c_all[t]), L.ptr(c_all[t + 1]), L.ptr(dgates[t]), L.ptr(dc[t & 1]), B, H, st)
-            if t > 0:
-                dh = ex["hh"].dgrad(dgates[t], B, dx_add=dh_out[t - 1])              # dL/dh_{t-1}, all paths
+        self._lstm_backward(gates, h_all, c_all, dh_out, dgates)
         dg = dgates.view(n, 4 * H)
         # ---- weight gradients as single GEMMs over all T*B rows
         ex["hh"].wgrad(h_all[:T].reshape(n, H), dg, n)
@@ -271,4 +313,4 @@ class AtariLstmModel(nn.Module):
             pi, v = pi.reshape(B, -1), v.reshape(B)
         elif lead == 0:
             pi, v = pi.reshape(-1), v.reshape(())
-        return pi, v, RnnState(h=hn, c=cn)
+        return pi, v, self.rnn_state_cls(h=hn, c=cn)

@@ -279,6 +279,24 @@ int cb_ppo_loss(const float* logits, const float* value, const int64_t* action, 
                 const float* advantage, const float* return_, const float* coef, float ratio_clip,
                 float value_coeff, float entropy_coeff, float* prob_out, float* terms, float* dlogits,
                 float* dvalue, int64_t n, int32_t a, void* stream);
+/* atari_lstm_model.py:144-145 fused: logits = h W_pi^T + b_pi (fp32 [n,A]), value = h w_v + b_v (fp32 [n]),
+ * prob = softmax(logits) (optional) in ONE pass over h (bf16 [n,H], 16-byte aligned rows); weights are the fp32
+ * masters (rounded to bf16 on the fly like the GEMM engines do), fp32 accumulation.  HBM-bound: n*H*2 bytes read.
+ * The value head is optional (w_v = b_v = value = NULL): the same kernel then serves any narrow Linear(H -> A)
+ * over bf16 rows, e.g. the last layer of ICM's inverse model (icm.py:88-92).
+ * cb_policy_heads_supported(H, outputs): outputs (= A + 1, or A without a value head) <= 8 and
+ * H in {256, 512, 1024, 2048}; other shapes use cb_conv_fwd. */
+int cb_policy_heads_supported(int32_t H, int32_t outputs);
+int cb_policy_heads_fwd(const void* h_bf16, const float* w_pi, const float* b_pi, const float* w_v,
+                        const float* b_v, float* logits, float* value, float* prob, int64_t n, int32_t H,
+                        int32_t A, void* stream);
+/* backward of both heads in one pass: dh (bf16 [n,H]) = (dlogits W_pi + dvalue w_v) .* act'(h) with h_act =
+ * CB_ACT_NONE (LSTM output) or CB_ACT_RELU (h is a ReLU output, icm.py:90);  dw_pi [A,H], db_pi [A], dw_v [H],
+ * db_v [1] (fp32, overwritten) = the weight / bias gradients.  n*H*2 bytes read + n*H*2 written.
+ * The value-head operands may be NULL together (see above). */
+int cb_policy_heads_bwd(const void* h_bf16, const float* dlogits, const float* dvalue, const float* w_pi,
+                        const float* w_v, void* dh_bf16, float* dw_pi, float* db_pi, float* dw_v, float* db_v,
+                        int64_t n, int32_t H, int32_t A, int32_t h_act, void* stream);
 /* out (bf16) = a + b (fp32, b may be NULL): gradient hand-over between fp32 loss heads and bf16 GEMM operands */
 int cb_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
 

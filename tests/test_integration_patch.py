@@ -40,5 +40,16 @@ def test_install_patches_reference_modules():
                                                          batch_norm=False, prediction_beta=1.0, forward_loss_wt=0.2))
         assert isinstance(model.curiosity_model, ICM)
         assert "curiosity_model.encoder.model.0.weight" in model.state_dict()
+        # opt-in: the policy network itself
+        patched = cbi.install(policy=True)
+        import rlpyt.agents.pg.atari as atari
+        from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel as Ours
+        assert alm.AtariLstmModel is Ours and atari.AtariLstmModel is Ours
+        assert atari.AtariLstmAgent.__init__.__defaults__ == (Ours,)
+        assert Ours.rnn_state_cls is alm.RnnState
+        agent = atari.AtariLstmAgent(model_kwargs=dict(curiosity_kwargs=dict(
+            curiosity_alg="icm", feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
+            forward_loss_wt=0.2)))
+        assert agent.ModelCls is Ours
     finally:
         sys.path.remove(REF)

@@ -1,5 +1,6 @@
 """Aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel.
-    python tools/launch_summary.py launches.csv [first_launch_index]   (default: second half = the timed step)"""
+    python tools/launch_summary.py launches.csv [first_launch_index [top_n [end_index]]]
+    (default: second half = the timed step)"""
 import collections
 import csv
 import sys
@@ -9,7 +10,8 @@ h = rows[0]
 ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 data = rows[1:]
 start = int(sys.argv[2]) if len(sys.argv) > 2 else len(data) // 2
-sel = data[start:]
+end = int(sys.argv[4]) if len(sys.argv) > 4 else len(data)
+sel = data[start:end]
 agg, cnt = collections.Counter(), collections.Counter()
 for r in sel:
     v = float(r[vi].replace(",", ""))
