@@ -289,6 +289,50 @@ def ndigo_model(args, rank, world, local):
 
 # ------------------------------------------------------------------------------ B200 arm
 # ------------------------------------------------------------------------------ ICM + LSTM PPO (BASELINE configs[3])
+def cpu_reference_ppo(T, B, A, epochs, steps, warmup, seconds_cap=60.0):
+    """The reference's CPU path of one PPO iteration (ICM bonus -> returns -> ``epochs`` x [policy forward, PPO
+    loss, ICM loss, backward, clip_grad_norm_, Adam]) restated in oracle/ (torch CPU fp32, all host threads)."""
+    import recipes as R
+    from oracle import curiosity_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    p = {k: v.clone().requires_grad_(True) for k, v in R.make_policy_params(A, 1).items()}
+    q = {k: v.clone().requires_grad_(True) for k, v in R.make_params(R.icm_shapes(A, "idf_burda"), 2).items()}
+    allp = list(p.values()) + list(q.values())
+    opt = torch.optim.Adam(allp, lr=1e-4)
+    obs, nxt = R.make_frames(3, T, B), R.make_frames(4, T, B)
+    prev, act = R.make_actions(5, T, B, A), R.make_actions(6, T, B, A)
+    old_prob = R.make_probs(7, T, B, A)
+    done = R.make_suffix_done(8, T, B, frac=0.01)
+    value, boot = R.make_normal(9, T, B), R.make_normal(10, B)
+    h0 = (R.make_normal(11, 1, B, 512) * 0.1, R.make_normal(12, 1, B, 512) * 0.1)
+
+    def step():
+        with torch.no_grad():
+            r_int = O.icm_bonus(q, obs, nxt, R.onehot(act, A), "idf_burda", 1.0)
+        adv, ret = O.generalized_advantage_estimation(r_int.clone(), value, done, boot, 0.99, 0.95)
+        valid = O.valid_from_done(done)
+        for _ in range(epochs):
+            opt.zero_grad()
+            pi, v, _ = O.policy_forward(p, obs, R.onehot(prev, A), h0)
+            loss = O.ppo_loss(pi, v, act, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)[0]
+            inv, fwd = O.icm_loss(q, obs, nxt, R.onehot(act, A), valid, "idf_burda", 0.2)
+            (loss + inv + fwd).backward()
+            torch.nn.utils.clip_grad_norm_(allp, 1.0)
+            opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    k = 0
+    for _ in range(steps):
+        step()
+        k += 1
+        if time.perf_counter() - t0 > seconds_cap:
+            break
+    dt = (time.perf_counter() - t0) / k
+    return T * B / dt, dt * 1e3, k
+
+
 def ppo_flops(A, epochs):
     """Algorithmic FLOP per sample of one PPO iteration (SURVEY 8d ii): ICM bonus forward + ``epochs`` x (policy
     forward/backward + ICM forward/backward).  Policy: Burda encoder + LSTM(512+A -> 512) + pi/value heads."""
@@ -389,6 +433,72 @@ def ppo_model(args, rank, world, local):
     p1.record()
     barrier()
     policy_ms = p0.elapsed_time(p1) / 3
+    # the same iteration with ICM.reuse_features: the first epoch's ICM forward is the bonus pass's (same inputs, same
+    # weights; guarded by an equality check of the frames) -- reported separately, the value above recomputes it
+    reuse = None
+    cm = model.curiosity_model
+    try:
+        cm.reuse_features = True
+        one_step()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hits0 = cm.reuse_hits["full"]
+        r0.record()
+        for _ in range(args.steps):
+            one_step()
+        r1.record()
+        barrier()
+        rms = torch.tensor([r0.elapsed_time(r1)], device=dev)
+        if world > 1:
+            dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+        reuse = {"ms_per_step": float(rms) / args.steps, "value": world * T * B / (float(rms) / args.steps * 1e-3),
+                 "unit": "samples/s", "full_hits": cm.reuse_hits["full"] - hits0,
+                 "note": "first-epoch ICM forward reused from the bonus pass (exact; guarded); not the headline value"}
+    finally:
+        cm.reuse_features = False
+        cm._cache = None
+    # end to end: every iteration uploads its batch from pinned host memory (both uint8 frame tensors + the small
+    # rollout tensors) on the compute stream and reads the loss back
+    e2e = None
+    if not args.no_e2e:
+        host = [t.cpu().pin_memory() for t in (obs, nxt, prev, act, old_prob, done, value, boot, h0, c0)]
+        h2d = sum(t.numel() * t.element_size() for t in host)
+
+        from curiosity_baselines_b200.agents.hooks import BatchPrefetcher
+        pre = BatchPrefetcher(dev)
+        pre.prefetch(host)
+
+        def e2e_step():
+            d = pre.get()
+            pre.prefetch(host)               # the next batch's upload runs under this iteration's compute
+            batch = PpoBatch(d[0], d[1], d[2], d[3], d[4], torch.zeros(T, B, device=dev), d[5], d[6], d[7], (d[8], d[9]))
+            out = algo.optimize_agent(0, batch)
+            return float(out[-1].loss)
+
+        e2e_step()
+        barrier()
+        k = max(2, args.steps // 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * T * B / (float(ems) / k * 1e-3), "unit": "samples/s", "ms_per_step": float(ems) / k,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "note": "every iteration's batch (14.8 GB of uint8 frames + the small rollout tensors) is uploaded from "
+                       "pinned host memory on a side stream under the previous iteration's compute (BatchPrefetcher)"}
+        pre.get()
+        del host, pre
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, cms, k = cpu_reference_ppo(T, args.cpu_B, A, epochs, 3, 1)
+        cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
+               "sample": f"T={T}, B={args.cpu_B} ({T * args.cpu_B} samples/iteration) of the same workload, {k} iterations, "
+                         f"{cms:.0f} ms each"}
     hbm, tf_burst, tf_sust, src = peaks()
     flop = ppo_flops(A, epochs)
     if rank == 0:
@@ -402,11 +512,11 @@ def ppo_model(args, rank, world, local):
                                    f"4x84x84 uint8, A={A}",
                        "global_B": B * world, "l2": "inputs (14.8 GB frames/GPU) larger than L2", "engine": args.engine,
                        "parallelism": f"dp{world} over B"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": None,
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
             "roofline": {"bound": "tensor", "kernel": "whole iteration", "achieved": tfl, "peak": tf_sust,
                          "unit": "TFLOP/s", "frac": tfl / tf_sust, "traffic": None,
                          "peak_source": f"{src} bf16 sustained", "mflop_per_sample": flop / 1e6},
-            "cpu_baseline": None, "policy_fwd_loss_bwd_ms": policy_ms,
+            "cpu_baseline": cpu, "with_feature_reuse": reuse, "policy_fwd_loss_bwd_ms": policy_ms,
             "loss": float(infos[-1].loss), "grad_norm": float(infos[-1].gradNorm)}))
     if world > 1:
         dist.destroy_process_group()
@@ -425,6 +535,7 @@ def main():
     ap.add_argument("--minibatches", type=int, default=1, help="ppo_icm: minibatches per epoch (launcher default 1)")
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="ppo_icm: skip the host-buffer end-to-end leg")
     ap.add_argument("--model", default="rnd", choices=["rnd", "icm", "disagreement", "ndigo", "ppo_icm"],
                     help="rnd = BASELINE configs[1] (the headline line); icm / disagreement: the same unit of work "
                          "for the other two conv curiosity models (device-resident inputs only)")

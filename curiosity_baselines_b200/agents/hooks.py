@@ -103,6 +103,36 @@ class FrameStager:
         self.free[self.current] = ev
 
 
+class BatchPrefetcher:
+    """Whole-batch host->device staging on a side stream for the full PPO iteration (ICM / Disagreement read all
+    four frames of observation AND next_observation, 2 x T x B x 28 224 bytes): ``prefetch(host_tensors)`` queues
+    the upload of the NEXT batch from pinned memory while the current one is being consumed; ``get()`` makes the
+    compute stream wait for it and hands the device tensors over.  Two batches are resident at a time."""
+
+    def __init__(self, device):
+        self.dev = torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.pending = None
+
+    def prefetch(self, host_tensors):
+        with torch.cuda.stream(self.stream):
+            dev_tensors = [t.to(self.dev, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending = (dev_tensors, ev)
+
+    def get(self):
+        dev_tensors, ev = self.pending
+        self.pending = None
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        for t in dev_tensors:
+            t.record_stream(cur)          # allocated on the side stream, consumed on the compute stream
+        return dev_tensors
+
+
 @torch.no_grad()
 def curiosity_step(self, curiosity_type, *args):
     dev = _device(self)

@@ -365,3 +365,14 @@ def test_ppo_optimize_agent_two_iterations_vs_oracle():
         d_ours = (named[k_].detach().cpu() - init).flatten()
         d_ref = (t.detach() - init).flatten()
         assert cosine(d_ours, d_ref) > 0.8, (k_, cosine(d_ours, d_ref))
+
+
+def test_batch_prefetcher_delivers_identical_tensors():
+    from curiosity_baselines_b200.agents.hooks import BatchPrefetcher
+    pre = BatchPrefetcher(DEV)
+    host = [R.make_frames(1, 3, 2).pin_memory(), R.make_actions(2, 3, 2, 4).pin_memory(), R.make_normal(3, 3, 2).pin_memory()]
+    for _ in range(3):
+        pre.prefetch(host)
+        got = pre.get()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(got, host))
