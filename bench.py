@@ -242,8 +242,8 @@ def other_model(args, rank, world, local):
 
 def ndigo_model(args, rank, world, local):
     """BASELINE configs[4]: NDIGO on PyColab-shaped 3x5x5 binary frames, A=5, horizon 3, 10 predictors -- the
-    small-tensor regime (0.8 MFLOP per sample): bonus (no grad) + loss forward/backward + Adam.  The GRU is
-    torch.nn.GRU (cuDNN) for now, so this line is a measurement, not a roofline claim."""
+    small-tensor regime (0.8 MFLOP per sample): bonus (no grad) + loss forward/backward + Adam.  Launch- and
+    bandwidth-bound: this line is a measurement, not a tensor-roofline claim."""
     from curiosity_baselines_b200 import _lib as L
     from curiosity_baselines_b200.curiosity.ndigo import NDIGO
     torch.cuda.set_device(local)
@@ -283,7 +283,7 @@ def ndigo_model(args, rank, world, local):
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"ndigo bonus+update, T={T}, B={B}, 3x5x5 binary frames, A={A}, horizon 3, 10 predictors",
-                       "note": "GRU = torch.nn.GRU (cuDNN); encoder / predictors / BCE in libcuriosity_b200"},
+                       "note": "encoder / GRU (cb_gru_sequence_*) / predictors / BCE all in libcuriosity_b200"},
             "gpu_launches": L.launch_count() - l0, "e2e": None, "roofline": None, "cpu_baseline": None, "loss": float(loss)}))
 
 

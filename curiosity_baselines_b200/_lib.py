@@ -78,6 +78,12 @@ _SIGS = {
     "cb_dot": [_P, _P, _P, _L, _P],
     "cb_lstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "cb_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cb_lstm_sequence_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cb_lstm_sequence_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cb_gru_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cb_gru_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cb_gru_sequence_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cb_gru_sequence_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "cb_softmax_fwd": [_P, _P, _L, _I, _P],
     "cb_softmax_bwd": [_P, _P, _P, _L, _I, _P],
     "cb_ppo_loss": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _L, _I, _P],

@@ -373,6 +373,87 @@ __global__ void __launch_bounds__(256, 2) policy_heads_bwd_kernel(
     if (threadIdx.x < AO) atomicAdd(threadIdx.x < A ? db_pi + threadIdx.x : db_v, sdb[threadIdx.x]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// torch.nn.GRU cell (ndigo.py:79,127; gate order r,z,n):  r = s(gi_r+gh_r), z = s(gi_z+gh_z),
+// n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h.  gi = x W_ih^T + b_ih (all T at once), gh = h W_hh^T + b_hh (per step).
+// gates (may alias gi) <- (r, z, n); ghn <- gh_n (needed by the backward); one thread per 4 hidden units.
+__global__ void gru_cell_fwd_kernel(const float* gi, const float* __restrict__ gh, const float* __restrict__ h_prev,
+                                    float* gates, float* __restrict__ ghn, float* __restrict__ h_out,
+                                    __nv_bfloat16* __restrict__ h_bf16, int B, int G) {
+    const int q = G >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * q) return;
+    const int b = (int)(idx / q), j = (int)(idx % q) * 4;
+    const size_t row = (size_t)b * 3 * G;
+    float4 ir = *reinterpret_cast<const float4*>(gi + row + j), iz = *reinterpret_cast<const float4*>(gi + row + G + j);
+    float4 in = *reinterpret_cast<const float4*>(gi + row + 2 * (size_t)G + j);
+    float4 hr = *reinterpret_cast<const float4*>(gh + row + j), hz = *reinterpret_cast<const float4*>(gh + row + G + j);
+    float4 hn = *reinterpret_cast<const float4*>(gh + row + 2 * (size_t)G + j);
+    float4 hp = *reinterpret_cast<const float4*>(h_prev + (size_t)b * G + j);
+    const float *pir = &ir.x, *piz = &iz.x, *pin = &in.x, *phr = &hr.x, *phz = &hz.x, *phn = &hn.x, *php = &hp.x;
+    float r[4], z[4], n[4], h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r[k] = sigmoidf_(pir[k] + phr[k]);
+        z[k] = sigmoidf_(piz[k] + phz[k]);
+        n[k] = tanhf(pin[k] + r[k] * phn[k]);
+        h[k] = (1.f - z[k]) * n[k] + z[k] * php[k];
+    }
+    *reinterpret_cast<float4*>(gates + row + j) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(gates + row + G + j) = make_float4(z[0], z[1], z[2], z[3]);
+    *reinterpret_cast<float4*>(gates + row + 2 * (size_t)G + j) = make_float4(n[0], n[1], n[2], n[3]);
+    *reinterpret_cast<float4*>(ghn + (size_t)b * G + j) = hn;
+    *reinterpret_cast<float4*>(h_out + (size_t)b * G + j) = make_float4(h[0], h[1], h[2], h[3]);
+    __nv_bfloat162 h01 = __floats2bfloat162_rn(h[0], h[1]), h23 = __floats2bfloat162_rn(h[2], h[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(h_bf16 + (size_t)b * G + j) = pk;
+}
+
+// dh = dout (fp32, gradient from the layers above at this step) + dh_rec (bf16, from step t+1; NULL at the end).
+// dgi / dgh: bf16 [B,3G] gradients w.r.t. the two pre-activation sums; dh_carry (bf16) = dh*z, the part of
+// dL/dh_{t-1} that does not go through W_hh (handed to the recurrent dgrad as its dx_add).
+__global__ void gru_cell_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dh_rec,
+                                    const float* __restrict__ gates, const float* __restrict__ ghn,
+                                    const float* __restrict__ h_prev, __nv_bfloat16* __restrict__ dgi,
+                                    __nv_bfloat16* __restrict__ dgh, __nv_bfloat16* __restrict__ dh_carry, int B, int G) {
+    const int q = G >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * q) return;
+    const int b = (int)(idx / q), j = (int)(idx % q) * 4;
+    const size_t row = (size_t)b * 3 * G, col = (size_t)b * G + j;
+    float4 vr = *reinterpret_cast<const float4*>(gates + row + j), vz = *reinterpret_cast<const float4*>(gates + row + G + j);
+    float4 vn = *reinterpret_cast<const float4*>(gates + row + 2 * (size_t)G + j);
+    float4 vhn = *reinterpret_cast<const float4*>(ghn + col), vhp = *reinterpret_cast<const float4*>(h_prev + col);
+    float4 vd = dout ? *reinterpret_cast<const float4*>(dout + col) : make_float4(0, 0, 0, 0);
+    float dh[4] = {vd.x, vd.y, vd.z, vd.w};
+    if (dh_rec) {
+        uint2 pk = *reinterpret_cast<const uint2*>(dh_rec + col);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk.x), c = *reinterpret_cast<__nv_bfloat162*>(&pk.y);
+        dh[0] += __low2float(a); dh[1] += __high2float(a); dh[2] += __low2float(c); dh[3] += __high2float(c);
+    }
+    const float *r = &vr.x, *z = &vz.x, *n = &vn.x, *hn = &vhn.x, *hp = &vhp.x;
+    float dar[4], daz[4], dan[4], dhn[4], carry[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dan[k] = dh[k] * (1.f - z[k]) * (1.f - n[k] * n[k]);
+        daz[k] = dh[k] * (hp[k] - n[k]) * z[k] * (1.f - z[k]);
+        dar[k] = dan[k] * hn[k] * r[k] * (1.f - r[k]);
+        dhn[k] = dan[k] * r[k];
+        carry[k] = dh[k] * z[k];
+    }
+    auto store4 = [&](__nv_bfloat16* dst, const float* v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), c = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 p;
+        p.x = *reinterpret_cast<uint32_t*>(&a); p.y = *reinterpret_cast<uint32_t*>(&c);
+        *reinterpret_cast<uint2*>(dst) = p;
+    };
+    store4(dgi + row + j, dar); store4(dgi + row + G + j, daz); store4(dgi + row + 2 * (size_t)G + j, dan);
+    store4(dgh + row + j, dar); store4(dgh + row + G + j, daz); store4(dgh + row + 2 * (size_t)G + j, dhn);
+    store4(dh_carry + col, carry);
+}
+
 }  // namespace
 
 extern "C" int cb_lstm_cell_fwd(const float* gx, const float* gh, const float* c_prev, float* gates, float* c_out,
@@ -489,5 +570,137 @@ extern "C" int cb_policy_heads_bwd(const void* h_bf16, const float* dlogits, con
                                                       (__nv_bfloat16*)dh_bf16, dw_pi, db_pi, dw_v, db_v, n, H, A,
                                                       h_act == CB_ACT_RELU ? 1 : 0);
     CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The recurrences over T as native host loops: 2 launches per timestep issued from C++ (a Python / ctypes round
+// trip per launch costs ~15 us, more than either kernel runs).  The per-step GEMMs go through the library's own
+// Linear entry points (tcgen05 where the shape has a specialisation).
+static void linear_desc(cb_conv_desc* d, int n, int in_c, int out_c, int engine) {
+    *d = cb_conv_desc{};
+    d->n = n; d->in_h = d->in_w = 1; d->in_c = in_c;
+    d->k_h = d->k_w = d->stride = 1; d->pad = 0;
+    d->out_h = d->out_w = 1; d->out_c = out_c;
+    d->in_dtype = CB_BF16;
+    d->in_stride_n = d->in_stride_h = d->in_stride_w = in_c; d->in_stride_c = 1;
+    d->act = CB_ACT_NONE; d->engine = engine;
+}
+
+extern "C" int cb_lstm_sequence_fwd(int32_t T, int32_t B, int32_t H, float* gates, const void* w_hh_bf16,
+                                    const float* b_hh, void* h_all_bf16, float* c_all, float* gh_ws, float* hn,
+                                    int32_t engine, void* stream) {
+    CB_REQUIRE(T >= 1 && B >= 1 && H >= 8 && H % 8 == 0 && gates && w_hh_bf16 && b_hh && h_all_bf16 && c_all && gh_ws,
+               CB_E_ARG, "cb_lstm_sequence_fwd: bad argument");
+    cb_conv_desc d; linear_desc(&d, B, H, 4 * H, engine);
+    __nv_bfloat16* h_all = (__nv_bfloat16*)h_all_bf16;
+    const size_t bh = (size_t)B * H;
+    for (int t = 0; t < T; ++t) {
+        cb_epilogue e{};
+        e.bias = b_hh; e.out_f32 = gh_ws;
+        int rc = cb_conv_fwd(&d, h_all + t * bh, w_hh_bf16, &e, stream);
+        if (rc) return rc;
+        float* g = gates + (size_t)t * 4 * bh;
+        rc = cb_lstm_cell_fwd(g, gh_ws, c_all + t * bh, g, c_all + (t + 1) * bh, h_all + (t + 1) * bh,
+                              (hn && t == T - 1) ? hn : nullptr, B, H, stream);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_lstm_sequence_bwd(int32_t T, int32_t B, int32_t H, const float* gates, const float* c_all,
+                                    const void* dh_out_bf16, const void* w_hh_t_bf16, void* dgates_bf16,
+                                    float* dc_ws, void* dh_ws_bf16, int32_t engine, void* stream) {
+    CB_REQUIRE(T >= 1 && B >= 1 && H >= 8 && H % 8 == 0 && gates && c_all && dh_out_bf16 && w_hh_t_bf16 && dgates_bf16 &&
+               dc_ws && dh_ws_bf16, CB_E_ARG, "cb_lstm_sequence_bwd: bad argument");
+    cb_conv_desc d; linear_desc(&d, B, H, 4 * H, engine);
+    const __nv_bfloat16* dh_out = (const __nv_bfloat16*)dh_out_bf16;
+    __nv_bfloat16* dgates = (__nv_bfloat16*)dgates_bf16;
+    __nv_bfloat16* dh_ws = (__nv_bfloat16*)dh_ws_bf16;
+    const size_t bh = (size_t)B * H;
+    const __nv_bfloat16* dh = dh_out + (size_t)(T - 1) * bh;
+    for (int t = T - 1; t >= 0; --t) {
+        int rc = cb_lstm_cell_bwd(dh, t < T - 1 ? dc_ws + (size_t)((t + 1) & 1) * bh : nullptr, gates + (size_t)t * 4 * bh,
+                                  c_all + t * bh, c_all + (t + 1) * bh, dgates + (size_t)t * 4 * bh,
+                                  dc_ws + (size_t)(t & 1) * bh, B, H, stream);
+        if (rc) return rc;
+        if (t > 0) {            // dL/dh_{t-1} = dgates_t W_hh + (gradient from the heads at t-1)
+            __nv_bfloat16* out = dh_ws + (size_t)(t & 1) * bh;
+            rc = cb_conv_dgrad(&d, dgates + (size_t)t * 4 * bh, w_hh_t_bf16, nullptr, CB_ACT_NONE,
+                               dh_out + (size_t)(t - 1) * bh, out, stream);
+            if (rc) return rc;
+            dh = out;
+        }
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* gates, float* ghn,
+                               float* h_out, void* h_bf16, int32_t B, int32_t G, void* stream) {
+    CB_REQUIRE(gi && gh && h_prev && gates && ghn && h_out && h_bf16 && B >= 1 && G >= 4 && G % 4 == 0, CB_E_ARG,
+               "cb_gru_cell_fwd: bad argument");
+    int64_t total = (int64_t)B * (G / 4);
+    gru_cell_fwd_kernel<<<(unsigned)cb::ceil_div<int64_t>(total, 256), 256, 0, cb::as_stream(stream)>>>(
+        gi, gh, h_prev, gates, ghn, h_out, (__nv_bfloat16*)h_bf16, B, G);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_gru_cell_bwd(const float* dout, const void* dh_rec_bf16, const float* gates, const float* ghn,
+                               const float* h_prev, void* dgi_bf16, void* dgh_bf16, void* dh_carry_bf16, int32_t B,
+                               int32_t G, void* stream) {
+    CB_REQUIRE((dout || dh_rec_bf16) && gates && ghn && h_prev && dgi_bf16 && dgh_bf16 && dh_carry_bf16 && B >= 1 &&
+               G >= 4 && G % 4 == 0, CB_E_ARG, "cb_gru_cell_bwd: bad argument");
+    int64_t total = (int64_t)B * (G / 4);
+    gru_cell_bwd_kernel<<<(unsigned)cb::ceil_div<int64_t>(total, 256), 256, 0, cb::as_stream(stream)>>>(
+        dout, (const __nv_bfloat16*)dh_rec_bf16, gates, ghn, h_prev, (__nv_bfloat16*)dgi_bf16, (__nv_bfloat16*)dgh_bf16,
+        (__nv_bfloat16*)dh_carry_bf16, B, G);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_gru_sequence_fwd(int32_t T, int32_t B, int32_t G, float* gates, const void* w_hh_bf16,
+                                   const float* b_hh, float* h_all, void* h_all_bf16, float* ghn_all, float* gh_ws,
+                                   int32_t engine, void* stream) {
+    CB_REQUIRE(T >= 1 && B >= 1 && G >= 8 && G % 8 == 0 && gates && w_hh_bf16 && b_hh && h_all && h_all_bf16 && ghn_all &&
+               gh_ws, CB_E_ARG, "cb_gru_sequence_fwd: bad argument");
+    cb_conv_desc d; linear_desc(&d, B, G, 3 * G, engine);
+    __nv_bfloat16* hb = (__nv_bfloat16*)h_all_bf16;
+    const size_t bg = (size_t)B * G;
+    for (int t = 0; t < T; ++t) {
+        cb_epilogue e{};
+        e.bias = b_hh; e.out_f32 = gh_ws;
+        int rc = cb_conv_fwd(&d, hb + t * bg, w_hh_bf16, &e, stream);
+        if (rc) return rc;
+        float* g = gates + (size_t)t * 3 * bg;
+        rc = cb_gru_cell_fwd(g, gh_ws, h_all + t * bg, g, ghn_all + t * bg, h_all + (t + 1) * bg, hb + (t + 1) * bg, B, G,
+                             stream);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_gru_sequence_bwd(int32_t T, int32_t B, int32_t G, const float* gates, const float* ghn_all,
+                                   const float* h_all, const float* dout, const void* w_hh_t_bf16, void* dgi_bf16,
+                                   void* dgh_bf16, void* dh_ws_bf16, int32_t engine, void* stream) {
+    CB_REQUIRE(T >= 1 && B >= 1 && G >= 8 && G % 8 == 0 && gates && ghn_all && h_all && dout && w_hh_t_bf16 && dgi_bf16 &&
+               dgh_bf16 && dh_ws_bf16, CB_E_ARG, "cb_gru_sequence_bwd: bad argument");
+    cb_conv_desc d; linear_desc(&d, B, G, 3 * G, engine);
+    __nv_bfloat16* dgi = (__nv_bfloat16*)dgi_bf16;
+    __nv_bfloat16* dgh = (__nv_bfloat16*)dgh_bf16;
+    __nv_bfloat16* ws = (__nv_bfloat16*)dh_ws_bf16;           // [3,B,G]: carry + two ping-pong dh buffers
+    const size_t bg = (size_t)B * G;
+    const __nv_bfloat16* dh_rec = nullptr;
+    for (int t = T - 1; t >= 0; --t) {
+        int rc = cb_gru_cell_bwd(dout + t * bg, dh_rec, gates + (size_t)t * 3 * bg, ghn_all + t * bg, h_all + t * bg,
+                                 dgi + (size_t)t * 3 * bg, dgh + (size_t)t * 3 * bg, ws, B, G, stream);
+        if (rc) return rc;
+        if (t > 0) {            // dL/dh_{t-1} (recurrent part) = dgh_t W_hh + dh_t * z_t
+            __nv_bfloat16* out = ws + (size_t)(1 + (t & 1)) * bg;
+            rc = cb_conv_dgrad(&d, dgh + (size_t)t * 3 * bg, w_hh_t_bf16, nullptr, CB_ACT_NONE, ws, out, stream);
+            if (rc) return rc;
+            dh_rec = out;
+        }
+    }
     return CB_OK;
 }

@@ -2,10 +2,12 @@
 ``state_dict`` keys, ``compute_bonus`` / ``compute_loss`` signatures and quirks: the GRU state is
 reset every call, ``valid`` and ``prediction_beta`` are ignored, horizon 10 has no predictor).
 
-The encoder, the multi-horizon predictor MLPs (the action window enters as a side input of the first
-Linear instead of a concatenation) and the BCE run in libcuriosity_b200.so; the 128-unit GRU between
-them is ``torch.nn.GRU`` (cuDNN) for now -- SURVEY 8(f) rank 3 -- so the pieces are tied together
-through ``torch.autograd.Function`` wrappers.
+The encoder, the 128-unit GRU (x W_ih^T for all T*B rows as one tcgen05 GEMM with the one-hot
+prev_action as its extra k-block, the recurrence and its back-propagation through time as ONE library call each,
+``cb_gru_sequence_fwd / _bwd``), the multi-horizon predictor MLPs (the action window enters as a side input of the
+first Linear instead of a concatenation) and the BCE all run in libcuriosity_b200.so; ``self.gru`` is a
+``torch.nn.GRU`` parameter holder that is never called.  The pieces are tied together through
+``torch.autograd.Function`` wrappers.
 """
 import torch
 from torch import nn
@@ -50,6 +52,54 @@ class _EncoderFn(torch.autograd.Function):
         for p, g in zip(ctx.params, saved):
             p.grad = g
         return (None, None, None) + tuple(grads)
+
+
+class _GruFn(torch.autograd.Function):
+    """belief[T,B,G] = GRU([phi, prev_action]) from a zero state (ndigo.py:79,127,145)."""
+
+    @staticmethod
+    def forward(ctx, model, phi, prev_actions, *params):
+        ex = model._exec
+        T, B, A = prev_actions.shape
+        n, G, dev = T * B, model.gru_size, phi.device
+        ih, hh = ex["gru_ih"], ex["gru_hh"]
+        xb = phi.to(torch.bfloat16).contiguous()
+        side = prev_actions.reshape(n, A).contiguous()
+        sp = pad_side(side) if A <= 64 and xb.shape[1] % 64 == 0 else None
+        _, gates = ih.forward(xb, n, side=side, side_pad=sp, out_bf16=False, out_f32=True)       # gi, [n,3G] fp32
+        h_all = torch.zeros(T + 1, B, G, dtype=torch.float32, device=dev)
+        hb = torch.zeros(T + 1, B, G, dtype=torch.bfloat16, device=dev)
+        ghn = torch.empty(T, B, G, dtype=torch.float32, device=dev)
+        gh = torch.empty(B, 3 * G, dtype=torch.float32, device=dev)
+        hh.prepare()
+        L.call("cb_gru_sequence_fwd", T, B, G, L.ptr(gates), L.ptr(hh.w_fwd), L.ptr(hh.bias), L.ptr(h_all), L.ptr(hb),
+               L.ptr(ghn), L.ptr(gh), LY.get_engine(), L.stream())
+        ctx.model, ctx.saved, ctx.params = model, (xb, side, gates, h_all, hb, ghn, T, B, n), params
+        return h_all[1:]
+
+    @staticmethod
+    def backward(ctx, dbelief):
+        ex = ctx.model._exec
+        xb, side, gates, h_all, hb, ghn, T, B, n = ctx.saved
+        G, dev = ctx.model.gru_size, xb.device
+        ih, hh = ex["gru_ih"], ex["gru_hh"]
+        dout = dbelief.to(torch.float32).contiguous()
+        dgi = torch.empty(n, 3 * G, dtype=torch.bfloat16, device=dev)
+        dgh = torch.empty(n, 3 * G, dtype=torch.bfloat16, device=dev)
+        ws = torch.empty(3, B, G, dtype=torch.bfloat16, device=dev)
+        hh.prepare()
+        L.call("cb_gru_sequence_bwd", T, B, G, L.ptr(gates), L.ptr(ghn), L.ptr(h_all), L.ptr(dout), L.ptr(hh.w_t),
+               L.ptr(dgi), L.ptr(dgh), L.ptr(ws), LY.get_engine(), L.stream())
+        saved = [p.grad for p in ctx.params]
+        for p in ctx.params:
+            p.grad = None
+        hh.wgrad(hb[:T].reshape(n, G), dgh, n)
+        ih.wgrad(xb, dgi, n, side=side)
+        dphi = ih.dgrad(dgi, n)
+        grads = [p.grad for p in ctx.params]
+        for p, g in zip(ctx.params, saved):
+            p.grad = g
+        return (None, dphi.float(), None) + tuple(grads)
 
 
 class _PredictorFn(torch.autograd.Function):
@@ -146,7 +196,10 @@ class NDIGO(nn.Module):
                     preds[k] = (l1, PaddedLinearLayer(seq[2], "none", in_features=l1.out_c))
                 else:
                     preds[k] = (linear_layer(seq[0], "relu", side_dim=k * self.action_size), linear_layer(seq[2], "none"))
-            self._exec = dict(dev=dev, chain=chain, perm=None if perm is None else perm.to(dev), preds=preds)
+            g = self.gru
+            self._exec = dict(dev=dev, chain=chain, perm=None if perm is None else perm.to(dev), preds=preds,
+                              gru_ih=linear_layer(LY.ParamPair(g.weight_ih_l0, g.bias_ih_l0), "none", self.action_size),
+                              gru_hh=linear_layer(LY.ParamPair(g.weight_hh_l0, g.bias_hh_l0), "none"))
         return self._exec
 
     # ------------------------------------------------------------------
@@ -157,9 +210,9 @@ class NDIGO(nn.Module):
         phi = _EncoderFn.apply(self, observations.reshape(n, *observations.shape[2:]), n, *self.encoder.parameters())
         if ex["perm"] is not None:
             phi = phi.index_select(1, ex["perm"])
-        gru_in = torch.cat([phi.reshape(T, B, -1), prev_actions.to(ex["dev"], torch.float32)], dim=2)
-        belief, _ = self.gru(gru_in, None)                 # zero state every call (ndigo.py:127,145)
-        return belief
+        prev = prev_actions.to(ex["dev"], torch.float32).reshape(T, B, -1)
+        g = self.gru                                        # zero state every call (ndigo.py:127,145)
+        return _GruFn.apply(self, phi, prev, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
 
     def _logits(self, belief, actions, k):
         """predictor k on belief[:T-k] with the k-step action window starting at each step."""

@@ -385,6 +385,14 @@ class PaddedLinearLayer(GemmLayer):
             w.grad[:, self.real_K:].add_(dsw[: self.real_out])
 
 
+class ParamPair:
+    """A (weight, bias) pair of an ``nn.LSTM`` / ``nn.GRU`` holder presented like a ``Linear`` to ``GemmLayer``."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+
 def pad_side(side):
     """fp32 [n, A] side input (one-hot action) -> bf16 [n, 64] zero padded: the extra k-block operand."""
     n, a = side.shape

@@ -7,9 +7,11 @@ holders; everything runs in libcuriosity_b200.so:
   conv encoder ........ the curiosity encoders' ``Chain`` (tcgen05 implicit GEMMs, uint8 frames read in place;
                         raw 0..255 pixels like the reference, atari_lstm_model.py:130-133)
   LSTM(F+A -> H) ...... x W_ih^T for all T*B rows as ONE tcgen05 GEMM (the one-hot prev_action is its extra
-                        k-block, like ``torch.cat`` at :136-139); per timestep h W_hh^T on the same GEMM kernel
-                        + ``cb_lstm_cell_fwd``; backward through time = ``cb_lstm_cell_bwd`` + the recurrent
-                        dgrad GEMM per step, then both weight gradients as single GEMMs over all T*B rows
+                        k-block, like ``torch.cat`` at :136-139); the recurrence is ONE library call
+                        (``cb_lstm_sequence_fwd``: per timestep h W_hh^T on the same GEMM kernel + the fused cell
+                        kernel, looped in C++); backward through time likewise (``cb_lstm_sequence_bwd``: cell
+                        backward + recurrent dgrad GEMM per step), then both weight gradients as single GEMMs
+                        over all T*B rows
   pi / value heads .... ``cb_policy_heads_fwd/_bwd``: both heads + softmax in one HBM-bound pass over the LSTM
                         output (A + 1 <= 8; larger action sets: generic Linear layers + ``cb_softmax_fwd``)
 
@@ -21,6 +23,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
+from .. import layers as LY
 from ..layers import linear_layer, pad_side
 from ..curiosity.encoders import BurdaHead, UniverseHead, MazeHead, frame_input
 from ..curiosity.icm import ICM, Disagreement, ENC_LAST_ACT
@@ -28,14 +31,6 @@ from ..curiosity.rnd import RND
 from ..curiosity.ndigo import NDIGO
 
 RnnState = namedtuple("RnnState", ["h", "c"])
-
-
-class _WB:
-    """(weight, bias) pair of an ``nn.LSTM`` holder presented like a ``Linear`` to ``GemmLayer``."""
-
-    def __init__(self, weight, bias):
-        self.weight, self.bias = weight, bias
-        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
 
 
 def _lead_dims(image):
@@ -160,8 +155,8 @@ class AtariLstmModel(nn.Module):
             self._exec = dict(
                 dev=dev, chain=chain, perm=None if perm is None else perm.to(dev),
                 inv_perm=None if perm is None else torch.argsort(perm).to(dev),
-                ih=linear_layer(_WB(ls.weight_ih_l0, ls.bias_ih_l0), "none", self.action_size),
-                hh=linear_layer(_WB(ls.weight_hh_l0, ls.bias_hh_l0), "none"),
+                ih=linear_layer(LY.ParamPair(ls.weight_ih_l0, ls.bias_ih_l0), "none", self.action_size),
+                hh=linear_layer(LY.ParamPair(ls.weight_hh_l0, ls.bias_hh_l0), "none"),
                 pi=linear_layer(self.pi, "none"), value=linear_layer(self.value, "none"))
         return self._exec
 
@@ -255,23 +250,23 @@ class AtariLstmModel(nn.Module):
         exit; h_all bf16 / c_all fp32 [T+1,B,H] with row 0 = the initial state; hn fp32 [1,B,H] or None."""
         ex, st = self._exec, L.stream()
         T, B, H = gates.shape[0], gates.shape[1], self.lstm_size
-        for t in range(T):
-            _, gh = ex["hh"].forward(h_all[t], B, out_bf16=False, out_f32=True)
-            L.call("cb_lstm_cell_fwd", L.ptr(gates[t]), L.ptr(gh), L.ptr(c_all[t]), L.ptr(gates[t]), L.ptr(c_all[t + 1]),
-                   L.ptr(h_all[t + 1]), L.ptr(hn) if (hn is not None and t == T - 1) else None, B, H, st)
+        hh = ex["hh"]
+        hh.prepare()
+        gh = torch.empty(B, 4 * H, dtype=torch.float32, device=gates.device)
+        L.call("cb_lstm_sequence_fwd", T, B, H, L.ptr(gates), L.ptr(hh.w_fwd), L.ptr(hh.bias), L.ptr(h_all), L.ptr(c_all),
+               L.ptr(gh), L.ptr(hn), LY.get_engine(), st)
 
     def _lstm_backward(self, gates, h_all, c_all, dh_out, dgates):
         """Back-propagation through time.  dh_out bf16 [T,B,H]: gradient arriving at every h_t from the heads;
         dgates bf16 [T,B,4H] receives the gradient w.r.t. the gate pre-activations."""
         ex, st = self._exec, L.stream()
         T, B, H = gates.shape[0], gates.shape[1], self.lstm_size
-        dc = [torch.empty(B, H, dtype=torch.float32, device=gates.device) for _ in range(2)]
-        dh = dh_out[T - 1]
-        for t in range(T - 1, -1, -1):
-            L.call("cb_lstm_cell_bwd", L.ptr(dh), L.ptr(dc[(t + 1) & 1]) if t < T - 1 else None, L.ptr(gates[t]),
-                   L.ptr(c_all[t]), L.ptr(c_all[t + 1]), L.ptr(dgates[t]), L.ptr(dc[t & 1]), B, H, st)
-            if t > 0:
-                dh = ex["hh"].dgrad(dgates[t], B, dx_add=dh_out[t - 1])              # dL/dh_{t-1}, all paths
+        hh = ex["hh"]
+        hh.prepare()
+        dc = torch.empty(2, B, H, dtype=torch.float32, device=gates.device)
+        dh = torch.empty(2, B, H, dtype=torch.bfloat16, device=gates.device)
+        L.call("cb_lstm_sequence_bwd", T, B, H, L.ptr(gates), L.ptr(c_all), L.ptr(dh_out), L.ptr(hh.w_t), L.ptr(dgates),
+               L.ptr(dc), L.ptr(dh), LY.get_engine(), st)
 
     def _run_backward(self, s, dlogits, dvalue):
         """dlogits fp32 [n,A], dvalue fp32 [n]: gradients of the loss w.r.t. the pi logits and the value.

@@ -266,6 +266,35 @@ int cb_lstm_cell_fwd(const float* gx, const float* gh, const float* c_prev, floa
  * dgates bf16 [B,4H] = gradient w.r.t. the pre-activations a; dc_prev fp32 [B,H]. */
 int cb_lstm_cell_bwd(const void* dh_bf16, const float* dc_next, const float* gates, const float* c_prev,
                      const float* c, void* dgates_bf16, float* dc_prev, int32_t B, int32_t H, void* stream);
+/* The whole recurrence of atari_lstm_model.py:142 as ONE call (the host loop over T runs inside the library: two
+ * launches per step without a Python round trip).  gates fp32 [T,B,4H]: x W_ih^T + b_ih on entry, the activated
+ * gates on exit; w_hh bf16 [4H,H]; h_all bf16 / c_all fp32 [T+1,B,H] with row 0 = the initial state; gh_ws fp32
+ * [B,4H] scratch; hn fp32 [B,H] or NULL receives h_T.  `engine` as in cb_conv_desc. */
+int cb_lstm_sequence_fwd(int32_t T, int32_t B, int32_t H, float* gates, const void* w_hh_bf16, const float* b_hh,
+                         void* h_all_bf16, float* c_all, float* gh_ws, float* hn, int32_t engine, void* stream);
+/* Back-propagation through time: dh_out bf16 [T,B,H] = gradient arriving at every h_t from the layers above;
+ * w_hh_t bf16 [H,4H]; dgates bf16 [T,B,4H] out; dc_ws fp32 [2,B,H] and dh_ws bf16 [2,B,H] scratch. */
+int cb_lstm_sequence_bwd(int32_t T, int32_t B, int32_t H, const float* gates, const float* c_all,
+                         const void* dh_out_bf16, const void* w_hh_t_bf16, void* dgates_bf16, float* dc_ws,
+                         void* dh_ws_bf16, int32_t engine, void* stream);
+/* torch.nn.GRU (ndigo.py:79,127; gate order r,z,n).  Cell: gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (fp32 [B,3G]);
+ * gates (may alias gi) <- (r, z, n); ghn <- gh_n; h_out = (1-z) n + z h_prev (fp32 + bf16 copies). */
+int cb_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* gates, float* ghn, float* h_out,
+                    void* h_bf16, int32_t B, int32_t G, void* stream);
+/* dh = dout (fp32, may be NULL) + dh_rec (bf16, may be NULL); dgi / dgh bf16 [B,3G]; dh_carry bf16 [B,G] = dh*z */
+int cb_gru_cell_bwd(const float* dout, const void* dh_rec_bf16, const float* gates, const float* ghn,
+                    const float* h_prev, void* dgi_bf16, void* dgh_bf16, void* dh_carry_bf16, int32_t B, int32_t G,
+                    void* stream);
+/* The recurrence over T in one call.  gates fp32 [T,B,3G] (gi on entry, (r,z,n) on exit); w_hh bf16 [3G,G];
+ * h_all fp32 and h_all_bf16 [T+1,B,G] with row 0 = the initial state (zeros for NDIGO); ghn_all fp32 [T,B,G];
+ * gh_ws fp32 [B,3G] scratch. */
+int cb_gru_sequence_fwd(int32_t T, int32_t B, int32_t G, float* gates, const void* w_hh_bf16, const float* b_hh,
+                        float* h_all, void* h_all_bf16, float* ghn_all, float* gh_ws, int32_t engine, void* stream);
+/* BPTT: dout fp32 [T,B,G] = gradient arriving at every h_t; w_hh_t bf16 [G,3G]; dgi / dgh bf16 [T,B,3G] out;
+ * dh_ws bf16 [3,B,G] scratch. */
+int cb_gru_sequence_bwd(int32_t T, int32_t B, int32_t G, const float* gates, const float* ghn_all, const float* h_all,
+                        const float* dout, const void* w_hh_t_bf16, void* dgi_bf16, void* dgh_bf16, void* dh_ws_bf16,
+                        int32_t engine, void* stream);
 /* atari_lstm_model.py:144: F.softmax over the last dimension, fp32 [n,a]; and its backward */
 int cb_softmax_fwd(const float* logits, float* prob, int64_t n, int32_t a, void* stream);
 int cb_softmax_bwd(const float* prob, const float* dprob, float* dlogits, int64_t n, int32_t a, void* stream);
