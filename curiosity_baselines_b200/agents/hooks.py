@@ -25,8 +25,16 @@ def _device(agent):
     return dev
 
 
+def _curiosity_model(agent):
+    """``agent.model.curiosity_model``, also when rlpyt's ``data_parallel()`` wrapped the model in
+    DistributedDataParallel (runners/sync_rl.py; the reference's hooks then fail on the missing attribute,
+    agents/pg/categorical.py:102 -- SURVEY 8f rank 4)."""
+    m = agent.model
+    return getattr(m, "module", m).curiosity_model
+
+
 def _onehot(agent, idx, dev):
-    n = agent.distribution.dim if hasattr(agent, "distribution") else agent.model.curiosity_model.action_size
+    n = agent.distribution.dim if hasattr(agent, "distribution") else _curiosity_model(agent).action_size
     idx = idx.to(dev).long()
     return torch.zeros(idx.shape + (n,), dtype=torch.float32, device=dev).scatter_(-1, idx.unsqueeze(-1), 1)
 
@@ -136,7 +144,7 @@ class BatchPrefetcher:
 @torch.no_grad()
 def curiosity_step(self, curiosity_type, *args):
     dev = _device(self)
-    cm = self.model.curiosity_model
+    cm = _curiosity_model(self)
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions = args
         r_int = cm.compute_bonus(observation.to(dev, non_blocking=True),
@@ -158,7 +166,7 @@ def curiosity_step(self, curiosity_type, *args):
 
 def curiosity_loss(self, curiosity_type, *args):
     dev = _device(self)
-    cm = self.model.curiosity_model
+    cm = _curiosity_model(self)
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions, valid = args
         inv, fwd = cm.compute_loss(observation.to(dev, non_blocking=True),

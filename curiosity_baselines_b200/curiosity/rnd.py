@@ -123,6 +123,29 @@ class RND(nn.Module):
         self._norm[0].copy_(self.obs_rms._mean)
         self._norm[1].copy_(self.obs_rms._var.rsqrt())
 
+    # ------------------------------------------------------------------ checkpointing of the running statistics
+    # The reference keeps obs_rms / rew_rms / rew_rff as NumPy attributes outside ``state_dict`` (rnd.py:34-36), so a
+    # resumed run restarts them from scratch.  These two methods carry them explicitly; the
+    # ``state_dict`` keys stay the reference's.
+    def stats_state_dict(self):
+        """CPU copies of the running statistics (float64 moments, fp32 per-env filter state)."""
+        self._build()
+        rff = self.rew_rff
+        return {"obs_rms": {k: v.cpu() for k, v in self.obs_rms.state_dict().items()},
+                "rew_rms": {k: v.cpu() for k, v in self.rew_rms.state_dict().items()},
+                "rew_rff": None if rff._rewems is None else {"rewems": rff._rewems.cpu(), "init": rff._init.cpu()}}
+
+    def load_stats_state_dict(self, sd):
+        self._build()
+        self.obs_rms.load_state_dict(sd["obs_rms"])
+        self.rew_rms.load_state_dict(sd["rew_rms"])
+        if sd.get("rew_rff") is not None:
+            r = sd["rew_rff"]
+            self.rew_rff._rewems = r["rewems"].to(self._dev, torch.float32).clone()
+            self.rew_rff._init = r["init"].to(self._dev, torch.int32).clone()
+        self._refresh_norm()
+        self._cache = None
+
     def _frame_view(self, obs):
         """Address the newest frame of each stack in place (rnd.py:130-131): base pointer and
         element strides (n, h, w, c) of the uint8 [T,B,C,H,W] tensor."""

@@ -153,3 +153,33 @@ def test_feature_reuse_is_exact_and_guarded():
     other = frames.clone(); other[0, 0, -1, 0, 0] ^= 1
     m1.compute_loss(other, valid, mask)
     assert m1.reuse_hits["miss"] == 1
+
+
+def test_running_statistics_checkpoint_roundtrip():
+    """stats_state_dict / load_stats_state_dict: a model restored from (state_dict, stats) continues bit-identically."""
+    T, B, seed = 6, 5, 909
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    a = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    a.load_state_dict(params)
+    for it in range(2):
+        a.compute_bonus(R.make_frames(seed + it, T, B).to(DEV), R.make_suffix_done(seed + 10 + it, T, B, frac=0.5).to(DEV))
+    b = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    b.load_state_dict(a.state_dict())
+    b.load_stats_state_dict(a.stats_state_dict())
+    frames, done = R.make_frames(seed + 5, T, B).to(DEV), R.make_suffix_done(seed + 15, T, B, frac=0.5).to(DEV)
+    ra, rb = a.compute_bonus(frames, done), b.compute_bonus(frames, done)
+    assert torch.equal(ra, rb)
+    assert (a.obs_rms.mean == b.obs_rms.mean).all() and a.rew_rms.count == b.rew_rms.count
+
+
+def test_hooks_unwrap_a_ddp_style_wrapper():
+    from types import SimpleNamespace
+    from curiosity_baselines_b200.agents import hooks
+    m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m.load_state_dict(R.make_params(R.rnd_shapes(), 3, gain=1.4))
+    plain = SimpleNamespace(model=SimpleNamespace(curiosity_model=m), device=DEV)
+    wrapped = SimpleNamespace(model=SimpleNamespace(module=SimpleNamespace(curiosity_model=m)), device=DEV)
+    assert hooks._curiosity_model(plain) is m and hooks._curiosity_model(wrapped) is m
+    frames, done = R.make_frames(4, 4, 3), R.make_suffix_done(5, 4, 3, frac=0.5)
+    out = hooks.curiosity_step(wrapped, "rnd", frames, done)
+    assert out.r_int.shape == (4, 3) and out.r_int.device.type == "cpu"
