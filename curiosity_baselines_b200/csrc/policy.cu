@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(512) policy_heads_fwd_kernel(
     const int AO = A + (w_v ? 1 : 0), lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const float bias = lane < A ? b_pi[lane] : ((lane == A && w_v) ? b_v[0] : 0.f);
-    constexpr int R = 2;            // rows in flight per warp
+    constexpr int R = 2;            // rows in flight per warp (4 rows at 110 registers / 16 warps per SM measured slower:
+                                    // 0.194 vs 0.166 ms at n = 262 144)
     for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < n; row0 += warps * R) {
         float acc[R][kHeadsMaxO];
 #pragma unroll
