@@ -553,7 +553,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        v, ms, k = cpu_reference(T, args.cpu_B, args.steps, args.warmup)
+        if args.model == "ppo_icm":
+            v, ms, k = cpu_reference_ppo(T, args.cpu_B, args.A or 4, args.epochs, args.steps, args.warmup, seconds_cap=120.0)
+            workload = (f"ICM + LSTM PPO full iteration (BASELINE configs[3]), T={T}, B={B}/GPU, 4x84x84 uint8, "
+                        f"A={args.A or 4}, {args.epochs} epochs")
+        else:
+            v, ms, k = cpu_reference(T, args.cpu_B, args.steps, args.warmup)
         sample = f"T={T}, B={args.cpu_B} ({T * args.cpu_B} samples/step) of the same workload, {k} steps"
         print(json.dumps({
             "impl": "reference", "metric": "intrinsic-reward samples/sec (bonus+update)", "value": v,
