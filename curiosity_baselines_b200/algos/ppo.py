@@ -38,6 +38,8 @@ def _onehot(idx, A):
 class PPO:
     """ppo.py:20-70 constructor arguments (same names and defaults)."""
 
+    twin_conv1 = True       # run the policy's and the curiosity encoder's first convolution over `observation` as one launch
+
     def __init__(self, discount=0.99, learning_rate=0.001, value_loss_coeff=1., entropy_loss_coeff=0.01,
                  clip_grad_norm=1., gae_lambda=1, minibatches=4, epochs=4, ratio_clip=0.1, linear_lr_schedule=True,
                  normalize_advantage=False, normalize_reward=False, curiosity_type="none"):
@@ -77,7 +79,16 @@ class PPO:
         st = L.stream()
         if init_rnn_state is not None:
             init_rnn_state = tuple(s.transpose(0, 1).contiguous() for s in init_rnn_state)
-        s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True)
+        # the policy's conv1 and the curiosity encoder's conv1 read the same uint8 frames: one twin launch (shared pixel
+        # conversion, N = 64 MMAs) computes both; the curiosity model picks its half up in loss_and_grads_ below
+        cm = getattr(m, "curiosity_model", None)
+        twin = None
+        if (self.twin_conv1 and self.curiosity_type in ("icm", "disagreement") and curiosity_inputs is not None
+                and curiosity_inputs[0] is observation):
+            twin = cm.twin_first_conv()
+        s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True, twin=twin)
+        if s["twin_out"] is not None:
+            cm._first_out_obs = (s["twin_out"], observation)
         validf = (torch.ones(n, device=dev) if valid is None else valid.to(dev, torch.float32).reshape(n)).contiguous()
         denom = dist.all_reduce_sum_(validf.sum().reshape(1)) if dist.world_size() > 1 else None
         coef = torch.empty(n, dtype=torch.float32, device=dev)

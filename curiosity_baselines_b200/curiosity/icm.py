@@ -263,10 +263,13 @@ class _IcmBase(nn.Module):
                               inv2=linear_layer(self.inverse_model[2], "none"))
         return self._exec
 
-    def _encode(self, frames, n):
+    def _encode(self, frames, n, first_out=None):
+        """``first_out``: this encoder's first-conv output for ``frames`` computed elsewhere (the policy network's
+        conv1 pass over the same frames runs it as a twin launch, algos/ppo.py)."""
         ex = self._exec
         keep, x, dtype, strides = frame_input(frames)
-        acts, phi_f = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=True, last_bf16=True)
+        acts, phi_f = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=True, last_bf16=True,
+                                          first_out=first_out)
         phi_b = acts[-1].reshape(n, -1)
         phi_f = phi_f.reshape(n, -1)
         if ex["perm"] is not None:                         # NHWC -> the reference's CHW feature order
@@ -283,7 +286,7 @@ class _IcmBase(nn.Module):
         ex["chain"].backward(enc["x"], enc["acts"], dphi_bf16.contiguous(), n, in_dtype=enc["dtype"],
                              strides=enc["strides"], accumulate=accumulate)
 
-    def _features(self, observations, next_observations, actions):
+    def _features(self, observations, next_observations, actions, first_out_obs=None):
         """Shared by bonus and loss: (T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action[n,A])."""
         self._build()
         if observations.dim() != 5:
@@ -291,7 +294,7 @@ class _IcmBase(nn.Module):
         T, B = observations.shape[:2]
         n = T * B
         shp = observations.shape[2:]
-        enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n)
+        enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n, first_out=first_out_obs)
         enc2, phi2_f, phi2_b = self._encode(next_observations.reshape(n, *shp), n)
         action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
         return T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action
@@ -326,11 +329,14 @@ class _IcmBase(nn.Module):
         """(T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action, saved, pred): features + forward-model outputs."""
         self._build()
         c = self._cache
+        # first-conv output of ``observations`` handed over by the policy pass (consumed once, only for that very tensor)
+        handed = self.__dict__.pop("_first_out_obs", None)
+        first_out_obs = handed[0] if handed is not None and handed[1] is observations else None
         if (self.reuse_features and not remember and c is not None and c["wver"] == self._weights_version()
                 and self._same_batch(c, observations, next_observations, actions)):
             self.reuse_hits["full"] += 1
             return c["out"]
-        feats = self._features(observations, next_observations, actions)
+        feats = self._features(observations, next_observations, actions, first_out_obs)
         T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action = feats
         saved, pred = self._forward_exec().run_forward(phi1_b, action, n)            # pred fp32, packed [n, E*F]
         out = feats + (saved, pred)
@@ -429,6 +435,17 @@ class _IcmBase(nn.Module):
 
     def _default_masks(self, T, B):
         return None
+
+    def twin_first_conv(self):
+        """The encoder's first layer when it is the tcgen05 uint8 first convolution (Burda head): a network reading
+        the same frames can run it as the twin of its own first conv (shared pixel conversion, N = 64 MMAs) and
+        hand the result back through ``_first_out_obs``.  None when the forward pass would be served from the cache."""
+        self._build()
+        c = self._cache
+        if self.reuse_features and c is not None and c["wver"] == self._weights_version():
+            return None
+        layer = self._exec["chain"].layers[0]
+        return layer if (layer.k, layer.stride, layer.pad, layer.out_c) == (8, 4, 0, 32) else None
 
     def invalidate_weights(self):
         """Call after the fp32 master weights were updated outside torch's version tracking (FlatAdam)."""

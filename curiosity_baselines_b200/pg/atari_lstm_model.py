@@ -170,10 +170,11 @@ class AtariLstmModel(nn.Module):
             cm.invalidate_weights()
 
     # ------------------------------------------------------------------ forward
-    def _run_forward(self, image, prev_action, init_rnn_state, save):
+    def _run_forward(self, image, prev_action, init_rnn_state, save, twin=None):
         """image uint8/float [T,B,C,H,W] on the device, prev_action one-hot [T,B,A], init_rnn_state (h, c) each
         [1,B,H] or None.  Returns a dict with logits [n,A], prob [n,A], value [n], hn / cn [1,B,H] and, when
-        ``save``, everything the backward pass needs."""
+        ``save``, everything the backward pass needs.  ``twin``: the first-conv layer of another network that reads the
+        same frames (the curiosity encoder); it is computed in the same conv1 launch and returned as ``twin_out``."""
         ex = self._build()
         dev, H, A = ex["dev"], self.lstm_size, self.action_size
         if not image.is_cuda:
@@ -182,7 +183,13 @@ class AtariLstmModel(nn.Module):
         n = T * B
         st = L.stream()
         keep, x, dtype, strides = frame_input(image.reshape(n, *image.shape[2:]))
-        acts, _ = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=False, last_bf16=True)
+        first_out = twin_out = None
+        l0 = ex["chain"].layers[0]
+        if (twin is not None and dtype == L.U8 and (l0.k, l0.stride, l0.pad, l0.out_c, l0.in_c) ==
+                (twin.k, twin.stride, twin.pad, twin.out_c, twin.in_c) and (l0.in_h, l0.in_w) == (twin.in_h, twin.in_w)):
+            first_out, _, twin_out = l0.forward(x, n, in_dtype=dtype, strides=strides, twin=twin)
+        acts, _ = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=False, last_bf16=True,
+                                      first_out=first_out)
         feat = acts[-1].reshape(n, -1)
         if ex["perm"] is not None:                       # NHWC -> the reference's CHW feature order
             feat = feat.index_select(1, ex["perm"])
@@ -213,7 +220,7 @@ class AtariLstmModel(nn.Module):
             _, value = ex["value"].forward(h_out, n, out_bf16=False, out_f32=True)
             L.call("cb_softmax_fwd", L.ptr(logits), L.ptr(prob), n, A, st)
         out = dict(T=T, B=B, n=n, logits=logits, prob=prob, value=value.reshape(n), hn=hn,
-                   cn=c_all[T].clone().unsqueeze(0))
+                   cn=c_all[T].clone().unsqueeze(0), twin_out=twin_out)
         if save:
             out.update(keep=keep, x=x, dtype=dtype, strides=strides, acts=acts, feat=feat, side=side, gates=gates,
                        h_all=h_all, c_all=c_all)
