@@ -438,3 +438,45 @@ def test_twin_first_conv_gives_the_same_losses_and_gradients():
         assert abs(float(getattr(ia, name)) - float(getattr(ib, name))) <= 1e-3 * max(1.0, abs(float(getattr(ib, name)))), name
     for k in ga:
         assert cosine(ga[k].cpu(), gb[k].cpu()) > 0.999, k
+
+
+def test_ppo_with_disagreement_curiosity_vs_oracle():
+    """PPO.loss with the Disagreement terms (ppo.py:226-229): policy + inverse + four-model ensemble loss in one
+    fused step, twin first conv included; dropout masks off on both sides."""
+    from curiosity_baselines_b200.curiosity.icm import Disagreement
+    T, B, A, seed = 6, 5, 7, 999
+    dis_kw = dict(ICM_KW, curiosity_alg="disagreement", device="cuda")
+    params = R.make_policy_params(A, seed)
+    dparams = R.make_params(R.disagreement_shapes(A, "idf_burda"), seed + 2)
+    m = AtariLstmModel((4, 84, 84), A, curiosity_kwargs=dis_kw).to(DEV)
+    assert isinstance(m.curiosity_model, Disagreement)
+    sd = dict(params)
+    sd.update({"curiosity_model." + k: v for k, v in dparams.items()})
+    m.load_state_dict(sd)
+    obs, nxt = R.make_frames(seed + 3, T, B), R.make_frames(seed + 4, T, B)
+    prev, act = R.make_actions(seed + 5, T, B, A), R.make_actions(seed + 6, T, B, A)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A), R.make_normal(seed + 8, T, B), R.make_normal(seed + 9, T, B)
+    valid = 1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    q = {k: v.clone().requires_grad_(True) for k, v in dparams.items()}
+    pi, v, _ = O.policy_forward(p, obs, R.onehot(prev, A), None)
+    pl = O.ppo_loss(pi, v, act, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)
+    inv, fwd = O.disagreement_loss(q, obs, nxt, R.onehot(act, A), valid, "idf_burda", 0.2, None)
+    total = pl[0] + inv + fwd
+    total.backward()
+    algo = PPO(curiosity_type="disagreement", clip_grad_norm=1e9)
+    algo.initialize(m, n_itr=10)
+    dv = lambda t: t.to(DEV)
+    o = dv(obs)
+    info = algo.loss_and_grads_(o, dv(prev), dv(act), dv(ret), dv(adv), dv(valid), dv(old_prob), None,
+                                (o, dv(nxt), dv(R.onehot(act, A))), None)
+    for ours, ref_ in [(info.loss, total), (info.inv_loss, inv), (info.forward_loss, fwd), (info.pi_loss, pl[1])]:
+        assert abs(float(ours) - float(ref_)) <= 1e-2 * max(abs(float(ref_)), 1e-2), (float(ours), float(ref_))
+    named = dict(m.named_parameters())
+    gn_ref = float(torch.sqrt(sum((t.grad.double() ** 2).sum() for t in list(p.values()) + list(q.values()))))
+    gn = float(torch.sqrt(sum((t.grad.double() ** 2).sum() for t in named.values())))
+    assert abs(gn - gn_ref) / gn_ref < 5e-2
+    for k in ("lstm.weight_hh_l0", "pi.weight", "curiosity_model.inverse_model.2.weight",
+              "curiosity_model.forward_model_3.lin_last.weight"):
+        ref_g = p[k].grad if k in p else q[k[len("curiosity_model."):]].grad
+        assert cosine(named[k].grad.cpu(), ref_g) > 0.99, k

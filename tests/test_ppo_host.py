@@ -57,3 +57,15 @@ def test_constructor_defaults_match_reference():
             assert k in ref and ref[k].default == prm.default, k
     finally:
         sys.path.remove(REF)
+
+
+def test_unaccelerated_policy_encoder_is_refused_loudly():
+    """feature_encoding='none' (Conv2dHeadModel, the RND policy encoder, atari_lstm_model.py:94-112) has no kernels yet:
+    the constructor must say so instead of building something that would run elsewhere."""
+    from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel
+    with pytest.raises(NotImplementedError):
+        AtariLstmModel((4, 84, 84), 4, curiosity_kwargs=dict(curiosity_alg="rnd", feature_encoding="none",
+                                                             prediction_beta=1.0, drop_probability=0.25, gamma=0.99,
+                                                             device="cpu"))
+    with pytest.raises(NotImplementedError):
+        AtariLstmModel((4, 84, 84), 4)            # curiosity_alg='none' -> Conv2dHeadModel as well
