@@ -101,10 +101,10 @@ def policy_shapes(action_size, feature_encoding="idf_burda", c_in=4, lstm=512):
                   ("value.weight", (1, lstm)), ("value.bias", (1,))]
 
 
-def make_policy_params(action_size, seed, feature_encoding="idf_burda", conv_gain=0.65):
+def make_policy_params(action_size, seed, feature_encoding="idf_burda", conv_gain=0.65, c_in=4):
     """Policy weights whose encoder is damped (gain < 1 per layer) so that raw 0..255 pixels give O(1)
     features: the LSTM gates then work in their non-saturated range and parity is informative."""
-    shapes = policy_shapes(action_size, feature_encoding)
+    shapes = policy_shapes(action_size, feature_encoding, c_in=c_in)
     conv = [s for s in shapes if s[0].startswith("conv.")]
     rest = [s for s in shapes if not s[0].startswith("conv.")]
     out = make_params(conv, seed, gain=conv_gain, bias_scale=conv_gain)

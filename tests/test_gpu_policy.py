@@ -480,3 +480,37 @@ def test_ppo_with_disagreement_curiosity_vs_oracle():
               "curiosity_model.forward_model_3.lin_last.weight"):
         ref_g = p[k].grad if k in p else q[k[len("curiosity_model."):]].grad
         assert cosine(named[k].grad.cpu(), ref_g) > 0.99, k
+
+
+@pytest.mark.parametrize("enc,shape,gain", [("idf", (4, 84, 84), 0.5), ("idf_maze", (3, 5, 5), 1.0)])
+def test_policy_with_the_other_curiosity_encoders(enc, shape, gain):
+    """atari_lstm_model.py:80-93: the policy's conv is UniverseHead ('idf', 288 features in CHW order) or MazeHead
+    ('idf_maze', 256 features, float {0,1} frames); outputs, loss and gradients against the oracle."""
+    T, B, A, seed = 5, 6, 5, 2024
+    kw = dict(ICM_KW, feature_encoding=enc)
+    params = R.make_policy_params(A, seed, feature_encoding=enc, conv_gain=gain, c_in=shape[0])
+    m = AtariLstmModel(shape, A, curiosity_kwargs=kw).to(DEV)
+    sd = dict(m.state_dict())
+    assert {k: tuple(v.shape) for k, v in sd.items() if not k.startswith("curiosity_model.")} == \
+        dict(R.policy_shapes(A, enc, c_in=shape[0]))
+    sd.update(params)
+    m.load_state_dict(sd)
+    obs = R.make_frames(seed + 3, T, B) if enc == "idf" else R.make_binary_frames(seed + 3, T, B)
+    prev, act = R.make_actions(seed + 5, T, B, A), R.make_actions(seed + 6, T, B, A)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A), R.make_normal(seed + 8, T, B), R.make_normal(seed + 9, T, B)
+    valid = 1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    pi, v, _ = O.policy_forward(p, obs, R.onehot(prev, A), None, feature_encoding=enc)
+    ref = O.ppo_loss(pi, v, act, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)
+    ref[0].backward()
+    dv = lambda t: t.to(DEV)
+    with torch.no_grad():
+        pi_g, v_g, _ = m(dv(obs), dv(R.onehot(prev, A)), torch.zeros(T, B), None)
+    assert rel_err(pi_g.cpu(), pi.detach()) < 1e-2 and rel_err(v_g.cpu(), v.detach()) < 1e-2
+    algo = PPO(curiosity_type="none", clip_grad_norm=1e9)
+    algo.initialize(m, n_itr=10)
+    info = algo.loss_and_grads_(dv(obs), dv(prev), dv(act), dv(ret), dv(adv), dv(valid), dv(old_prob), None)
+    assert abs(float(info.loss) - float(ref[0])) <= 1e-2 * abs(float(ref[0]))
+    named = dict(m.named_parameters())
+    for k, t in p.items():
+        assert cosine(named[k].grad.cpu(), t.grad) > 0.99, (k, cosine(named[k].grad.cpu(), t.grad))
