@@ -100,3 +100,28 @@ def test_gru_cell_kernels_match_torch_fp32():
     assert torch.allclose(dgi.float(), gi_r.grad, rtol=1e-2, atol=1e-3)
     assert torch.allclose(dgh.float(), gh_r.grad, rtol=1e-2, atol=1e-3)
     assert torch.allclose(carry.float(), (dout + drec.float()) * z.detach(), rtol=1e-2, atol=1e-3)
+
+
+def test_gru_sequence_vs_torch_gru_at_large_batch():
+    """B = 1024 (several GEMM row tiles per step): same gate as the small-batch test."""
+    T, B, A, F, G, seed = 5, 1024, 5, 256, 128, 6
+    m = NDIGO(image_shape=(3, 5, 5), action_size=A, horizon=1).to(DEV)
+    m._build()
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    phi = torch.randn(T * B, F, generator=gen).to(DEV).requires_grad_(True)
+    prev = R.onehot(R.make_actions(seed, T, B, A), A).to(DEV)
+    dout = torch.randn(T, B, G, generator=gen).to(DEV)
+    ref = torch.nn.GRU(F + A, G).to(DEV)
+    ref.load_state_dict(m.gru.state_dict())
+    x = torch.cat([phi.detach().reshape(T, B, F), prev], 2).requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=False):
+        out_ref, _ = ref(x, None)
+    (out_ref * dout).sum().backward()
+    g = m.gru
+    out = _GruFn.apply(m, phi, prev, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
+    (out * dout).sum().backward()
+    assert float((out - out_ref).abs().max()) < 1e-2
+    cos = lambda a, b: float((a.flatten() @ b.flatten()) / (a.norm() * b.norm()))
+    assert cos(phi.grad, x.grad[:, :, :F].reshape(T * B, F)) > 0.999
+    for name in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+        assert cos(getattr(g, name).grad, getattr(ref, name).grad) > 0.999, name
