@@ -51,6 +51,9 @@ _SIGS = {
     "cb_rms_merge_moments": [_P, _P, C.c_double, _P, _P, _P, _P],
     "cb_valid_count": [_P, _P, _L, _P],
     "cb_masked_normalize": [_P, _P, _F, _P, _L, _P],
+    "cb_rms_update_columns": [_P, _L, _I, _P, _P, _P, _P],
+    "cb_masked_moments": [_P, _P, _L, _P, _P, _P],
+    "cb_normalize_apply": [_P, _P, _F, _P, _L, _P],
     "cb_rnd_scale_bonus": [_P, _P, _P, _F, _P, _L, _P],
     "cb_conv_fwd": [C.POINTER(ConvDesc), _P, _P, C.POINTER(Epilogue), _P],
     "cb_conv_dgrad": [C.POINTER(ConvDesc), _P, _P, _P, _I, _P, _P, _P],
@@ -94,7 +97,6 @@ _SIGS = {
     "cb_sumsq": [_P, _L, _P, _P],
     "cb_adam_clip_step": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P],
     "cb_h2d_2d": [_P, _L, _P, _L, _L, _L, _P],
-    "cb_umma_probe": [_P, _I, _P, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I, _I, _I, _I, _I, _P, _P],
     "cb_prepare_conv_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
     "cb_unprepare_conv_grad": [_P, _P, _I, _I, _I, _I, _F, _P],
 }
@@ -154,3 +156,28 @@ def call(name, *args):
     _launches += 1
     if rc != 0:
         raise CuriosityLibError(f"{name} failed ({rc}): {lib.cb_last_error().decode()}")
+
+
+_probe = None
+
+
+def load_probe():
+    """The kernel author's descriptor probe (csrc/umma_probe.cu), a separate test-only library."""
+    global _probe
+    if _probe is None:
+        path = os.path.join(_HERE, "libcuriosity_b200_probe.so")
+        if not os.path.exists(path):
+            raise CuriosityLibError(f"{path} is missing: `python -m curiosity_baselines_b200.build --probe`")
+        lib = C.CDLL(path)
+        lib.cb_umma_probe.argtypes = [_P, _I, _P, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _I, _I, _I, _I, _I, _P, _P]
+        lib.cb_umma_probe.restype = C.c_int
+        lib.cb_probe_last_error.restype = C.c_char_p
+        _probe = lib
+    return _probe
+
+
+def call_probe(*args):
+    lib = load_probe()
+    rc = lib.cb_umma_probe(*args)
+    if rc != 0:
+        raise CuriosityLibError(f"cb_umma_probe failed ({rc}): {lib.cb_probe_last_error().decode()}")

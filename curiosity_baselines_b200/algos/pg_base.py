@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
+from .. import dist
 from ..utils.averages import RunningMeanStd, RewardForwardFilter
 from .utils import _dev
 
@@ -51,8 +52,13 @@ def returns_on_device(reward, done, value, bootstrap_value, discount, gae_lambda
         valid = torch.empty_like(done)
         L.call("cb_valid_from_done", L.ptr(done), L.ptr(valid), T, B, st)
     if normalize_advantage:   # base.py:95-103
+        # masked {sum, sum^2, count} -> all-reduce -> apply: a sharded batch normalises with the global moments
         out = torch.empty_like(adv)
-        L.call("cb_masked_normalize", L.ptr(adv), L.ptr(valid), 1e-6, L.ptr(out), T * B, st)
+        sums = torch.empty(3, dtype=torch.float64, device=adv.device)
+        ws = torch.empty(1536, dtype=torch.float64, device=adv.device)
+        L.call("cb_masked_moments", L.ptr(adv), L.ptr(valid), T * B, L.ptr(sums), L.ptr(ws), st)
+        dist.all_reduce_sum_(sums)
+        L.call("cb_normalize_apply", L.ptr(adv), L.ptr(sums), 1e-6, L.ptr(out), T * B, st)
         adv = out
     return ret, adv, valid, reward
 

@@ -239,7 +239,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __r
 __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                  const float* __restrict__ g, int64_t n,
                                  const double* __restrict__ sumsq, float max_norm, float lr,
-                                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+                                 float beta1, float beta2, float eps, float step_size, float bc2_sqrt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // torch.nn.utils.clip_grad_norm_: coef = max_norm/(norm+1e-6), clamped to 1
@@ -251,7 +251,7 @@ __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, f
     m[i] = mi; v[i] = vi;
     // torch Adam: denom = sqrt(v)/sqrt(bc2) + eps ; p -= lr/bc1 * m/denom
     float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    p[i] -= step_size * (mi / denom);
 }
 
 __global__ void prepare_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
@@ -403,10 +403,12 @@ extern "C" int cb_adam_clip_step(float* p, float* m, float* v, const float* g, i
                                  const double* sumsq, float max_norm, float lr, float beta1, float beta2,
                                  float eps, int32_t step, void* stream) {
     CB_REQUIRE(p && m && v && g && sumsq && n >= 1 && step >= 1, CB_E_ARG, "cb_adam_clip_step: bad argument");
-    float bc1 = 1.f - powf(beta1, (float)step);
-    float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    // bias corrections in double like torch's Python scalars (1 - powf(0.999f, 1) loses ~1e-5 relative in fp32)
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
     adam_clip_kernel<<<(unsigned)cb::ceil_div<int64_t>(n, 256), 256, 0, cb::as_stream(stream)>>>(
-        p, m, v, g, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2s);
+        p, m, v, g, n, sumsq, max_norm, lr, beta1, beta2, eps, step_size, bc2s);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

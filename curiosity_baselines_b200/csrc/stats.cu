@@ -248,6 +248,66 @@ __global__ void masked_normalize_kernel(const float* __restrict__ x, const float
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = __fdiv_rn(__fsub_rn(x[i], mf), sd);
 }
 
+// ---- generic RunningMeanStd.update(x) (averages.py:48-52): x f64 [n, d], one block per column -----------------
+// batch mean and population variance are computed in two passes like numpy, then Chan-merged with the OLD count;
+// the count itself is bumped by a second one-thread launch once every column has been merged.
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = cb::warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+    if (wid == 0) { v = cb::warp_sum(v); if (lane == 0) sm[0] = v; }
+    __syncthreads();
+    return sm[0];
+}
+__global__ void rms_update_columns_kernel(const double* __restrict__ x, int64_t n, int d, double* __restrict__ mean,
+                                          double* __restrict__ var, const double* __restrict__ count) {
+    __shared__ double sm[32];
+    const int c = blockIdx.x;
+    double s = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i * d + c];
+    const double bm = block_sum(s, sm) / (double)n;
+    double q = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double t = x[i * d + c] - bm; q += t * t; }
+    const double bv = block_sum(q, sm) / (double)n;
+    if (threadIdx.x == 0) {
+        double m = mean[c], v = var[c];
+        chan_merge(m, v, *count, bm, bv, (double)n);
+        mean[c] = m; var[c] = v;
+    }
+}
+__global__ void add_count_kernel(double* count, double n) { *count += n; }
+
+// ---- advantage normalisation in two stages (algos/pg/base.py:95-103) ------------------------------------------
+// stage 1: per-block f64 partials of {sum x, sum x^2, count} over mask > 0, folded into sums[3]; a data-parallel
+// host all-reduces `sums`; stage 2 applies (x - mean) / max(std_unbiased, floor) to every element.
+__global__ void masked_moments_partial_kernel(const float* __restrict__ x, const float* __restrict__ mask, int64_t n,
+                                              double* __restrict__ ws) {
+    double s = 0, q = 0, c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!mask || __ldg(mask + i) > 0.f) { const double d = (double)__ldg(x + i); s += d; q += d * d; c += 1.0; }
+    __shared__ double sm[32];
+    s = block_sum(s, sm); q = block_sum(q, sm); c = block_sum(c, sm);
+    if (threadIdx.x == 0) { ws[blockIdx.x] = s; ws[512 + blockIdx.x] = q; ws[1024 + blockIdx.x] = c; }
+}
+__global__ void masked_moments_finish_kernel(int nblocks, const double* __restrict__ ws, double* __restrict__ sums) {
+    double s = 0, q = 0, c = 0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) { s += ws[i]; q += ws[512 + i]; c += ws[1024 + i]; }
+    s = cb::warp_sum(s); q = cb::warp_sum(q); c = cb::warp_sum(c);
+    if (threadIdx.x == 0) { sums[0] = s; sums[1] = q; sums[2] = c; }
+}
+__global__ void normalize_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, float floor_std,
+                                       float* __restrict__ out, int64_t n) {
+    const double c = sums[2], mean = sums[0] / c;
+    double m2 = sums[1] - sums[0] * mean;                  // sum (x - mean)^2
+    if (m2 < 0) m2 = 0;
+    const float mf = (float)mean, sd = fmaxf((float)sqrt(m2 / (c - 1.0)), floor_std);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __fdiv_rn(__fsub_rn(x[i], mf), sd);
+}
+
 __global__ void rnd_scale_bonus_kernel(const float* __restrict__ err, const float* __restrict__ done,
                                        const double* __restrict__ rew_var, float beta,
                                        float* __restrict__ out, int64_t n) {
@@ -360,6 +420,37 @@ extern "C" int cb_masked_normalize(const float* x, const float* mask, float floo
                                    int64_t n, void* stream) {
     CB_REQUIRE(x && out && n >= 2, CB_E_ARG, "cb_masked_normalize: bad argument");
     masked_normalize_kernel<<<1, 1024, 0, cb::as_stream(stream)>>>(x, mask, floor_std, out, n);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_rms_update_columns(const double* x, int64_t n, int32_t d, double* mean, double* var, double* count,
+                                     void* stream) {
+    CB_REQUIRE(x && mean && var && count && n >= 1 && d >= 1, CB_E_ARG, "cb_rms_update_columns: bad argument");
+    cudaStream_t s = cb::as_stream(stream);
+    rms_update_columns_kernel<<<d, 256, 0, s>>>(x, n, d, mean, var, count);
+    CB_LAUNCH_CHECK();
+    add_count_kernel<<<1, 1, 0, s>>>(count, (double)n);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_masked_moments(const float* x, const float* mask, int64_t n, double* sums, double* ws, void* stream) {
+    CB_REQUIRE(x && sums && ws && n >= 1, CB_E_ARG, "cb_masked_moments: bad argument");
+    cudaStream_t s = cb::as_stream(stream);
+    int nblocks = (int)std::min<int64_t>(512, cb::ceil_div<int64_t>(n, 1024));
+    masked_moments_partial_kernel<<<nblocks, 256, 0, s>>>(x, mask, n, ws);
+    CB_LAUNCH_CHECK();
+    masked_moments_finish_kernel<<<1, 32, 0, s>>>(nblocks, ws, sums);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_normalize_apply(const float* x, const double* sums, float floor_std, float* out, int64_t n,
+                                  void* stream) {
+    CB_REQUIRE(x && sums && out && n >= 1, CB_E_ARG, "cb_normalize_apply: bad argument");
+    int nblocks = (int)std::min<int64_t>(148 * 8, cb::ceil_div<int64_t>(n, 256));
+    normalize_apply_kernel<<<nblocks, 256, 0, cb::as_stream(stream)>>>(x, sums, floor_std, out, n);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

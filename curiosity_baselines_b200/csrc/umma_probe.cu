@@ -1,10 +1,20 @@
-// Descriptor probe (test infrastructure for the kernel author, exported as cb_umma_probe):
+// Descriptor probe (test infrastructure for the kernel author).  Built into its OWN library
+// (libcuriosity_b200_probe.so, `python -m curiosity_baselines_b200.build --probe`), never into the product .so:
 // copies caller-supplied raw shared-memory images for A and B, issues `ksteps` tcgen05.mma with
 // caller-supplied descriptor fields and reads the accumulator back.  Lets the tests pin down the
 // hardware semantics of MN-major layouts and of the descriptor base_offset on B200 without
 // recompiling.  Single CTA; never on the product path.
 #include "common.cuh"
 #include "umma_common.cuh"
+
+namespace cb { thread_local char g_err[512] = ""; }     // this library's own error text (api.cu is not linked in)
+extern "C" const char* cb_probe_last_error(void) { return cb::g_err; }
+static int probe_device_ok() {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
 
 namespace {
 
@@ -74,7 +84,7 @@ extern "C" int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, 
                              const int* b_desc, int a_mn_major, int b_mn_major, int M, int N, int ksteps,
                              float* d_out, void* stream) {
     CB_REQUIRE(a_img && b_img && a_desc && b_desc && d_out, CB_E_ARG, "cb_umma_probe: null pointer");
-    CB_REQUIRE(cb_device_supports_umma(), CB_E_ARCH, "cb_umma_probe: needs sm_100");
+    CB_REQUIRE(probe_device_ok(), CB_E_ARCH, "cb_umma_probe: needs sm_100");
     CB_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_bytes + b_bytes <= 200 * 1024 && N % 8 == 0 && N <= 256,
                CB_E_ARG, "cb_umma_probe: bad sizes");
     ProbeParams p{};

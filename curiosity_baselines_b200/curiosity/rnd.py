@@ -121,7 +121,8 @@ class RND(nn.Module):
         """fp32 mean and 1/sqrt(var) of the current obs_rms (rnd.py:162-169)."""
         self._norm_ver = getattr(self, "_norm_ver", 0) + 1
         self._norm[0].copy_(self.obs_rms._mean)
-        self._norm[1].copy_(self.obs_rms._var.rsqrt())
+        # same arithmetic as cb_rms_merge_from_sums (1 / sqrtf((float)var)) so a resumed run normalises bit-identically
+        self._norm[1].copy_(torch.sqrt(self.obs_rms._var.float()).reciprocal())
 
     # ------------------------------------------------------------------ checkpointing of the running statistics
     # The reference keeps obs_rms / rew_rms / rew_rff as NumPy attributes outside ``state_dict`` (rnd.py:34-36), so a

@@ -54,6 +54,17 @@ class RunningMeanStd:
     def count(self):
         return float(self._count.item())
 
+    def update(self, x):
+        """averages.py:48-52: merge the batch ``x`` [n, *shape] (any float dtype, on the device) -- per-element mean
+        and population variance over axis 0 in float64, two passes like numpy, then the Chan merge."""
+        if self._mean is None:
+            self._alloc(x.device)
+        x = x.to(self._mean.device, torch.float64).reshape(x.shape[0], -1).contiguous()
+        if x.shape[1] != self.n:
+            raise ValueError(f"RunningMeanStd.update: expected trailing shape {self.shape}")
+        L.call("cb_rms_update_columns", L.ptr(x), x.shape[0], self.n, L.ptr(self._mean), L.ptr(self._var),
+               L.ptr(self._count), L.stream())
+
     def update_from_values(self, x, count_num=None, count_den=1.0):
         """Merge the moments of all elements of the fp32 device tensor ``x`` into a scalar
         state (averages.py:54-68).  The batch count is ``count_num / count_den`` when
@@ -97,6 +108,13 @@ class RewardForwardFilter:
         if self._rewems is None or int(self._init.item()) == 0:
             return None
         return self._rewems.cpu().numpy()
+
+    def update(self, rews, mask=None):
+        """averages.py:75-89 for one step: ``rews`` fp32 device [B]; ``mask`` is the NOT-done mask RND passes
+        (rnd.py:185-188), None = no masking.  Returns the copy of the running sums [B]."""
+        rews = rews.reshape(1, -1).to(torch.float32).contiguous()
+        done = torch.zeros_like(rews) if mask is None else (1.0 - mask.reshape(1, -1).to(rews.device, torch.float32))
+        return self.update_sequence(rews, done.contiguous())[0]
 
     def update_sequence(self, rews, done):
         """rews, done: fp32 device [T,B].  Applies rnd.py:186-189 for t = 0..T-1 and returns

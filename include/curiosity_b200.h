@@ -118,6 +118,15 @@ int cb_valid_count(const float* done, double* out, int64_t n, void* stream);
  * the elements where mask > 0 (all when mask is NULL) */
 int cb_masked_normalize(const float* x, const float* mask, float floor_std, float* out,
                         int64_t n, void* stream);
+/* averages.py:48-68 for a vector-shaped state: x f64 [n, d] row-major; batch mean / population variance per column
+ * (two passes, like numpy) Chan-merged into mean[d], var[d]; count[1] += n. */
+int cb_rms_update_columns(const double* x, int64_t n, int32_t d, double* mean, double* var, double* count,
+                          void* stream);
+/* algos/pg/base.py:95-103 in two stages so that a data-parallel host can all-reduce in between:
+ * sums = {sum x, sum x^2, count} over the elements with mask > 0 (all when mask is NULL), f64, deterministic
+ * (ws >= 1536 f64); then out = (x - mean) / max(std_unbiased, floor) from `sums`. */
+int cb_masked_moments(const float* x, const float* mask, int64_t n, double* sums, double* ws, void* stream);
+int cb_normalize_apply(const float* x, const double* sums, float floor_std, float* out, int64_t n, void* stream);
 /* rnd.py:198-203: r = beta * err / sqrt(var) * |done-1| */
 int cb_rnd_scale_bonus(const float* err, const float* done, const double* rew_var,
                        float beta, float* out, int64_t n, void* stream);
@@ -357,16 +366,6 @@ int cb_unprepare_conv_grad(const float* g, float* dst, int32_t o, int32_t i, int
  * pitch dst_pitch, asynchronously on `stream`. */
 int cb_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch,
               int64_t width_bytes, int64_t rows, void* stream);
-
-/* ------------------------------------------------------------------------------------
- * Kernel-author diagnostics (not on the product path): run `ksteps` tcgen05.mma over raw
- * shared-memory images with explicit descriptor fields {start, lbo, sbo, base_offset, kstep, layout}
- * (bytes; layout 0 = SWIZZLE_128B, else the raw 3-bit layout code) and return the [128][N] fp32 accumulator.  Used by tests/test_gpu_umma_probe.py to pin
- * the MN-major / base_offset descriptor semantics on the installed hardware.
- * ---------------------------------------------------------------------------------- */
-int cb_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, const int* a_desc_host,
-                  const int* b_desc_host, int a_mn_major, int b_mn_major, int M, int N, int ksteps,
-                  float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

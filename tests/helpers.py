@@ -50,4 +50,6 @@ def check_grads(named_grads, gold, cos_min, norm_tol, prefix="g."):
         c = cosine(grad_sample(g), gold[key + ".sample"])
         if gn > 0 and (abs(n - gn) / gn > norm_tol or c < cos_min):
             bad.append((name, n, gn, c))
+        if gn > 0 and os.environ.get("CB_GRAD_REPORT"):
+            print(f"GRADREPORT {name} cos={c:.5f} normerr={abs(n - gn) / gn:.4f}")
     return bad

@@ -45,8 +45,10 @@ def test_icm_golden(enc, A):
     assert abs(float(fwd) - float(g["fwd_loss"])) / float(g["fwd_loss"]) < 1e-2
     grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     assert len(grads) == len(list(m.parameters()))
-    # 12-15 samples and raw 0..255 inputs: deepest conv gradients see bf16 mask flips; norm within 5%
-    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)
+    # 12-15 samples: one bf16-flipped LeakyReLU mask is visible in the deepest conv gradients (measured worst
+    # cosine 0.9939, norm 3.0 %); the SURVEY 8(d) gate 0.999 / 1e-2 is enforced on >= 1024 samples in
+    # tests/test_gpu_parity_scale.py
+    bad = check_grads(grads, g, cos_min=0.99, norm_tol=4e-2)
     assert not bad, bad
 
 
@@ -60,15 +62,14 @@ def test_disagreement_golden():
     act = R.onehot(R.make_actions(seed + 3, T, B, A), A).to(DEV)
     valid = (1 - R.make_suffix_done(seed + 4, T, B, frac=0.5)).to(DEV)
     bonus = m.compute_bonus(obs, nxt, act)
-    # ensemble variance of nearly equal predictions: differences of bf16-rounded features -> 3e-2
-    assert relmax(bonus, g["bonus"]) < 3e-2
+    assert relmax(bonus, g["bonus"]) < 1e-2          # measured 1.6e-3 (two-pass variance of the fp32 accumulators)
     masks = [R.make_mask(seed + 10 + e, (T, B, 512), 0.2).to(DEV) for e in range(4)]
     inv, fwd = m.compute_loss(obs, nxt, act, valid, dropout_masks=masks)
     (inv + fwd).backward()
     assert abs(float(inv) - float(g["inv_loss"])) / float(g["inv_loss"]) < 1e-2
     assert abs(float(fwd) - float(g["fwd_loss"])) / float(g["fwd_loss"]) < 1e-2
     grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
-    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)
+    bad = check_grads(grads, g, cos_min=0.99, norm_tol=4e-2)      # few-sample case, see test_icm_golden
     assert not bad, bad
     inv2, fwd2 = m.compute_loss(obs, nxt, act, valid, dropout_masks=None)
     assert abs(float(fwd2) - float(g["fwd_loss_nodrop"])) / float(g["fwd_loss_nodrop"]) < 1e-2
@@ -107,7 +108,8 @@ def test_icm_oracle_parity(enc, A, T, B):
     for k, prm in m.named_parameters():
         gref, gg = p[k].grad.flatten(), prm.grad.cpu().flatten()
         cos = float(gg @ gref / (gg.norm() * gref.norm()).clamp_min(1e-30))
-        # bias gradients are signed sums of bf16-rounded dy rows (cancellation): allow 8% on their norm
+        # 72-128 samples: bias gradients are signed sums of bf16-rounded dy rows (cancellation), 8 % on their norm;
+        # the strict 0.999 / 1e-2 gate runs at n >= 1024 in test_gpu_parity_scale.py
         tol = 8e-2 if gg.numel() <= 64 else 3e-2
         assert cos > 0.99 and abs(float(gg.norm() / gref.norm()) - 1) < tol, (k, cos, float(gg.norm() / gref.norm()))
 

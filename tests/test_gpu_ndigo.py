@@ -35,7 +35,7 @@ def test_golden(H):
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-2
     grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     assert len(grads) == len(list(m.parameters()))
-    bad = check_grads(grads, g, cos_min=0.98, norm_tol=8e-2)
+    bad = check_grads(grads, g, cos_min=0.99, norm_tol=4e-2)      # few samples; strict gate: test_gpu_parity_scale.py
     assert not bad, bad
 
 

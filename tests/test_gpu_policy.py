@@ -234,7 +234,7 @@ def test_policy_and_ppo_loss_golden():
         assert abs(float(val) - ref) <= 1e-2 * max(abs(ref), 1e-2), (name, float(val), ref)
     grads = {k: p.grad for k, p in m.named_parameters()}
     assert all(v is not None for v in grads.values())
-    bad = check_grads(grads, g, cos_min=0.98, norm_tol=5e-2)      # 18 samples: same allowance as the ICM golden case
+    bad = check_grads(grads, g, cos_min=0.99, norm_tol=4e-2)      # 18 samples: same allowance as the ICM golden case
     assert not bad, bad
     gn = float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())))
     assert abs(gn - float(g["grad_norm"])) / float(g["grad_norm"]) < 5e-2

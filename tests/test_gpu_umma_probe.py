@@ -23,7 +23,7 @@ def bits(x):
 def run(a_img, b_img, a_desc, b_desc, a_mn, b_mn, M, N, ksteps):
     a, b = torch.from_numpy(a_img).to(DEV), torch.from_numpy(b_img).to(DEV)
     out = torch.full((128, N), float("nan"), device=DEV)
-    L.call("cb_umma_probe", L.ptr(a), a.numel() * 2, L.ptr(b), b.numel() * 2, (C.c_int * 6)(*(tuple(a_desc) + (0,) * (6 - len(a_desc)))),
+    L.call_probe(L.ptr(a), a.numel() * 2, L.ptr(b), b.numel() * 2, (C.c_int * 6)(*(tuple(a_desc) + (0,) * (6 - len(a_desc)))),
            (C.c_int * 6)(*(tuple(b_desc) + (0,) * (6 - len(b_desc)))), a_mn, b_mn, M, N, ksteps, L.ptr(out), L.stream())
     torch.cuda.synchronize()
     return out.cpu()

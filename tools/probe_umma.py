@@ -30,7 +30,7 @@ def run(a_img, b_img, a_desc, b_desc, a_mn, b_mn, M, N, ksteps):
     out = torch.full((128, N), float("nan"), device=dev)
     ad = (C.c_int * 6)(*(tuple(a_desc) + (0,) * (6 - len(a_desc))))
     bd = (C.c_int * 6)(*(tuple(b_desc) + (0,) * (6 - len(b_desc))))
-    L.call("cb_umma_probe", L.ptr(a), a.numel() * 2, L.ptr(b), b.numel() * 2, ad, bd, a_mn, b_mn, M, N, ksteps,
+    L.call_probe(L.ptr(a), a.numel() * 2, L.ptr(b), b.numel() * 2, ad, bd, a_mn, b_mn, M, N, ksteps,
            L.ptr(out), L.stream())
     torch.cuda.synchronize()
     return out.cpu()
