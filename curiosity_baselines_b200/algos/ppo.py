@@ -42,7 +42,8 @@ class PPO:
 
     def __init__(self, discount=0.99, learning_rate=0.001, value_loss_coeff=1., entropy_loss_coeff=0.01,
                  clip_grad_norm=1., gae_lambda=1, minibatches=4, epochs=4, ratio_clip=0.1, linear_lr_schedule=True,
-                 normalize_advantage=False, normalize_reward=False, curiosity_type="none"):
+                 normalize_advantage=False, normalize_reward=False, curiosity_type="none",
+                 initial_optim_state_dict=None):
         self.discount, self.learning_rate = discount, learning_rate
         self.value_loss_coeff, self.entropy_loss_coeff = value_loss_coeff, entropy_loss_coeff
         self.clip_grad_norm, self.gae_lambda = clip_grad_norm, gae_lambda
@@ -51,6 +52,7 @@ class PPO:
         self.linear_lr_schedule = linear_lr_schedule
         self.normalize_advantage, self.normalize_reward = normalize_advantage, normalize_reward
         self.curiosity_type = curiosity_type
+        self.initial_optim_state_dict = initial_optim_state_dict      # algos/pg/base.py:45-46
         self.intrinsic_rewards = None
         self.update_counter = 0
         self._returns_state = None
@@ -61,9 +63,19 @@ class PPO:
         self.model, self.n_itr = model, n_itr
         self.opt = FlatAdam(model.parameters(), lr=self.learning_rate, max_norm=self.clip_grad_norm)
         self.rng = rng or np.random
+        if self.initial_optim_state_dict is not None:
+            self.opt.load_state_dict(self.initial_optim_state_dict)
         if self.normalize_reward:
             from .pg_base import ReturnsState
             self._returns_state = ReturnsState(self.discount)
+
+    def optim_state_dict(self):
+        """algos/base.py: what the runner snapshots as ``optimizer_state_dict`` (runners/minibatch_rl.py:148), in
+        torch.optim.Adam's layout so that it interchanges with the reference."""
+        return self.opt.state_dict()
+
+    def load_optim_state_dict(self, sd):
+        self.opt.load_state_dict(sd)
 
     # ------------------------------------------------------------------ loss + gradients of one minibatch
     def loss_and_grads_(self, observation, prev_action, action, return_, advantage, valid, old_prob, init_rnn_state,

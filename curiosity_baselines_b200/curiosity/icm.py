@@ -166,6 +166,7 @@ class GroupedResForward:
             mod.weight.grad[:, :F].copy_(dw[e * F:(e + 1) * F])
             mod.weight.grad[:, F:].copy_(dsw[e * F:(e + 1) * F])
             mod.bias.grad.copy_(db[e * F:(e + 1) * F])
+            dist.grads_ready((mod.weight.grad, mod.bias.grad))
 
     def run_forward(self, phi1_bf16, action, n):
         """-> (saved activations, predictions fp32 packed [n, E*F])."""
@@ -277,14 +278,14 @@ class _IcmBase(nn.Module):
             phi_b = phi_b.index_select(1, ex["perm"])
         return dict(keep=keep, x=x, dtype=dtype, strides=strides, acts=acts), phi_f, phi_b
 
-    def _encode_backward(self, enc, dphi_bf16, n, accumulate):
+    def _encode_backward(self, enc, dphi_bf16, n, accumulate, final=True):
         ex = self._exec
         if ex["inv_perm"] is not None:
             dphi_bf16 = dphi_bf16.index_select(1, ex["inv_perm"])
         last = ex["chain"].layers[-1]
         dphi_bf16 = dphi_bf16.reshape(n * last.out_h * last.out_w, last.out_c)      # back to NHWC rows
         ex["chain"].backward(enc["x"], enc["acts"], dphi_bf16.contiguous(), n, in_dtype=enc["dtype"],
-                             strides=enc["strides"], accumulate=accumulate)
+                             strides=enc["strides"], accumulate=accumulate, final=final)
 
     def _features(self, observations, next_observations, actions, first_out_obs=None):
         """Shared by bonus and loss: (T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action[n,A])."""
@@ -356,7 +357,11 @@ class _IcmBase(nn.Module):
             observations, next_observations, actions, remember=False)
         ex, st, dev, F = self._exec, L.stream(), self._exec["dev"], self.feature_size
         valid = valid.to(dev, torch.float32).reshape(n).contiguous()
-        denom = dist.all_reduce_sum_(valid.sum().reshape(1)) if dist.world_size() > 1 else None
+        # Normaliser convention.  Fused path (``inplace``: FlatAdam SUMS the gradients over ranks): every rank divides
+        # by the GLOBAL sum(valid), so the summed gradient is the single-process one.  Autograd path (rlpyt's own
+        # optimiser; under SyncRl torch DDP AVERAGES gradients and the reference uses the per-rank valid_mean,
+        # utils/tensor.py:39-46): local sum(valid), returned losses are per-rank means like the reference's.
+        denom = dist.all_reduce_sum_(valid.sum().reshape(1)) if (inplace and dist.world_size() > 1) else None
         # inverse model (icm.py:88-92, 125)
         cat = torch.cat([phi1_b, phi2_b], 1)
         h, _ = ex["inv0"].forward(cat, n)
@@ -412,13 +417,14 @@ class _IcmBase(nn.Module):
             dh = torch.empty(n, F, dtype=torch.bfloat16, device=dev)
             L.call("cb_policy_heads_bwd", L.ptr(h), L.ptr(dlogits), None, L.ptr(inv2.weight), None, L.ptr(dh),
                    L.ptr(inv2.weight.grad), L.ptr(inv2.bias.grad), None, None, n, F, self.action_size, L.ACT_RELU, st)
+            dist.grads_ready((inv2.weight.grad, inv2.bias.grad))
         else:
             dlog_b = dlogits.to(torch.bfloat16)
             ex["inv2"].wgrad(h, dlog_b, n)
             dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
         ex["inv0"].wgrad(cat, dh, n)
         dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
-        self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False)
+        self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False, final=False)
         self._encode_backward(enc2, dcat[:, F:].contiguous(), n, accumulate=True)
         if inplace:
             return losses[0], losses[1], None, None

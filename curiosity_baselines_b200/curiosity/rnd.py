@@ -109,8 +109,10 @@ class RND(nn.Module):
         self._dev = dev
         self.obs_rms.to(dev); self.rew_rms.to(dev)
         px = h * w
-        self._sum = torch.zeros(2, px, dtype=torch.int64, device=dev)
-        self._n_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        # per-pixel integer sums and the frame count share one buffer: ONE all-reduce per bonus under data parallelism
+        self._stat = torch.zeros(2 * px + 1, dtype=torch.int64, device=dev)
+        self._sum = self._stat[:2 * px].view(2, px)
+        self._n_total = self._stat[2 * px:]
         self._mean_len = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm = (torch.zeros(px, dtype=torch.float32, device=dev),
                       torch.ones(px, dtype=torch.float32, device=dev))
@@ -223,8 +225,7 @@ class RND(nn.Module):
         self._sum.zero_()
         L.call("cb_obs_moments_u8", base, strides[0], px, L.ptr(n_valid), T, B,
                L.ptr(self._sum[0]), L.ptr(self._sum[1]), st)
-        dist.all_reduce_sum_(self._sum)          # exact integer sums: sharded == single process
-        dist.all_reduce_sum_(self._n_total)
+        dist.all_reduce_sum_(self._stat)         # exact integer sums + count: sharded == single process
         rms = self.obs_rms
         L.call("cb_rms_merge_from_sums", L.ptr(self._sum[0]), L.ptr(self._sum[1]),
                L.ptr(self._n_total), L.ptr(rms._mean), L.ptr(rms._var), L.ptr(rms._count),
@@ -239,8 +240,13 @@ class RND(nn.Module):
                T * B, self.feature_size, st)
         # reward normalisation (rnd.py:184-203)
         total = self.rew_rff.update_sequence(err, done)
-        L.call("cb_valid_count", L.ptr(done), L.ptr(self._mean_len), T * B, st)
-        dist.all_reduce_sum_(self._mean_len)
+        # sum |done-1| over the GLOBAL batch (numerator of the mean valid length, rnd.py:190): for 0/1 dones it is the
+        # frame count that was just all-reduced with the pixel sums; anything else is summed and reduced separately
+        if bool(getattr(self, "binary_done", True)):
+            self._mean_len.copy_(self._n_total)
+        else:
+            L.call("cb_valid_count", L.ptr(done), L.ptr(self._mean_len), T * B, st)
+            dist.all_reduce_sum_(self._mean_len)
         self.rew_rms.update_from_values(total, self._mean_len, float(B * dist.world_size()))
         out = torch.empty_like(err)
         L.call("cb_rnd_scale_bonus", L.ptr(err), L.ptr(done), L.ptr(self.rew_rms._var),
@@ -272,7 +278,9 @@ class RND(nn.Module):
         L.call("cb_rowwise_sqerr", L.ptr(phi_hat), L.ptr(phi), 1.0 / F, L.ptr(err), n, F, st)
         coef = torch.empty(n, dtype=torch.float32, device=self._dev)
         denom = None
-        if dist.world_size() > 1:     # global sum(valid): every rank divides by the same count
+        # fused path (FlatAdam sums gradients over ranks): global sum(valid).  Autograd path (rlpyt's optimiser; DDP
+        # averages gradients, the reference takes the per-rank valid_mean): local sum(valid).  See icm.py.
+        if inplace and dist.world_size() > 1:
             denom = dist.all_reduce_sum_(valid.sum().reshape(1))
         L.call("cb_loss_coef", L.ptr(valid), L.ptr(mask), 1.0, L.ptr(denom), L.ptr(coef), n, st)
         loss = torch.empty(1, dtype=torch.float32, device=self._dev)

@@ -28,6 +28,88 @@ def all_reduce_sum_(t):
     return t
 
 
+class BucketReducer:
+    """Gradient all-reduce overlapped with the backward pass (ppo.py:147-150 under data
+    parallelism).  ``flat`` is the optimiser's flat fp32 gradient buffer.  As weight-gradient kernels finish being
+    enqueued the model reports their tensors with ``ready``; adjacent reported ranges coalesce and every range that
+    reaches ``bucket_bytes`` is all-reduced asynchronously (NCCL runs it on its own stream behind the work already
+    queued on the compute stream, so it overlaps the remaining dgrad / wgrad launches).  ``finish`` reduces whatever
+    has not been reduced yet -- including parameters nobody reported -- and makes the compute stream wait.  Every
+    element is reduced exactly once per step; a range reported twice raises."""
+
+    def __init__(self, flat, bucket_bytes=2 << 20):
+        self.flat = flat
+        self.bucket = max(1, bucket_bytes // flat.element_size())
+        self.pending, self.reduced, self.works = [], [], []
+        self.launched = 0
+
+    def _insert(self, ivals, lo, hi):
+        out, placed = [], False
+        for a, b in ivals:
+            if b < lo or a > hi:
+                out.append((a, b))
+            else:
+                lo, hi = min(a, lo), max(b, hi)
+        out.append((lo, hi))
+        out.sort()
+        return out
+
+    def _launch(self, lo, hi):
+        self.works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self.reduced = self._insert(self.reduced, lo, hi)
+        self.launched += 1
+
+    def ready(self, tensors):
+        if world_size() == 1:
+            return
+        base, es, n = self.flat.data_ptr(), self.flat.element_size(), self.flat.numel()
+        for t in tensors:
+            if t is None:
+                continue
+            off = (t.data_ptr() - base) // es
+            if off < 0 or off >= n or not t.is_contiguous():
+                continue                                   # not a view of this buffer
+            lo, hi = off, off + t.numel()
+            for a, b in self.reduced + self.pending:
+                if lo < b and a < hi:
+                    raise RuntimeError("BucketReducer: gradient range reported twice in one step")
+            self.pending = self._insert(self.pending, lo, hi)
+        keep = []
+        for a, b in self.pending:
+            if b - a >= self.bucket:
+                self._launch(a, b)
+            else:
+                keep.append((a, b))
+        self.pending = keep
+
+    def finish(self):
+        """All-reduce every element not reduced yet, wait for all launched reductions, reset for the next step."""
+        if world_size() > 1:
+            pos, n = 0, self.flat.numel()
+            for a, b in list(self.reduced) + [(n, n)]:
+                if a > pos:
+                    self._launch(pos, a)
+                pos = max(pos, b)
+            for w in self.works:
+                w.wait()
+        self.pending, self.reduced, self.works = [], [], []
+
+
+_reducer = None
+
+
+def set_grad_reducer(r):
+    """The optimiser that owns the flat gradient buffer registers its reducer here; the layers report finished
+    weight gradients through ``grads_ready`` without knowing about the optimiser."""
+    global _reducer
+    _reducer = r
+
+
+def grads_ready(tensors):
+    if _reducer is not None:
+        _reducer.ready(tensors)
+
+
 def shard_columns(B, r=None, w=None):
     """Contiguous block of env columns owned by rank r: [lo, hi)."""
     r = rank() if r is None else r

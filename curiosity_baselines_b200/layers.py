@@ -11,6 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from . import dist
 
 ACT = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "elu": L.ACT_ELU}
 
@@ -186,11 +187,17 @@ class GemmLayer:
                L.ptr(dx_add), L.ptr(dx), L.stream())
         return dx
 
-    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False, final=True):
         """Weight / bias gradients written (or accumulated) into the holder's ``.grad`` in the
-        torch layout."""
+        torch layout.  ``final``: no later pass of this step accumulates into them any more, so the data-parallel
+        reducer may start summing them across ranks (dist.BucketReducer)."""
         if not self.trainable:
             return
+        self._wgrad_impl(x, dy, n, in_dtype=in_dtype, strides=strides, side=side, norm=norm, accumulate=accumulate)
+        if final:
+            dist.grads_ready((self.module.weight.grad, self.module.bias.grad))
+
+    def _wgrad_impl(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
         self.prepare()
         dev = dy.device
         w, b = self.module.weight, self.module.bias
@@ -303,9 +310,7 @@ class DenseConvLayer(GemmLayer):
         kw.pop("norm", None)
         return super().forward(self._flat_input(x, n), n, **kw)
 
-    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
-        if not self.trainable:
-            return
+    def _wgrad_impl(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
         self.prepare()
         w, b = self.module.weight, self.module.bias
         dev = dy.device
@@ -363,9 +368,7 @@ class PaddedLinearLayer(GemmLayer):
                 self.w_ext[:, self.K: self.K + self.side_dim] = sw.to(torch.bfloat16)
         self._version = ver
 
-    def wgrad(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
-        if not self.trainable:
-            return
+    def _wgrad_impl(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
         self.prepare()
         w, b = self.module.weight, self.module.bias
         dev = dy.device
@@ -452,18 +455,18 @@ class Chain:
         return acts, out_f32
 
     def backward(self, x, acts, dy, n, in_dtype=L.BF16, strides=None, norm=None, accumulate=False,
-                 need_dx=False, x_saved=None, x_act="none"):
+                 need_dx=False, x_saved=None, x_act="none", final=True):
         """dy: bf16 gradient w.r.t. the last layer's (pre-loss) output.  Fills ``.grad`` of all
         trainable holders; returns the gradient w.r.t. the chain input when ``need_dx``."""
         for i in range(len(self.layers) - 1, -1, -1):
             layer = self.layers[i]
             if i == 0:
                 layer.wgrad(x, dy, n, in_dtype=in_dtype, strides=strides, norm=norm,
-                            accumulate=accumulate)
+                            accumulate=accumulate, final=final)
                 if need_dx:
                     return layer.dgrad(dy, n, x_saved=x_saved, x_act=x_act)
                 return None
             prev = self.layers[i - 1]
-            layer.wgrad(acts[i - 1], dy, n, accumulate=accumulate)
+            layer.wgrad(acts[i - 1], dy, n, accumulate=accumulate, final=final)
             dy = layer.dgrad(dy, n, x_saved=acts[i - 1], x_act=self.ACT_NAME[prev.act])
         return None

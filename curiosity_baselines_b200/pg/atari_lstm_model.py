@@ -23,6 +23,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
+from .. import dist
 from .. import layers as LY
 from ..layers import linear_layer, pad_side
 from ..curiosity.encoders import BurdaHead, UniverseHead, MazeHead, frame_input
@@ -242,6 +243,7 @@ class AtariLstmModel(nn.Module):
             L.call("cb_policy_heads_bwd", L.ptr(h_out), L.ptr(dlogits), L.ptr(dvalue), L.ptr(self.pi.weight),
                    L.ptr(self.value.weight), L.ptr(dh), L.ptr(self.pi.weight.grad), L.ptr(self.pi.bias.grad),
                    L.ptr(self.value.weight.grad), L.ptr(self.value.bias.grad), n, H, A, L.ACT_NONE, st)
+            dist.grads_ready((self.pi.weight.grad, self.pi.bias.grad, self.value.weight.grad, self.value.bias.grad))
             return dh
         dlog_b = torch.empty(n, A, dtype=torch.bfloat16, device=dev)
         dval_b = torch.empty(n, 1, dtype=torch.bfloat16, device=dev)

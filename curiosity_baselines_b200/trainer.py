@@ -18,12 +18,19 @@ class FlatAdam:
     (ppo.py:147-150).  Parameters are re-pointed to views of ``self.flat``; ``.grad`` to views of
     ``self.grad`` so the wgrad kernels write in place."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+    LOG_SLOTS = 8           # fp32 scalars riding at the tail of the gradient buffer (summed across ranks for free)
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, bucket_bytes=2 << 20):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
+        self.n = n
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._grad_all = torch.zeros(n + self.LOG_SLOTS, dtype=torch.float32, device=dev)
+        self.grad = self._grad_all[:n]
+        self.logged = self._grad_all[n:]          # per-rank partial sums of logged scalars (loss, ...)
+        self.reducer = dist.BucketReducer(self._grad_all, bucket_bytes)
+        dist.set_grad_reducer(self.reducer)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -39,9 +46,10 @@ class FlatAdam:
 
     def step(self):
         st = L.stream()
-        n = self.flat.numel()
-        if dist.world_size() > 1:
-            dist.all_reduce_sum_(self.grad)       # coef already carries 1/global sum(valid)
+        n = self.n
+        # gradients were all-reduced bucket by bucket while the backward pass ran (coef already carries
+        # 1 / global sum(valid), so the reduction is a plain SUM); this reduces the rest and waits
+        self.reducer.finish()
         self.sumsq.zero_()
         L.call("cb_sumsq", L.ptr(self.grad), n, L.ptr(self.sumsq), st)
         self.step_count += 1
@@ -51,6 +59,54 @@ class FlatAdam:
 
     def grad_norm(self):
         return float(self.sumsq.sqrt().item())
+
+    def log_scalar(self, slot, value):
+        """Stage a per-rank partial sum (a loss normalised by the GLOBAL sum(valid)) in the tail of the gradient
+        buffer: the final bucket of ``step`` sums it across ranks together with the gradients.  Returns the view
+        that holds the global value once ``step`` has run (single process: the value itself)."""
+        self.logged[slot].copy_(value.detach().reshape(()))
+        return self.logged[slot]
+
+    # ------------------------------------------------------------------ checkpointing (runners/minibatch_rl.py:148)
+    def state_dict(self):
+        """``torch.optim.Adam.state_dict()`` layout -- {'state': {i: {step, exp_avg, exp_avg_sq}}, 'param_groups'} with
+        the parameters in construction order -- so that a snapshot's ``optimizer_state_dict`` interchanges with the
+        reference's (agent.parameters() order, algos/pg/base.py:44)."""
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            if self.step_count > 0:
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off:off + k].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[off:off + k].view(p.shape).clone()}
+            off += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self.params):
+            raise ValueError(f"optimizer state has {len(ids)} parameters, this optimiser {len(self.params)}")
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+        steps, off = set(), 0
+        self.m.zero_(); self.v.zero_()
+        for pos, p in zip(ids, self.params):
+            k = p.numel()
+            st = sd["state"].get(pos)
+            if st is not None:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {pos}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+                self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            off += k
+        if len(steps) > 1:
+            raise ValueError("FlatAdam keeps one step counter; the loaded state has several")
+        self.step_count = steps.pop() if steps else 0
 
 
 class RndStep:
@@ -70,6 +126,7 @@ class RndStep:
         ret, adv, valid, _ = returns_on_device(reward, done, value, bootstrap, self.discount,
                                                self.gae_lambda)
         loss = m.loss_and_grads_(next_obs, valid, mask)
+        loss = self.opt.log_scalar(0, loss)
         self.opt.step()
         m.invalidate_weights()
         return loss, r_int, adv, ret
@@ -90,6 +147,7 @@ class IcmStep:
         reward.add_(r_int)
         ret, adv, valid, _ = returns_on_device(reward, done, value, bootstrap, self.discount, self.gae_lambda)
         inv, fwd = m.loss_and_grads_(obs, next_obs, action, valid, dropout_masks)
+        loss = self.opt.log_scalar(0, inv + fwd)
         self.opt.step()
         m.invalidate_weights()
-        return inv + fwd, r_int, adv, ret
+        return loss, r_int, adv, ret

@@ -73,3 +73,35 @@ def test_shard_columns():
         raise AssertionError("expected ValueError")
     except ValueError:
         pass
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from curiosity_baselines_b200 import dist as D
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red = D.BucketReducer(flat, bucket_bytes=4 * 100)
+    views = [flat[900:1000], flat[700:900], flat[650:700], flat[0:30]]       # backward order: last layer first
+    red.ready(views[:1])
+    assert red.launched == 1                                                   # 100 elements reach the bucket size
+    red.ready(views[2:3])
+    assert red.launched == 1 and red.pending == [(650, 700)]                 # 50 elements wait for neighbours
+    red.ready(views[1:2])
+    assert red.launched == 2 and red.reduced == [(650, 1000)]                # coalesced with the adjacent range
+    red.ready(views[3:])
+    try:
+        red.ready([flat[10:20]])
+        raise AssertionError("a range reported twice must raise")
+    except RuntimeError:
+        pass
+    red.finish()                                                               # the rest, reported or not
+    assert red.pending == [] and red.reduced == []
+    if rank == 0:
+        torch.save(flat, out)
+    dist.destroy_process_group()
+
+
+def test_bucket_reducer_sums_every_element_once(tmp_path):
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_reducer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.equal(torch.load(out), torch.arange(1000, dtype=torch.float32) * 3)

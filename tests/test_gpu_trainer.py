@@ -31,6 +31,46 @@ def test_flat_adam_matches_torch():
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), it
 
 
+def test_flat_adam_state_dict_interchanges_with_torch_adam():
+    """the optimiser state must survive a checkpoint.  torch.optim.Adam's state_dict loads into FlatAdam
+    (and back) and both continue identically -- Adam moments, step count (bias correction) and learning rate."""
+    torch.manual_seed(1)
+    shapes = [(6, 5), (17,), (3, 2, 2, 2)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    opt_ref = torch.optim.Adam(ref, lr=3e-3)
+    grads = [[torch.randn(s, device=DEV) for s in shapes] for _ in range(5)]
+    for it in range(2):
+        for q, g in zip(ref, grads[it]):
+            q.grad = g.clone()
+        opt_ref.step()
+    ps = [torch.nn.Parameter(q.detach().clone()) for q in ref]
+    opt = FlatAdam(ps, lr=1.0, max_norm=1e9)
+    opt.load_state_dict(opt_ref.state_dict())
+    assert opt.step_count == 2 and opt.lr == 3e-3
+    for it in range(2, 4):
+        for p, q, g in zip(ps, ref, grads[it]):
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        opt_ref.step()
+        opt.step()
+    for p, q in zip(ps, ref):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    # ... and back: a fresh torch Adam resumes from FlatAdam's state
+    ref2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = torch.optim.Adam(ref2, lr=3e-3)
+    opt2.load_state_dict(opt.state_dict())
+    for p, q, g in zip(ps, ref2, grads[4]):
+        p.grad.copy_(g)
+        q.grad = g.clone()
+    opt.step()
+    opt2.step()
+    for p, q in zip(ps, ref2):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == [0, 1, 2]
+    assert float(sd["state"][0]["step"]) == 5.0
+
+
 def test_rnd_step_against_oracle_two_iterations():
     T, B, seed = 12, 6, 77
     params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
