@@ -20,6 +20,18 @@ opt-in because the library has no CPU path: use it with samplers that evaluate t
 """
 import importlib
 
+_originals = []        # (object, attribute, previous value) in patch order, for uninstall()
+
+
+def uninstall():
+    """Undo every ``install()``: put the reference's own classes / functions back (newest patch first)."""
+    from .curiosity.icm import ICM, Disagreement
+    from .curiosity.rnd import RND
+    while _originals:
+        target, leaf, old = _originals.pop()
+        setattr(target, leaf, old)
+    RND.default_reuse_features = ICM.default_reuse_features = Disagreement.default_reuse_features = False
+
 
 def install(strict=True, reuse_features=True, policy=False):
     """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
@@ -49,6 +61,7 @@ def install(strict=True, reuse_features=True, policy=False):
             *path, leaf = k.split(".")
             for part in path:
                 target = getattr(target, part)
+            _originals.append((target, leaf, getattr(target, leaf)))
             setattr(target, leaf, v)
             patched.append(f"{modname}.{k}")
 
@@ -69,6 +82,7 @@ def install(strict=True, reuse_features=True, policy=False):
         from .pg import atari_lstm_model as ours
         try:
             ref = importlib.import_module("rlpyt.models.pg.atari_lstm_model")
+            _originals.append((ours.AtariLstmModel, "rnn_state_cls", ours.AtariLstmModel.rnn_state_cls))
             ours.AtariLstmModel.rnn_state_cls = ref.RnnState       # a namedarraytuple: the agents slice / transpose it
         except Exception:
             if strict:
@@ -78,6 +92,7 @@ def install(strict=True, reuse_features=True, policy=False):
         try:
             atari = importlib.import_module("rlpyt.agents.pg.atari")
             for cls in (atari.AtariLstmAgent, atari.AlternatingAtariLstmAgent):
+                _originals.append((cls.__init__, "__defaults__", cls.__init__.__defaults__))
                 cls.__init__.__defaults__ = (ours.AtariLstmModel,)
                 patched.append(f"rlpyt.agents.pg.atari.{cls.__name__}.__init__ (ModelCls default)")
         except Exception:
