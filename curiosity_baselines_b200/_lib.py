@@ -64,6 +64,9 @@ _SIGS = {
     "cb_conv1_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_conv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_side_wgrad": [_P, _P, _P, _L, _I, _I, _F, _P],
+    "cb_im2col": [C.POINTER(ConvDesc), _P, _P, _I, _I, _I, _P],
+    "cb_col2im": [C.POINTER(ConvDesc), _P, _I, _P, _I, _P, _P, _L, _L, _L, _I, _I, _P],
+    "cb_colsum_bf16": [_P, _L, _I, _P, _F, _P],
     "cb_grouped_linear_fwd": [_I, _I, _I, _I, _I, _P, _P, _I, C.POINTER(Epilogue), _P],
     "cb_grouped_linear_dgrad": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
     "cb_grouped_linear_wgrad": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P],

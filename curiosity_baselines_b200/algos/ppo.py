@@ -131,7 +131,14 @@ class PPO:
         elif self.curiosity_type == "rnd":
             fwd = m.curiosity_model.loss_and_grads_(*curiosity_inputs, valid)
         elif self.curiosity_type == "ndigo":
-            raise NotImplementedError("fused PPO step for NDIGO: use the autograd path (compute_loss)")
+            # ndigo.py:220-274 (``valid`` is ignored there).  NDIGO's stages are tied together by autograd Functions
+            # whose backward passes run in the library; the gradients accumulate into the flat buffer's views.
+            cm_params = [p for p in m.curiosity_model.parameters() if p.grad is not None]
+            for p in cm_params:
+                p.grad.zero_()
+            fwd = m.curiosity_model.compute_loss(*curiosity_inputs, valid)
+            fwd.backward()
+            fwd = fwd.detach()
         loss = loss + inv + fwd
         return OptInfo(loss, pi_loss, value_loss, entropy_loss, inv, fwd, means[2], means[3], None)
 
@@ -187,6 +194,9 @@ class PPO:
                     cur = (obs, sl(batch.next_observation), _onehot(act, self.model.action_size))
                 elif self.curiosity_type == "rnd":
                     cur = (sl(batch.next_observation),)
+                elif self.curiosity_type == "ndigo":
+                    A = self.model.action_size
+                    cur = (obs, _onehot(sl(batch.prev_action), A), _onehot(act, A))
                 info = self.loss_and_grads_(obs, sl(batch.prev_action), act, sl(ret), sl(adv), sl(valid),
                                             sl(batch.old_prob), rnn, cur, dropout_masks)
                 self.step()

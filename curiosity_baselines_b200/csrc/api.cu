@@ -22,7 +22,13 @@ bool umma_supports_wgrad(const cb_conv_desc*);
 int umma_grouped_fwd(int, int, int, int, int, const void*, const void*, int, const cb_epilogue*, cudaStream_t);
 int umma_grouped_dgrad(int, int, int, int, const void*, const void*, const void*, int, const void*, void*, cudaStream_t);
 int umma_grouped_wgrad(int, int, int, int, int, const void*, const void*, float*, float*, float, cudaStream_t);
+int colsum_bf16(const void* dy, int64_t rows, int c, float* out, float beta, cudaStream_t s);
 }  // namespace cb
+
+extern "C" int cb_colsum_bf16(const void* dy, int64_t rows, int32_t c, float* out, float beta, void* stream) {
+    CB_REQUIRE(dy && out && rows >= 1 && c >= 1, CB_E_ARG, "cb_colsum_bf16: bad argument");
+    return cb::colsum_bf16(dy, rows, c, out, beta, cb::as_stream(stream));
+}
 
 extern "C" int cb_grouped_linear_fwd(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
                                      const void* w_all, int32_t act, const cb_epilogue* e, void* stream) {

@@ -388,6 +388,193 @@ class PaddedLinearLayer(GemmLayer):
             w.grad[:, self.real_K:].add_(dsw[: self.real_out])
 
 
+class Im2colConvLayer(GemmLayer):
+    """Any convolution without an implicit-GEMM specialisation (UniverseHead's 3x3 stride-2 pad-1 layers,
+    encoders.py:7-35; the policy's Conv2dHeadModel convolutions, models/conv2d.py:67-118) on the tensor cores through
+    an explicit patch matrix: ``cb_im2col`` gathers [rows, k_pad] bf16 rows (rows = samples x out_h x out_w), the row
+    GEMM kernels do forward / dgrad / wgrad on it, ``cb_col2im`` gathers the data gradient back.  The patch matrix
+    costs HBM traffic the implicit kernels avoid, so it is built per chunk of samples in a bounded scratch buffer and
+    recomputed in the backward pass instead of being kept.
+
+    ``in_row_c``: channels per pixel row of the input tensor when it is wider than ``in_c`` (the policy's conv2 reads
+    the first 16 of the 32 channels the padded first convolution writes)."""
+
+    SCRATCH_BYTES = 1 << 30
+
+    def __init__(self, module, in_shape, act="none", trainable=True, in_row_c=None):
+        k, s, pd = module.kernel_size[0], module.stride[0], module.padding[0]
+        super().__init__(module, in_shape, k, s, pd, module.out_channels, act, 0, trainable)
+        if self.out_c % 32:
+            raise L.CuriosityLibError("Im2colConvLayer: out_channels must be a multiple of 32")
+        self.in_row_c = in_row_c or self.in_c
+        self.k_pad = (self.K + 63) // 64 * 64           # forward / dgrad: k-blocks of 64
+        self.k_pad_wg = (self.K + 127) // 128 * 128     # wgrad: the patch matrix is the 128-row MMA operand
+        self.P = self.out_h * self.out_w
+        self._scratch = None
+
+    def prepare(self, force=False):
+        w, b = self.module.weight, self.module.bias
+        ver = (w._version, w.data_ptr(), b._version)
+        if not force and ver == self._version:
+            return
+        dev = w.device
+        flat = w.detach().permute(0, 2, 3, 1).reshape(self.out_c, self.K)            # [o][kh][kw][ci]
+        self.w_fwd = torch.zeros(self.out_c, self.k_pad, dtype=torch.bfloat16, device=dev)
+        self.w_fwd[:, : self.K] = flat
+        self.w_t = self.w_fwd.t().contiguous()                                       # [k_pad, out_c]
+        self.bias = b.detach()
+        self.side_w = self.w_ext = None
+        self._version = ver
+
+    def _chunks(self, n, k_pad):
+        per = max(1, self.SCRATCH_BYTES // (self.P * k_pad * 2))
+        return [(a, min(n, a + per)) for a in range(0, n, per)]
+
+    def _buf(self, rows, k_pad, dev):
+        need = rows * k_pad
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+            self._scratch = torch.empty(need, dtype=torch.bfloat16, device=dev)
+        return self._scratch[:need]
+
+    def _rows_desc(self, rows, k, out_c, act=L.ACT_NONE):
+        """The [rows, k] x [out_c, k]^T product as a Linear layer."""
+        d = L.ConvDesc()
+        d.n, d.in_h, d.in_w, d.in_c = rows, 1, 1, k
+        d.k_h = d.k_w = d.stride = 1
+        d.pad = 0
+        d.out_h = d.out_w = 1
+        d.out_c = out_c
+        d.in_dtype = L.BF16
+        d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = k, k, k, 1
+        d.act = act
+        d.engine = _engine
+        return d
+
+    def _conv_desc(self, n, in_dtype, strides):
+        if strides is None:
+            rc = self.in_row_c
+            strides = (self.in_h * self.in_w * rc, self.in_w * rc, rc, 1)
+        return self.desc(n, in_dtype, strides)
+
+    def forward(self, x, n, in_dtype=L.BF16, strides=None, side=None, residual=None, norm=None,
+                out_bf16=True, out_f32=False, twin=None, side_pad=None):
+        if norm is not None or residual is not None or side is not None or twin is not None:
+            raise L.CuriosityLibError("Im2colConvLayer: plain convolution only")
+        self.prepare()
+        dev = self.w_fwd.device
+        m = n * self.P
+        yb = torch.empty(m, self.out_c, dtype=torch.bfloat16, device=dev) if out_bf16 else None
+        yf = torch.empty(m, self.out_c, dtype=torch.float32, device=dev) if out_f32 else None
+        cd = self._conv_desc(n, in_dtype, strides)
+        xp = x if isinstance(x, int) else L.ptr(x)
+        st = L.stream()
+        for a, b in self._chunks(n, self.k_pad):
+            rows = (b - a) * self.P
+            col = self._buf(rows, self.k_pad, dev)
+            L.call("cb_im2col", C.byref(cd), xp, L.ptr(col), self.k_pad, a, b, st)
+            e = L.Epilogue()
+            e.bias = L.ptr(self.bias)
+            e.out_bf16 = L.ptr(yb[a * self.P:]) if yb is not None else None
+            e.out_f32 = L.ptr(yf[a * self.P:]) if yf is not None else None
+            rd = self._rows_desc(rows, self.k_pad, self.out_c, self.act)
+            L.call("cb_conv_fwd", C.byref(rd), L.ptr(col), L.ptr(self.w_fwd), C.byref(e), st)
+        return yb, yf
+
+    def dgrad(self, dy, n, x_saved=None, x_act="none", dx_add=None):
+        self.prepare()
+        dev, rc = dy.device, self.in_row_c
+        alloc = torch.zeros if rc != self.in_c else torch.empty
+        dx = alloc(n * self.in_h * self.in_w, rc, dtype=torch.bfloat16, device=dev)
+        cd = self._conv_desc(n, L.BF16, None)
+        st = L.stream()
+        for a, b in self._chunks(n, self.k_pad):
+            rows = (b - a) * self.P
+            dcol = self._buf(rows, self.k_pad, dev)
+            rd = self._rows_desc(rows, self.k_pad, self.out_c)
+            L.call("cb_conv_dgrad", C.byref(rd), L.ptr(dy[a * self.P:]), L.ptr(self.w_t), None, L.ACT_NONE, None,
+                   L.ptr(dcol), st)
+            L.call("cb_col2im", C.byref(cd), L.ptr(dcol), self.k_pad, L.ptr(x_saved), ACT[x_act], L.ptr(dx_add),
+                   L.ptr(dx), self.in_h * self.in_w * rc, self.in_w * rc, rc, a, b, st)
+        return dx
+
+    def _wgrad_impl(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+        self.prepare()
+        w, b = self.module.weight, self.module.bias
+        dev = dy.device
+        if w.grad is None:
+            w.grad = torch.zeros_like(w)
+        if b.grad is None:
+            b.grad = torch.zeros_like(b)
+        kp = self.k_pad_wg
+        # dW^T [k_pad, out_c] = col^T dy: the patch matrix plays the 128-row operand of the split-K wgrad kernel
+        dwt = torch.empty(kp, self.out_c, dtype=torch.float32, device=dev)
+        cd = self._conv_desc(n, in_dtype, strides)
+        xp = x if isinstance(x, int) else L.ptr(x)
+        st = L.stream()
+        for i, (a, c) in enumerate(self._chunks(n, kp)):
+            rows = (c - a) * self.P
+            col = self._buf(rows, kp, dev)
+            L.call("cb_im2col", C.byref(cd), xp, L.ptr(col), kp, a, c, st)
+            rd = self._rows_desc(rows, self.out_c, kp)
+            L.call("cb_conv_wgrad", C.byref(rd), L.ptr(dy[a * self.P:]), L.ptr(col), None, None, L.ptr(dwt), None,
+                   1.0 if i else 0.0, st)
+        L.call("cb_colsum_bf16", L.ptr(dy), n * self.P, self.out_c, L.ptr(b.grad), 1.0 if accumulate else 0.0, st)
+        g = dwt[: self.K].t().reshape(self.out_c, self.k, self.k, self.in_c).contiguous()     # [o][kh][kw][ci]
+        L.call("cb_unprepare_conv_grad", L.ptr(g), L.ptr(w.grad), self.out_c, self.in_c, self.k, self.k,
+               1.0 if accumulate else 0.0, st)
+
+
+class PaddedConv1Layer(GemmLayer):
+    """A first convolution 8x8 stride 4 over uint8 frames with FEWER than 32 output channels (the policy's
+    Conv2dHeadModel: 4 -> 16, models/pg/atari_lstm_model.py:94-101) on the 32-channel tcgen05 first-conv kernel:
+    weights and bias are zero-padded to 32 outputs, the padded channels come out as act(0) = 0 and their gradient
+    rows are dropped.  Callers see 32-channel NHWC rows of which ``real_out`` are meaningful."""
+
+    def __init__(self, module, in_shape, act="none", trainable=True):
+        self.real_out = module.out_channels
+        super().__init__(module, in_shape, 8, 4, 0, 32, act, 0, trainable)
+
+    def prepare(self, force=False):
+        w, b = self.module.weight, self.module.bias
+        ver = (w._version, w.data_ptr(), b._version)
+        if not force and ver == self._version:
+            return
+        dev = w.device
+        self.w_native = torch.zeros(32, self.K, dtype=torch.bfloat16, device=dev)
+        self.w_native[: self.real_out] = w.detach().reshape(self.real_out, -1)
+        self.bias = torch.zeros(32, dtype=torch.float32, device=dev)
+        self.bias[: self.real_out] = b.detach()
+        self.w_fwd = self.w_native                         # (only the first-conv kernel runs this layer)
+        self.side_w = self.w_ext = self.w_t = self.w_shuffle = None
+        self._version = ver
+
+    def forward(self, x, n, in_dtype=L.BF16, strides=None, **kw):
+        d = self.desc(n, in_dtype, strides)
+        self.prepare()
+        if not self._use_conv1(d):
+            raise L.CuriosityLibError("PaddedConv1Layer: needs uint8 NCHW frames (8x8 stride 4, <= 4 channels) on sm_100")
+        return super().forward(x, n, in_dtype=in_dtype, strides=strides, **kw)
+
+    def _wgrad_impl(self, x, dy, n, in_dtype=L.BF16, strides=None, side=None, norm=None, accumulate=False):
+        self.prepare()
+        w, b = self.module.weight, self.module.bias
+        if w.grad is None:
+            w.grad = torch.zeros_like(w)
+        if b.grad is None:
+            b.grad = torch.zeros_like(b)
+        dev = dy.device
+        dw = torch.empty(32, self.K, dtype=torch.float32, device=dev)
+        db = torch.empty(32, dtype=torch.float32, device=dev)
+        d = self.desc(n, in_dtype, strides)
+        xp = x if isinstance(x, int) else L.ptr(x)
+        L.call("cb_conv1_wgrad", C.byref(d), xp, L.ptr(dy), None, None, L.ptr(dw), L.ptr(db), 0.0, L.stream())
+        r = self.real_out
+        if accumulate:
+            w.grad.add_(dw[:r].view_as(w)); b.grad.add_(db[:r])
+        else:
+            w.grad.copy_(dw[:r].view_as(w)); b.grad.copy_(db[:r])
+
+
 class ParamPair:
     """A (weight, bias) pair of an ``nn.LSTM`` / ``nn.GRU`` holder presented like a ``Linear`` to ``GemmLayer``."""
 
@@ -404,9 +591,30 @@ def pad_side(side):
     return out
 
 
-def conv_layer(module, in_shape, act, trainable=True):
+def _has_implicit_kernel(in_shape, k, s, p, out_c):
+    """Shapes the implicit-GEMM tcgen05 kernels cover (umma_conv1.cu / umma_window.cuh / umma_conv.cu)."""
+    h, w, c = in_shape
+    if (k, s, p, out_c) == (8, 4, 0, 32) and c <= 4:
+        return True                                                   # uint8 first convolution
+    if s == 2 and k == 4 and p == 0 and c == 32 and out_c in (64, 128) and h % 2 == 0 and w % 2 == 0:
+        return True                                                   # Burda conv2
+    if s == 1 and c == 64 and out_c in (64, 128) and k > 1 and (h + 2 * p) * (w + 2 * p) <= 256:
+        return True                                                   # Burda conv3
+    return False
+
+
+def conv_layer(module, in_shape, act, trainable=True, in_row_c=None):
+    """The layer object that runs ``module`` (a Conv2d holder): the implicit-GEMM kernels where a specialisation
+    exists, else the explicit patch-matrix path -- every convolution of the path runs its MACs on tcgen05.  The SIMT
+    engine is only reachable by forcing it (``set_engine('simt')``, the cross-check of the tensor-core kernels)."""
     k, s, p = module.kernel_size[0], module.stride[0], module.padding[0]
-    return GemmLayer(module, in_shape, k, s, p, module.out_channels, act, 0, trainable)
+    oc = module.out_channels
+    if _engine != L.ENGINE_SIMT and not _has_implicit_kernel(in_shape, k, s, p, oc):
+        if (k, s, p) == (8, 4, 0) and in_shape[2] <= 4 and oc < 32:
+            return PaddedConv1Layer(module, in_shape, act, trainable)
+        if oc % 32 == 0:
+            return Im2colConvLayer(module, in_shape, act, trainable, in_row_c=in_row_c)
+    return GemmLayer(module, in_shape, k, s, p, oc, act, 0, trainable)
 
 
 def linear_layer(module, act="none", side_dim=0, spatial=None, trainable=True):

@@ -27,11 +27,66 @@ from .. import dist
 from .. import layers as LY
 from ..layers import linear_layer, pad_side
 from ..curiosity.encoders import BurdaHead, UniverseHead, MazeHead, frame_input
-from ..curiosity.icm import ICM, Disagreement, ENC_LAST_ACT
+from ..curiosity.icm import ICM, Disagreement
+from ..curiosity.icm import ENC_LAST_ACT as _CUR_LAST_ACT
 from ..curiosity.rnd import RND
 from ..curiosity.ndigo import NDIGO
 
 RnnState = namedtuple("RnnState", ["h", "c"])
+ENC_LAST_ACT = dict(_CUR_LAST_ACT, none="relu")          # Conv2dHeadModel applies its nonlinearity at the end
+
+
+class _Holder(nn.Module):
+    pass
+
+
+class Conv2dHeadModel(nn.Module):
+    """models/conv2d.py:67-118 as used by the policy when the curiosity model brings no encoder of its own
+    (``feature_encoding='none'``: RND, or no curiosity at all; atari_lstm_model.py:94-112): Conv2d(c -> 16, k8 s4),
+    ReLU, Conv2d(16 -> 32, k4 s2 p1), ReLU, flatten (CHW), Linear(-> fc_sizes), ReLU.  Parameter holder with the
+    reference's ``state_dict`` keys (``conv.conv.{0,2}.*``, ``head.model.0.*``); the layers run in the library:
+    the first convolution on the uint8 tcgen05 kernel (outputs zero-padded to 32 channels), the second through the
+    explicit patch matrix (layers.Im2colConvLayer), the Linear as a k x k convolution over the NHWC map."""
+
+    def __init__(self, image_shape, channels, kernel_sizes, strides, hidden_sizes, paddings=None, use_maxpool=False):
+        super().__init__()
+        if use_maxpool:
+            raise NotImplementedError("use_maxpool=True is outside the hot-path scope (launcher default is False)")
+        if isinstance(hidden_sizes, (list, tuple)):
+            if len(hidden_sizes) != 1:
+                raise NotImplementedError("one hidden layer after the convolutions (launcher default fc_sizes=512)")
+            hidden_sizes = hidden_sizes[0]
+        paddings = paddings or [0] * len(channels)
+        c, h, w = image_shape
+        self.image_shape = image_shape
+        seq, ic = [], c
+        for oc, k, s, p in zip(channels, kernel_sizes, strides, paddings):
+            seq += [nn.Conv2d(ic, oc, kernel_size=k, stride=s, padding=p), nn.ReLU()]
+            h, w = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+            ic = oc
+        self.conv = _Holder()
+        self.conv.conv = nn.Sequential(*seq)
+        self.head = _Holder()
+        self.head.model = nn.Sequential(nn.Linear(h * w * ic, hidden_sizes), nn.ReLU())
+        self._map = (h, w, ic)
+        self.output_size = hidden_sizes
+
+    def build_chain(self, trainable=True, last_act="relu"):
+        c, h, w = self.image_shape
+        layers, shape, row_c = [], (h, w, c), None
+        convs = [m for m in self.conv.conv if isinstance(m, nn.Conv2d)]
+        for m in convs:
+            lay = LY.conv_layer(m, shape, "relu", trainable, in_row_c=row_c)
+            layers.append(lay)
+            shape = (lay.out_h, lay.out_w, getattr(lay, "real_out", lay.out_c))
+            row_c = lay.out_c if lay.out_c != shape[2] else None       # padded rows: the next layer reads a prefix
+        if row_c is not None:
+            raise NotImplementedError("the last convolution must write dense rows")
+        mh, mw, mc = self._map
+        if mh != mw:
+            raise NotImplementedError("square feature maps only")
+        layers.append(LY.linear_layer(self.head.model[0], "relu", spatial=(mh, mc), trainable=trainable))
+        return LY.Chain(layers), None
 
 
 def _lead_dims(image):
@@ -128,10 +183,13 @@ class AtariLstmModel(nn.Module):
         elif enc == "idf_maze":                                    # :89-93
             self.conv = MazeHead(image_shape=image_shape, output_size=self.curiosity_model.feature_size,
                                  batch_norm=bn)
-        else:
-            raise NotImplementedError("feature_encoding='none' (Conv2dHeadModel policy encoder, :94-112) is not on "
-                                      "the accelerated path yet; use the reference model for it")
-        self.conv.output_size = self.curiosity_model.feature_size
+        else:                                                      # :94-112 ('none': RND, or no curiosity model)
+            self.conv = Conv2dHeadModel(image_shape=image_shape, channels=channels or [16, 32],
+                                        kernel_sizes=kernel_sizes or [8, 4], strides=strides or [4, 2],
+                                        paddings=paddings or [0, 1], use_maxpool=use_maxpool, hidden_sizes=fc_sizes)
+            enc = "none"
+        if enc != "none":
+            self.conv.output_size = self.curiosity_model.feature_size
         self.feature_encoding = enc
         self.lstm_size = lstm_size
         self.lstm = nn.LSTM(self.conv.output_size + output_size, lstm_size)

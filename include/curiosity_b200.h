@@ -208,6 +208,20 @@ int cb_grouped_linear_dgrad(int32_t n, int32_t groups, int32_t k, int32_t f, con
                             const void* x_saved, int32_t x_act, const void* dx_add, void* dx, void* stream);
 int cb_grouped_linear_wgrad(int32_t n, int32_t groups, int32_t k, int32_t f, int32_t x_shared, const void* x,
                             const void* dy, float* dw_all, float* dbias_all, float beta, void* stream);
+/* Explicit im2col for convolution shapes without an implicit-GEMM specialisation (UniverseHead's 3x3 stride-2 pad-1
+ * layers, encoders.py:7-35; the policy's Conv2dHeadModel, models/conv2d.py:67-118): their MACs then run on the tensor
+ * cores through cb_conv_fwd / cb_conv_dgrad / cb_conv_wgrad on the [rows, k_pad] patch matrix.
+ * col (bf16, row stride k_pad, k = (kh*k_w + kw)*in_c + ci, columns >= K zero) holds the out_h*out_w patch rows of
+ * samples [n0, n1); x is addressed through the descriptor's strides (CB_U8 or CB_BF16). */
+int cb_im2col(const cb_conv_desc* d, const void* x, void* col, int32_t k_pad, int32_t n0, int32_t n1, void* stream);
+/* inverse gather for the data gradient: dx[n,ih,iw,ci] = (sum over the taps reading that pixel of dcol + dx_add)
+ * .* act'(x_saved) for samples [n0, n1); dcol bf16 [(n1-n0)*out_h*out_w, k_pad]; dx / x_saved / dx_add bf16 with element
+ * strides dx_stride_{n,h,w} (channel stride 1; 16-byte vector path when in_c % 8 == 0). */
+int cb_col2im(const cb_conv_desc* d, const void* dcol, int32_t k_pad, const void* x_saved, int32_t x_act,
+              const void* dx_add, void* dx, int64_t dx_stride_n, int64_t dx_stride_h, int64_t dx_stride_w,
+              int32_t n0, int32_t n1, void* stream);
+/* bias gradient: out[c] = beta*out[c] + sum_rows dy[row, c]  (dy bf16 [rows, c]) */
+int cb_colsum_bf16(const void* dy, int64_t rows, int32_t c, float* out, float beta, void* stream);
 /* side-input weight gradient: dsw[out_c,side_dim] = beta*dsw + dy^T side */
 int cb_side_wgrad(const void* dy, const float* side, float* dsw, int64_t m, int32_t out_c,
                   int32_t side_dim, float beta, void* stream);

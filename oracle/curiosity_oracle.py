@@ -26,6 +26,7 @@ Reference lines restated (all under rlpyt/):
   discount_return / gae / valid_from_done algos/utils.py:8-40,104-112
   process_returns ....................... algos/pg/base.py:53-108
   valid_mean ............................ utils/tensor.py:39-46
+  conv2d_head ........................... models/conv2d.py:7-118 (the policy's own encoder, 'none')
   lstm_sequence / policy_forward ........ models/pg/atari_lstm_model.py:114-154
   ppo_loss .............................. algos/pg/ppo.py:192-242, distributions/categorical.py:33-46
 """
@@ -34,6 +35,52 @@ import math
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- optional operand rounding
+# The product computes with bf16 GEMM / convolution OPERANDS and fp32 accumulation (north_star).  Against this
+# fp32 oracle that shows up as (i) ~1e-3 relative noise on outputs and (ii) a few ReLU / LeakyReLU masks that flip
+# for pre-activations within that noise of zero -- which no kernel can avoid.  ``operand_rounding(True)`` makes the
+# oracle round the two operands of every Linear / convolution to bf16 (straight-through gradient), i.e. the same
+# numerical model with fp32 everywhere else, so that a test can separate quantisation from implementation error.
+# Default OFF: every parity gate quoted in DESIGN.md is against the plain fp32 oracle unless it says otherwise.
+_ROUND = False
+
+
+class operand_rounding:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _ROUND
+        self.prev, _ROUND = _ROUND, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _ROUND
+        _ROUND = self.prev
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _bf(x):
+    return _RoundSTE.apply(x) if _ROUND else x
+
+
+def _linear(x, w, b=None):
+    return F.linear(_bf(x), _bf(w), b)
+
+
+def _conv2d(x, w, b=None, **kw):
+    return F.conv2d(_bf(x), _bf(w), b, **kw)
 
 
 # --------------------------------------------------------------------------- helpers
@@ -58,32 +105,41 @@ def burda_head(x, p):
     conv(C->32,k8,s4) lrelu conv(32->64,k4,s2) lrelu conv(64->64,k3,s1) lrelu
     flatten(CHW order) linear(3136->512); no activation after the linear.
     """
-    h = F.leaky_relu(F.conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=4))
-    h = F.leaky_relu(F.conv2d(h, p["model.2.weight"], p["model.2.bias"], stride=2))
-    h = F.leaky_relu(F.conv2d(h, p["model.4.weight"], p["model.4.bias"], stride=1))
+    h = F.leaky_relu(_conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=4))
+    h = F.leaky_relu(_conv2d(h, p["model.2.weight"], p["model.2.bias"], stride=2))
+    h = F.leaky_relu(_conv2d(h, p["model.4.weight"], p["model.4.bias"], stride=1))
     h = h.reshape(h.shape[0], -1)
-    return F.linear(h, p["model.7.weight"], p["model.7.bias"])
+    return _linear(h, p["model.7.weight"], p["model.7.bias"])
 
 
 def universe_head(x, p):
     """encoders.py:7-35.  5x [conv 3x3 s2 p1 -> 32, ELU]; flatten -> [N,288]."""
     h = x
     for layer in range(5):
-        h = F.elu(F.conv2d(h, p[f"model.{2 * layer}.weight"], p[f"model.{2 * layer}.bias"],
+        h = F.elu(_conv2d(h, p[f"model.{2 * layer}.weight"], p[f"model.{2 * layer}.bias"],
                            stride=2, padding=1))
     return h.reshape(h.shape[0], -1)
 
 
 def maze_head(x, p):
     """encoders.py:37-66.  conv3x3 s1 p1 relu conv3x3 s2 p2 relu flatten linear relu."""
-    h = F.relu(F.conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=1, padding=1))
-    h = F.relu(F.conv2d(h, p["model.2.weight"], p["model.2.bias"], stride=2, padding=2))
+    h = F.relu(_conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=1, padding=1))
+    h = F.relu(_conv2d(h, p["model.2.weight"], p["model.2.bias"], stride=2, padding=2))
     h = h.reshape(h.shape[0], -1)
-    return F.relu(F.linear(h, p["model.5.weight"], p["model.5.bias"]))
+    return F.relu(_linear(h, p["model.5.weight"], p["model.5.bias"]))
+
+
+def conv2d_head(x, p):
+    """models/conv2d.py:67-118 with the policy's defaults (atari_lstm_model.py:94-112): conv(C->16,k8,s4) relu
+    conv(16->32,k4,s2,p1) relu flatten(CHW) linear(->512) relu.  Keys conv.conv.{0,2}.*, head.model.0.*."""
+    h = F.relu(_conv2d(x, p["conv.conv.0.weight"], p["conv.conv.0.bias"], stride=4))
+    h = F.relu(_conv2d(h, p["conv.conv.2.weight"], p["conv.conv.2.bias"], stride=2, padding=1))
+    h = h.reshape(h.shape[0], -1)
+    return F.relu(_linear(h, p["head.model.0.weight"], p["head.model.0.bias"]))
 
 
 ENCODERS = {"idf": (universe_head, 288), "idf_burda": (burda_head, 512),
-            "idf_maze": (maze_head, 256)}
+            "idf_maze": (maze_head, 256), "none": (conv2d_head, 512)}
 
 
 def encode(obs, p, feature_encoding):
@@ -101,7 +157,7 @@ def res_forward(phi, action, p):
     """icm.py:9-43.  Ten Linear(F+A -> F); the one-hot action is concatenated at
     every layer.  phi [T,B,F], action [T,B,A] -> [T,B,F]."""
     def lin(x, name):
-        return F.linear(torch.cat([x, action], 2), p[name + ".weight"], p[name + ".bias"])
+        return _linear(torch.cat([x, action], 2), p[name + ".weight"], p[name + ".bias"])
     x = F.leaky_relu(lin(phi, "lin_1"))
     for blk in range(1, 5):
         r = F.leaky_relu(lin(x, f"res_block_{blk}.lin_1"))
@@ -112,9 +168,9 @@ def res_forward(phi, action, p):
 
 def inverse_model(phi1, phi2, p):
     """icm.py:88-92: Linear(2F->F) ReLU Linear(F->A) on [phi1 | phi2]."""
-    h = F.relu(F.linear(torch.cat([phi1, phi2], 2), p["inverse_model.0.weight"],
+    h = F.relu(_linear(torch.cat([phi1, phi2], 2), p["inverse_model.0.weight"],
                         p["inverse_model.0.bias"]))
-    return F.linear(h, p["inverse_model.2.weight"], p["inverse_model.2.bias"])
+    return _linear(h, p["inverse_model.2.weight"], p["inverse_model.2.bias"])
 
 
 def icm_forward(p, obs, next_obs, action, feature_encoding="idf_burda"):
@@ -249,13 +305,13 @@ class RewardForwardFilter:
 def _rnd_net(x, p, predictor):
     """rnd.py:54-117: Burda-shaped stack on one channel; the predictor adds
     ReLU Linear ReLU Linear after the 3136->512 layer."""
-    h = F.leaky_relu(F.conv2d(x, p["0.weight"], p["0.bias"], stride=4))
-    h = F.leaky_relu(F.conv2d(h, p["2.weight"], p["2.bias"], stride=2))
-    h = F.leaky_relu(F.conv2d(h, p["4.weight"], p["4.bias"], stride=1))
-    h = F.linear(h.reshape(h.shape[0], -1), p["7.weight"], p["7.bias"])
+    h = F.leaky_relu(_conv2d(x, p["0.weight"], p["0.bias"], stride=4))
+    h = F.leaky_relu(_conv2d(h, p["2.weight"], p["2.bias"], stride=2))
+    h = F.leaky_relu(_conv2d(h, p["4.weight"], p["4.bias"], stride=1))
+    h = _linear(h.reshape(h.shape[0], -1), p["7.weight"], p["7.bias"])
     if predictor:
-        h = F.linear(F.relu(h), p["9.weight"], p["9.bias"])
-        h = F.linear(F.relu(h), p["11.weight"], p["11.bias"])
+        h = _linear(F.relu(h), p["9.weight"], p["9.bias"])
+        h = _linear(F.relu(h), p["11.weight"], p["11.bias"])
     return h
 
 
@@ -324,8 +380,8 @@ def gru_sequence(x, p, hidden):
     h = torch.zeros(B, hidden)
     outs = []
     for t in range(T):
-        gi = F.linear(x[t], w_ih, b_ih)
-        gh = F.linear(h, w_hh, b_hh)
+        gi = _linear(x[t], w_ih, b_ih)
+        gh = _linear(h, w_hh, b_hh)
         i_r, i_z, i_n = gi.chunk(3, 1)
         h_r, h_z, h_n = gh.chunk(3, 1)
         r = torch.sigmoid(i_r + h_r)
@@ -344,8 +400,8 @@ def _action_windows(actions, k):
 
 def _ndigo_predict(bel, seq, p, k):
     q = _sub(p, f"forward_model_{k}.model.")
-    h = F.relu(F.linear(torch.cat([bel, seq], 2), q["0.weight"], q["0.bias"]))
-    return F.linear(h, q["2.weight"], q["2.bias"])
+    h = F.relu(_linear(torch.cat([bel, seq], 2), q["0.weight"], q["0.bias"]))
+    return _linear(h, q["2.weight"], q["2.bias"])
 
 
 def _bce(logits, target):
@@ -470,7 +526,7 @@ def lstm_sequence(x, p, h0, c0):
     h, c = h0, c0
     outs = []
     for t in range(x.shape[0]):
-        a = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        a = _linear(x[t], w_ih, b_ih) + _linear(h, w_hh, b_hh)
         a_i, a_f, a_g, a_o = a.chunk(4, 1)
         c = torch.sigmoid(a_f) * c + torch.sigmoid(a_i) * torch.tanh(a_g)
         h = torch.sigmoid(a_o) * torch.tanh(c)
@@ -496,8 +552,8 @@ def policy_forward(p, image, prev_action, init_rnn_state=None, feature_encoding=
         h0, c0 = init_rnn_state[0][0], init_rnn_state[1][0]
     out, hn, cn = lstm_sequence(lstm_in, p, h0, c0)
     flat = out.view(T * B, -1)
-    pi = F.softmax(F.linear(flat, p["pi.weight"], p["pi.bias"]), dim=-1)
-    v = F.linear(flat, p["value.weight"], p["value.bias"]).squeeze(-1)
+    pi = F.softmax(_linear(flat, p["pi.weight"], p["pi.bias"]), dim=-1)
+    v = _linear(flat, p["value.weight"], p["value.bias"]).squeeze(-1)
     return pi.view(T, B, -1), v.view(T, B), (hn.unsqueeze(0), cn.unsqueeze(0))
 
 

@@ -73,8 +73,12 @@ def make_agent_and_algo(curiosity_kwargs, A, T, B, n_itr=10, ppo_kwargs=None, im
     from rlpyt.utils.quick_args import save__init__args  # noqa: F401  (import check)
     from rlpyt.samplers.collections import BatchSpec
     agent = AtariLstmAgent(model_kwargs=dict(curiosity_kwargs=dict(curiosity_kwargs)), no_extrinsic=True)
-    dtype = "uint8" if image_shape[-1] > 16 else "float32"
-    agent.initialize(EnvSpaces(observation=IntBox(0, 255, shape=tuple(image_shape), dtype=dtype), action=IntBox(0, A)),
+    if image_shape[-1] > 16:
+        obs_space = IntBox(0, 255, shape=tuple(image_shape), dtype="uint8")
+    else:                                   # PyColab mazes: float {0,1} masks (mazeworld_env.py:60-74)
+        from rlpyt.spaces.float_box import FloatBox
+        obs_space = FloatBox(0.0, 1.0, shape=tuple(image_shape))
+    agent.initialize(EnvSpaces(observation=obs_space, action=IntBox(0, A)),
                      share_memory=False, global_B=B, obs_stats=None, env_ranks=list(range(B)))
     if cuda_idx is not None:
         agent.to_device(cuda_idx)

@@ -91,9 +91,19 @@ def ndigo_shapes(action_size, c_in=3, hw=5, gru=128, num_predictors=10):
     return out
 
 
+def conv2d_head_shapes(prefix, c_in, fc=512):
+    """Conv2dHeadModel with the policy's defaults (models/conv2d.py:67-118, atari_lstm_model.py:94-112)."""
+    return [(prefix + "conv.conv.0.weight", (16, c_in, 8, 8)), (prefix + "conv.conv.0.bias", (16,)),
+            (prefix + "conv.conv.2.weight", (32, 16, 4, 4)), (prefix + "conv.conv.2.bias", (32,)),
+            (prefix + "head.model.0.weight", (fc, 3200)), (prefix + "head.model.0.bias", (fc,))]
+
+
 def policy_shapes(action_size, feature_encoding="idf_burda", c_in=4, lstm=512):
     """AtariLstmModel minus its curiosity_model (atari_lstm_model.py:80-114)."""
-    enc, feat = encoder_shapes(feature_encoding, c_in)
+    if feature_encoding == "none":
+        enc, feat = conv2d_head_shapes("encoder.", c_in), 512
+    else:
+        enc, feat = encoder_shapes(feature_encoding, c_in)
     enc = [(k.replace("encoder.", "conv.", 1), s) for k, s in enc]
     return enc + [("lstm.weight_ih_l0", (4 * lstm, feat + action_size)), ("lstm.weight_hh_l0", (4 * lstm, lstm)),
                   ("lstm.bias_ih_l0", (4 * lstm,)), ("lstm.bias_hh_l0", (4 * lstm,)),

@@ -27,37 +27,53 @@ def _params(kind, A, seed):
         shapes = R.icm_shapes(A, "idf_burda") if kind == "icm" else R.disagreement_shapes(A, "idf_burda")
         pol.update({"curiosity_model." + k: v for k, v in R.make_params(shapes, seed + 2).items()})
         return pol
+    if kind == "rnd":          # the policy brings its own 16/32-channel encoder (atari_lstm_model.py:94-101)
+        pol = R.make_policy_params(A, seed, feature_encoding="none", conv_gain=0.5)
+        pol.update({"curiosity_model." + k: v for k, v in R.make_params(R.rnd_shapes(), seed + 2, gain=1.4).items()})
+        return pol
+    if kind == "ndigo":
+        pol = R.make_policy_params(A, seed, feature_encoding="idf_maze", conv_gain=1.0, c_in=3)
+        pol.update({"curiosity_model." + k: v for k, v in R.make_params(R.ndigo_shapes(A), seed + 2).items()})
+        return pol
     raise ValueError(kind)
 
 
-def _samples(A, T, B, seed):
+def _samples(A, T, B, seed, kind="icm"):
+    frames = (lambda s: R.make_binary_frames(s, T, B)) if kind == "ndigo" else (lambda s: R.make_frames(s, T, B))
     return refshim.make_samples(
-        R.make_frames(seed + 3, T, B), R.make_frames(seed + 4, T, B), R.make_actions(seed + 6, T, B, A),
+        frames(seed + 3), frames(seed + 4), R.make_actions(seed + 6, T, B, A),
         R.make_actions(seed + 5, T, B, A), R.make_probs(seed + 7, T, B, A), R.make_normal(seed + 8, T, B),
         R.make_normal(seed + 9, B), torch.zeros(T, B), R.make_suffix_done(seed + 10, T, B, frac=0.3))
 
 
 def _one_iteration(kind, ck, A, T, B, seed, cuda_idx):
     agent, algo = refshim.make_agent_and_algo(ck, A, T, B, cuda_idx=cuda_idx,
+                                              image_shape=(3, 5, 5) if kind == "ndigo" else (4, 84, 84),
                                               ppo_kwargs=dict(epochs=2, minibatches=1, gae_lambda=0.95, learning_rate=1e-4))
     agent.model.load_state_dict(_params(kind, A, seed))
     before = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
-    s = _samples(A, T, B, seed)
+    s = _samples(A, T, B, seed, kind)
     agent.train_mode(0)
     info, _ = algo.optimize_agent(0, s)
     after = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
-    out = {f: [float(x) for x in getattr(info, f)] for f in FIELDS}
+    out = {f: [float(x) for x in getattr(info, f)] for f in FIELDS if len(getattr(info, f))}
     out["gradNorm"] = [float(x) for x in info.gradNorm]
     return out, before, after, s.env.reward.clone(), np.array(algo.intrinsic_rewards), agent
 
 
-@pytest.mark.parametrize("kind", ["icm", "disagreement"])
+@pytest.mark.parametrize("kind", ["icm", "disagreement", "rnd", "ndigo"])
 def test_reference_optimize_agent_through_install(kind):
     import curiosity_baselines_b200.integration as cbi
     refshim.import_reference()
-    A, T, B, seed = 4, 16, 8, 55
+    A, T, B, seed = (5 if kind == "ndigo" else 4), 16, 8, 55
     ck = dict(curiosity_alg=kind, feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
               forward_loss_wt=0.2, device="cpu")
+    if kind == "rnd":          # launch.py's kwargs for RND (drop_probability 0: the mask rand > 0 keeps every sample)
+        ck = dict(curiosity_alg="rnd", feature_encoding="none", prediction_beta=1.0, drop_probability=0.0, gamma=0.99,
+                  device="cpu")
+    if kind == "ndigo":
+        ck = dict(curiosity_alg="ndigo", feature_encoding="idf_maze", pred_horizon=3, batch_norm=False,
+                  num_predictors=10, device="cpu")
     if kind == "disagreement":
         # the reference's dropout draws from torch's global generator; keep it out of the comparison
         import rlpyt.models.curiosity.disagreement as ref_dis
@@ -94,7 +110,8 @@ def test_reference_optimize_agent_through_install(kind):
     # bonus added into the sampler's reward buffer in place (base.py:66), kept as numpy on the algo (:67)
     assert float((our_reward - ref_reward).abs().max()) <= 1e-2 * float(ref_reward.abs().max())
     assert our_rint.shape == ref_rint.shape == (T, B)
-    for f in FIELDS + ("gradNorm",):
+    for f in [f for f in FIELDS + ("gradNorm",) if f in ref]:
+        assert len(ours[f]) == len(ref[f])
         for step, (a, b) in enumerate(zip(ours[f], ref[f])):
             tol = 1e-2 if step == 0 else 2e-2                    # step 1 sees weights updated by step 0's bf16 gradients
             assert abs(a - b) <= tol * max(abs(b), 1e-3), (f, step, a, b)

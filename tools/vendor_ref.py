@@ -24,7 +24,7 @@ HOT_PATH_MODULES = [
     "rlpyt.models.curiosity.ndigo", "rlpyt.models.curiosity.encoders", "rlpyt.models.pg.atari_lstm_model",
     "rlpyt.algos.utils", "rlpyt.algos.pg.base", "rlpyt.algos.pg.ppo", "rlpyt.algos.pg.a2c",
     "rlpyt.agents.pg.atari", "rlpyt.agents.pg.categorical", "rlpyt.utils.averages", "rlpyt.utils.tensor",
-    "rlpyt.samplers.collections", "rlpyt.envs.base", "rlpyt.spaces.int_box", "rlpyt.distributions.categorical",
+    "rlpyt.samplers.collections", "rlpyt.envs.base", "rlpyt.spaces.int_box", "rlpyt.spaces.float_box", "rlpyt.distributions.categorical",
 ]
 
 
