@@ -59,13 +59,20 @@ def test_constructor_defaults_match_reference():
         sys.path.remove(REF)
 
 
-def test_unaccelerated_policy_encoder_is_refused_loudly():
-    """feature_encoding='none' (Conv2dHeadModel, the RND policy encoder, atari_lstm_model.py:94-112) has no kernels yet:
-    the constructor must say so instead of building something that would run elsewhere."""
+def test_policy_own_encoder_builds_with_the_reference_keys():
+    """feature_encoding='none' (Conv2dHeadModel, the RND policy encoder, atari_lstm_model.py:94-112) and the
+    curiosity-free policy: the holder carries the reference's parameter names and shapes; unsupported options are
+    refused loudly instead of building something that would run elsewhere."""
+    import recipes as R
     from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel
-    with pytest.raises(NotImplementedError):
-        AtariLstmModel((4, 84, 84), 4, curiosity_kwargs=dict(curiosity_alg="rnd", feature_encoding="none",
+    m = AtariLstmModel((4, 84, 84), 4, curiosity_kwargs=dict(curiosity_alg="rnd", feature_encoding="none",
                                                              prediction_beta=1.0, drop_probability=0.25, gamma=0.99,
                                                              device="cpu"))
+    keys = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("curiosity_model.")}
+    assert keys == dict(R.policy_shapes(4, "none"))
+    assert {k[len("curiosity_model."):]: tuple(v.shape) for k, v in m.state_dict().items()
+            if k.startswith("curiosity_model.")} == dict(R.rnd_shapes())
+    m = AtariLstmModel((4, 84, 84), 6)            # curiosity_alg='none' -> Conv2dHeadModel as well
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(R.policy_shapes(6, "none"))
     with pytest.raises(NotImplementedError):
-        AtariLstmModel((4, 84, 84), 4)            # curiosity_alg='none' -> Conv2dHeadModel as well
+        AtariLstmModel((4, 84, 84), 4, use_maxpool=True)
