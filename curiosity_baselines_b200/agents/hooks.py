@@ -39,78 +39,6 @@ def _onehot(agent, idx, dev):
     return torch.zeros(idx.shape + (n,), dtype=torch.float32, device=dev).scatter_(-1, idx.unsqueeze(-1), 1)
 
 
-def newest_frame_to_device(frames, dev):
-    """[T,B,C,H,W] uint8 (host or device) -> device [T,B,1,H,W] holding only the newest frame."""
-    if frames.is_cuda:
-        return frames
-    from .. import _lib as L
-    T, B, C, H, W = frames.shape
-    if frames.dtype != torch.uint8 or not frames.is_contiguous():
-        return frames[:, :, -1:].contiguous().to(dev, non_blocking=True)
-    out = torch.empty((T, B, 1, H, W), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        L.call("cb_h2d_2d", out.data_ptr(), H * W, frames.data_ptr() + (C - 1) * H * W, C * H * W,
-               H * W, T * B, L.stream())
-    return out
-
-
-class FrameStager:
-    """Double-buffered host->device staging of the newest frame of pinned uint8 stacks on a side
-    stream.  Per batch:  ``buf = get()`` (compute stream waits for the upload),
-    queue the compute that reads ``buf``, ``done()`` (marks the point after which ``buf`` may be
-    overwritten), ``prefetch(next_frames)``: the upload of batch i+1 runs under the compute of batch i and
-    only waits for batch i-1 to release its buffer (an event, not a whole-stream dependency)."""
-
-    def __init__(self, device):
-        self.dev = torch.device(device)
-        if self.dev.index is None:
-            self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.stream = torch.cuda.Stream(device=self.dev)
-        self.bufs, self.events, self.free, self.k = [None, None], [None, None], [None, None], 0
-        self.extras = [None, None]
-        self.pending = self.current = None
-
-    def prefetch(self, frames, extras=()):
-        """``extras``: the batch's small pinned host tensors (done, value, ...).  They ride on the same
-        stream AHEAD of the frames: separate small uploads on the compute stream would queue behind the
-        next batch's 0.9 GB frame copy in the copy engine and stall the step (measured: 27 -> 40 ms)."""
-        from .. import _lib as L
-        T, B, C, H, W = frames.shape
-        i = self.k
-        if self.bufs[i] is None or self.bufs[i].shape != (T, B, 1, H, W):
-            self.bufs[i] = torch.empty((T, B, 1, H, W), dtype=torch.uint8, device=self.dev)
-            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
-        if self.free[i] is not None:
-            self.stream.wait_event(self.free[i])       # the last reader of buffer i has finished
-        with torch.cuda.stream(self.stream):
-            if self.extras[i] is None or len(self.extras[i]) != len(extras):
-                self.extras[i] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in extras]
-            for d, t in zip(self.extras[i], extras):
-                d.copy_(t, non_blocking=True)
-            L.call("cb_h2d_2d", self.bufs[i].data_ptr(), H * W, frames.data_ptr() + (C - 1) * H * W, C * H * W, H * W,
-                   T * B, self.stream.cuda_stream)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self.events[i] = ev
-        self.pending = i
-        self.k ^= 1
-
-    def get(self):
-        i = self.pending
-        torch.cuda.current_stream(self.dev).wait_event(self.events[i])
-        self.current = i
-        return self.bufs[i]
-
-    def get_extras(self):
-        """Device copies of the ``extras`` of the batch returned by the last ``get()``."""
-        return self.extras[self.current]
-
-    def done(self):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.dev))
-        self.free[self.current] = ev
-
-
 class BatchPrefetcher:
     """Whole-batch host->device staging on a side stream for the full PPO iteration (ICM / Disagreement read all
     four frames of observation AND next_observation, 2 x T x B x 28 224 bytes): ``prefetch(host_tensors)`` queues
@@ -141,23 +69,192 @@ class BatchPrefetcher:
         return dev_tensors
 
 
+class BatchStaging:
+    """Host -> device staging of one training iteration's ``Samples`` on the REAL call path: the
+    reference hands the same sampler buffers to ``curiosity_step`` (the bonus, algos/pg/base.py:64-73) and to
+    ``curiosity_loss`` (every epoch / minibatch, ppo.py:93-110, 226-238).  Each host tensor crosses PCIe ONCE per
+    iteration:
+
+      * entries are keyed on (address, shape, dtype, newest-frame-only) and validated with a strided fingerprint of
+        the host bytes, so a buffer that was rewritten in place (the sampler reuses its buffers every iteration, and
+        shared-memory writes do not bump ``_version``) is uploaded again instead of being served stale;
+      * every upload bumps ``generation`` -- the models key their feature caches on it (ADVICE r1);
+      * with ``pin_host`` (off by default; ``integration.install(pin_sampler_buffers=True)`` turns it on for rlpyt,
+        whose sample buffers are numpy shared memory allocated once for the whole run, samplers/buffer.py) large
+        unpinned buffers are page-locked in place once with ``cudaHostRegister`` so the copies run at PCIe speed,
+        asynchronously, on a side stream.  Only for buffers that outlive the staging object: freeing registered
+        memory without ``release_host_registrations()`` is an error;
+      * ``prefetch`` stages a batch ahead of its iteration (double-buffered runners, rlpyt's AsyncRl): the upload of
+        batch i+1 then runs under the compute of batch i.
+    RND reads only the newest frame of each stack (rnd.py:130-131): 7056 of 28224 bytes per sample are uploaded with
+    one strided DMA (``cb_h2d_2d``)."""
+
+    PIN_MIN_BYTES = 1 << 20
+    default_pin_host = False
+
+    def __init__(self, device, pin_host=None):
+        self.pin_host = self.default_pin_host if pin_host is None else bool(pin_host)
+        self.dev = torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.entries = {}
+        self.iteration = 0
+        self.generation = 0
+        self.bytes_uploaded = 0
+        self.hits = 0
+        self._registered = {}
+
+    # ------------------------------------------------------------------ host side
+    @staticmethod
+    def _fingerprint(t):
+        """64 evenly spaced 8-byte words + size: detects in-place rewrites of a sampler buffer for microseconds."""
+        import numpy as np
+        flat = t.detach().reshape(-1)
+        nbytes = flat.numel() * flat.element_size()
+        raw = flat.view(torch.uint8) if flat.dtype != torch.bool else flat.to(torch.uint8)
+        words = raw[: nbytes // 8 * 8].view(torch.int64)
+        if words.numel() == 0:
+            return (nbytes, tuple(raw.tolist()))
+        idx = np.linspace(0, words.numel() - 1, num=min(64, words.numel())).astype(np.int64)
+        return (nbytes, tuple(words[torch.from_numpy(idx)].tolist()))
+
+    def _pin(self, t):
+        """Page-lock a large host buffer in place (once); returns whether async copies from it are possible."""
+        if t.is_pinned():
+            return True
+        nbytes = t.numel() * t.element_size()
+        if not self.pin_host or nbytes < self.PIN_MIN_BYTES or not t.is_contiguous():
+            return False
+        key = (t.data_ptr(), nbytes)
+        if key not in self._registered:
+            rt = torch.cuda.cudart()
+            rc = rt.cudaHostRegister(t.data_ptr(), nbytes, 0)
+            self._registered[key] = int(rc) == 0
+            if int(rc) != 0:
+                rt.cudaGetLastError()         # a refused registration must not poison the next CUDA call
+        return self._registered[key]
+
+    def release_host_registrations(self):
+        for (ptr, _), ok in self._registered.items():
+            if ok:
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+        self._registered.clear()
+
+    # ------------------------------------------------------------------ uploads
+    def new_iteration(self):
+        """Called by the first consumer of an iteration (the bonus): drops the previous iteration's device copies;
+        batches staged ahead with ``prefetch`` stay."""
+        self.iteration += 1
+        self.entries = {k: e for k, e in self.entries.items() if e["iteration"] >= self.iteration}
+
+    def _upload(self, t, newest_only, iteration, fp=None):
+        from .. import _lib as L
+        cur = torch.cuda.current_stream(self.dev)
+        if newest_only:
+            T, B, C, H, W = t.shape
+            out = torch.empty((T, B, 1, H, W), dtype=t.dtype, device=self.dev)
+        else:
+            out = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+        self.stream.wait_stream(cur)                 # the block may have been used by earlier compute-stream work
+        pinned = self._pin(t)
+        with torch.cuda.stream(self.stream):
+            if newest_only and t.is_contiguous() and t.dtype == torch.uint8:
+                L.call("cb_h2d_2d", out.data_ptr(), H * W, t.data_ptr() + (C - 1) * H * W, C * H * W, H * W, T * B,
+                       self.stream.cuda_stream)
+            elif newest_only:
+                out.copy_(t[:, :, -1:], non_blocking=pinned)
+            else:
+                out.copy_(t, non_blocking=pinned)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        out.record_stream(self.stream)
+        self.generation += 1
+        out._b200_staged = self.generation       # filled once, never refilled: the models may trust object identity
+        self.bytes_uploaded += out.numel() * out.element_size()
+        return dict(tensor=out, event=ev, fp=fp if fp is not None else self._fingerprint(t), iteration=iteration,
+                    generation=self.generation)
+
+    def _key(self, t, newest_only):
+        return (t.data_ptr(), tuple(t.shape), t.dtype, bool(newest_only))
+
+    def prefetch(self, t, newest_only=False):
+        """Stage ``t`` for the NEXT iteration without making the compute stream wait."""
+        if t.is_cuda:
+            return
+        self.entries[self._key(t, newest_only)] = self._upload(t, newest_only, self.iteration + 1)
+
+    def get(self, t, newest_only=False):
+        """Device copy of ``t`` (uploaded now unless this iteration already did); the compute stream waits for it."""
+        if t.is_cuda:
+            return t
+        key, fp = self._key(t, newest_only), self._fingerprint(t)
+        e = self.entries.get(key)
+        if e is None or e["fp"] != fp:
+            e = self._upload(t, newest_only, self.iteration, fp)
+            self.entries[key] = e
+        else:
+            self.hits += 1
+        torch.cuda.current_stream(self.dev).wait_event(e["event"])
+        return e["tensor"]
+
+    def generation_of(self, dev_tensor):
+        """Generation stamp of a staged device tensor (None if it is not one of ours): the curiosity models compare it
+        instead of ``_version``, which a raw-pointer upload never bumps."""
+        for e in self.entries.values():
+            if e["tensor"] is dev_tensor:
+                return e["generation"]
+        return None
+
+
+def staging(agent):
+    """The agent's ``BatchStaging`` (created on first use, on the agent's device)."""
+    st = getattr(agent, "_b200_staging", None)
+    if st is None:
+        st = BatchStaging(_device(agent))
+        try:
+            agent._b200_staging = st
+        except AttributeError:
+            pass
+    return st
+
+
+def prefetch_samples(agent, curiosity_type, samples):
+    """Stage the frame tensors of the NEXT iteration's ``samples`` while the current one is being optimised
+    (double-buffered runners)."""
+    st = staging(agent)
+    if curiosity_type == "rnd":
+        st.prefetch(samples.env.next_observation, newest_only=True)
+    elif curiosity_type in ("icm", "disagreement"):
+        st.prefetch(samples.env.observation)
+        st.prefetch(samples.env.next_observation)
+    elif curiosity_type == "ndigo":
+        st.prefetch(samples.env.observation)
+
+
+def _small(t, dev, dtype=None):
+    t = torch.as_tensor(t)
+    return t.to(dev, dtype, non_blocking=True) if dtype is not None else t.to(dev, non_blocking=True)
+
+
 @torch.no_grad()
 def curiosity_step(self, curiosity_type, *args):
     dev = _device(self)
     cm = _curiosity_model(self)
+    st = staging(self)
+    st.new_iteration()                      # the bonus is the first consumer of an iteration's samples
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions = args
-        r_int = cm.compute_bonus(observation.to(dev, non_blocking=True),
-                                 next_observation.to(dev, non_blocking=True), _onehot(self, actions, dev))
+        r_int = cm.compute_bonus(st.get(observation), st.get(next_observation), _onehot(self, actions, dev))
         info = IcmInfo()
     elif curiosity_type == "ndigo":
         observation, prev_actions, actions = args
-        r_int = cm.compute_bonus(observation.to(dev, non_blocking=True), _onehot(self, prev_actions, dev),
-                                 _onehot(self, actions, dev))
+        r_int = cm.compute_bonus(st.get(observation), _onehot(self, prev_actions, dev), _onehot(self, actions, dev))
         info = NdigoInfo(prev_gru_state=None)
     elif curiosity_type == "rnd":
         next_observation, done = args
-        r_int = cm.compute_bonus(newest_frame_to_device(next_observation, dev), done.to(dev))
+        frames = next_observation if next_observation.is_cuda else st.get(next_observation, newest_only=True)
+        r_int = cm.compute_bonus(frames, _small(done, dev))
         info = RndInfo()
     else:
         raise ValueError(curiosity_type)
@@ -167,19 +264,20 @@ def curiosity_step(self, curiosity_type, *args):
 def curiosity_loss(self, curiosity_type, *args):
     dev = _device(self)
     cm = _curiosity_model(self)
+    st = staging(self)
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions, valid = args
-        inv, fwd = cm.compute_loss(observation.to(dev, non_blocking=True),
-                                   next_observation.to(dev, non_blocking=True),
-                                   _onehot(self, actions, dev), valid.to(dev))
+        inv, fwd = cm.compute_loss(st.get(observation), st.get(next_observation), _onehot(self, actions, dev),
+                                   _small(valid, dev))
         return inv.to("cpu"), fwd.to("cpu")
     if curiosity_type == "ndigo":
         observations, prev_actions, actions, valid = args
-        loss = cm.compute_loss(observations.to(dev, non_blocking=True), _onehot(self, prev_actions, dev),
-                               _onehot(self, actions, dev), valid.to(dev))
+        loss = cm.compute_loss(st.get(observations), _onehot(self, prev_actions, dev), _onehot(self, actions, dev),
+                               _small(valid, dev))
         return loss.to("cpu")
     if curiosity_type == "rnd":
         next_observation, valid = args
-        loss = cm.compute_loss(newest_frame_to_device(next_observation, dev), valid.to(dev))
+        frames = next_observation if next_observation.is_cuda else st.get(next_observation, newest_only=True)
+        loss = cm.compute_loss(frames, _small(valid, dev))
         return loss.to("cpu")
     raise ValueError(curiosity_type)

@@ -313,12 +313,13 @@ class _IcmBase(nn.Module):
             return False
         dev = self._exec["dev"]
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        for a, b in ((observations, c["obs"]), (next_observations, c["next"])):
+        for a, b, ref in ((observations, c["obs"], c["ref_obs"]), (next_observations, c["next"], c["ref_next"])):
             if a.dtype != torch.uint8 or not a.is_cuda:
                 return False
-            a, b = a.contiguous(), b.contiguous()
-            if a.data_ptr() == b.data_ptr() and a._version == b._version:
-                continue
+            if (a is b and getattr(a, "_b200_staged", None) is not None
+                    and (getattr(a, "_b200_staged"), int(a._version)) == c["versions"][id(b)]):
+                continue              # the very BatchStaging tensor the bonus saw (never refilled), untouched since
+            a, b = a.contiguous(), ref.contiguous()      # tensors we do not own: compare with the private copy
             per = a[0, 0].numel()
             if per % 16 or (a.data_ptr() | b.data_ptr()) & 15:
                 return False
@@ -342,7 +343,11 @@ class _IcmBase(nn.Module):
         saved, pred = self._forward_exec().run_forward(phi1_b, action, n)            # pred fp32, packed [n, E*F]
         out = feats + (saved, pred)
         if self.reuse_features and remember:
-            self._cache = dict(obs=observations, next=next_observations, act=action.clone(), wver=self._weights_version(),
+            own = lambda t: t if getattr(t, "_b200_staged", None) is not None else t.clone()
+            self._cache = dict(obs=observations, next=next_observations, ref_obs=own(observations),
+                               ref_next=own(next_observations), act=action.clone(), wver=self._weights_version(),
+                               versions={id(t): (getattr(t, "_b200_staged", None), int(t._version))
+                                         for t in (observations, next_observations)},
                                shapes=(tuple(observations.shape), tuple(next_observations.shape), tuple(actions.shape)),
                                out=out)
         elif not remember:

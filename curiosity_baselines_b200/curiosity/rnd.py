@@ -190,8 +190,12 @@ class RND(nn.Module):
         return (self._wver,) + tuple(p._version for p in self.forward_model.parameters())
 
     def _remember(self, obs, T, B, phi, phi_hat, acts):
-        self._cache = dict(obs=obs, shape=(T, B), phi=phi, phi_hat=phi_hat, acts=acts,
-                           norm_ver=self._norm_ver, wver=self._weights_version())
+        staged = getattr(obs, "_b200_staged", None)
+        # a tensor we do not own may be refilled behind torch's back (raw-pointer uploads keep address and _version):
+        # the guard then compares against a PRIVATE copy of the newest frames (0.93 GB at T=128, B=1024; ~0.3 ms)
+        ref = obs if staged is not None else obs[:, :, -1:].clone()
+        self._cache = dict(obs=obs, ref=ref, obs_version=int(obs._version), staged=staged, shape=(T, B), phi=phi,
+                           phi_hat=phi_hat, acts=acts, norm_ver=self._norm_ver, wver=self._weights_version())
 
     def _reusable(self, obs, T, B, base, strides):
         """None, or the cached entry whose frames equal `obs` under the current observation statistics."""
@@ -199,8 +203,13 @@ class RND(nn.Module):
         if not self.reuse_features or c is None or c["shape"] != (T, B) or c["norm_ver"] != self._norm_ver:
             return None
         co = c["obs"]
-        if co.data_ptr() != obs.data_ptr() or co._version != obs._version or co.shape != obs.shape:
-            cobs, _, _, cbase, cstrides = self._frame_view(co)
+        # Provably the same frames only when it is the very tensor object the bonus saw, it was produced by the hooks'
+        # BatchStaging (filled once at creation, never refilled: tagged ``_b200_staged``) and nobody wrote to it through
+        # torch since.  Anything else -- another tensor, or a persistent buffer that a raw-pointer upload may have
+        # refilled without bumping ``_version`` -- is compared on the device against the reference kept by _remember.
+        if (co is not obs or c["staged"] is None or getattr(obs, "_b200_staged", None) != c["staged"]
+                or c["obs_version"] != int(obs._version)):
+            cobs, _, _, cbase, cstrides = self._frame_view(c["ref"])
             if not ((base | cbase | strides[0] | cstrides[0]) & 15 == 0):
                 return None
             flag = torch.zeros(1, dtype=torch.int32, device=self._dev)

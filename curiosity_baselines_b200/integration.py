@@ -31,9 +31,11 @@ def uninstall():
         target, leaf, old = _originals.pop()
         setattr(target, leaf, old)
     RND.default_reuse_features = ICM.default_reuse_features = Disagreement.default_reuse_features = False
+    from .agents import hooks
+    hooks.BatchStaging.default_pin_host = False
 
 
-def install(strict=True, reuse_features=True, policy=False):
+def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=False):
     """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
     that fail to import (e.g. optional dependencies missing).  ``reuse_features``: RND models built afterwards reuse
     a batch's features between compute_bonus and compute_loss when the frames are verified equal (the reference
@@ -46,6 +48,9 @@ def install(strict=True, reuse_features=True, policy=False):
     from .agents import hooks
 
     patched = []
+    # rlpyt allocates its sample buffers once per run as numpy shared memory (samplers/buffer.py): page-locking them in
+    # place lets the hooks' uploads run at PCIe speed and asynchronously (agents/hooks.BatchStaging)
+    hooks.BatchStaging.default_pin_host = bool(pin_sampler_buffers)
     RND.default_reuse_features = bool(reuse_features)
     ICM.default_reuse_features = Disagreement.default_reuse_features = bool(reuse_features)
 

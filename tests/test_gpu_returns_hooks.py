@@ -100,24 +100,82 @@ def test_hooks_icm_index_actions():
     assert inv.device.type == "cpu" and m.encoder.model[0].weight.grad is not None
 
 
-def test_frame_stager_double_buffering():
-    """agents/hooks.FrameStager: the newest frame of every pinned stack (and the batch's small tensors) arrive
-    on the device for successive batches, buffers alternating, while earlier batches are still in use."""
-    from curiosity_baselines_b200.agents.hooks import FrameStager
-    T, B = 5, 3
-    st = FrameStager("cuda")
-    batches = [torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8).pin_memory() for _ in range(4)]
-    extras = [[torch.randn(T, B).pin_memory(), torch.randn(B).pin_memory()] for _ in range(4)]
-    st.prefetch(batches[0], extras[0])
-    kept = []
-    for i in range(4):
-        buf = st.get()
-        ex = st.get_extras()
-        kept.append((buf.clone(), [e.clone() for e in ex]))
-        st.done()
-        if i + 1 < 4:
-            st.prefetch(batches[i + 1], extras[i + 1])
-    torch.cuda.synchronize()
-    for i, (buf, ex) in enumerate(kept):
-        assert torch.equal(buf.cpu(), batches[i][:, :, -1:])
-        assert all(torch.equal(a.cpu(), b) for a, b in zip(ex, extras[i]))
+def test_batch_staging_uploads_once_per_iteration_and_detects_rewrites():
+    """agents/hooks.BatchStaging on the real call path: curiosity_step and curiosity_loss of one iteration share ONE
+    upload of the frames (the loss then reuses the bonus's features without a device-side comparison or host sync);
+    a sampler buffer rewritten in place for the next iteration -- same address, no ``_version`` bump -- is uploaded
+    again; a batch staged ahead with ``prefetch_samples`` is picked up without a second upload."""
+    T, B, seed = 6, 4, 21
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m.load_state_dict(params)
+    m.reuse_features = True
+    agent = _agent(m, 4)
+    frames = R.make_frames(seed, T, B)                       # pageable, like rlpyt's numpy shared memory
+    done = R.make_suffix_done(seed + 1, T, B, frac=0.5)
+    st = hooks.staging(agent)
+    st.pin_host, st.PIN_MIN_BYTES = True, 1 << 16            # page-lock the "sampler buffer" in place (it outlives st)
+    per_batch = T * B * 84 * 84
+    o = O.RndOracle(drop_probability=0.0)
+    for it in range(3):
+        if it:                                               # the sampler refills its buffer in place
+            frames.numpy()[...] = R.make_frames(seed + 10 * it, T, B).numpy()
+        before = st.bytes_uploaded
+        step = hooks.curiosity_step(agent, "rnd", frames, done)
+        loss = hooks.curiosity_loss(agent, "rnd", frames, torch.ones(T, B))
+        loss2 = hooks.curiosity_loss(agent, "rnd", frames, torch.ones(T, B))       # second epoch
+        assert st.bytes_uploaded - before == per_batch, it    # newest frames only, once
+        ref = o.compute_bonus(params, frames, done)
+        nz = ref.abs() > 0
+        assert float(((step.r_int - ref).abs()[nz] / ref.abs()[nz]).max()) < 1e-2, it
+        assert float(loss) == float(loss2)
+    assert m.reuse_hits["full"] == 6 and m.reuse_hits["miss"] == 0
+    # double-buffered runner: next batch staged during this iteration
+    nxt = R.make_frames(seed + 99, T, B)
+    Env2 = namedtuple("Env2", ["next_observation", "observation"])
+    hooks.prefetch_samples(agent, "rnd", SimpleNamespace(env=Env2(nxt, nxt)))
+    before = st.bytes_uploaded
+    step = hooks.curiosity_step(agent, "rnd", nxt, done)
+    assert st.bytes_uploaded == before and st.hits >= 1
+    ref = o.compute_bonus(params, nxt, done)
+    nz = ref.abs() > 0
+    assert float(((step.r_int - ref).abs()[nz] / ref.abs()[nz]).max()) < 1e-2
+    st.release_host_registrations()
+
+
+def test_icm_hooks_share_one_upload_per_tensor():
+    T, B, A, seed = 4, 3, 4, 9
+    m = ICM(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+    m.load_state_dict(R.make_params(R.icm_shapes(A, "idf_burda"), seed))
+    m.reuse_features = True
+    agent = _agent(m, A)
+    obs, nxt = R.make_frames(seed + 1, T, B), R.make_frames(seed + 2, T, B)
+    idx = R.make_actions(seed + 3, T, B, A)
+    st = hooks.staging(agent)
+    hooks.curiosity_step(agent, "icm", obs, nxt, idx)
+    inv, fwd = hooks.curiosity_loss(agent, "icm", obs, nxt, idx, torch.ones(T, B))
+    assert st.bytes_uploaded == 2 * obs.numel() and st.hits == 2
+    assert m.reuse_hits == {"full": 1, "miss": 0}
+
+
+def test_refilled_persistent_buffer_is_not_served_stale():
+    """a device buffer refilled through a raw pointer keeps its address AND its ``_version``; the feature
+    cache must not trust either -- only BatchStaging tensors (never refilled) take the comparison-free path."""
+    from curiosity_baselines_b200 import _lib as L
+    T, B, seed = 4, 3, 33
+    m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m.load_state_dict(R.make_params(R.rnd_shapes(), seed, gain=1.4))
+    m.reuse_features = True
+    a, b = R.make_frames(seed, T, B).pin_memory(), R.make_frames(seed + 1, T, B).pin_memory()
+    buf = a.to(DEV)
+    done, ones = torch.zeros(T, B, device=DEV), torch.ones(T, B, device=DEV)
+    m.compute_bonus(buf, done)
+    version = buf._version
+    L.call("cb_h2d_2d", buf.data_ptr(), buf[0, 0].numel(), b.data_ptr(), buf[0, 0].numel(), buf[0, 0].numel(), T * B, L.stream())
+    assert buf._version == version                       # invisible to torch
+    stale_or_not = m.compute_loss(buf, ones, ones)
+    m2 = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+    m2.load_state_dict(m.state_dict())
+    m2.compute_bonus(a.to(DEV), done)                   # same statistics as m
+    fresh = m2.compute_loss(b.to(DEV), ones, ones)
+    assert float(stale_or_not) == float(fresh) and m.reuse_hits["miss"] == 1

@@ -111,9 +111,9 @@ def test_rnd_step_against_oracle_two_iterations():
 
 
 def test_host_staging_of_newest_frame():
-    from curiosity_baselines_b200.agents.hooks import newest_frame_to_device
+    from curiosity_baselines_b200.agents.hooks import BatchStaging
     frames = R.make_frames(3, 5, 4).pin_memory()
-    out = newest_frame_to_device(frames, torch.device(DEV))
+    out = BatchStaging(DEV).get(frames, newest_only=True)
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), frames[:, :, -1:])
 
