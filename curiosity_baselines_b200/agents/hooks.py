@@ -175,20 +175,22 @@ class BatchStaging:
         return dict(tensor=out, event=ev, fp=fp if fp is not None else self._fingerprint(t), iteration=iteration,
                     generation=self.generation)
 
-    def _key(self, t, newest_only):
-        return (t.data_ptr(), tuple(t.shape), t.dtype, bool(newest_only))
+    def _key(self, t, newest_only, iteration):
+        # the iteration is part of the key: a runner that refills ONE host buffer can stage iteration i+1 while
+        # iteration i's copy is still being consumed
+        return (t.data_ptr(), tuple(t.shape), t.dtype, bool(newest_only), iteration)
 
     def prefetch(self, t, newest_only=False):
         """Stage ``t`` for the NEXT iteration without making the compute stream wait."""
         if t.is_cuda:
             return
-        self.entries[self._key(t, newest_only)] = self._upload(t, newest_only, self.iteration + 1)
+        self.entries[self._key(t, newest_only, self.iteration + 1)] = self._upload(t, newest_only, self.iteration + 1)
 
     def get(self, t, newest_only=False):
         """Device copy of ``t`` (uploaded now unless this iteration already did); the compute stream waits for it."""
         if t.is_cuda:
             return t
-        key, fp = self._key(t, newest_only), self._fingerprint(t)
+        key, fp = self._key(t, newest_only, self.iteration), self._fingerprint(t)
         e = self.entries.get(key)
         if e is None or e["fp"] != fp:
             e = self._upload(t, newest_only, self.iteration, fp)

@@ -167,6 +167,7 @@ class PPO:
         ret, adv, valid, _ = returns_on_device(batch.reward, batch.done, batch.value, batch.bootstrap_value,
                                                self.discount, self.gae_lambda, self.normalize_reward,
                                                self.normalize_advantage, True, self._returns_state)
+        self.last_return, self.last_advantage = ret, adv
         return ret, adv, valid
 
     def minibatch_indices(self, B):
@@ -206,3 +207,94 @@ class PPO:
             self.opt.lr = self.learning_rate * frac
             self.ratio_clip = self._ratio_clip * (self.n_itr - itr) / self.n_itr
         return infos
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# rlpyt-facing entry: ``PPO.optimize_agent(itr, samples)`` on the sampler's HOST buffers (ppo.py:72-190)
+# ----------------------------------------------------------------------------------------------------------------------
+RefOptInfo = namedtuple("OptInfo", ["return_", "intrinsic_rewards", "valpred", "advantage", "loss", "pi_loss",
+                                    "value_loss", "entropy_loss", "inv_loss", "forward_loss", "reward_total_std",
+                                    "curiosity_loss", "gradNorm", "entropy", "perplexity"])
+RefOptInfo.__doc__ = "rlpyt/algos/pg/base.py:9-23 (same fields, same order): what the runner logs."
+
+
+def stage_samples(agent, curiosity_type, samples, st=None):
+    """rlpyt ``Samples`` on the host -> ``PpoBatch`` on the device through the agent's ``BatchStaging``: every tensor
+    crosses PCIe once per iteration (the reference uploads ``observation`` twice and clones both frame tensors on the
+    host first, ppo.py:81-98), frames asynchronously on the staging stream; a batch staged ahead with
+    ``hooks.prefetch_samples`` is picked up without another upload."""
+    from ..agents import hooks
+    st = st or hooks.staging(agent)
+    st.new_iteration()
+    dev = st.dev
+    env, ag = samples.env, samples.agent
+    T, B = env.reward.shape[:2]
+    f32 = lambda t: torch.as_tensor(t).to(dev, torch.float32, non_blocking=True)
+    obs = st.get(env.observation)
+    nxt = st.get(env.next_observation) if curiosity_type in ("icm", "disagreement", "rnd") else obs
+    rnn = getattr(ag.agent_info, "prev_rnn_state", None)
+    init = None
+    if rnn is not None:
+        init = tuple(torch.as_tensor(s[0]).to(dev, non_blocking=True) for s in (rnn.h, rnn.c))       # T = 0: [B,N,H]
+    return PpoBatch(obs, nxt, torch.as_tensor(ag.prev_action).to(dev, non_blocking=True).long(),
+                    torch.as_tensor(ag.action).to(dev, non_blocking=True).long(), f32(ag.agent_info.dist_info.prob),
+                    f32(env.reward).reshape(T, B).contiguous(), f32(env.done).reshape(T, B).contiguous(),
+                    f32(ag.agent_info.value).reshape(T, B).contiguous(), f32(ag.bootstrap_value).reshape(-1).contiguous(),
+                    init)
+
+
+def optimize_agent_from_samples(native, agent, itr, samples):
+    """One iteration of the fused PPO on rlpyt ``Samples``: stage -> ``PPO.optimize_agent`` -> the reference's
+    ``OptInfo`` (lists of python floats, one entry per gradient step) read back in ONE device->host copy.  Side
+    effects of the reference are kept: the bonus is added into ``samples.env.reward`` in place and kept as numpy in
+    ``intrinsic_rewards`` (algos/pg/base.py:66-67)."""
+    batch = stage_samples(agent, native.curiosity_type, samples)
+    reward_before = batch.reward.clone() if native.curiosity_type != "none" else None
+    infos = native.optimize_agent(itr, batch)
+    fields = ("loss", "pi_loss", "value_loss", "entropy_loss", "inv_loss", "forward_loss", "gradNorm", "entropy",
+              "perplexity")
+    packed = torch.stack([torch.stack([torch.as_tensor(getattr(i, f), dtype=torch.float32, device=batch.reward.device)
+                                       .reshape(()) for f in fields]) for i in infos])
+    extra = torch.stack([native.last_return.mean(), native.last_advantage.mean(), batch.value.mean()])
+    host = torch.cat([packed.reshape(-1), extra]).cpu()                 # the iteration's only blocking read-back
+    vals = host[:-3].reshape(len(infos), len(fields))
+    out = {f: [float(v) for v in vals[:, j]] for j, f in enumerate(fields)}
+    r_mean = []
+    if native.intrinsic_rewards is not None:
+        r_host = native.intrinsic_rewards.cpu()
+        samples.env.reward.copy_(batch.reward.reshape(samples.env.reward.shape).cpu())      # in-place add (base.py:66)
+        native.intrinsic_rewards_numpy = r_host.numpy()
+        r_mean = [float(r_host.mean())] * len(infos)
+    ctype = native.curiosity_type
+    return RefOptInfo(return_=[float(host[-3])], intrinsic_rewards=r_mean, valpred=[float(host[-1])],
+                      advantage=[float(host[-2])], loss=out["loss"], pi_loss=out["pi_loss"], value_loss=out["value_loss"],
+                      entropy_loss=out["entropy_loss"], inv_loss=out["inv_loss"] if ctype in ("icm", "disagreement") else [],
+                      forward_loss=out["forward_loss"] if ctype != "none" else [], reward_total_std=[], curiosity_loss=[],
+                      gradNorm=out["gradNorm"], entropy=out["entropy"], perplexity=out["perplexity"])
+
+
+def rlpyt_optimize_agent(self, itr, samples):
+    """Drop-in for rlpyt ``PPO.optimize_agent`` (bound by ``integration.install(policy=True, algo=True)``): the
+    reference algo object keeps its hyper-parameters and its place in the runner; the iteration itself -- staging, bonus,
+    returns, epochs x minibatches of loss / backward / clip / Adam -- runs on the fused path.  The optimiser state lives
+    in ``FlatAdam`` and is exposed through ``optim_state_dict()`` in torch.optim.Adam's layout."""
+    native = getattr(self, "_b200_native", None)
+    model = getattr(self.agent.model, "module", self.agent.model)
+    if native is None:
+        native = PPO(discount=self.discount, learning_rate=self.learning_rate, value_loss_coeff=self.value_loss_coeff,
+                     entropy_loss_coeff=self.entropy_loss_coeff, clip_grad_norm=self.clip_grad_norm,
+                     gae_lambda=self.gae_lambda, minibatches=self.minibatches, epochs=self.epochs,
+                     ratio_clip=self.ratio_clip, linear_lr_schedule=self.linear_lr_schedule,
+                     normalize_advantage=self.normalize_advantage, normalize_reward=self.normalize_reward,
+                     curiosity_type=self.curiosity_type)
+        sd = self.optimizer.state_dict()
+        native.initialize(model, n_itr=self.n_itr)
+        if sd["state"]:
+            native.load_optim_state_dict(sd)
+        self._b200_native = native
+        self.optim_state_dict = native.optim_state_dict
+    info = optimize_agent_from_samples(native, self.agent, itr, samples)
+    self.intrinsic_rewards = getattr(native, "intrinsic_rewards_numpy", None)
+    self.ratio_clip = native.ratio_clip
+    self.update_counter = native.update_counter
+    return info, dict()

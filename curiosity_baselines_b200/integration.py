@@ -17,6 +17,11 @@ With ``policy=True`` the policy network is replaced as well:
 The reference's ``PPO.loss`` then back-propagates through our kernels via the model's autograd boundary.  It is
 opt-in because the library has no CPU path: use it with samplers that evaluate the agent on the GPU
 (``GpuSampler``); ``CpuSampler`` workers evaluate a CPU copy of the model and need the reference class.
+With ``policy=True, algo=True`` the whole iteration is replaced as well:
+  rlpyt/algos/pg/ppo.py:72-190 PPO.optimize_agent                     -> algos.ppo.rlpyt_optimize_agent
+  (the sampler's host buffers are staged once per iteration -- the reference clones both frame tensors on the host
+  and uploads ``observation`` twice -- then bonus, returns and every epoch x minibatch gradient step run on the fused
+  path with one FlatAdam over policy U curiosity parameters; the runner still gets the reference's ``OptInfo``).
 """
 import importlib
 
@@ -35,7 +40,7 @@ def uninstall():
     hooks.BatchStaging.default_pin_host = False
 
 
-def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=False):
+def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=False, algo=False):
     """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
     that fail to import (e.g. optional dependencies missing).  ``reuse_features``: RND models built afterwards reuse
     a batch's features between compute_bonus and compute_loss when the frames are verified equal (the reference
@@ -103,4 +108,9 @@ def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=
         except Exception:
             if strict:
                 raise
+    if algo:
+        if not policy:
+            raise ValueError("install(algo=True) runs the fused PPO iteration on our policy network: needs policy=True")
+        from .algos.ppo import rlpyt_optimize_agent
+        patch("rlpyt.algos.pg.ppo", **{"PPO.optimize_agent": rlpyt_optimize_agent})
     return patched

@@ -61,8 +61,11 @@ def _one_iteration(kind, ck, A, T, B, seed, cuda_idx):
     return out, before, after, s.env.reward.clone(), np.array(algo.intrinsic_rewards), agent
 
 
-@pytest.mark.parametrize("kind", ["icm", "disagreement", "rnd", "ndigo"])
-def test_reference_optimize_agent_through_install(kind):
+@pytest.mark.parametrize("kind,native_algo", [("icm", False), ("disagreement", False), ("rnd", False), ("ndigo", False),
+                                              ("icm", True), ("rnd", True), ("ndigo", True)])
+def test_reference_optimize_agent_through_install(kind, native_algo):
+    """native_algo: ``install(policy=True, algo=True)`` -- the runner-level call ``algo.optimize_agent(itr, samples)`` on
+    host ``Samples`` lands on the fused iteration (algos.ppo.rlpyt_optimize_agent) instead of the reference's loop."""
     import curiosity_baselines_b200.integration as cbi
     refshim.import_reference()
     A, T, B, seed = (5 if kind == "ndigo" else 4), 16, 8, 55
@@ -90,7 +93,7 @@ def test_reference_optimize_agent_through_install(kind):
     from rlpyt.models.pg.atari_lstm_model import AtariLstmModel as RefModel
     assert isinstance(ref_agent.model, RefModel)
     calls0 = L.launch_count()
-    cbi.install(policy=True)
+    cbi.install(policy=True, algo=native_algo)
     try:
         from curiosity_baselines_b200.pg.atari_lstm_model import AtariLstmModel as Ours
         from curiosity_baselines_b200.curiosity.icm import Disagreement
@@ -105,6 +108,8 @@ def test_reference_optimize_agent_through_install(kind):
             del Disagreement._default_masks
         cbi.uninstall()
     assert L.launch_count() - calls0 > 100                       # the iteration ran in the library
+    if native_algo:
+        assert hasattr(agent, "_b200_staging") and agent._b200_staging.bytes_uploaded > 0
     import rlpyt.models.pg.atari_lstm_model as alm
     assert alm.AtariLstmModel is RefModel                        # uninstall() restored the reference
     # bonus added into the sampler's reward buffer in place (base.py:66), kept as numpy on the algo (:67)
