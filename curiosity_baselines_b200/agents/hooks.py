@@ -200,6 +200,16 @@ class BatchStaging:
         torch.cuda.current_stream(self.dev).wait_event(e["event"])
         return e["tensor"]
 
+    def alias(self, host_tensor, dev_tensor):
+        """Remember that ``host_tensor`` is a read-back of ``dev_tensor`` (process_returns hands ``valid`` back to the
+        caller on the host and the caller passes it on to ``curiosity_loss``, ppo.py:93-110): ``get`` then returns the
+        device original instead of uploading the copy again."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.entries[self._key(host_tensor, False, self.iteration)] = dict(
+            tensor=dev_tensor, event=ev, fp=self._fingerprint(host_tensor), iteration=self.iteration,
+            generation=self.generation)
+
     def generation_of(self, dev_tensor):
         """Generation stamp of a staged device tensor (None if it is not one of ours): the curiosity models compare it
         instead of ``_version``, which a raw-pointer upload never bumps."""
@@ -234,9 +244,9 @@ def prefetch_samples(agent, curiosity_type, samples):
         st.prefetch(samples.env.observation)
 
 
-def _small(t, dev, dtype=None):
-    t = torch.as_tensor(t)
-    return t.to(dev, dtype, non_blocking=True) if dtype is not None else t.to(dev, non_blocking=True)
+def _onehot_staged(agent, st, idx, dev):
+    """One-hot of an int64 action tensor; a host tensor is uploaded once per iteration through the staging cache."""
+    return _onehot(agent, st.get(torch.as_tensor(idx)), dev)
 
 
 @torch.no_grad()
@@ -247,16 +257,17 @@ def curiosity_step(self, curiosity_type, *args):
     st.new_iteration()                      # the bonus is the first consumer of an iteration's samples
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions = args
-        r_int = cm.compute_bonus(st.get(observation), st.get(next_observation), _onehot(self, actions, dev))
+        r_int = cm.compute_bonus(st.get(observation), st.get(next_observation), _onehot_staged(self, st, actions, dev))
         info = IcmInfo()
     elif curiosity_type == "ndigo":
         observation, prev_actions, actions = args
-        r_int = cm.compute_bonus(st.get(observation), _onehot(self, prev_actions, dev), _onehot(self, actions, dev))
+        r_int = cm.compute_bonus(st.get(observation), _onehot_staged(self, st, prev_actions, dev),
+                                 _onehot_staged(self, st, actions, dev))
         info = NdigoInfo(prev_gru_state=None)
     elif curiosity_type == "rnd":
         next_observation, done = args
         frames = next_observation if next_observation.is_cuda else st.get(next_observation, newest_only=True)
-        r_int = cm.compute_bonus(frames, _small(done, dev))
+        r_int = cm.compute_bonus(frames, st.get(torch.as_tensor(done)).to(torch.float32))
         info = RndInfo()
     else:
         raise ValueError(curiosity_type)
@@ -269,17 +280,17 @@ def curiosity_loss(self, curiosity_type, *args):
     st = staging(self)
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions, valid = args
-        inv, fwd = cm.compute_loss(st.get(observation), st.get(next_observation), _onehot(self, actions, dev),
-                                   _small(valid, dev))
+        inv, fwd = cm.compute_loss(st.get(observation), st.get(next_observation), _onehot_staged(self, st, actions, dev),
+                                   st.get(torch.as_tensor(valid)))
         return inv.to("cpu"), fwd.to("cpu")
     if curiosity_type == "ndigo":
         observations, prev_actions, actions, valid = args
-        loss = cm.compute_loss(st.get(observations), _onehot(self, prev_actions, dev), _onehot(self, actions, dev),
-                               _small(valid, dev))
+        loss = cm.compute_loss(st.get(observations), _onehot_staged(self, st, prev_actions, dev),
+                               _onehot_staged(self, st, actions, dev), st.get(torch.as_tensor(valid)))
         return loss.to("cpu")
     if curiosity_type == "rnd":
         next_observation, valid = args
         frames = next_observation if next_observation.is_cuda else st.get(next_observation, newest_only=True)
-        loss = cm.compute_loss(frames, _small(valid, dev))
+        loss = cm.compute_loss(frames, st.get(torch.as_tensor(valid)))
         return loss.to("cpu")
     raise ValueError(curiosity_type)

@@ -104,6 +104,13 @@ def process_returns(self, samples):
                                         [self.kernel_line, self.kernel_gauss]), device=dev)
     host = reward_host.device
     shape = reward_host.shape
-    ret, adv = ret.reshape(shape).to(host), adv.reshape(shape).to(host)
-    valid = valid.reshape(shape).to(host) if valid is not None else None
-    return ret, adv, valid
+    ret_h, adv_h = ret.reshape(shape).to(host), adv.reshape(shape).to(host)
+    valid_h = valid.reshape(shape).to(host) if valid is not None else None
+    if host.type == "cpu" and valid_h is not None and hasattr(self.agent, "curiosity_loss"):
+        # the caller hands ``valid`` straight back to agent.curiosity_loss (ppo.py:93-110): remember its device original
+        try:
+            from ..agents import hooks
+            hooks.staging(self.agent).alias(valid_h, valid.reshape(shape))
+        except Exception:
+            pass
+    return ret_h, adv_h, valid_h

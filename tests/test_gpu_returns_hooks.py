@@ -124,7 +124,7 @@ def test_batch_staging_uploads_once_per_iteration_and_detects_rewrites():
         step = hooks.curiosity_step(agent, "rnd", frames, done)
         loss = hooks.curiosity_loss(agent, "rnd", frames, torch.ones(T, B))
         loss2 = hooks.curiosity_loss(agent, "rnd", frames, torch.ones(T, B))       # second epoch
-        assert st.bytes_uploaded - before == per_batch, it    # newest frames only, once
+        assert per_batch <= st.bytes_uploaded - before < per_batch + 4096, it    # newest frames once (+ the tiny valid masks)
         ref = o.compute_bonus(params, frames, done)
         nz = ref.abs() > 0
         assert float(((step.r_int - ref).abs()[nz] / ref.abs()[nz]).max()) < 1e-2, it
@@ -136,7 +136,7 @@ def test_batch_staging_uploads_once_per_iteration_and_detects_rewrites():
     hooks.prefetch_samples(agent, "rnd", SimpleNamespace(env=Env2(nxt, nxt)))
     before = st.bytes_uploaded
     step = hooks.curiosity_step(agent, "rnd", nxt, done)
-    assert st.bytes_uploaded == before and st.hits >= 1
+    assert st.bytes_uploaded - before < 4096 and st.hits >= 1
     ref = o.compute_bonus(params, nxt, done)
     nz = ref.abs() > 0
     assert float(((step.r_int - ref).abs()[nz] / ref.abs()[nz]).max()) < 1e-2
@@ -154,7 +154,7 @@ def test_icm_hooks_share_one_upload_per_tensor():
     st = hooks.staging(agent)
     hooks.curiosity_step(agent, "icm", obs, nxt, idx)
     inv, fwd = hooks.curiosity_loss(agent, "icm", obs, nxt, idx, torch.ones(T, B))
-    assert st.bytes_uploaded == 2 * obs.numel() and st.hits == 2
+    assert 2 * obs.numel() <= st.bytes_uploaded < 2 * obs.numel() + 4096 and st.hits >= 3      # frames x2, actions
     assert m.reuse_hits == {"full": 1, "miss": 0}
 
 
