@@ -56,6 +56,15 @@ def icm_flops(A, E):
     return 2 * (2 * fwd + bwd)
 
 
+def icm_flops_dedup(A, E):
+    """The same unit when next_obs[t] == obs[t+1] is exploited: ONE encoder pass (forward and backward) per phase."""
+    F = 512
+    resf, inv = 10 * (F + A) * F, 2 * F * F + F * A
+    fwd = ENC_MAC + inv + E * resf
+    bwd = (2 * ENC_MAC - 256 * 32 * 400) + 2 * inv + E * (2 * resf - (F + A) * F)
+    return 2 * (2 * fwd + bwd)
+
+
 def policy_macs(A, enc_mac, conv1_mac, F=512, H=512):
     lstm, heads = (F + A) * 4 * H + H * 4 * H, H * (A + 1)
     fwd = enc_mac + lstm + heads
@@ -63,11 +72,14 @@ def policy_macs(A, enc_mac, conv1_mac, F=512, H=512):
     return fwd, bwd
 
 
-def ppo_icm_flops(A, epochs):
+def ppo_icm_flops(A, epochs, dedup=False):
+    F = 512
     pf, pb = policy_macs(A, ENC_MAC, 256 * 32 * 400)
-    unit = icm_flops(A, 1) // 2
-    icm_fwd = 2 * ENC_MAC + 2 * 512 * 512 + 512 * A + 10 * (512 + A) * 512
-    return 2 * (icm_fwd + epochs * (pf + pb + unit - icm_fwd))
+    resf, inv = 10 * (F + A) * F, 2 * F * F + F * A
+    passes = 1 if dedup else 2
+    icm_fwd = passes * ENC_MAC + inv + resf
+    icm_bwd = passes * (2 * ENC_MAC - 256 * 32 * 400) + 2 * inv + (2 * resf - (F + A) * F)
+    return 2 * (icm_fwd + epochs * (pf + pb + icm_fwd + icm_bwd))
 
 
 def ppo_rnd_flops(A, epochs):
@@ -241,8 +253,13 @@ def synth(dev, seed, T, B, A, frames="u8", next_frames=True, rnn=False):
 def host_samples(d, T, B, rnn=False):
     """The same rollout as pinned host tensors in rlpyt's ``Samples`` layout (what the sampler hands the algorithm)."""
     pin = lambda t: t.cpu().pin_memory()
-    obs = pin(d["obs"])
-    nxt = pin(d["nxt"]) if "nxt" in d else obs
+    if "nxt" in d and d["nxt"].data_ptr() == d["obs"].data_ptr() + d["obs"][0].numel() * d["obs"].element_size():
+        both = torch.empty((T + 1,) + tuple(d["obs"].shape[1:]), dtype=d["obs"].dtype).pin_memory()      # collector layout
+        both[:T].copy_(d["obs"]); both[T].copy_(d["nxt"][T - 1])
+        obs, nxt = both[:T], both[1:]
+    else:
+        obs = pin(d["obs"])
+        nxt = pin(d["nxt"]) if "nxt" in d else obs
     rs = None
     if rnn:
         rs = RnnState(h=pin(d["h0"]).unsqueeze(0), c=pin(d["c0"]).unsqueeze(0))      # [T=1 slice][B,N,H]
@@ -360,7 +377,9 @@ class CuriosityWorkload:
         elif self.kind == "ndigo":
             self.h2d = nbytes(s.env.observation) + small + nbytes(s.agent.prev_action)
         else:
-            self.h2d = nbytes(s.env.observation, s.env.next_observation) + small
+            shifted = s.env.next_observation.data_ptr() == s.env.observation.data_ptr() + s.env.observation[0].numel()
+            self.h2d = (nbytes(s.env.observation) * (self.T + 1) // self.T if shifted else
+                        nbytes(s.env.observation, s.env.next_observation)) + small
         self.d2h = 4 * self.T * self.B * 4 + 8              # r_int, return, advantage, valid + the loss scalars
         self.agent._hooks.prefetch_samples(self.agent, self.kind, s)
 
@@ -396,6 +415,19 @@ class CuriosityWorkload:
 
     def reuse_hits(self):
         return dict(getattr(self.model, "reuse_hits", {}))
+
+    def enable_dedup(self):
+        """Lay the rollout out as the collectors produce it: next_obs[t] IS obs[t+1] (two views of one T+1 buffer)."""
+        if self.kind not in ("icm", "disagreement"):
+            return False
+        d, T = self.d, self.T
+        buf = torch.empty((T + 1,) + tuple(d["obs"].shape[1:]), dtype=torch.uint8, device=self.ctx.dev)
+        buf[:T].copy_(d["obs"])
+        buf[T].copy_(d["nxt"][T - 1])
+        d["obs"], d["nxt"] = buf[:T], buf[1:]
+        self.agent._hooks.staging(self.agent).assume_shifted = True
+        self.flop_dedup = icm_flops_dedup(self.A, 1 if self.kind == "icm" else 4)
+        return True
 
 
 class PpoWorkload:
@@ -444,7 +476,9 @@ class PpoWorkload:
         self.hooks = hooks
         self.samples = host_samples(self.d, self.T, self.B, rnn=True)
         s = self.samples
-        self.h2d = nbytes(s.env.observation, s.env.next_observation, s.agent.action, s.agent.prev_action,
+        shifted = s.env.next_observation.data_ptr() == s.env.observation.data_ptr() + s.env.observation[0].numel()
+        frames = nbytes(s.env.observation) * (self.T + 1) // self.T if shifted else nbytes(s.env.observation, s.env.next_observation)
+        self.h2d = frames + nbytes(s.agent.action, s.agent.prev_action,
                           s.agent.agent_info.dist_info.prob, s.agent.agent_info.value, s.env.done, s.env.reward,
                           s.agent.bootstrap_value, s.agent.agent_info.prev_rnn_state.h, s.agent.agent_info.prev_rnn_state.c)
         self.d2h = 2 * self.T * self.B * 4 + 4 * 12 * self.epochs * self.minibatches
@@ -452,8 +486,12 @@ class PpoWorkload:
 
     def _prefetch(self):
         st = self.hooks.staging(self.agent)
-        st.prefetch(self.samples.env.observation)
-        st.prefetch(self.samples.env.next_observation)
+        if getattr(self, "hooks_staging_shifted", False):
+            st.assume_shifted = True
+            st.prefetch_shifted(self.samples.env.observation, self.samples.env.next_observation)
+        else:
+            st.prefetch(self.samples.env.observation)
+            st.prefetch(self.samples.env.next_observation)
 
     def e2e_step(self):
         from curiosity_baselines_b200.algos.ppo import optimize_agent_from_samples
@@ -470,6 +508,18 @@ class PpoWorkload:
 
     def reuse_hits(self):
         return dict(self.model.curiosity_model.reuse_hits)
+
+    def enable_dedup(self):
+        if self.ctype != "icm":
+            return False
+        d, T = self.d, self.T
+        buf = torch.empty((T + 1,) + tuple(d["obs"].shape[1:]), dtype=torch.uint8, device=self.ctx.dev)
+        buf[:T].copy_(d["obs"])
+        buf[T].copy_(d["nxt"][T - 1])
+        d["obs"], d["nxt"] = buf[:T], buf[1:]
+        self.hooks_staging_shifted = True
+        self.flop_dedup = ppo_icm_flops(self.A, self.epochs, dedup=True)
+        return True
 
 
 def make_workload(kind, ctx, T, B, args):
@@ -640,8 +690,10 @@ def kernel_table(model, T, B, ms_per_step, dev):
     launches per step and its share of the step.  ncu DRAM traffic per launch is attached where a capture of the same
     kernel at the same size is recorded in profiles/r2_kernel_traffic.json."""
     from curiosity_baselines_b200 import _lib as L
+    from curiosity_baselines_b200 import dist as D
     hbm, tf_burst, tf_sust, src = peaks()
     n = T * B
+    reducer, D._reducer = D._reducer, None          # single launches, no data-parallel gradient exchange
     pred, targ = model._chains
     c1, c2, c3, fc, l9, l11 = pred.layers
     bf = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
@@ -693,6 +745,7 @@ def kernel_table(model, T, B, ms_per_step, dev):
         for prm in (p.module.weight, p.module.bias):
             if prm.grad is not None:
                 prm.grad.zero_()
+    D._reducer = reducer
     rows.sort(key=lambda r: -r["share_of_step"])
     top = rows[0]
     frac = top["hbm_frac"] if top["bound"] == "hbm" else top["tensor_frac_of_burst"]
@@ -779,13 +832,32 @@ def run_workload(kind, ctx, args, T, B, steps, warmup, headline):
                       "staging": "pinned host Samples, uploaded once per iteration by hooks.BatchStaging on a side stream; "
                                  "the next batch is staged under this batch's compute"}
         w.samples = None
+    # ---- observation de-duplication (next_obs[t] == obs[t+1], the layout rlpyt's collectors produce): T+1 steps are
+    # uploaded and encoded instead of 2T.  Reported separately; the headline value above encodes both tensors in full.
+    if not args.no_dedup and w.enable_dedup():
+        dms, _ = timed(ctx, w.step, 2, max(3, steps // 2))
+        hbm, tf_burst, tf_sust, src = peaks()
+        dd = {"ms_per_step": dms, "value": n_global / (dms * 1e-3), "unit": "samples/s",
+              "frac_of_sustained_vs_full_flops": w.flop * T * B / (dms * 1e-3) / 1e12 / tf_sust,
+              "frac_of_sustained_vs_dedup_flops": w.flop_dedup * T * B / (dms * 1e-3) / 1e12 / tf_sust,
+              "note": "exact: the encoder runs once over the T+1 distinct steps (icm.py shifted()); not the headline value"}
+        if not args.no_e2e and not (kind.startswith("ppo_") and ctx.world > 2):
+            w.e2e_prepare()
+            k = max(3, min(steps, 8))
+            ems, _ = wall_timed(ctx, w.e2e_step, 2, k)
+            dd["e2e"] = {"value": n_global / (ems * 1e-3), "unit": "samples/s", "ms_per_step": ems,
+                         "h2d_bytes_per_step": w.h2d, "note": "hooks.BatchStaging.get_shifted: T+1 steps cross PCIe"}
+            w.samples = None
+        rec["with_obs_dedup"] = dd
     if headline:
         rec["roofline"] = kernel_table(w.model, T, B, ms, ctx.dev)
     A, flop = w.A, w.flop
     del w
     torch.cuda.empty_cache()
     # ---- strong scaling: global batch fixed, B/N columns per GPU
-    if ctx.world > 1 and not args.no_strong and B % ctx.world == 0:
+    if kind == "disagreement" and ctx.world > 1:
+        rec["scaling"] = "strong"                       # configs[2]: the B=1024 batch is already sharded over the GPUs
+    elif ctx.world > 1 and not args.no_strong and B % ctx.world == 0:
         Bs = B // ctx.world
         ws = make_workload(kind, ctx, T, Bs, args)
         sms, _ = timed(ctx, ws.step, warmup, steps)
@@ -819,6 +891,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reuse", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-dedup", action="store_true")
     args = ap.parse_args()
     ctx = Ctx()
     kind, T = args.workload, args.T
@@ -885,7 +958,7 @@ def main():
         "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head.get("e2e"),
         "roofline": head.get("roofline") or head["step_roofline"], "step_roofline": head["step_roofline"],
         "cpu_baseline": head.get("cpu_baseline"), "with_feature_reuse": head.get("with_feature_reuse"),
-        "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
+        "with_obs_dedup": head.get("with_obs_dedup"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
         {"per_gpu": h2d_gbs, "aggregate": h2d_gbs * ctx.world, "note": "1 GiB pinned copies, all ranks at once"},
         "configs": [dict(finish(k, r), name=k) for k, r in others],
     }

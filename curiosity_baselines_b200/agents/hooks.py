@@ -91,9 +91,15 @@ class BatchStaging:
 
     PIN_MIN_BYTES = 1 << 20
     default_pin_host = False
+    default_assume_shifted = False
 
-    def __init__(self, device, pin_host=None):
+    def __init__(self, device, pin_host=None, assume_shifted=None):
         self.pin_host = self.default_pin_host if pin_host is None else bool(pin_host)
+        # rlpyt's collectors write next_observation[t] and observation[t+1] from the same array
+        # (samplers/parallel/cpu/collectors.py:118,156): with ``assume_shifted`` only T+1 steps cross PCIe (see
+        # get_shifted).  Opt-in (``integration.install(shifted_next_observation=True)``): it relies on that contract
+        # of the sampler, spot-checked on the host.
+        self.assume_shifted = self.default_assume_shifted if assume_shifted is None else bool(assume_shifted)
         self.dev = torch.device(device)
         if self.dev.index is None:
             self.dev = torch.device("cuda", torch.cuda.current_device())
@@ -178,7 +184,7 @@ class BatchStaging:
     def _key(self, t, newest_only, iteration):
         # the iteration is part of the key: a runner that refills ONE host buffer can stage iteration i+1 while
         # iteration i's copy is still being consumed
-        return (t.data_ptr(), tuple(t.shape), t.dtype, bool(newest_only), iteration)
+        return (t.data_ptr(), tuple(t.shape), t.dtype, newest_only, iteration)
 
     def prefetch(self, t, newest_only=False):
         """Stage ``t`` for the NEXT iteration without making the compute stream wait."""
@@ -199,6 +205,68 @@ class BatchStaging:
             self.hits += 1
         torch.cuda.current_stream(self.dev).wait_event(e["event"])
         return e["tensor"]
+
+    @staticmethod
+    def _spot_check_shifted(obs, nxt, words=4096):
+        """next_observation[:-1] == observation[1:] on ``words`` evenly spaced 8-byte words (host side, microseconds).
+        Catches a caller whose two tensors are unrelated; it is NOT a proof -- the proof is the sampler's contract."""
+        import numpy as np
+        if obs.shape != nxt.shape or obs.dtype != nxt.dtype or obs.shape[0] < 2:
+            return obs.shape == nxt.shape and obs.dtype == nxt.dtype
+        a = obs[1:].reshape(-1).view(torch.uint8)
+        b = nxt[:-1].reshape(-1).view(torch.uint8)
+        nw = a.numel() // 8
+        if nw == 0:
+            return bool(torch.equal(a, b))
+        idx = torch.from_numpy(np.linspace(0, nw - 1, num=min(words, nw)).astype(np.int64))
+        return bool(torch.equal(a[: nw * 8].view(torch.int64)[idx], b[: nw * 8].view(torch.int64)[idx]))
+
+    def get_shifted(self, observation, next_observation):
+        """(obs, next_obs) as two views, one time step apart, of ONE device buffer holding the T+1 distinct steps of a
+        rollout: ``observation`` [T,B,...] is uploaded in full, of ``next_observation`` only the last step.  Halves the
+        PCIe traffic of ICM / Disagreement and lets the models run their encoder once (icm.py ``shifted``).  Falls
+        back to two plain uploads when the host-side spot check finds the tensors unrelated."""
+        if observation.is_cuda or next_observation.is_cuda:
+            return self.get(observation), self.get(next_observation)
+        key = self._key(observation, "shifted", self.iteration)
+        fp = (self._fingerprint(observation), self._fingerprint(next_observation[-1]))
+        e = self.entries.get(key)
+        if e is None or e["fp"] != fp:
+            if not (observation.is_contiguous() and next_observation.is_contiguous()
+                    and self._spot_check_shifted(observation, next_observation)):
+                return self.get(observation), self.get(next_observation)
+            e = self._upload_shifted(observation, next_observation, self.iteration, fp)
+            self.entries[key] = e
+        else:
+            self.hits += 1
+        torch.cuda.current_stream(self.dev).wait_event(e["event"])
+        return e["tensor"]
+
+    def prefetch_shifted(self, observation, next_observation):
+        if observation.is_cuda or not self._spot_check_shifted(observation, next_observation):
+            self.prefetch(observation); self.prefetch(next_observation)
+            return
+        fp = (self._fingerprint(observation), self._fingerprint(next_observation[-1]))
+        self.entries[self._key(observation, "shifted", self.iteration + 1)] = \
+            self._upload_shifted(observation, next_observation, self.iteration + 1, fp)
+
+    def _upload_shifted(self, observation, next_observation, iteration, fp):
+        T = observation.shape[0]
+        cur = torch.cuda.current_stream(self.dev)
+        buf = torch.empty((T + 1,) + tuple(observation.shape[1:]), dtype=observation.dtype, device=self.dev)
+        self.stream.wait_stream(cur)
+        p1, p2 = self._pin(observation), self._pin(next_observation)
+        with torch.cuda.stream(self.stream):
+            buf[:T].copy_(observation, non_blocking=p1)
+            buf[T].copy_(next_observation[T - 1], non_blocking=p2)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        buf.record_stream(self.stream)
+        self.generation += 1
+        self.bytes_uploaded += buf.numel() * buf.element_size()
+        obs, nxt = buf[:T], buf[1:]
+        obs._b200_staged = nxt._b200_staged = self.generation
+        return dict(tensor=(obs, nxt), event=ev, fp=fp, iteration=iteration, generation=self.generation, buffer=buf)
 
     def alias(self, host_tensor, dev_tensor):
         """Remember that ``host_tensor`` is a read-back of ``dev_tensor`` (process_returns hands ``valid`` back to the
@@ -238,10 +306,19 @@ def prefetch_samples(agent, curiosity_type, samples):
     if curiosity_type == "rnd":
         st.prefetch(samples.env.next_observation, newest_only=True)
     elif curiosity_type in ("icm", "disagreement"):
-        st.prefetch(samples.env.observation)
-        st.prefetch(samples.env.next_observation)
+        if st.assume_shifted:
+            st.prefetch_shifted(samples.env.observation, samples.env.next_observation)
+        else:
+            st.prefetch(samples.env.observation)
+            st.prefetch(samples.env.next_observation)
     elif curiosity_type == "ndigo":
         st.prefetch(samples.env.observation)
+
+
+def _frames_pair(st, observation, next_observation):
+    if st.assume_shifted:
+        return st.get_shifted(observation, next_observation)
+    return st.get(observation), st.get(next_observation)
 
 
 def _onehot_staged(agent, st, idx, dev):
@@ -257,7 +334,8 @@ def curiosity_step(self, curiosity_type, *args):
     st.new_iteration()                      # the bonus is the first consumer of an iteration's samples
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions = args
-        r_int = cm.compute_bonus(st.get(observation), st.get(next_observation), _onehot_staged(self, st, actions, dev))
+        obs_d, nxt_d = _frames_pair(st, observation, next_observation)
+        r_int = cm.compute_bonus(obs_d, nxt_d, _onehot_staged(self, st, actions, dev))
         info = IcmInfo()
     elif curiosity_type == "ndigo":
         observation, prev_actions, actions = args
@@ -280,8 +358,8 @@ def curiosity_loss(self, curiosity_type, *args):
     st = staging(self)
     if curiosity_type in ("icm", "disagreement"):
         observation, next_observation, actions, valid = args
-        inv, fwd = cm.compute_loss(st.get(observation), st.get(next_observation), _onehot_staged(self, st, actions, dev),
-                                   st.get(torch.as_tensor(valid)))
+        obs_d, nxt_d = _frames_pair(st, observation, next_observation)
+        inv, fwd = cm.compute_loss(obs_d, nxt_d, _onehot_staged(self, st, actions, dev), st.get(torch.as_tensor(valid)))
         return inv.to("cpu"), fwd.to("cpu")
     if curiosity_type == "ndigo":
         observations, prev_actions, actions, valid = args

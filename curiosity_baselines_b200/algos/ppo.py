@@ -96,7 +96,8 @@ class PPO:
         cm = getattr(m, "curiosity_model", None)
         twin = None
         if (self.twin_conv1 and self.curiosity_type in ("icm", "disagreement") and curiosity_inputs is not None
-                and curiosity_inputs[0] is observation):
+                and curiosity_inputs[0] is observation
+                and not (cm.dedup_shifted_observations and cm.shifted(curiosity_inputs[0], curiosity_inputs[1]))):
             twin = cm.twin_first_conv()
         s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True, twin=twin)
         if s["twin_out"] is not None:
@@ -230,8 +231,11 @@ def stage_samples(agent, curiosity_type, samples, st=None):
     env, ag = samples.env, samples.agent
     T, B = env.reward.shape[:2]
     f32 = lambda t: torch.as_tensor(t).to(dev, torch.float32, non_blocking=True)
-    obs = st.get(env.observation)
-    nxt = st.get(env.next_observation) if curiosity_type in ("icm", "disagreement", "rnd") else obs
+    if curiosity_type in ("icm", "disagreement") and st.assume_shifted:
+        obs, nxt = st.get_shifted(env.observation, env.next_observation)
+    else:
+        obs = st.get(env.observation)
+        nxt = st.get(env.next_observation) if curiosity_type in ("icm", "disagreement", "rnd") else obs
     rnn = getattr(ag.agent_info, "prev_rnn_state", None)
     init = None
     if rnn is not None:

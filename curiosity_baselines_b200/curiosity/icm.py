@@ -287,6 +287,28 @@ class _IcmBase(nn.Module):
         ex["chain"].backward(enc["x"], enc["acts"], dphi_bf16.contiguous(), n, in_dtype=enc["dtype"],
                              strides=enc["strides"], accumulate=accumulate, final=final)
 
+    # ------------------------------------------------------------------ observation de-duplication
+    # rlpyt's collectors write next_observation[t] and observation[t+1] from the same array
+    # (samplers/parallel/cpu/collectors.py:118,156), so a rollout holds T+1 distinct frame stacks, not 2T.  When the two
+    # arguments are PROVABLY that -- views one time step apart into one device buffer of T+1 steps, which is how
+    # agents/hooks.BatchStaging.get_shifted lays them out -- the encoder runs once over the T+1 steps and phi(obs) /
+    # phi(next_obs) are row ranges of its output; the backward pass adds the two feature gradients and runs once.
+    # Exact (same kernels, same operands per frame); roughly 40 % fewer FLOPs per ICM step.
+    dedup_shifted_observations = True
+
+    @staticmethod
+    def shifted(observations, next_observations):
+        """True iff next_observations[t] aliases observations[t+1] for every t (structural, no content check)."""
+        a, b = observations, next_observations
+        if not (a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.uint8 and a.dim() == 5 and a.shape == b.shape
+                and a.is_contiguous() and b.is_contiguous() and a.shape[0] >= 1):
+            return False
+        step = a[0].numel()
+        if b.data_ptr() != a.data_ptr() + step:
+            return False
+        st = a.untyped_storage()
+        return st.data_ptr() == b.untyped_storage().data_ptr() and st.nbytes() >= a.storage_offset() + (a.shape[0] + 1) * step
+
     def _features(self, observations, next_observations, actions, first_out_obs=None):
         """Shared by bonus and loss: (T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action[n,A])."""
         self._build()
@@ -295,6 +317,14 @@ class _IcmBase(nn.Module):
         T, B = observations.shape[:2]
         n = T * B
         shp = observations.shape[2:]
+        if self.dedup_shifted_observations and self.shifted(observations, next_observations):
+            n1 = (T + 1) * B
+            allf = torch.as_strided(observations, (T + 1, B) + tuple(shp), observations.stride(),
+                                    observations.storage_offset())
+            enc, phi_f, phi_b = self._encode(allf.reshape(n1, *shp), n1)
+            action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
+            self.dedup_hits = getattr(self, "dedup_hits", 0) + 1
+            return T, B, n, dict(shared=enc, n1=n1), None, phi_b[:n], phi_f[B:], phi_b[B:], action
         enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n, first_out=first_out_obs)
         enc2, phi2_f, phi2_b = self._encode(next_observations.reshape(n, *shp), n)
         action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
@@ -429,8 +459,15 @@ class _IcmBase(nn.Module):
             dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
         ex["inv0"].wgrad(cat, dh, n)
         dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
-        self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False, final=False)
-        self._encode_backward(enc2, dcat[:, F:].contiguous(), n, accumulate=True)
+        if enc2 is None:            # one encoder pass over the T+1 distinct steps: d phi[t] = d phi1[t] + d phi2[t-1]
+            n1 = enc1["n1"]
+            dall = torch.zeros(n1, F, dtype=torch.bfloat16, device=dev)
+            dall[:n] = dcat[:, :F]
+            dall[n1 - n:] += dcat[:, F:]
+            self._encode_backward(enc1["shared"], dall, n1, accumulate=False)
+        else:
+            self._encode_backward(enc1, dcat[:, :F].contiguous(), n, accumulate=False, final=False)
+            self._encode_backward(enc2, dcat[:, F:].contiguous(), n, accumulate=True)
         if inplace:
             return losses[0], losses[1], None, None
         g_inv, g_fwd = [], []

@@ -38,9 +38,11 @@ def uninstall():
     RND.default_reuse_features = ICM.default_reuse_features = Disagreement.default_reuse_features = False
     from .agents import hooks
     hooks.BatchStaging.default_pin_host = False
+    hooks.BatchStaging.default_assume_shifted = False
 
 
-def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=False, algo=False):
+def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=False, algo=False,
+            shifted_next_observation=False):
     """Patch rlpyt in place; returns the list of patched attributes.  ``strict=False`` skips modules
     that fail to import (e.g. optional dependencies missing).  ``reuse_features``: RND models built afterwards reuse
     a batch's features between compute_bonus and compute_loss when the frames are verified equal (the reference
@@ -56,6 +58,9 @@ def install(strict=True, reuse_features=True, policy=False, pin_sampler_buffers=
     # rlpyt allocates its sample buffers once per run as numpy shared memory (samplers/buffer.py): page-locking them in
     # place lets the hooks' uploads run at PCIe speed and asynchronously (agents/hooks.BatchStaging)
     hooks.BatchStaging.default_pin_host = bool(pin_sampler_buffers)
+    # rlpyt's collectors fill next_observation[t] and observation[t+1] from the same array (cpu/collectors.py:118,156):
+    # upload T+1 steps instead of 2T and run the ICM / Disagreement encoder once over them (opt-in: sampler contract)
+    hooks.BatchStaging.default_assume_shifted = bool(shifted_next_observation)
     RND.default_reuse_features = bool(reuse_features)
     ICM.default_reuse_features = Disagreement.default_reuse_features = bool(reuse_features)
 

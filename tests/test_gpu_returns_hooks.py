@@ -179,3 +179,69 @@ def test_refilled_persistent_buffer_is_not_served_stale():
     m2.compute_bonus(a.to(DEV), done)                   # same statistics as m
     fresh = m2.compute_loss(b.to(DEV), ones, ones)
     assert float(stale_or_not) == float(fresh) and m.reuse_hits["miss"] == 1
+
+
+def _shifted_rollout(seed, T, B):
+    frames = R.make_frames(seed, T + 1, B)
+    return frames, frames[:T].clone(), frames[1:].clone()       # what a collector writes: next_obs[t] == obs[t+1]
+
+
+@pytest.mark.parametrize("cls_name", ["icm", "disagreement"])
+def test_shifted_views_run_the_encoder_once_and_match_two_passes(cls_name):
+    """Observation de-duplication: when next_observations is provably observations shifted by one
+    step (two views of one T+1 buffer) the encoder runs once over T+1 steps.  Bonus and losses equal the two-pass
+    result bit for bit, gradients up to summation order and one bf16 add."""
+    from curiosity_baselines_b200.curiosity.icm import Disagreement
+    T, B, A, seed = 6, 5, 4, 61
+    cls = ICM if cls_name == "icm" else Disagreement
+    shapes = R.icm_shapes(A, "idf_burda") if cls_name == "icm" else R.disagreement_shapes(A, "idf_burda")
+    params = R.make_params(shapes, seed)
+    frames, _, _ = _shifted_rollout(seed + 1, T, B)
+    buf = frames.to(DEV)
+    obs, nxt = buf[:T], buf[1:]
+    act = R.onehot(R.make_actions(seed + 3, T, B, A), A).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 4, T, B, frac=0.3)).to(DEV)
+
+    def run(dedup):
+        m = cls(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+        m.load_state_dict(params)
+        m.dedup_shifted_observations = dedup
+        assert m.shifted(obs, nxt) and not m.shifted(obs, nxt.clone())
+        bonus = m.compute_bonus(obs, nxt, act)
+        inv, fwd = m.compute_loss(obs, nxt, act, valid, **({} if cls_name == "icm" else dict(dropout_masks=None)))
+        (inv + fwd).backward()
+        return m, bonus, inv.detach(), fwd.detach(), {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    m0, b0, i0, f0, g0 = run(False)
+    m1, b1, i1, f1, g1 = run(True)
+    assert getattr(m0, "dedup_hits", 0) == 0 and m1.dedup_hits == 2
+    assert torch.equal(b0, b1) and torch.equal(i0, i1) and torch.equal(f0, f1)
+    for k in g0:
+        a, b = g0[k].double().flatten(), g1[k].double().flatten()
+        assert float(a @ b / (a.norm() * b.norm())) > 0.9999 and abs(float(b.norm() / a.norm()) - 1) < 5e-3, k
+
+
+def test_hooks_upload_t_plus_one_steps_when_the_sampler_contract_is_assumed():
+    T, B, A, seed = 5, 3, 4, 71
+    m = ICM(image_shape=(4, 84, 84), action_size=A, feature_encoding="idf_burda").to(DEV)
+    params = R.make_params(R.icm_shapes(A, "idf_burda"), seed)
+    m.load_state_dict(params)
+    agent = _agent(m, A)
+    _, obs, nxt = _shifted_rollout(seed + 1, T, B)
+    idx = R.make_actions(seed + 3, T, B, A)
+    st = hooks.staging(agent)
+    st.assume_shifted = True
+    step = hooks.curiosity_step(agent, "icm", obs, nxt, idx)
+    inv, fwd = hooks.curiosity_loss(agent, "icm", obs, nxt, idx, torch.ones(T, B))
+    per_step = B * 4 * 84 * 84
+    assert (T + 1) * per_step <= st.bytes_uploaded < (T + 1) * per_step + 4096          # not 2T steps
+    assert m.dedup_hits == 2
+    ref = O.icm_bonus(params, obs, nxt, R.onehot(idx, A), "idf_burda", 1.0)
+    assert float(((step.r_int - ref).abs() / ref.abs()).max()) < 1e-2
+    inv_r, fwd_r = O.icm_loss(params, obs, nxt, R.onehot(idx, A), torch.ones(T, B), "idf_burda", 0.2)
+    assert abs(float(inv) - float(inv_r)) / float(inv_r) < 1e-2 and abs(float(fwd) - float(fwd_r)) / float(fwd_r) < 1e-2
+    # unrelated tensors: the host-side spot check refuses, two plain uploads, two encoder passes
+    other = R.make_frames(seed + 9, T, B)
+    before, hits = st.bytes_uploaded, m.dedup_hits
+    hooks.curiosity_step(agent, "icm", obs, other, idx)
+    assert st.bytes_uploaded - before >= 2 * T * per_step and m.dedup_hits == hits
