@@ -79,6 +79,8 @@ _SIGS = {
     "cb_ensemble_variance": [_P, _I, _F, _P, _L, _I, _P],
     "cb_cross_entropy": [_P, _P, _P, _P, _P, _L, _I, _P],
     "cb_bce_logits": [_P, _P, _F, _P, _F, _P, _L, _I, _P],
+    "cb_bce_horizons": [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), _P, _F, _P, _P],
+    "cb_action_windows": [_P, _I, _I, _I, _I, _P, _P, _P],
     "cb_weighted_mean": [_P, _P, _P, _L, _P],
     "cb_loss_coef": [_P, _P, _F, _P, _P, _L, _P],
     "cb_dot": [_P, _P, _P, _L, _P],

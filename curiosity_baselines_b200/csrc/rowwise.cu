@@ -132,6 +132,66 @@ __global__ void bce_logits_kernel(const float* __restrict__ z, const float* __re
     if (lane == 0 && row) row[r] = acc * scale;
 }
 
+// All of NDIGO's horizons in one pass (ndigo.py:154-163, 194-206, 234-268).  logits [n, G*fp] holds predictor g+1's
+// outputs in columns [g*fp, g*fp + d) (the grouped-GEMM layout, fp = d rounded up to the tile); row (t,b) of predictor
+// k = g+1 is scored against obs[t+k, b]; rows with t + k >= T belong to no pair and contribute nothing.
+//   row_loss[g][t*B+b] = row_scale_g * sum_f bce      dz[n, G*fp] (bf16) = grad_scale_g * (sigmoid - target), 0 elsewhere
+// with row_scale_g = 1/d (bonus) or 1/((T-k)*B*d) (loss, so that the sum over rows is the mean over the pairs),
+// grad_scale_g = upstream / ((T-k)*B*d).
+struct HorizonOffsets { int off[16]; };
+__global__ void bce_horizons_kernel(const float* __restrict__ z, const float* __restrict__ obs, int T, int B, int d,
+                                    int G, int fp, int mean_over_pairs, float* __restrict__ row_loss, float upstream,
+                                    __nv_bfloat16* __restrict__ dz, HorizonOffsets ho) {
+    const int64_t n = (int64_t)T * B;
+    const int64_t r = (int64_t)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(r / B), b = (int)(r - (int64_t)t * B);
+    for (int g = 0; g < G; ++g) {
+        const int k = g + 1;
+        const bool live = t + k < T;
+        const float pairs = (float)(T - k) * (float)B * (float)d;
+        const float rs = mean_over_pairs ? 1.f / pairs : 1.f / (float)d, gs = upstream / pairs;
+        const float* zr = z + (r * G + g) * fp;
+        const float* y = obs + ((int64_t)(t + ho.off[g]) * B + b) * d;
+        __nv_bfloat16* dr = dz ? dz + (r * G + g) * fp : nullptr;
+        float acc = 0.f;
+        for (int j = lane; j < fp; j += 32) {
+            float grad = 0.f;
+            if (live && j < d) {
+                const float zz = zr[j], yy = y[j];
+                const float p = 1.f / (1.f + expf(-zz));
+                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+                acc -= yy * lp + (1.f - yy) * lq;
+                grad = gs * (p - yy);
+            }
+            if (dr) dr[j] = cb::f2bf(grad);
+        }
+        acc = cb::warp_sum(acc);
+        if (lane == 0 && row_loss) row_loss[(int64_t)g * n + r] = live ? acc * rs : 0.f;
+    }
+}
+
+// Sliding action windows of NDIGO (ndigo.py:154-163, 236-240: the reference builds them with a Python double loop):
+// win[(t,b), j*A + a] = onehot[t+j, b, a] for j < W and t + j < T, zero otherwise and in the padding columns.
+// Written twice: bf16 [n, 64] (the extra k-block of the grouped first layer) and fp32 [n, W*A] (side weight gradient).
+__global__ void action_windows_kernel(const float* __restrict__ onehot, int T, int B, int A, int W,
+                                      __nv_bfloat16* __restrict__ win_bf16, float* __restrict__ win_f32) {
+    const int64_t n = (int64_t)T * B;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 64) return;
+    const int64_t r = idx >> 6;
+    const int c = (int)(idx & 63);
+    const int t = (int)(r / B), b = (int)(r - (int64_t)t * B);
+    float v = 0.f;
+    if (c < W * A) {
+        const int j = c / A, a = c - j * A;
+        if (t + j < T) v = __ldg(onehot + ((int64_t)(t + j) * B + b) * A + a);
+        if (win_f32) win_f32[r * (W * A) + c] = v;
+    }
+    win_bf16[idx] = cb::f2bf(v);
+}
+
 // one thread per row; A (actions) is small
 __global__ void cross_entropy_kernel(const float* __restrict__ logits, const float* __restrict__ onehot,
                                      const float* __restrict__ coef, float* __restrict__ loss,
@@ -365,6 +425,37 @@ extern "C" int cb_bce_logits(const float* logits, const float* target, float sca
     CB_REQUIRE(logits && target && (row_loss || dlogits) && m >= 1 && f >= 1, CB_E_ARG, "cb_bce_logits: bad argument");
     bce_logits_kernel<<<(unsigned)cb::ceil_div<int64_t>(m, kRowThreads / 32), kRowThreads, 0, cb::as_stream(stream)>>>(
         logits, target, scale, row_loss, gscale, dlogits, m, f);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_bce_horizons(const float* logits, const float* obs, int32_t T, int32_t B, int32_t d, int32_t groups,
+                               int32_t fp, int32_t mean_over_pairs, const int32_t* target_offset_host, float* row_loss,
+                               float upstream, void* dlogits_bf16, void* stream) {
+    CB_REQUIRE(logits && obs && (row_loss || dlogits_bf16) && T >= 1 && B >= 1 && d >= 1 && groups >= 1 && groups <= 16 &&
+               fp >= d, CB_E_ARG, "cb_bce_horizons: bad argument");
+    HorizonOffsets ho;
+    for (int g = 0; g < 16; ++g) ho.off[g] = g + 1;
+    if (target_offset_host)
+        for (int g = 0; g < groups; ++g) {
+            CB_REQUIRE(target_offset_host[g] >= 0 && target_offset_host[g] <= g + 1, CB_E_ARG,
+                       "cb_bce_horizons: target offset of predictor k must be in [0, k]");
+            ho.off[g] = target_offset_host[g];
+        }
+    const int64_t n = (int64_t)T * B;
+    bce_horizons_kernel<<<(unsigned)cb::ceil_div<int64_t>(n, kRowThreads / 32), kRowThreads, 0, cb::as_stream(stream)>>>(
+        logits, obs, T, B, d, groups, fp, mean_over_pairs, row_loss, upstream, (__nv_bfloat16*)dlogits_bf16, ho);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_action_windows(const float* onehot, int32_t T, int32_t B, int32_t A, int32_t W, void* win_bf16,
+                                 float* win_f32, void* stream) {
+    CB_REQUIRE(onehot && win_bf16 && T >= 1 && B >= 1 && A >= 1 && W >= 1 && W * A <= 64, CB_E_ARG,
+               "cb_action_windows: bad argument (W*A must be <= 64)");
+    const int64_t total = (int64_t)T * B * 64;
+    action_windows_kernel<<<(unsigned)cb::ceil_div<int64_t>(total, 256), 256, 0, cb::as_stream(stream)>>>(
+        onehot, T, B, A, W, (__nv_bfloat16*)win_bf16, win_f32);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -405,8 +405,9 @@ bool umma_supports_grouped(int groups, int k, int f) {
 int umma_grouped_fwd(int n, int groups, int k, int f, int x_shared, const void* x, const void* w_all, int act,
                      const cb_epilogue* e, cudaStream_t s) {
     CB_REQUIRE(x && w_all && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_grouped_linear_fwd: null pointer");
-    CB_REQUIRE(umma_supports_grouped(groups, k, f) && e->side_dim <= 16 && !e->norm_mean, CB_E_ARG,
-               "cb_grouped_linear_fwd: unsupported shape or device");
+    // (side inputs folded in as one more k-block -- side_bf16 -- may be up to 64 wide; the epilogue path keeps 16)
+    CB_REQUIRE(umma_supports_grouped(groups, k, f) && (e->side_dim <= 16 || (e->side_bf16 && e->side_dim <= 64)) &&
+               !e->norm_mean, CB_E_ARG, "cb_grouped_linear_fwd: unsupported shape or device");
     Plan pl{};
     pl.bn = pick_bn(f, &pl.mt, n);
     Geo g{n, 1, 1, x_shared ? k : groups * k, 1, 1, 1, 0, 1, 1};

@@ -9,6 +9,8 @@ first Linear instead of a concatenation) and the BCE all run in libcuriosity_b20
 ``torch.nn.GRU`` parameter holder that is never called.  The pieces are tied together through
 ``torch.autograd.Function`` wrappers.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
@@ -137,6 +139,149 @@ class _PredictorFn(torch.autograd.Function):
         return (None, dx.float(), None) + tuple(grads)
 
 
+class _HorizonStack:
+    """NDIGO's ten multi-horizon predictors (ndigo.py:19-34, 82-111) as TWO grouped layers over all (t,b) rows at once
+    (SURVEY 8f rank 3): the reference -- and our round-1 code -- looped over k in Python, building each action window
+    with torch.cat and launching every predictor separately (~25 launches per horizon).
+
+      layer 1   h[n, G*64]   = relu([belief | window10] W1_all^T + b1)     ONE grouped tcgen05 launch: every predictor
+                reads the SAME belief rows (x_shared) and the same 10-step action window as its extra k-block; predictor
+                k's weights for the window steps j >= k are zero, which is exactly its k-step window
+      layer 2   z[n, G*FP]   = h_g W2_g^T + b2_g                          ONE grouped launch (block diagonal)
+      loss      cb_bce_horizons: predictor k's row (t,b) against obs[t+k,b], rows with t+k >= T masked, every horizon
+                in one pass; it also writes d z in the bf16 operand layout of the backward GEMMs
+    Backward: grouped wgrad / dgrad of layer 2, then layer 1's weight gradient and d belief as PLAIN GEMMs -- the
+    contraction over the stacked G*64 outputs is the sum over horizons."""
+
+    F1, WIN = 64, 10
+
+    def __init__(self, model):
+        self.m = model
+        self.A, self.Gs, self.D = model.action_size, model.gru_size, model.obs_dim
+        self.FP = (self.D + 63) // 64 * 64
+        self.supported = (self.Gs % 64 == 0 and self.WIN * self.A <= 64 and LY.get_engine() != L.ENGINE_SIMT)
+        self._key = None
+
+    def _params(self, k):
+        seq = getattr(self.m, f"forward_model_{k}").model
+        return seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias
+
+    def prepare(self):
+        key = tuple((p._version, p.data_ptr()) for k in range(1, 11) for p in self._params(k))
+        if key == self._key:
+            return
+        dev = self.m.gru.weight_ih_l0.device
+        G, F1, Gs, D, FP, A = 10, self.F1, self.Gs, self.D, self.FP, self.A
+        w1 = torch.zeros(G * F1, Gs + 64, dtype=torch.float32, device=dev)
+        b1 = torch.zeros(G * F1, dtype=torch.float32, device=dev)
+        w2 = torch.zeros(G * FP, F1, dtype=torch.float32, device=dev)
+        b2 = torch.zeros(G * FP, dtype=torch.float32, device=dev)
+        for g in range(G):
+            a, ab, c, cb_ = self._params(g + 1)
+            w1[g * F1:(g + 1) * F1, : Gs + (g + 1) * A] = a.detach()
+            b1[g * F1:(g + 1) * F1] = ab.detach()
+            w2[g * FP: g * FP + D] = c.detach()
+            b2[g * FP: g * FP + D] = cb_.detach()
+        self.w1 = w1.to(torch.bfloat16).contiguous()                          # [G*64, Gs + 64]
+        self.side_w = w1[:, Gs: Gs + self.WIN * A].contiguous()               # fp32 [G*64, 50] (only read on fallback paths)
+        self.b1, self.b2 = b1, b2
+        self.w2 = w2.to(torch.bfloat16).contiguous()                          # [G*FP, 64]
+        self.w2_t = torch.cat([w2[g * FP:(g + 1) * FP].t() for g in range(G)]).to(torch.bfloat16).contiguous()   # [G*64, FP]
+        self._w1_t = {}
+        self._w1_f32 = w1
+        self._key = key
+
+    def w1_t(self, G):
+        if G not in self._w1_t:      # [Gs, G*64]: operand of the plain d-belief GEMM
+            self._w1_t[G] = self._w1_f32[: G * self.F1, : self.Gs].t().to(torch.bfloat16).contiguous()
+        return self._w1_t[G]
+
+    def forward(self, belief_bf16, onehot_actions, T, B, G):
+        """-> (window fp32 [n, 50], window bf16 [n,64], h [n, G*64] bf16, logits [n, G*FP] fp32)."""
+        self.prepare()
+        n, dev, st = T * B, belief_bf16.device, L.stream()
+        A, F1, FP = self.A, self.F1, self.FP
+        win_b = torch.empty(n, 64, dtype=torch.bfloat16, device=dev)
+        win_f = torch.empty(n, self.WIN * A, dtype=torch.float32, device=dev)
+        L.call("cb_action_windows", L.ptr(onehot_actions), T, B, A, self.WIN, L.ptr(win_b), L.ptr(win_f), st)
+        h = torch.empty(n, G * F1, dtype=torch.bfloat16, device=dev)
+        e = L.Epilogue()
+        e.bias = L.ptr(self.b1)
+        e.side, e.side_w, e.side_dim, e.side_bf16 = L.ptr(win_f), L.ptr(self.side_w), self.WIN * A, L.ptr(win_b)
+        e.out_bf16 = L.ptr(h)
+        L.call("cb_grouped_linear_fwd", n, G, self.Gs, F1, 1, L.ptr(belief_bf16), L.ptr(self.w1), L.ACT_RELU, C.byref(e), st)
+        z = torch.empty(n, G * FP, dtype=torch.float32, device=dev)
+        e2 = L.Epilogue()
+        e2.bias, e2.out_f32 = L.ptr(self.b2), L.ptr(z)
+        L.call("cb_grouped_linear_fwd", n, G, F1, FP, 0, L.ptr(h), L.ptr(self.w2), L.ACT_NONE, C.byref(e2), st)
+        return win_f, win_b, h, z
+
+    def backward(self, belief_bf16, win_f, h, dz, T, B, G):
+        """dz bf16 [n, G*FP] -> (d belief bf16 [n, Gs], per-predictor parameter gradients {k: (dW1, db1, dW2, db2)})."""
+        n, dev, st = T * B, h.device, L.stream()
+        A, F1, FP, Gs, D = self.A, self.F1, self.FP, self.Gs, self.D
+        dw2 = torch.empty(G * FP, F1, dtype=torch.float32, device=dev)
+        db2 = torch.empty(G * FP, dtype=torch.float32, device=dev)
+        L.call("cb_grouped_linear_wgrad", n, G, F1, FP, 0, L.ptr(h), L.ptr(dz), L.ptr(dw2), L.ptr(db2), 0.0, st)
+        dh = torch.empty(n, G * F1, dtype=torch.bfloat16, device=dev)
+        L.call("cb_grouped_linear_dgrad", n, G, F1, FP, L.ptr(dz), L.ptr(self.w2_t), L.ptr(h), L.ACT_RELU, None, L.ptr(dh), st)
+        # layer 1: the stacked outputs make both remaining products plain GEMMs
+        d = L.ConvDesc()
+        d.n, d.in_h, d.in_w, d.in_c = n, 1, 1, Gs
+        d.k_h = d.k_w = d.stride = 1
+        d.out_h = d.out_w = 1
+        d.out_c = G * F1
+        d.in_dtype = L.BF16
+        d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = Gs, Gs, Gs, 1
+        d.engine = LY.get_engine()
+        dw1 = torch.empty(G * F1, Gs, dtype=torch.float32, device=dev)
+        db1 = torch.empty(G * F1, dtype=torch.float32, device=dev)
+        L.call("cb_conv_wgrad", C.byref(d), L.ptr(belief_bf16), L.ptr(dh), None, None, L.ptr(dw1), L.ptr(db1), 0.0, st)
+        dsw = torch.empty(G * F1, self.WIN * A, dtype=torch.float32, device=dev)
+        L.call("cb_side_wgrad", L.ptr(dh), L.ptr(win_f), L.ptr(dsw), n, G * F1, self.WIN * A, 0.0, st)
+        dbel = torch.empty(n, Gs, dtype=torch.bfloat16, device=dev)
+        L.call("cb_conv_dgrad", C.byref(d), L.ptr(dh), L.ptr(self.w1_t(G)), None, L.ACT_NONE, None, L.ptr(dbel), st)
+        grads = {}
+        for g in range(G):
+            k = g + 1
+            grads[k] = (torch.cat([dw1[g * F1:(g + 1) * F1], dsw[g * F1:(g + 1) * F1, : k * A]], 1),
+                        db1[g * F1:(g + 1) * F1], dw2[g * FP: g * FP + D], db2[g * FP: g * FP + D])
+        return dbel, grads
+
+
+class _HorizonLossFn(torch.autograd.Function):
+    """sum_{k <= K} mean BCE(sigmoid(M_k(belief[:T-k], window_k)), obs[k:])   (ndigo.py:234-268) on the grouped stack."""
+
+    @staticmethod
+    def forward(ctx, model, belief, onehot_actions, obs_flat, K, *params):
+        hs = model._horizons
+        T, B = onehot_actions.shape[:2]
+        n = T * B
+        G = (K + 1) // 2 * 2                               # layer 1's weight gradient tiles 128 stacked outputs
+        xb = belief.reshape(n, -1).to(torch.bfloat16).contiguous()
+        win_f, win_b, h, z = hs.forward(xb, onehot_actions.contiguous(), T, B, G)
+        rows = torch.empty(G, n, dtype=torch.float32, device=xb.device)
+        need = any(ctx.needs_input_grad)
+        dz = torch.empty(n, G * hs.FP, dtype=torch.bfloat16, device=xb.device) if need else None
+        L.call("cb_bce_horizons", L.ptr(z), L.ptr(obs_flat), T, B, hs.D, G, hs.FP, 1, None, L.ptr(rows), 1.0, L.ptr(dz),
+               L.stream())
+        if need and G > K:
+            dz.view(n, G, hs.FP)[:, K:].zero_()            # the padding horizon is not part of the loss
+        ctx.saved = (xb, win_f, h, dz, T, B, G, K)
+        ctx.model = model
+        return rows[:K].sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, win_f, h, dz, T, B, G, K = ctx.saved
+        hs = ctx.model._horizons
+        dbel, grads = hs.backward(xb, win_f, h, dz, T, B, G)
+        out = []
+        for k in range(1, 11):
+            out += [t * g for t in grads[k]] if k <= K else [None] * 4
+        return (None, (dbel.float() * g).reshape(T, B, -1), None, None, None) + tuple(out)
+
+
 class _BceMeanFn(torch.autograd.Function):
     """mean over all elements of binary_cross_entropy(sigmoid(logits), target)."""
 
@@ -197,6 +342,7 @@ class NDIGO(nn.Module):
                 else:
                     preds[k] = (linear_layer(seq[0], "relu", side_dim=k * self.action_size), linear_layer(seq[2], "none"))
             g = self.gru
+            self._horizons = _HorizonStack(self)
             self._exec = dict(dev=dev, chain=chain, perm=None if perm is None else perm.to(dev), preds=preds,
                               gru_ih=linear_layer(LY.ParamPair(g.weight_ih_l0, g.bias_ih_l0), "none", self.action_size),
                               gru_hh=linear_layer(LY.ParamPair(g.weight_hh_l0, g.bias_hh_l0), "none"))
@@ -241,8 +387,21 @@ class NDIGO(nn.Module):
         flat = observations.to(dev, torch.float32).reshape(T, B, -1)
 
         # ndigo.py:194-206: M_H(bel[:T-H]) vs obs[H:], M_{H+1}(bel[:T-H-1]) vs obs[H:-1]
-        loss_t = _row_losses(self, belief, actions, H, flat[H:], dev, B)
-        loss_tm1 = _row_losses(self, belief, actions, H + 1, flat[H:-1], dev, B)
+        hs = self._horizons
+        if hs.supported and T > H + 1:
+            n, G = T * B, (H + 2) // 2 * 2
+            xb = belief.reshape(n, -1).to(torch.bfloat16).contiguous()
+            _, _, _, z = hs.forward(xb, actions.reshape(T, B, -1).contiguous(), T, B, G)
+            rows = torch.empty(G, n, dtype=torch.float32, device=dev)
+            # predictor H+1 starts one step earlier and is scored against the SAME frame as predictor H (ndigo.py:199-206)
+            offs = (C.c_int32 * G)(*[H if g == H else g + 1 for g in range(G)])
+            L.call("cb_bce_horizons", L.ptr(z), L.ptr(flat.contiguous()), T, B, hs.D, G, hs.FP, 0, offs, L.ptr(rows), 0.0,
+                   None, L.stream())
+            rows = rows.view(G, T, B)
+            loss_t, loss_tm1 = rows[H - 1, : T - H], rows[H, : T - H - 1]
+        else:
+            loss_t = _row_losses(self, belief, actions, H, flat[H:], dev, B)
+            loss_tm1 = _row_losses(self, belief, actions, H + 1, flat[H:-1], dev, B)
         r = torch.zeros(T, B, dtype=torch.float32, device=dev)
         r[H:T - 1] = loss_tm1 - loss_t[1:]
         return r
@@ -259,6 +418,11 @@ class NDIGO(nn.Module):
         actions = actions.to(dev, torch.float32)
         belief = self._beliefs(observations, prev_actions)
         flat = observations.to(dev, torch.float32).reshape(T, B, -1)
+        hs = self._horizons
+        if hs.supported and T > self.num_predictors:
+            params = [p for k in range(1, 11) for p in hs._params(k)]
+            return _HorizonLossFn.apply(self, belief, actions.reshape(T, B, -1), flat.contiguous(), self.num_predictors,
+                                        *params)
         loss = None
         for k in range(1, self.num_predictors + 1):
             logits = self._logits(belief, actions, k)

@@ -264,6 +264,22 @@ int cb_cross_entropy(const float* logits, const float* onehot, const float* coef
  * dlogits[m,f] = gscale * (sigmoid - target) (NULL to skip). */
 int cb_bce_logits(const float* logits, const float* target, float scale, float* row_loss, float gscale,
                   float* dlogits, int64_t m, int32_t f, void* stream);
+/* All of NDIGO's prediction horizons in one pass (ndigo.py:154-163, 194-206, 234-268): logits fp32 [T*B, groups*fp]
+ * holds predictor k = g+1 in columns [g*fp, g*fp+d) (the grouped-GEMM layout); row (t,b) of predictor k is scored
+ * against obs[t+off_g, b] (obs fp32 [T*B, d]) with off_g = k (the loss, ndigo.py:265-268) unless target_offset_host
+ * (HOST array of `groups` ints, each in [0, k]) says otherwise -- the bonus scores predictor H+1 against obs[t+H]
+ * (ndigo.py:199-206); rows with t+k >= T belong to no pair (loss 0, gradient 0).  groups <= 16.
+ * row_loss [groups, T*B] = scale * sum_f bce with scale 1/d, or 1/((T-k)*B*d) when mean_over_pairs (the sum over rows
+ * is then torch's mean over the pairs); dlogits_bf16 [T*B, groups*fp] = upstream/((T-k)*B*d) * (sigmoid - target),
+ * zero in the padding columns.  Either output may be NULL. */
+int cb_bce_horizons(const float* logits, const float* obs, int32_t T, int32_t B, int32_t d, int32_t groups, int32_t fp,
+                    int32_t mean_over_pairs, const int32_t* target_offset_host, float* row_loss, float upstream,
+                    void* dlogits_bf16, void* stream);
+/* ndigo.py:154-163, 236-240 (a Python double loop in the reference): sliding windows of the one-hot actions,
+ * win[(t,b), j*A + a] = onehot[t+j, b, a] for j < W, t+j < T, else 0.  win_bf16 [T*B, 64] (zero padded: the extra k-block
+ * of the grouped predictor layer), win_f32 [T*B, W*A] or NULL.  W*A <= 64. */
+int cb_action_windows(const float* onehot, int32_t T, int32_t B, int32_t A, int32_t W, void* win_bf16, float* win_f32,
+                      void* stream);
 /* utils/tensor.py:39-46: out[0] = sum(x*w)/sum(w) (w NULL -> mean); deterministic order.
  * Also writes out[1] = sum(w). */
 int cb_weighted_mean(const float* x, const float* w, float* out, int64_t n, void* stream);
