@@ -80,7 +80,7 @@ _SIGS = {
     "cb_cross_entropy": [_P, _P, _P, _P, _P, _L, _I, _P],
     "cb_bce_logits": [_P, _P, _F, _P, _F, _P, _L, _I, _P],
     "cb_bce_horizons": [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), _P, _F, _P, _P],
-    "cb_action_windows": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "cb_action_windows": [_P, _I, _I, _I, _I, _P, _I, _P, _P],
     "cb_weighted_mean": [_P, _P, _P, _L, _P],
     "cb_loss_coef": [_P, _P, _F, _P, _P, _L, _P],
     "cb_dot": [_P, _P, _P, _L, _P],
@@ -92,6 +92,9 @@ _SIGS = {
     "cb_gru_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "cb_gru_sequence_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "cb_gru_sequence_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cb_gru_persistent_supported": [_I],
+    "cb_gru_persistent_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cb_gru_persistent_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "cb_softmax_fwd": [_P, _P, _L, _I, _P],
     "cb_softmax_bwd": [_P, _P, _P, _L, _I, _P],
     "cb_ppo_loss": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _L, _I, _P],

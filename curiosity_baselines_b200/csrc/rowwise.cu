@@ -159,9 +159,11 @@ __global__ void bce_horizons_kernel(const float* __restrict__ z, const float* __
         for (int j = lane; j < fp; j += 32) {
             float grad = 0.f;
             if (live && j < d) {
+                // torch's formula (fp32 sigmoid, both logs clamped at -100) on the fast SFU intrinsics: ~2 ulp, far inside
+                // the 1e-2 gate; this pass is otherwise bound by its 2 logs + exp + divide per element, not by HBM
                 const float zz = zr[j], yy = y[j];
-                const float p = 1.f / (1.f + expf(-zz));
-                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+                const float p = __fdividef(1.f, 1.f + __expf(-zz));
+                const float lp = fmaxf(__logf(p), -100.f), lq = fmaxf(__logf(1.f - p), -100.f);
                 acc -= yy * lp + (1.f - yy) * lq;
                 grad = gs * (p - yy);
             }
@@ -176,7 +178,7 @@ __global__ void bce_horizons_kernel(const float* __restrict__ z, const float* __
 // win[(t,b), j*A + a] = onehot[t+j, b, a] for j < W and t + j < T, zero otherwise and in the padding columns.
 // Written twice: bf16 [n, 64] (the extra k-block of the grouped first layer) and fp32 [n, W*A] (side weight gradient).
 __global__ void action_windows_kernel(const float* __restrict__ onehot, int T, int B, int A, int W,
-                                      __nv_bfloat16* __restrict__ win_bf16, float* __restrict__ win_f32) {
+                                      __nv_bfloat16* __restrict__ win_bf16, int ld, float* __restrict__ win_f32) {
     const int64_t n = (int64_t)T * B;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * 64) return;
@@ -189,7 +191,7 @@ __global__ void action_windows_kernel(const float* __restrict__ onehot, int T, i
         if (t + j < T) v = __ldg(onehot + ((int64_t)(t + j) * B + b) * A + a);
         if (win_f32) win_f32[r * (W * A) + c] = v;
     }
-    win_bf16[idx] = cb::f2bf(v);
+    win_bf16[r * ld + c] = cb::f2bf(v);
 }
 
 // one thread per row; A (actions) is small
@@ -450,12 +452,12 @@ extern "C" int cb_bce_horizons(const float* logits, const float* obs, int32_t T,
 }
 
 extern "C" int cb_action_windows(const float* onehot, int32_t T, int32_t B, int32_t A, int32_t W, void* win_bf16,
-                                 float* win_f32, void* stream) {
-    CB_REQUIRE(onehot && win_bf16 && T >= 1 && B >= 1 && A >= 1 && W >= 1 && W * A <= 64, CB_E_ARG,
-               "cb_action_windows: bad argument (W*A must be <= 64)");
+                                 int32_t ld_bf16, float* win_f32, void* stream) {
+    CB_REQUIRE(onehot && win_bf16 && T >= 1 && B >= 1 && A >= 1 && W >= 1 && W * A <= 64 && ld_bf16 >= 64, CB_E_ARG,
+               "cb_action_windows: bad argument (W*A must be <= 64, ld_bf16 >= 64)");
     const int64_t total = (int64_t)T * B * 64;
     action_windows_kernel<<<(unsigned)cb::ceil_div<int64_t>(total, 256), 256, 0, cb::as_stream(stream)>>>(
-        onehot, T, B, A, W, (__nv_bfloat16*)win_bf16, win_f32);
+        onehot, T, B, A, W, (__nv_bfloat16*)win_bf16, ld_bf16, win_f32);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

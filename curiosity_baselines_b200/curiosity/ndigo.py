@@ -72,12 +72,19 @@ class _GruFn(torch.autograd.Function):
         h_all = torch.zeros(T + 1, B, G, dtype=torch.float32, device=dev)
         hb = torch.zeros(T + 1, B, G, dtype=torch.bfloat16, device=dev)
         ghn = torch.empty(T, B, G, dtype=torch.float32, device=dev)
-        gh = torch.empty(B, 3 * G, dtype=torch.float32, device=dev)
         hh.prepare()
-        L.call("cb_gru_sequence_fwd", T, B, G, L.ptr(gates), L.ptr(hh.w_fwd), L.ptr(hh.bias), L.ptr(h_all), L.ptr(hb),
-               L.ptr(ghn), L.ptr(gh), LY.get_engine(), L.stream())
+        if model.persistent_gru and LY.get_engine() != L.ENGINE_SIMT and L.load().cb_gru_persistent_supported(G):
+            # one persistent launch for all T steps (csrc/recurrent.cu) instead of two launches per step
+            L.call("cb_gru_persistent_fwd", T, B, G, L.ptr(gates), L.ptr(hh.w_fwd), L.ptr(hh.bias), L.ptr(h_all), L.ptr(hb),
+                   L.ptr(ghn), L.stream())
+        else:
+            gh = torch.empty(B, 3 * G, dtype=torch.float32, device=dev)
+            L.call("cb_gru_sequence_fwd", T, B, G, L.ptr(gates), L.ptr(hh.w_fwd), L.ptr(hh.bias), L.ptr(h_all), L.ptr(hb),
+                   L.ptr(ghn), L.ptr(gh), LY.get_engine(), L.stream())
         ctx.model, ctx.saved, ctx.params = model, (xb, side, gates, h_all, hb, ghn, T, B, n), params
-        return h_all[1:]
+        out = h_all[1:]
+        model._belief_pair = (out, hb[1:])          # the recurrence also wrote h in bf16: the predictors' GEMM operand
+        return out
 
     @staticmethod
     def backward(ctx, dbelief):
@@ -88,10 +95,14 @@ class _GruFn(torch.autograd.Function):
         dout = dbelief.to(torch.float32).contiguous()
         dgi = torch.empty(n, 3 * G, dtype=torch.bfloat16, device=dev)
         dgh = torch.empty(n, 3 * G, dtype=torch.bfloat16, device=dev)
-        ws = torch.empty(3, B, G, dtype=torch.bfloat16, device=dev)
         hh.prepare()
-        L.call("cb_gru_sequence_bwd", T, B, G, L.ptr(gates), L.ptr(ghn), L.ptr(h_all), L.ptr(dout), L.ptr(hh.w_t),
-               L.ptr(dgi), L.ptr(dgh), L.ptr(ws), LY.get_engine(), L.stream())
+        if ctx.model.persistent_gru and LY.get_engine() != L.ENGINE_SIMT and L.load().cb_gru_persistent_supported(G):
+            L.call("cb_gru_persistent_bwd", T, B, G, L.ptr(gates), L.ptr(ghn), L.ptr(h_all), L.ptr(dout), L.ptr(hh.w_t),
+                   L.ptr(dgi), L.ptr(dgh), L.stream())
+        else:
+            ws = torch.empty(3, B, G, dtype=torch.bfloat16, device=dev)
+            L.call("cb_gru_sequence_bwd", T, B, G, L.ptr(gates), L.ptr(ghn), L.ptr(h_all), L.ptr(dout), L.ptr(hh.w_t),
+                   L.ptr(dgi), L.ptr(dgh), L.ptr(ws), LY.get_engine(), L.stream())
         saved = [p.grad for p in ctx.params]
         for p in ctx.params:
             p.grad = None
@@ -197,26 +208,24 @@ class _HorizonStack:
         return self._w1_t[G]
 
     def forward(self, belief_bf16, onehot_actions, T, B, G):
-        """-> (window fp32 [n, 50], window bf16 [n,64], h [n, G*64] bf16, logits [n, G*FP] fp32)."""
+        """-> (packed input [n, Gs+64] bf16 = [belief | 10-step action window], h [n, G*64] bf16, logits [n, G*FP] fp32)."""
         self.prepare()
         n, dev, st = T * B, belief_bf16.device, L.stream()
-        A, F1, FP = self.A, self.F1, self.FP
-        win_b = torch.empty(n, 64, dtype=torch.bfloat16, device=dev)
-        win_f = torch.empty(n, self.WIN * A, dtype=torch.float32, device=dev)
-        L.call("cb_action_windows", L.ptr(onehot_actions), T, B, A, self.WIN, L.ptr(win_b), L.ptr(win_f), st)
+        A, F1, FP, Gs = self.A, self.F1, self.FP, self.Gs
+        xcat = torch.empty(n, Gs + 64, dtype=torch.bfloat16, device=dev)
+        xcat[:, :Gs].copy_(belief_bf16)
+        L.call("cb_action_windows", L.ptr(onehot_actions), T, B, A, self.WIN, xcat.data_ptr() + 2 * Gs, Gs + 64, None, st)
         h = torch.empty(n, G * F1, dtype=torch.bfloat16, device=dev)
         e = L.Epilogue()
-        e.bias = L.ptr(self.b1)
-        e.side, e.side_w, e.side_dim, e.side_bf16 = L.ptr(win_f), L.ptr(self.side_w), self.WIN * A, L.ptr(win_b)
-        e.out_bf16 = L.ptr(h)
-        L.call("cb_grouped_linear_fwd", n, G, self.Gs, F1, 1, L.ptr(belief_bf16), L.ptr(self.w1), L.ACT_RELU, C.byref(e), st)
+        e.bias, e.out_bf16 = L.ptr(self.b1), L.ptr(h)
+        L.call("cb_grouped_linear_fwd", n, G, Gs + 64, F1, 1, L.ptr(xcat), L.ptr(self.w1), L.ACT_RELU, C.byref(e), st)
         z = torch.empty(n, G * FP, dtype=torch.float32, device=dev)
         e2 = L.Epilogue()
         e2.bias, e2.out_f32 = L.ptr(self.b2), L.ptr(z)
         L.call("cb_grouped_linear_fwd", n, G, F1, FP, 0, L.ptr(h), L.ptr(self.w2), L.ACT_NONE, C.byref(e2), st)
-        return win_f, win_b, h, z
+        return xcat, h, z
 
-    def backward(self, belief_bf16, win_f, h, dz, T, B, G):
+    def backward(self, xcat, h, dz, T, B, G):
         """dz bf16 [n, G*FP] -> (d belief bf16 [n, Gs], per-predictor parameter gradients {k: (dW1, db1, dW2, db2)})."""
         n, dev, st = T * B, h.device, L.stream()
         A, F1, FP, Gs, D = self.A, self.F1, self.FP, self.Gs, self.D
@@ -225,27 +234,30 @@ class _HorizonStack:
         L.call("cb_grouped_linear_wgrad", n, G, F1, FP, 0, L.ptr(h), L.ptr(dz), L.ptr(dw2), L.ptr(db2), 0.0, st)
         dh = torch.empty(n, G * F1, dtype=torch.bfloat16, device=dev)
         L.call("cb_grouped_linear_dgrad", n, G, F1, FP, L.ptr(dz), L.ptr(self.w2_t), L.ptr(h), L.ACT_RELU, None, L.ptr(dh), st)
-        # layer 1: the stacked outputs make both remaining products plain GEMMs
-        d = L.ConvDesc()
-        d.n, d.in_h, d.in_w, d.in_c = n, 1, 1, Gs
-        d.k_h = d.k_w = d.stride = 1
-        d.out_h = d.out_w = 1
-        d.out_c = G * F1
-        d.in_dtype = L.BF16
-        d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = Gs, Gs, Gs, 1
-        d.engine = LY.get_engine()
-        dw1 = torch.empty(G * F1, Gs, dtype=torch.float32, device=dev)
+        # layer 1: the stacked outputs make both remaining products plain GEMMs; the packed input gives the belief AND
+        # the action-window weight gradients in one of them
+        def desc(k):
+            d = L.ConvDesc()
+            d.n, d.in_h, d.in_w, d.in_c = n, 1, 1, k
+            d.k_h = d.k_w = d.stride = 1
+            d.out_h = d.out_w = 1
+            d.out_c = G * F1
+            d.in_dtype = L.BF16
+            d.in_stride_n, d.in_stride_h, d.in_stride_w, d.in_stride_c = k, k, k, 1
+            d.engine = LY.get_engine()
+            return d
+        dw1 = torch.empty(G * F1, Gs + 64, dtype=torch.float32, device=dev)
         db1 = torch.empty(G * F1, dtype=torch.float32, device=dev)
-        L.call("cb_conv_wgrad", C.byref(d), L.ptr(belief_bf16), L.ptr(dh), None, None, L.ptr(dw1), L.ptr(db1), 0.0, st)
-        dsw = torch.empty(G * F1, self.WIN * A, dtype=torch.float32, device=dev)
-        L.call("cb_side_wgrad", L.ptr(dh), L.ptr(win_f), L.ptr(dsw), n, G * F1, self.WIN * A, 0.0, st)
+        dk = desc(Gs + 64)
+        L.call("cb_conv_wgrad", C.byref(dk), L.ptr(xcat), L.ptr(dh), None, None, L.ptr(dw1), L.ptr(db1), 0.0, st)
         dbel = torch.empty(n, Gs, dtype=torch.bfloat16, device=dev)
-        L.call("cb_conv_dgrad", C.byref(d), L.ptr(dh), L.ptr(self.w1_t(G)), None, L.ACT_NONE, None, L.ptr(dbel), st)
+        dg = desc(Gs)
+        L.call("cb_conv_dgrad", C.byref(dg), L.ptr(dh), L.ptr(self.w1_t(G)), None, L.ACT_NONE, None, L.ptr(dbel), st)
         grads = {}
         for g in range(G):
             k = g + 1
-            grads[k] = (torch.cat([dw1[g * F1:(g + 1) * F1], dsw[g * F1:(g + 1) * F1, : k * A]], 1),
-                        db1[g * F1:(g + 1) * F1], dw2[g * FP: g * FP + D], db2[g * FP: g * FP + D])
+            grads[k] = (dw1[g * F1:(g + 1) * F1, : Gs + k * A], db1[g * F1:(g + 1) * F1], dw2[g * FP: g * FP + D],
+                        db2[g * FP: g * FP + D])
         return dbel, grads
 
 
@@ -258,8 +270,8 @@ class _HorizonLossFn(torch.autograd.Function):
         T, B = onehot_actions.shape[:2]
         n = T * B
         G = (K + 1) // 2 * 2                               # layer 1's weight gradient tiles 128 stacked outputs
-        xb = belief.reshape(n, -1).to(torch.bfloat16).contiguous()
-        win_f, win_b, h, z = hs.forward(xb, onehot_actions.contiguous(), T, B, G)
+        xb = model._belief_bf16(belief, n)
+        xcat, h, z = hs.forward(xb, onehot_actions.contiguous(), T, B, G)
         rows = torch.empty(G, n, dtype=torch.float32, device=xb.device)
         need = any(ctx.needs_input_grad)
         dz = torch.empty(n, G * hs.FP, dtype=torch.bfloat16, device=xb.device) if need else None
@@ -267,15 +279,15 @@ class _HorizonLossFn(torch.autograd.Function):
                L.stream())
         if need and G > K:
             dz.view(n, G, hs.FP)[:, K:].zero_()            # the padding horizon is not part of the loss
-        ctx.saved = (xb, win_f, h, dz, T, B, G, K)
+        ctx.saved = (xcat, h, dz, T, B, G, K)
         ctx.model = model
         return rows[:K].sum()
 
     @staticmethod
     def backward(ctx, g):
-        xb, win_f, h, dz, T, B, G, K = ctx.saved
+        xcat, h, dz, T, B, G, K = ctx.saved
         hs = ctx.model._horizons
-        dbel, grads = hs.backward(xb, win_f, h, dz, T, B, G)
+        dbel, grads = hs.backward(xcat, h, dz, T, B, G)
         out = []
         for k in range(1, 11):
             out += [t * g for t in grads[k]] if k <= K else [None] * 4
@@ -310,6 +322,8 @@ class NdigoForward(nn.Module):
 
 
 class NDIGO(nn.Module):
+    persistent_gru = True        # the recurrence as one persistent launch when the hidden size is specialised (128)
+
     def __init__(self, image_shape, action_size, horizon, feature_encoding="idf_maze", gru_size=128, batch_norm=False,
                  obs_stats=None, num_predictors=10, device="cpu"):
         super().__init__()
@@ -360,6 +374,13 @@ class NDIGO(nn.Module):
         g = self.gru                                        # zero state every call (ndigo.py:127,145)
         return _GruFn.apply(self, phi, prev, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)
 
+    def _belief_bf16(self, belief, n):
+        """bf16 rows of ``belief`` [T,B,G]: the copy the GRU kernel wrote alongside the fp32 one when it is that tensor."""
+        pair = getattr(self, "_belief_pair", None)
+        if pair is not None and pair[0].data_ptr() == belief.data_ptr() and pair[0].shape == belief.shape:
+            return pair[1].reshape(n, -1)
+        return belief.reshape(n, -1).to(torch.bfloat16).contiguous()
+
     def _logits(self, belief, actions, k):
         """predictor k on belief[:T-k] with the k-step action window starting at each step."""
         T, B = actions.shape[:2]
@@ -390,8 +411,8 @@ class NDIGO(nn.Module):
         hs = self._horizons
         if hs.supported and T > H + 1:
             n, G = T * B, (H + 2) // 2 * 2
-            xb = belief.reshape(n, -1).to(torch.bfloat16).contiguous()
-            _, _, _, z = hs.forward(xb, actions.reshape(T, B, -1).contiguous(), T, B, G)
+            xb = self._belief_bf16(belief, n)
+            _, _, z = hs.forward(xb, actions.reshape(T, B, -1).contiguous(), T, B, G)
             rows = torch.empty(G, n, dtype=torch.float32, device=dev)
             # predictor H+1 starts one step earlier and is scored against the SAME frame as predictor H (ndigo.py:199-206)
             offs = (C.c_int32 * G)(*[H if g == H else g + 1 for g in range(G)])

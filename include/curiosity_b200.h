@@ -276,10 +276,11 @@ int cb_bce_horizons(const float* logits, const float* obs, int32_t T, int32_t B,
                     int32_t mean_over_pairs, const int32_t* target_offset_host, float* row_loss, float upstream,
                     void* dlogits_bf16, void* stream);
 /* ndigo.py:154-163, 236-240 (a Python double loop in the reference): sliding windows of the one-hot actions,
- * win[(t,b), j*A + a] = onehot[t+j, b, a] for j < W, t+j < T, else 0.  win_bf16 [T*B, 64] (zero padded: the extra k-block
- * of the grouped predictor layer), win_f32 [T*B, W*A] or NULL.  W*A <= 64. */
-int cb_action_windows(const float* onehot, int32_t T, int32_t B, int32_t A, int32_t W, void* win_bf16, float* win_f32,
-                      void* stream);
+ * win[(t,b), j*A + a] = onehot[t+j, b, a] for j < W, t+j < T, else 0.  win_bf16: 64 columns per row (zero padded) with
+ * row stride ld_bf16 elements -- e.g. columns [G, G+64) of the predictors' packed [belief | window] input matrix;
+ * win_f32 [T*B, W*A] or NULL.  W*A <= 64. */
+int cb_action_windows(const float* onehot, int32_t T, int32_t B, int32_t A, int32_t W, void* win_bf16, int32_t ld_bf16,
+                      float* win_f32, void* stream);
 /* utils/tensor.py:39-46: out[0] = sum(x*w)/sum(w) (w NULL -> mean); deterministic order.
  * Also writes out[1] = sum(w). */
 int cb_weighted_mean(const float* x, const float* w, float* out, int64_t n, void* stream);
@@ -334,6 +335,16 @@ int cb_gru_sequence_fwd(int32_t T, int32_t B, int32_t G, float* gates, const voi
 int cb_gru_sequence_bwd(int32_t T, int32_t B, int32_t G, const float* gates, const float* ghn_all, const float* h_all,
                         const float* dout, const void* w_hh_t_bf16, void* dgi_bf16, void* dgh_bf16, void* dh_ws_bf16,
                         int32_t engine, void* stream);
+/* The same recurrence as ONE persistent launch (csrc/recurrent.cu): the batch is partitioned over CTAs by rows (the
+ * recurrence is independent across environment columns), W_hh stays in registers as tensor-core fragments, the hidden
+ * state in registers / shared memory; no per-step launches, no fp32 gh round trip through HBM.  BPTT likewise, with
+ * dL/dh carried in fp32.  Same operands as cb_gru_sequence_fwd / _bwd minus the scratch buffers.
+ * cb_gru_persistent_supported(G): 1 for the specialised hidden size (128, ndigo.py:47). */
+int cb_gru_persistent_supported(int32_t G);
+int cb_gru_persistent_fwd(int32_t T, int32_t B, int32_t G, float* gates, const void* w_hh_bf16, const float* b_hh,
+                          float* h_all, void* h_all_bf16, float* ghn_all, void* stream);
+int cb_gru_persistent_bwd(int32_t T, int32_t B, int32_t G, const float* gates, const float* ghn_all, const float* h_all,
+                          const float* dout, const void* w_hh_t_bf16, void* dgi_bf16, void* dgh_bf16, void* stream);
 /* atari_lstm_model.py:144: F.softmax over the last dimension, fp32 [n,a]; and its backward */
 int cb_softmax_fwd(const float* logits, float* prob, int64_t n, int32_t a, void* stream);
 int cb_softmax_bwd(const float* prob, const float* dprob, float* dlogits, int64_t n, int32_t a, void* stream);
