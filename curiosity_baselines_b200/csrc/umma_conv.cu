@@ -160,9 +160,7 @@ int dispatch(const Plan& pl, cudaStream_t s) {
 // the math.  Used when there are enough rows to keep every SM busy with the larger tiles.
 int pick_bn(int n_total, int* mt, long long rows = 0) {
     if (n_total % 256 == 0) {
-        static int big = -1;
-        if (big < 0) { const char* e = getenv("CB_NO_BIG_TILE"); big = (e && e[0] == '1') ? 0 : 1; }
-        *mt = (big && rows >= 256LL * 2 * 148) ? 2 : 1;
+        *mt = rows >= 256LL * 2 * 148 ? 2 : 1;
         return 256;
     }
     if (n_total % 128 == 0) { *mt = 2; return 128; }
@@ -301,11 +299,7 @@ int window_conv_dgrad(const cb_conv_desc* d, const void* dy, const void* w_t, co
                       const void* dx_add, void* dx, cudaStream_t s);
 int window_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffle, const void* x_saved,
                          int x_act, const void* dx_add, void* dx, cudaStream_t s);
-static bool use_window() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CB_NO_WINDOW"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1;
-}
+static constexpr bool use_window() { return true; }      // (the TMA-gather GEMM remains the path for shapes the window kernels do not tile)
 
 bool umma_supports_fwd(const cb_conv_desc* d, const cb_epilogue* e) {
     if (use_window() && window_supports_fwd(d, e)) return true;
@@ -560,7 +554,7 @@ void taps_s1(WindowGeo& g, int k, bool flipped) {
 
 template <int BN, int EPI>
 int launch_window_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, umma::WindowParams& p, cudaStream_t s) {
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CB_EPI_DEBUG"); dbg = e ? atoi(e) : 0; } p.epi.debug = dbg; }
+    p.epi.debug = 0;
     const int w_bytes = p.kb_count * BN * 128;
     // forward-simple epilogue: let the tensor cores add the bias when its operand blocks (4 KB + BN*32 B) fit
     int extra = 0;
@@ -671,11 +665,9 @@ int window_conv_fwd_s2_flat(const cb_conv_desc* d, const void* x, const void* w,
 int window_conv_fwd(const cb_conv_desc* d, const void* x, const void* w, const cb_epilogue* e, cudaStream_t s) {
     CB_REQUIRE(x && w && e && (e->out_bf16 || e->out_f32), CB_E_ARG, "cb_conv_fwd: null pointer");
     {
-        static int flat = -1;
-        if (flat < 0) { const char* ev = getenv("CB_NO_FLAT"); flat = (ev && ev[0] == '1') ? 0 : 1; }
         const int gw = d->in_w / 2, gh = d->in_h / 2;
         // worth it when whole samples leave many of the 256 tile rows empty
-        if (flat && d->stride == 2 && !e->residual && gw <= 128 && (256 / (gh * gw)) * gh * gw < (256 / gw) * gw - gw &&
+        if (d->stride == 2 && !e->residual && gw <= 128 && (256 / (gh * gw)) * gh * gw < (256 / gw) * gw - gw &&
             (long long)d->n * gh < (1ll << 31))
             return window_conv_fwd_s2_flat(d, x, w, e, s);
     }

@@ -1010,7 +1010,7 @@ int fill(Conv1Params& p, const cb_conv_desc* d, const void* x, const float* mean
     if (p.pitch % 128 == 0) p.pitch += 16;
     p.units = d->n * d->in_c;
     p.mean = mean; p.rstd = rstd;
-    { const char* e = getenv("CB_CONV1_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.debug = 0;
     return CB_OK;
 }
 
@@ -1062,9 +1062,7 @@ int conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const 
     p.w_bf16[0] = (const __nv_bfloat16*)w_native; p.bias[0] = e->bias; p.out[0] = (__nv_bfloat16*)e->out_bf16;
     p.w_bf16[1] = (const __nv_bfloat16*)w2; p.bias[1] = bias2; p.out[1] = (__nv_bfloat16*)out2;
     p.act = d->act;
-    static int im2col = -1;
-    if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
-    if (!im2col && s2d_ok(d) && ((uintptr_t)x & 15) == 0) return launch_s2d_fwd(p, s);
+    if (s2d_ok(d) && ((uintptr_t)x & 15) == 0) return launch_s2d_fwd(p, s);
     return launch<false>(p, s);
 }
 
@@ -1076,9 +1074,7 @@ int conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const floa
     int rc = fill(p, d, x, mean, rstd); if (rc) return rc;
     p.dy = (const __nv_bfloat16*)dy; p.dw = dw; p.nets = 1;
     rc = scale_buffer(dw, (int64_t)32 * d->in_c * 64, beta, s); if (rc) return rc;
-    static int im2col = -1;
-    if (im2col < 0) { const char* e = getenv("CB_CONV1_IM2COL"); im2col = (e && e[0] == '1') ? 1 : 0; }
-    const bool s2d = !im2col && s2d_ok(d) && s2d_wgrad_ok(d) && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0;
+    const bool s2d = s2d_ok(d) && s2d_wgrad_ok(d) && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0;
     // Bias gradient: in the s2d kernel dy is summed on the tensor cores (the same A windows times an N = 16 block
     // of ones, 29 more small MMAs per sample) instead of a second pass over the 25.6 KB/sample of dy.
     if (dbias) {
