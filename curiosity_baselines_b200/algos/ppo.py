@@ -94,14 +94,15 @@ class PPO:
         # the policy's conv1 and the curiosity encoder's conv1 read the same uint8 frames: one twin launch (shared pixel
         # conversion, N = 64 MMAs) computes both; the curiosity model picks its half up in loss_and_grads_ below
         cm = getattr(m, "curiosity_model", None)
-        twin = None
+        twin, twin_steps = None, T
         if (self.twin_conv1 and self.curiosity_type in ("icm", "disagreement") and curiosity_inputs is not None
-                and curiosity_inputs[0] is observation
-                and not (cm.dedup_shifted_observations and cm.shifted(curiosity_inputs[0], curiosity_inputs[1]))):
+                and curiosity_inputs[0] is observation):
             twin = cm.twin_first_conv()
-        s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True, twin=twin)
+            if twin is not None and cm.dedup_shifted_observations and cm.shifted(curiosity_inputs[0], curiosity_inputs[1]):
+                twin_steps = T + 1          # next_obs = obs shifted by one step: the curiosity encoder wants all T+1 steps
+        s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True, twin=twin, twin_steps=twin_steps)
         if s["twin_out"] is not None:
-            cm._first_out_obs = (s["twin_out"], observation)
+            cm._first_out_obs = (s["twin_out"], observation, twin_steps * B)
         validf = (torch.ones(n, device=dev) if valid is None else valid.to(dev, torch.float32).reshape(n)).contiguous()
         denom = dist.all_reduce_sum_(validf.sum().reshape(1)) if dist.world_size() > 1 else None
         coef = torch.empty(n, dtype=torch.float32, device=dev)

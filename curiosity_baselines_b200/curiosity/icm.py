@@ -321,11 +321,13 @@ class _IcmBase(nn.Module):
             n1 = (T + 1) * B
             allf = torch.as_strided(observations, (T + 1, B) + tuple(shp), observations.stride(),
                                     observations.storage_offset())
-            enc, phi_f, phi_b = self._encode(allf.reshape(n1, *shp), n1)
+            fo = first_out_obs[0] if first_out_obs is not None and first_out_obs[1] == n1 else None
+            enc, phi_f, phi_b = self._encode(allf.reshape(n1, *shp), n1, first_out=fo)
             action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
             self.dedup_hits = getattr(self, "dedup_hits", 0) + 1
             return T, B, n, dict(shared=enc, n1=n1), None, phi_b[:n], phi_f[B:], phi_b[B:], action
-        enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n, first_out=first_out_obs)
+        fo = first_out_obs[0] if first_out_obs is not None and first_out_obs[1] == n else None
+        enc1, _, phi1_b = self._encode(observations.reshape(n, *shp), n, first_out=fo)
         enc2, phi2_f, phi2_b = self._encode(next_observations.reshape(n, *shp), n)
         action = actions.to(self._exec["dev"], torch.float32).reshape(n, -1).contiguous()
         return T, B, n, enc1, enc2, phi1_b, phi2_f, phi2_b, action
@@ -363,7 +365,9 @@ class _IcmBase(nn.Module):
         c = self._cache
         # first-conv output of ``observations`` handed over by the policy pass (consumed once, only for that very tensor)
         handed = self.__dict__.pop("_first_out_obs", None)
-        first_out_obs = handed[0] if handed is not None and handed[1] is observations else None
+        first_out_obs = None
+        if handed is not None and handed[1] is observations:
+            first_out_obs = (handed[0], handed[2] if len(handed) > 2 else observations.shape[0] * observations.shape[1])
         if (self.reuse_features and not remember and c is not None and c["wver"] == self._weights_version()
                 and self._same_batch(c, observations, next_observations, actions)):
             self.reuse_hits["full"] += 1

@@ -229,7 +229,7 @@ class AtariLstmModel(nn.Module):
             cm.invalidate_weights()
 
     # ------------------------------------------------------------------ forward
-    def _run_forward(self, image, prev_action, init_rnn_state, save, twin=None):
+    def _run_forward(self, image, prev_action, init_rnn_state, save, twin=None, twin_steps=None):
         """image uint8/float [T,B,C,H,W] on the device, prev_action one-hot [T,B,A], init_rnn_state (h, c) each
         [1,B,H] or None.  Returns a dict with logits [n,A], prob [n,A], value [n], hn / cn [1,B,H] and, when
         ``save``, everything the backward pass needs.  ``twin``: the first-conv layer of another network that reads the
@@ -246,7 +246,11 @@ class AtariLstmModel(nn.Module):
         l0 = ex["chain"].layers[0]
         if (twin is not None and dtype == L.U8 and (l0.k, l0.stride, l0.pad, l0.out_c, l0.in_c) ==
                 (twin.k, twin.stride, twin.pad, twin.out_c, twin.in_c) and (l0.in_h, l0.in_w) == (twin.in_h, twin.in_w)):
-            first_out, _, twin_out = l0.forward(x, n, in_dtype=dtype, strides=strides, twin=twin)
+            # ``twin_steps`` = T + 1: the frames tensor is a view of a T+1-step rollout buffer (icm.py ``shifted``) and the
+            # twin network wants every step; this network keeps the first T steps of its own output
+            n_tw = (twin_steps or T) * B
+            first_out, _, twin_out = l0.forward(x, n_tw, in_dtype=dtype, strides=strides, twin=twin)
+            first_out = first_out[: n * l0.out_h * l0.out_w]
         acts, _ = ex["chain"].forward(x, n, in_dtype=dtype, strides=strides, last_f32=False, last_bf16=True,
                                       first_out=first_out)
         feat = acts[-1].reshape(n, -1)

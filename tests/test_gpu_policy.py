@@ -562,3 +562,35 @@ def test_recurrence_rows_are_independent_at_large_batch():
         c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
         h = torch.sigmoid(o) * torch.tanh(c)
         assert rel_err(full[1][t + 1].cpu(), c.cpu()) < 1e-2 and rel_err(full[0][t + 1].float().cpu(), h.cpu()) < 2e-2
+
+
+def test_ppo_icm_on_a_collector_layout_rollout_matches_separate_tensors():
+    """PPO + ICM when next_observation is observation shifted by one step (two views of one T+1 buffer, what
+    BatchStaging.get_shifted builds from rlpyt's sampler buffers): the curiosity encoder runs once over T+1 steps and its
+    first convolution rides the policy's conv1 launch (twin, N = 64 MMAs over one converted image).  Every loss term equals
+    the run on two separate tensors with the same content to 1e-4 (the twin and the single-network first convolution add
+    their bias in different places of the fp32 pipeline); gradients agree up to summation order."""
+    T, B, A, seed = 6, 4, 4, 4242
+    params = R.make_policy_params(A, seed)
+    icm_params = R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2)
+    frames = R.make_frames(seed + 3, T + 1, B).to(DEV)
+    prev, act = R.make_actions(seed + 5, T, B, A).to(DEV), R.make_actions(seed + 6, T, B, A).to(DEV)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A).to(DEV), R.make_normal(seed + 8, T, B).to(DEV), R.make_normal(seed + 9, T, B).to(DEV)
+    valid = (1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)).to(DEV)
+
+    def run(shifted):
+        m = make_model(A, params, icm_params)
+        obs, nxt = (frames[:T], frames[1:]) if shifted else (frames[:T].clone(), frames[1:].clone())
+        algo = PPO(curiosity_type="icm", clip_grad_norm=1e9)
+        algo.initialize(m, n_itr=10)
+        info = algo.loss_and_grads_(obs, prev, act, ret, adv, valid, old_prob, None, (obs, nxt, R.onehot(act.cpu(), A).to(DEV)), None)
+        return m, info, {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    m0, i0, g0 = run(False)
+    m1, i1, g1 = run(True)
+    assert getattr(m1.curiosity_model, "dedup_hits", 0) == 1 and getattr(m0.curiosity_model, "dedup_hits", 0) == 0
+    for f in ("loss", "pi_loss", "value_loss", "inv_loss", "forward_loss"):
+        assert abs(float(getattr(i0, f)) - float(getattr(i1, f))) <= 1e-4 * max(1.0, abs(float(getattr(i0, f)))), f
+    for k in g0:
+        a, b = g0[k].double().flatten(), g1[k].double().flatten()
+        assert float(a @ b / (a.norm() * b.norm())) > 0.9999, k
