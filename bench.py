@@ -340,8 +340,32 @@ class CuriosityWorkload:
     def frame_desc(self):
         return "3x5x5 binary frames" if self.kind == "ndigo" else "4x84x84 uint8"
 
+    def enable_graph(self):
+        """Capture the fused step in a CUDA graph (trainer.GraphedStep); False when capture is not possible."""
+        from curiosity_baselines_b200.trainer import GraphedStep
+        if self.driver is None:
+            return False
+        d, T, B = self.d, self.T, self.B
+        self._zero = torch.zeros(T, B, device=self.ctx.dev)
+        self._rew = torch.zeros(T, B, device=self.ctx.dev)
+        if self.kind == "rnd":
+            ins = (d["obs"], d["done"], self._rew, d["value"], d["boot"], d["mask"])
+        else:
+            ins = (d["obs"], d["nxt"], d["onehot"], d["done"], self._rew, d["value"], d["boot"])
+        try:
+            self.graphed = GraphedStep(self.driver, ins)
+            self._graph_ins = ins
+            return True
+        except Exception as e:                                  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {str(e)[:200]}); eager launches", file=sys.stderr)
+            self.graphed = None
+            return False
+
     def step(self):
         d, T, B = self.d, self.T, self.B
+        if getattr(self, "graphed", None) is not None:
+            self._rew.copy_(self._zero)                         # no_extrinsic: the step adds the bonus in place
+            return self.graphed(*self._graph_ins)[0]
         rew = torch.zeros(T, B, device=self.ctx.dev)           # no_extrinsic
         if self.kind == "rnd":
             return self.driver(d["obs"], d["done"], rew, d["value"], d["boot"], d["mask"])[0]
@@ -805,6 +829,12 @@ def run_workload(kind, ctx, args, T, B, steps, warmup, headline):
     if kind.startswith("ppo_"):
         rec["workload"] += f", {w.epochs} epochs x {w.minibatches} minibatches"
     rec["step_roofline"] = whole_step_roofline(w.flop, T, B, ms)
+    # ---- the same step replayed from a CUDA graph (one launch per step instead of ~85-300)
+    if args.graph and hasattr(w, "enable_graph") and w.enable_graph():
+        gms, gloss = timed(ctx, w.step, 3, steps)
+        rec["cuda_graph"] = {"ms_per_step": gms, "value": n_global / (gms * 1e-3), "unit": "samples/s",
+                             "loss": float(gloss), "note": "trainer.GraphedStep: the whole step captured once, replayed per step"}
+        w.graphed = None
     # ---- the same iteration with exact feature reuse between bonus and loss (NOT the headline value)
     if not args.no_reuse and w.set_reuse(True):
         h0 = w.reuse_hits()
@@ -892,6 +922,7 @@ def main():
     ap.add_argument("--no-reuse", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-dedup", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     args = ap.parse_args()
     ctx = Ctx()
     kind, T = args.workload, args.T
@@ -958,7 +989,7 @@ def main():
         "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head.get("e2e"),
         "roofline": head.get("roofline") or head["step_roofline"], "step_roofline": head["step_roofline"],
         "cpu_baseline": head.get("cpu_baseline"), "with_feature_reuse": head.get("with_feature_reuse"),
-        "with_obs_dedup": head.get("with_obs_dedup"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
+        "with_obs_dedup": head.get("with_obs_dedup"), "cuda_graph": head.get("cuda_graph"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
         {"per_gpu": h2d_gbs, "aggregate": h2d_gbs * ctx.world, "note": "1 GiB pinned copies, all ranks at once"},
         "configs": [dict(finish(k, r), name=k) for k, r in others],
     }

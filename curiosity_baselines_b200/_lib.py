@@ -104,6 +104,7 @@ _SIGS = {
     "cb_policy_heads_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "cb_sumsq": [_P, _L, _P, _P],
     "cb_adam_clip_step": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P],
+    "cb_adam_clip_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P, _P],
     "cb_h2d_2d": [_P, _L, _P, _L, _L, _L, _P],
     "cb_prepare_conv_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
     "cb_unprepare_conv_grad": [_P, _P, _I, _I, _I, _I, _F, _P],

@@ -316,6 +316,34 @@ __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, f
     p[i] -= step_size * (mi / denom);
 }
 
+// The same update with the learning rate and the step counter read from DEVICE memory (the counter is bumped by a
+// one-thread launch first): nothing step-dependent is baked into the launch parameters, so a captured CUDA graph of a
+// whole training step replays correctly while the schedule moves on.
+__global__ void bump_step_kernel(int32_t* step) { *step += 1; }
+__global__ void adam_clip_dev_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                     const float* __restrict__ g, int64_t n, const double* __restrict__ sumsq,
+                                     float max_norm, float beta1, float beta2, float eps, const float* __restrict__ lr,
+                                     const int32_t* __restrict__ step) {
+    __shared__ float s_step_size, s_bc2;
+    if (threadIdx.x == 0) {       // bias corrections in double, like torch's Python scalars
+        const double st = (double)(*step);
+        const double bc1 = 1.0 - pow((double)beta1, st), bc2 = 1.0 - pow((double)beta2, st);
+        s_step_size = (float)((double)(*lr) / bc1);
+        s_bc2 = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float norm = (float)sqrt(*sumsq);
+    float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+    float gi = g[i] * coef;
+    float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / s_bc2 + eps;
+    p[i] -= s_step_size * (mi / denom);
+}
+
 __global__ void prepare_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                            __nv_bfloat16* __restrict__ wt, int o, int c, int kh, int kw) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,6 +530,19 @@ extern "C" int cb_adam_clip_step(float* p, float* m, float* v, const float* g, i
     const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
     adam_clip_kernel<<<(unsigned)cb::ceil_div<int64_t>(n, 256), 256, 0, cb::as_stream(stream)>>>(
         p, m, v, g, n, sumsq, max_norm, lr, beta1, beta2, eps, step_size, bc2s);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_adam_clip_step_dev(float* p, float* m, float* v, const float* g, int64_t n, const double* sumsq,
+                                     float max_norm, float beta1, float beta2, float eps, const float* lr_dev,
+                                     int32_t* step_dev, void* stream) {
+    CB_REQUIRE(p && m && v && g && sumsq && lr_dev && step_dev && n >= 1, CB_E_ARG, "cb_adam_clip_step_dev: bad argument");
+    cudaStream_t s = cb::as_stream(stream);
+    bump_step_kernel<<<1, 1, 0, s>>>(step_dev);
+    CB_LAUNCH_CHECK();
+    adam_clip_dev_kernel<<<(unsigned)cb::ceil_div<int64_t>(n, 256), 256, 0, s>>>(p, m, v, g, n, sumsq, max_norm, beta1,
+                                                                                  beta2, eps, lr_dev, step_dev);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -41,8 +41,29 @@ class FlatAdam:
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
             off += k
-        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
-        self.step_count = 0
+        # learning rate and step counter live on the device (cb_adam_clip_step_dev): nothing that changes from step to
+        # step is a launch parameter, so the whole training step can be captured in a CUDA graph (GraphedStep)
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._lr = float(lr)
+        self.betas, self.eps, self.max_norm = betas, eps, max_norm
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self._lr = float(value)
+        self._lr_dev.fill_(self._lr)
+
+    @property
+    def step_count(self):
+        return int(self._step_dev.item())
+
+    @step_count.setter
+    def step_count(self, value):
+        self._step_dev.fill_(int(value))
 
     def step(self):
         st = L.stream()
@@ -52,10 +73,9 @@ class FlatAdam:
         self.reducer.finish()
         self.sumsq.zero_()
         L.call("cb_sumsq", L.ptr(self.grad), n, L.ptr(self.sumsq), st)
-        self.step_count += 1
-        L.call("cb_adam_clip_step", L.ptr(self.flat), L.ptr(self.m), L.ptr(self.v), L.ptr(self.grad), n,
-               L.ptr(self.sumsq), float(self.max_norm), float(self.lr), float(self.betas[0]),
-               float(self.betas[1]), float(self.eps), self.step_count, st)
+        L.call("cb_adam_clip_step_dev", L.ptr(self.flat), L.ptr(self.m), L.ptr(self.v), L.ptr(self.grad), n,
+               L.ptr(self.sumsq), float(self.max_norm), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+               L.ptr(self._lr_dev), L.ptr(self._step_dev), st)
 
     def grad_norm(self):
         return float(self.sumsq.sqrt().item())
@@ -72,11 +92,11 @@ class FlatAdam:
         """``torch.optim.Adam.state_dict()`` layout -- {'state': {i: {step, exp_avg, exp_avg_sq}}, 'param_groups'} with
         the parameters in construction order -- so that a snapshot's ``optimizer_state_dict`` interchanges with the
         reference's (agent.parameters() order, algos/pg/base.py:44)."""
-        state, off = {}, 0
+        state, off, steps_done = {}, 0, self.step_count
         for i, p in enumerate(self.params):
             k = p.numel()
-            if self.step_count > 0:
-                state[i] = {"step": torch.tensor(float(self.step_count)),
+            if steps_done > 0:
+                state[i] = {"step": torch.tensor(float(steps_done)),
                             "exp_avg": self.m[off:off + k].view(p.shape).clone(),
                             "exp_avg_sq": self.v[off:off + k].view(p.shape).clone()}
             off += k
@@ -151,3 +171,36 @@ class IcmStep:
         self.opt.step()
         m.invalidate_weights()
         return loss, r_int, adv, ret
+
+
+class GraphedStep:
+    """CUDA-graph replay of a fused step driver (``RndStep`` / ``IcmStep``): the ~85 (RND) to ~300 (Disagreement) kernel
+    launches of one bonus + returns + update step are captured once and replayed with a single launch, which removes
+    the per-launch host cost that dominates when the per-GPU batch is small (strong scaling: B/N env columns per GPU).
+
+    Everything that changes from step to step is device-resident (Adam's step counter and learning rate,
+    ``cb_adam_clip_step_dev``; the running statistics; the reward filter), so a replay is a full training step.  The
+    inputs are STATIC tensors: pass the same tensor objects on every call (e.g. the staging buffers the uploads land
+    in) or let ``__call__`` copy into them.  Data-parallel runs capture the NCCL all-reduces with the rest."""
+
+    def __init__(self, step, example_inputs, warmup=3):
+        self.step = step
+        self.static_in = list(example_inputs)
+        dev = next(t for t in self.static_in if torch.is_tensor(t)).device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                   # first-use allocations and attribute calls happen here
+            for _ in range(warmup):
+                step(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = step(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if torch.is_tensor(dst) and dst is not src:
+                dst.copy_(src)
+        self.graph.replay()
+        return self.static_out

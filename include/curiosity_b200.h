@@ -390,6 +390,12 @@ int cb_adam_clip_step(float* p, float* m, float* v, const float* g, int64_t n,
                       const double* sumsq, float max_norm, float lr, float beta1, float beta2,
                       float eps, int32_t step, void* stream);
 
+/* The same update with the learning rate (fp32 [1]) and the step counter (int32 [1], incremented by this call before
+ * use) in DEVICE memory: no step-dependent launch parameter, so a CUDA graph of a whole training step can be replayed
+ * while the linear learning-rate schedule (ppo.py:66-70) and the bias correction move on. */
+int cb_adam_clip_step_dev(float* p, float* m, float* v, const float* g, int64_t n, const double* sumsq, float max_norm,
+                          float beta1, float beta2, float eps, const float* lr_dev, int32_t* step_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Layout helpers for prepared weights.
  * ---------------------------------------------------------------------------------- */

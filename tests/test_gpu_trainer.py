@@ -158,3 +158,39 @@ def test_disagreement_step_against_oracle_two_iterations():
         if float(d_ref.norm()) > 0:
             cos = float(d @ d_ref / (d.norm() * d_ref.norm()).clamp_min(1e-30))
             assert cos > 0.9, (k, cos)
+
+
+def test_graphed_step_replays_a_full_training_step():
+    """trainer.GraphedStep: the RND step captured in a CUDA graph and replayed gives the same sequence of losses,
+    bonuses and parameters as eager launches -- Adam's step counter / learning rate and all running statistics are
+    device-resident, so nothing is frozen at capture time."""
+    from curiosity_baselines_b200.trainer import GraphedStep
+    T, B, seed = 8, 6, 91
+    params = R.make_params(R.rnd_shapes(), seed, gain=1.4)
+    frames = [R.make_frames(seed + i, T, B).to(DEV) for i in range(4)]
+    done = R.make_suffix_done(seed + 10, T, B, frac=0.4).to(DEV)
+    value, boot, ones = R.make_normal(seed + 20, T, B).to(DEV), R.make_normal(seed + 30, B).to(DEV), torch.ones(T, B, device=DEV)
+
+    def build():
+        m = RND(image_shape=(4, 84, 84), drop_probability=0.0).to(DEV)
+        m.load_state_dict(params)
+        return m, RndStep(m, lr=1e-3)
+
+    m0, eager = build()
+    ref = []
+    for i in range(3 + 3):                                  # GraphedStep runs 3 warm-up steps, then captures (no execution)
+        f = frames[0] if i < 3 else frames[i - 2]
+        loss, r_int, adv, ret = eager(f, done, torch.zeros(T, B, device=DEV), value, boot, ones)
+        ref.append((float(loss), r_int.clone()))
+    m1, drv = build()
+    static_frames, rew = frames[0].clone(), torch.zeros(T, B, device=DEV)
+    g = GraphedStep(drv, (static_frames, done, rew, value, boot, ones))
+    assert drv.opt.step_count == 3                         # the warm-up steps really trained; capture itself executes nothing
+    for i in range(1, 4):
+        rew.zero_()
+        loss, r_int, adv, ret = g(frames[i], done, rew, value, boot, ones)
+        assert abs(float(loss) - ref[2 + i][0]) <= 1e-4 * abs(ref[2 + i][0]), i
+        assert torch.allclose(r_int, ref[2 + i][1], rtol=1e-3, atol=1e-6), i
+    assert drv.opt.step_count == 6
+    diff = (drv.opt.flat - eager.opt.flat).abs()
+    assert float(diff.max()) <= 2e-3 and float(diff.mean()) <= 2e-6         # same training trajectory (atomics reorder sums)
