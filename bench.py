@@ -502,6 +502,8 @@ class PpoWorkload:
         s = self.samples
         shifted = s.env.next_observation.data_ptr() == s.env.observation.data_ptr() + s.env.observation[0].numel()
         frames = nbytes(s.env.observation) * (self.T + 1) // self.T if shifted else nbytes(s.env.observation, s.env.next_observation)
+        if self.ctype == "rnd":
+            frames = nbytes(s.env.observation) + nbytes(s.env.next_observation) // 4
         self.h2d = frames + nbytes(s.agent.action, s.agent.prev_action,
                           s.agent.agent_info.dist_info.prob, s.agent.agent_info.value, s.env.done, s.env.reward,
                           s.agent.bootstrap_value, s.agent.agent_info.prev_rnn_state.h, s.agent.agent_info.prev_rnn_state.c)
@@ -510,7 +512,10 @@ class PpoWorkload:
 
     def _prefetch(self):
         st = self.hooks.staging(self.agent)
-        if getattr(self, "hooks_staging_shifted", False):
+        if self.ctype == "rnd":
+            st.prefetch(self.samples.env.observation)
+            st.prefetch(self.samples.env.next_observation, newest_only=True)
+        elif getattr(self, "hooks_staging_shifted", False):
             st.assume_shifted = True
             st.prefetch_shifted(self.samples.env.observation, self.samples.env.next_observation)
         else:
@@ -519,9 +524,10 @@ class PpoWorkload:
 
     def e2e_step(self):
         from curiosity_baselines_b200.algos.ppo import optimize_agent_from_samples
-        self._prefetch()
         self.samples.env.reward.zero_()
-        info = optimize_agent_from_samples(self.algo, self.agent, 0, self.samples)
+        # the NEXT batch is staged right after this iteration's own (small) uploads: one DMA engine serves host->device
+        # copies in order, so issuing it first would stall them behind 7-15 GB of frames
+        info = optimize_agent_from_samples(self.algo, self.agent, 0, self.samples, after_staging=self._prefetch)
         return info.loss[-1]
 
     def set_reuse(self, on):

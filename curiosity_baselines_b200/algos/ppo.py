@@ -236,7 +236,10 @@ def stage_samples(agent, curiosity_type, samples, st=None):
         obs, nxt = st.get_shifted(env.observation, env.next_observation)
     else:
         obs = st.get(env.observation)
-        nxt = st.get(env.next_observation) if curiosity_type in ("icm", "disagreement", "rnd") else obs
+        if curiosity_type == "rnd":            # RND reads the newest frame of each stack only (rnd.py:130-131)
+            nxt = st.get(env.next_observation, newest_only=True)
+        else:
+            nxt = st.get(env.next_observation) if curiosity_type in ("icm", "disagreement") else obs
     rnn = getattr(ag.agent_info, "prev_rnn_state", None)
     init = None
     if rnn is not None:
@@ -248,12 +251,14 @@ def stage_samples(agent, curiosity_type, samples, st=None):
                     init)
 
 
-def optimize_agent_from_samples(native, agent, itr, samples):
+def optimize_agent_from_samples(native, agent, itr, samples, after_staging=None):
     """One iteration of the fused PPO on rlpyt ``Samples``: stage -> ``PPO.optimize_agent`` -> the reference's
     ``OptInfo`` (lists of python floats, one entry per gradient step) read back in ONE device->host copy.  Side
     effects of the reference are kept: the bonus is added into ``samples.env.reward`` in place and kept as numpy in
     ``intrinsic_rewards`` (algos/pg/base.py:66-67)."""
     batch = stage_samples(agent, native.curiosity_type, samples)
+    if after_staging is not None:      # e.g. stage the NEXT batch now: behind this iteration's small uploads in the DMA queue
+        after_staging()
     reward_before = batch.reward.clone() if native.curiosity_type != "none" else None
     infos = native.optimize_agent(itr, batch)
     fields = ("loss", "pi_loss", "value_loss", "entropy_loss", "inv_loss", "forward_loss", "gradNorm", "entropy",

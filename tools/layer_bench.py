@@ -15,6 +15,7 @@ ap.add_argument("--n", type=int, default=131072)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--only", default="")
 ap.add_argument("--engine", default="auto")
+ap.add_argument("--warmup", type=int, default=2)
 args = ap.parse_args()
 dev = "cuda"
 n = args.n
@@ -23,7 +24,7 @@ torch.manual_seed(0)
 
 
 def timeit(fn, flops, name):
-    for _ in range(2):
+    for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
