@@ -765,8 +765,8 @@ WgradKind wgrad_kind(const cb_conv_desc* d) {
     if (!device_ok() || !dense_nhwc(d)) return WG_NONE;
     const long long K = (long long)d->k_h * d->k_w * d->in_c;
     if (d->k_h == d->in_h && d->k_w == d->in_w && d->pad == 0 && d->out_h == 1 && d->out_w == 1 &&
-        d->out_c % 128 == 0 && K % 8 == 0)
-        return WG_ROWS;
+        d->out_c % 8 == 0 && K % 8 == 0)
+        return WG_ROWS;        // (an output dimension that is not a multiple of 128 runs a partly empty last row tile)
     if (d->stride == 1 && d->k_h == d->k_w && d->k_h > 1 && d->k_h * d->k_w <= 2 * umma::kMaxAcc &&
         d->in_c == 64 && d->out_c == 64 && (d->in_h + 2 * d->pad) * (d->in_w + 2 * d->pad) <= 81)
         return WG_CONV_S1;
@@ -816,7 +816,9 @@ int wgrad_rows(int n, int out_c, int K, int groups, int x_shared, const void* x,
     p.a_box_bytes = p.b_box_bytes = 8192; p.a_box_stride = p.b_box_stride = 8192;
     p.b_offset = 2 * MC * 8192; p.stage_bytes = (2 * MC + 4) * 8192; p.stages = MC == 2 ? 3 : 4; p.slack_bytes = 0; p.k_rows = 64;
     const int n_tiles = (K + 255) / 256;
-    p.units = (out_all / (128 * MC)) * n_tiles; p.unit_div = n_tiles;
+    const int m_units = (out_all + 128 * MC - 1) / (128 * MC);
+    p.units = m_units * n_tiles; p.unit_div = n_tiles;
+    if (out_all % (128 * MC)) { p.m_total = out_all; p.m_unit_rows = 128 * MC; }      // last row tile partly past the end: TMA zero-fills, stores are guarded
     if (groups > 1) { p.group_units = out_c / (128 * MC); p.b_group_koff = x_shared ? 0 : K; }
     p.slabs_total = (n + 63) / 64;
     p.n_acc = MC;

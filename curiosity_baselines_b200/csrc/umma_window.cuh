@@ -247,6 +247,8 @@ struct WgradParams {
     long long acc_base0[kMaxAcc], acc_base1[kMaxAcc];      // base1 < 0: upper half unused
     long long m_stride, n_stride, unit_m_off, unit_n_off;
     int n_cols_total, n_unit_cols;         // valid columns: min(BN, n_cols_total - unit_n*n_unit_cols)
+    int m_total, m_unit_rows;              // row-major weight gradients whose output dimension is not a multiple of 128:
+                                           // accumulator row a_unit*m_unit_rows + g*128 + row is stored only if < m_total
     float* dw;
 };
 
@@ -355,6 +357,8 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ncols = left < BN ? left : BN;
             }
             for (int g = 0; g < p.n_acc; ++g) {
+                // (the tcgen05.ld below is warp-collective: a row past the end only skips its stores)
+                const bool row_ok = !p.m_total || a_unit * p.m_unit_rows + g * 128 + row < p.m_total;
                 const long long base = row < 64 ? p.acc_base0[g] : p.acc_base1[g];
                 const long long o = base + (long long)(row & 63) * p.m_stride + (long long)a_unit * p.unit_m_off +
                                     (long long)b_unit * p.unit_n_off;
@@ -363,7 +367,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     uint32_t raw[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * BN + cb * 32), raw);
                     tmem_ld_wait();
-                    if (base >= 0) {
+                    if (base >= 0 && row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = cb * 32 + j;

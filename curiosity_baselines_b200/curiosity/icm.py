@@ -15,7 +15,7 @@ from torch import nn
 
 from .. import _lib as L
 from .. import dist
-from ..layers import linear_layer, pad_side, ACT
+from ..layers import linear_layer, narrow_head, NarrowHead, pad_side, ACT
 from .encoders import make_encoder, frame_input
 
 ENC_LAST_ACT = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}
@@ -261,7 +261,7 @@ class _IcmBase(nn.Module):
                               perm=None if perm is None else perm.to(dev),
                               inv_perm=None if perm is None else torch.argsort(perm).to(dev),
                               inv0=linear_layer(self.inverse_model[0], "relu"),
-                              inv2=linear_layer(self.inverse_model[2], "none"))
+                              inv2=narrow_head(self.inverse_model[2]))
         return self._exec
 
     def _encode(self, frames, n, first_out=None):
@@ -412,7 +412,10 @@ class _IcmBase(nn.Module):
             L.call("cb_policy_heads_fwd", L.ptr(h), L.ptr(inv2.weight), L.ptr(inv2.bias), None, None, L.ptr(logits),
                    None, None, n, F, self.action_size, st)
         else:
-            _, logits = ex["inv2"].forward(h, n, out_bf16=False, out_f32=True)
+            if isinstance(ex["inv2"], NarrowHead):
+                logits = ex["inv2"].forward(h, n)
+            else:
+                _, logits = ex["inv2"].forward(h, n, out_bf16=False, out_f32=True)
         ce = torch.empty(n, dtype=torch.float32, device=dev)
         coef_inv = torch.empty(n, dtype=torch.float32, device=dev)
         L.call("cb_loss_coef", L.ptr(valid), None, float(self.inverse_loss_wt), L.ptr(denom), L.ptr(coef_inv), n, st)
@@ -458,9 +461,12 @@ class _IcmBase(nn.Module):
                    L.ptr(inv2.weight.grad), L.ptr(inv2.bias.grad), None, None, n, F, self.action_size, L.ACT_RELU, st)
             dist.grads_ready((inv2.weight.grad, inv2.bias.grad))
         else:
-            dlog_b = dlogits.to(torch.bfloat16)
-            ex["inv2"].wgrad(h, dlog_b, n)
-            dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
+            if isinstance(ex["inv2"], NarrowHead):
+                dh = ex["inv2"].backward(h, dlogits, n, x_saved=h, x_act="relu")
+            else:
+                dlog_b = dlogits.to(torch.bfloat16)
+                ex["inv2"].wgrad(h, dlog_b, n)
+                dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
         ex["inv0"].wgrad(cat, dh, n)
         dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
         if enc2 is None:            # one encoder pass over the T+1 distinct steps: d phi[t] = d phi1[t] + d phi2[t-1]

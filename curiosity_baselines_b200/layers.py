@@ -575,6 +575,44 @@ class PaddedConv1Layer(GemmLayer):
             w.grad.copy_(dw[:r].view_as(w)); b.grad.copy_(db[:r])
 
 
+class NarrowHead:
+    """A Linear(K -> few outputs) head (the policy's pi / value for action sets the fused heads kernel does not cover,
+    ICM's inverse-model output for A > 8: e.g. the 12 actions of SuperMarioBros' COMPLEX_MOVEMENT) on the tcgen05 GEMM:
+    the outputs are zero-padded to one 128-wide tile (``PaddedLinearLayer``); callers pass and receive fp32 tensors of
+    the real width.  No SIMT launch on this path."""
+
+    def __init__(self, module, act="none"):
+        self.layer = PaddedLinearLayer(module, act)
+        self.real_out = module.out_features
+
+    def prepare(self):
+        self.layer.prepare()
+
+    @property
+    def _version(self):
+        return self.layer._version
+
+    @_version.setter
+    def _version(self, v):
+        self.layer._version = v
+
+    def forward(self, x_bf16, n):
+        _, yf = self.layer.forward(x_bf16, n, out_bf16=False, out_f32=True)
+        return yf[:, : self.real_out].contiguous()
+
+    def backward(self, x_bf16, dy_f32, n, x_saved=None, x_act="none", dx_add=None):
+        """Weight / bias gradients into the holder's ``.grad``; returns d x (bf16 [n, K])."""
+        dy = torch.zeros(n, self.layer.out_c, dtype=torch.bfloat16, device=dy_f32.device)
+        dy[:, : self.real_out] = dy_f32.reshape(n, self.real_out)
+        self.layer.wgrad(x_bf16, dy, n)
+        return self.layer.dgrad(dy, n, x_saved=x_saved, x_act=x_act, dx_add=dx_add)
+
+
+def narrow_head(module, act="none"):
+    """``NarrowHead`` on the tensor cores, or the generic layer when the SIMT cross-check engine is forced."""
+    return NarrowHead(module, act) if _engine != L.ENGINE_SIMT else linear_layer(module, act)
+
+
 class ParamPair:
     """A (weight, bias) pair of an ``nn.LSTM`` / ``nn.GRU`` holder presented like a ``Linear`` to ``GemmLayer``."""
 

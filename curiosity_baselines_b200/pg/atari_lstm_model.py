@@ -216,7 +216,7 @@ class AtariLstmModel(nn.Module):
                 inv_perm=None if perm is None else torch.argsort(perm).to(dev),
                 ih=linear_layer(LY.ParamPair(ls.weight_ih_l0, ls.bias_ih_l0), "none", self.action_size),
                 hh=linear_layer(LY.ParamPair(ls.weight_hh_l0, ls.bias_hh_l0), "none"),
-                pi=linear_layer(self.pi, "none"), value=linear_layer(self.value, "none"))
+                pi=LY.narrow_head(self.pi), value=LY.narrow_head(self.value))
         return self._exec
 
     def invalidate_weights(self):
@@ -279,8 +279,11 @@ class AtariLstmModel(nn.Module):
             L.call("cb_policy_heads_fwd", L.ptr(h_out), L.ptr(self.pi.weight), L.ptr(self.pi.bias),
                    L.ptr(self.value.weight), L.ptr(self.value.bias), L.ptr(logits), L.ptr(value), L.ptr(prob), n, H, A, st)
         else:
-            _, logits = ex["pi"].forward(h_out, n, out_bf16=False, out_f32=True)
-            _, value = ex["value"].forward(h_out, n, out_bf16=False, out_f32=True)
+            if isinstance(ex["pi"], LY.NarrowHead):          # A + 1 > 8: padded tcgen05 GEMMs
+                logits, value = ex["pi"].forward(h_out, n), ex["value"].forward(h_out, n)
+            else:
+                _, logits = ex["pi"].forward(h_out, n, out_bf16=False, out_f32=True)
+                _, value = ex["value"].forward(h_out, n, out_bf16=False, out_f32=True)
             L.call("cb_softmax_fwd", L.ptr(logits), L.ptr(prob), n, A, st)
         out = dict(T=T, B=B, n=n, logits=logits, prob=prob, value=value.reshape(n), hn=hn,
                    cn=c_all[T].clone().unsqueeze(0), twin_out=twin_out)
@@ -307,6 +310,9 @@ class AtariLstmModel(nn.Module):
                    L.ptr(self.value.weight.grad), L.ptr(self.value.bias.grad), n, H, A, L.ACT_NONE, st)
             dist.grads_ready((self.pi.weight.grad, self.pi.bias.grad, self.value.weight.grad, self.value.bias.grad))
             return dh
+        if isinstance(ex["pi"], LY.NarrowHead):
+            dh = ex["pi"].backward(h_out, dlogits, n)
+            return ex["value"].backward(h_out, dvalue.reshape(n, 1), n, dx_add=dh)
         dlog_b = torch.empty(n, A, dtype=torch.bfloat16, device=dev)
         dval_b = torch.empty(n, 1, dtype=torch.bfloat16, device=dev)
         L.call("cb_add_to_bf16", L.ptr(dlogits), None, L.ptr(dlog_b), n * A, st)

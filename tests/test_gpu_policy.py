@@ -594,3 +594,42 @@ def test_ppo_icm_on_a_collector_layout_rollout_matches_separate_tensors():
     for k in g0:
         a, b = g0[k].double().flatten(), g1[k].double().flatten()
         assert float(a @ b / (a.norm() * b.norm())) > 0.9999, k
+
+
+def test_twelve_actions_run_entirely_on_tcgen05():
+    """SuperMarioBros' COMPLEX_MOVEMENT has 12 actions (envs/gym.py:190): too wide for the fused heads kernel.  The policy's
+    pi / value heads and ICM's inverse-model output then run as zero-padded tcgen05 GEMMs (layers.NarrowHead), not on
+    the SIMT cross-check engine: with the engine forced to 'umma' (which raises on any shape without a tcgen05
+    specialisation) a full PPO + ICM loss / gradient pass goes through and matches the oracle."""
+    T, B, A, seed = 6, 8, 12, 1212
+    params = R.make_policy_params(A, seed)
+    icm_params = R.make_params(R.icm_shapes(A, "idf_burda"), seed + 2)
+    obs, nxt = R.make_frames(seed + 3, T, B), R.make_frames(seed + 4, T, B)
+    prev_action, action = R.make_actions(seed + 5, T, B, A), R.make_actions(seed + 6, T, B, A)
+    old_prob, ret, adv = R.make_probs(seed + 7, T, B, A), R.make_normal(seed + 8, T, B), R.make_normal(seed + 9, T, B)
+    valid = 1 - R.make_suffix_done(seed + 10, T, B, frac=0.3)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    q = {k: v.clone().requires_grad_(True) for k, v in icm_params.items()}
+    pi, v, _ = O.policy_forward(p, obs, R.onehot(prev_action, A), None)
+    ref = O.ppo_loss(pi, v, action, old_prob, ret, adv, valid, 0.1, 1.0, 0.01)
+    inv, fwd = O.icm_loss(q, obs, nxt, R.onehot(action, A), valid, "idf_burda", 0.2)
+    (ref[0] + inv + fwd).backward()
+    LY.set_engine("umma")
+    try:
+        m = make_model(A, params, icm_params)
+        assert not m._fused_heads()
+        algo = PPO(curiosity_type="icm", clip_grad_norm=1e9)
+        algo.initialize(m, n_itr=10)
+        dv = lambda t: t.to(DEV)
+        o = dv(obs)
+        info = algo.loss_and_grads_(o, dv(prev_action), dv(action), dv(ret), dv(adv), dv(valid), dv(old_prob), None,
+                                    (o, dv(nxt), dv(R.onehot(action, A))), None)
+    finally:
+        LY.set_engine("auto")
+    assert abs(float(info.loss) - float(ref[0] + inv + fwd)) <= 1e-2 * abs(float(ref[0] + inv + fwd))
+    assert abs(float(info.inv_loss) - float(inv)) <= 1e-2 * float(inv)
+    named = dict(m.named_parameters())
+    for k in ("pi.weight", "pi.bias", "value.weight", "value.bias", "lstm.weight_hh_l0"):
+        assert cosine(named[k].grad.cpu(), p[k].grad) > 0.995, (k, cosine(named[k].grad.cpu(), p[k].grad))
+    for k in ("inverse_model.2.weight", "inverse_model.2.bias", "inverse_model.0.weight"):
+        assert cosine(named["curiosity_model." + k].grad.cpu(), q[k].grad) > 0.995, k
