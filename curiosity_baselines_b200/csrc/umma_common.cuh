@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Consumes every value of v[] in a real instruction (a store of their XOR to a per-warp scratch word of shared
+// memory): the shared-memory loads that produced them have RETURNED, not merely been issued, before whatever follows
+// in program order -- e.g. the mbarrier arrive that hands the buffer they read back to the TMA producer.  (An arrive
+// carries no scoreboard dependency on the warp's outstanding loads by itself; observed as one warp's worth of stale
+// pixels in a frame once in a few thousand samples.)
+template <int N>
+__device__ __forceinline__ void loads_landed(uint32_t scratch_saddr, const uint32_t (&v)[N]) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x ^= v[i];
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(scratch_saddr), "r"(x) : "memory");
+}
+
 // One lane of a converged warp (elect.sync).  The MMA-issuing warp runs its loops with all 32 lanes so that
 // loop state, barrier phases and descriptors stay provably warp-uniform (uniform registers, no per-MMA
 // "waterfall" loop moving operands into them); only the tcgen05 instructions themselves are predicated on this.

@@ -499,6 +499,7 @@ __global__ void __launch_bounds__((4 * CG + kEW + 2) * 32, 1) umma_conv1s_fwd_ke
                         px[i] = g < groups ? raw[g] : 0u;
                     }
                 }
+                umma::loads_landed(bar_base + 320u + 4u * warp, px);   // the slot is refilled as soon as it is released
                 __syncwarp();                                 // one arrival per warp
                 if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));
                 if (cc == 0) umma::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -816,6 +817,7 @@ umma_conv1s_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const Conv1Pa
 #pragma unroll
                         for (int i = 0; i < kMaxGroups; ++i) px[i] = gidx[i] >= 0 ? raw[gidx[i]] : 0u;
                     }
+                    umma::loads_landed(bar_base + 256u + 4u * warp, px);   // the slot is refilled as soon as it is released
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(rempty_bar(rslot));       // one arrival per warp
                     if (++rslot == p.raw_slots) { rslot = 0; rphase ^= 1u; }

@@ -1,0 +1,452 @@
+// RND trunk, first two convolutions of ONE network in one kernel (rnd.py:55-61 / 40-46):
+//
+//   uint8 newest frame [84x84] --normalise, clamp +-5 (rnd.py:169-170)--> conv 8x8 s4 (1->32) + LeakyReLU
+//                                                                      --> conv 4x4 s2 (32->64) + LeakyReLU  -> a2 [n,9,9,64] bf16
+//
+// The 20x20x32 activation between the two layers (25.6 KB per sample, 3.4 GB per 131 072-sample pass written and
+// read again by the separate kernels) never leaves the SM.  Both layers run on tcgen05:
+//   layer 1  the space-to-depth form of umma_conv1.cu: the normalised frame is written once as [21x21 blocks][16 px]
+//            (32-byte rows) and the 8x8/stride-4 convolution is four K = 16 MMAs per 128-row tile, each reading a
+//            row-shifted window of that image; its accumulators (TMEM) are drained by the producer warps, which apply
+//            LeakyReLU and deposit bf16 pixels in the two-plane, two-pixels-per-128-byte-row swizzled slab that
+//   layer 2  the window convolution of umma_window.cuh reads with shifted UMMA descriptors (same taps, same
+//            bias-by-MMA, same epilogue), one sample per 128-row tile.
+// When the caller needs the intermediate activation (predictor in the loss pass: conv2's weight gradient reads it),
+// the slab is also written out by TMA, two plane stores per sample.
+// (A first version computed layer 1 with warp-level mma.sync in the producer warps: HMMA.16816 issues once per ~16
+// cycles per scheduler on this part -- an eighth of the tcgen05 rate -- and the kernel ran at 2.1 ms per 131 072
+// samples, slower than the two separate kernels.)
+//
+// Warp roles (576 threads): 0 = loader (conv2 weights by TMA, raw frames by bulk copy), 1 = TMEM owner + tcgen05
+// issuer for both layers, 2-9 = conv2 epilogue, 10-17 = producers (frame conversion and first-layer drain).  Raw
+// slots, block images, first-layer accumulators and slab stages are all double-buffered on the sample parity.
+#include "common.cuh"
+#include "umma_window.cuh"
+
+namespace cb {
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle);
+}
+
+namespace {
+
+using namespace umma;
+
+constexpr int kH = 84, kPx = kH * kH;                 // 7056 pixels = 1764 groups of four
+constexpr int kBW = 21, kBRows = kBW * kBW;           // 4x4-pixel blocks per frame row / per frame
+constexpr int kO1 = 20, kC1 = 32, kG = 10, kO2 = 9, kC2 = 64;
+constexpr int kTaps = 8;
+constexpr int kEpiGroups = 2;                         // conv2 epilogue warps per TMEM lane quarter
+constexpr int kProdWarp0 = kEpiWarp0 + 4 * kEpiGroups;
+constexpr int kProdWarps = 8, kProdThreads = kProdWarps * 32;
+constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;
+constexpr int kItems = (kPx / 4 + kProdThreads - 1) / kProdThreads;   // 4-pixel groups per producer thread (7)
+
+constexpr uint32_t kW2Bytes = kTaps * kC2 * 128;      // 65536
+constexpr uint32_t kW1Bytes = 4 * kC1 * 32;           // four taps of [32 channels][16 pixels]
+constexpr uint32_t kPlaneBytes = 13312;               // 100 rows of 128 B, rounded up to the 1024-byte swizzle atom
+constexpr uint32_t kStageBytes = 2 * kPlaneBytes;
+constexpr uint32_t kS2dBytes = 14336;                 // 441 block rows of 32 B, rounded
+constexpr uint32_t kRawBytes = kPx, kTabBytes = 2 * kPx * 4;
+constexpr uint32_t kW1Off = kW2Bytes;
+constexpr uint32_t kSlabOff = kW1Off + kW1Bytes;
+constexpr uint32_t kS2dOff = kSlabOff + 2 * kStageBytes;      // shifted windows of the last slab plane / block image read
+constexpr uint32_t kRawOff = kS2dOff + 2 * kS2dBytes;         // on into whatever follows: rows that are never stored
+constexpr uint32_t kTabOff = kRawOff + 2 * kRawBytes;
+constexpr uint32_t kBarOff = (kTabOff + kTabBytes + 1023u) & ~1023u;
+constexpr uint32_t kOnesOff = kBarOff + 512u, kBias2Off = kOnesOff + 4096u, kBias1Off = kBias2Off + kC2 * 32u;
+constexpr uint32_t kSmemBytes = kBias1Off + kC1 * 32u + 1024u /*alignment*/;
+static_assert(kSmemBytes <= 227u * 1024u, "shared memory");
+static_assert(kSlabOff % 1024 == 0 && kS2dOff % 1024 == 0 && kRawOff % 16 == 0 && kRawBytes % 16 == 0 && kTabOff % 16 == 0,
+              "alignment");
+
+struct Rnd12Params {
+    const uint8_t* x; long long stride_n; int n;      // newest frame of sample i at x + i*stride_n (16-byte aligned)
+    const float* mean; const float* rstd;             // per-pixel statistics [7056]
+    const __nv_bfloat16* w1; const float* b1;         // conv1 weights [32][64] in torch's (kh, kw) order, bias [32]
+    int store_a1; int debug;
+    GemmParams epi;                                   // conv2 epilogue (bias, activation, out_bf16)
+};
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory"); }
+// four uint8 pixels -> fp32 without the quarter-rate I2F (PRMT builds 2^23 + x, one FADD removes 2^23)
+__device__ __forceinline__ void u8x4_to_f32(uint32_t px, float (&v)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u | j)) - 8388608.f;
+}
+__device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
+// SWIZZLE_32B descriptor: rows of 32 B, 8-row atoms of 256 B
+__device__ __forceinline__ uint64_t desc32(uint32_t saddr) {
+    return (make_smem_desc(saddr, 16, 256) & ~((uint64_t)7 << 61)) | ((uint64_t)6 << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA1, const Rnd12Params p) {
+    constexpr int BN = kC2;
+    // TMEM columns: [0,128) second-layer accumulators (two stages of 64), [128,384) first-layer accumulators (two
+    // stages x four row tiles x 32 channels)
+    constexpr uint32_t TMEM_COLS = 512, kAcc1Col = 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + kBarOff;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };           // slab stage written            (group -> MMA)
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };    // slab stage consumed           (MMA -> group)
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (4 + a); };    // conv2 accumulator ready       (MMA -> epilogue)
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (6 + a); };   // conv2 accumulator drained     (epilogue -> MMA)
+    auto rfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };    // raw frame landed              (loader -> group)
+    auto rempty_bar = [&](int s) { return bar_base + 8u * (10 + s); };  // raw frame consumed            (group -> loader)
+    auto ifull_bar = [&](int s) { return bar_base + 8u * (12 + s); };   // block image written           (group -> MMA)
+    auto iempty_bar = [&](int s) { return bar_base + 8u * (14 + s); };  // block image consumed          (MMA -> group)
+    auto c1full_bar = [&](int s) { return bar_base + 8u * (16 + s); };  // conv1 accumulators ready      (MMA -> group)
+    auto c1empty_bar = [&](int s) { return bar_base + 8u * (18 + s); }; // conv1 accumulators drained    (group -> MMA)
+    const uint32_t w_bar = bar_base + 8u * 20;
+    const uint32_t tmem_slot = bar_base + 8u * 21;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + kBarOff + 8u * 21);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* bias2 = stage_bias(p.epi, gen + kBarOff + 256u);
+    // per-pixel statistics, resident for the whole kernel
+    {
+        float* tab = reinterpret_cast<float*>(gen + kTabOff);
+        for (int i = threadIdx.x; i < kPx; i += blockDim.x) { tab[i] = __ldg(p.mean + i); tab[kPx + i] = __ldg(p.rstd + i); }
+    }
+    // first-layer weights: per tap (bh, bw) a K-major [32 channels][16 = (py, px)] block, SWIZZLE_32B
+    for (int i = threadIdx.x; i < 4 * kC1 * 16; i += blockDim.x) {
+        const int e = i & 15, n = (i >> 4) & 31, t = i >> 9;
+        const int kh = 4 * (t >> 1) + (e >> 2), kw = 4 * (t & 1) + (e & 3);
+        *reinterpret_cast<__nv_bfloat16*>(gen + kW1Off + swz32((uint32_t)((t * kC1 + n) * 32 + e * 2))) = p.w1[n * 64 + kh * 8 + kw];
+    }
+    // bias-by-MMA operands (SWIZZLE_32B rows of 32 B): ones [128 rows], hi/mid/lo split of bias2 [64 rows], bias1 [32 rows]
+    {
+        uint8_t* ob = gen + kOnesOff;
+        for (uint32_t i = threadIdx.x; i < (4096u + (BN + kC1) * 32u) / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(ob)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (threadIdx.x < 128)
+            *reinterpret_cast<uint2*>(ob + swz32(threadIdx.x * 32u)) = make_uint2(0x3f803f80u, 0x00003f80u);
+        if ((int)threadIdx.x < BN + kC1) {
+            const float b = (int)threadIdx.x < BN ? __ldg(p.epi.bias + threadIdx.x) : __ldg(p.b1 + (threadIdx.x - BN));
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const float r1 = b - __bfloat162float(hi);
+            const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+            *reinterpret_cast<uint2*>(ob + 4096u + swz32(threadIdx.x * 32u)) =
+                make_uint2((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                           (uint32_t)__bfloat16_as_ushort(lo));
+        }
+    }
+    // slab padding rows, block-image tails and everything a shifted window may touch start out as zeros
+    {
+        uint4* z = reinterpret_cast<uint4*>(gen + kSlabOff);
+        for (uint32_t i = threadIdx.x; i < (kTabOff - kSlabOff) / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmW);
+        if (p.store_a1) prefetch_tmap(&tmA1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
+            mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * kEpiGroups);
+            mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kProdWarps);
+            mbar_init(ifull_bar(s), 1); mbar_init(iempty_bar(s), 1);
+            mbar_init(c1full_bar(s), 1); mbar_init(c1empty_bar(s), 1);
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int my_tiles = (p.n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // this CTA's samples
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_bar, kW2Bytes);
+            for (int kb = 0; kb < kTaps; ++kb) tma_load_2d(smem_base + kb * BN * 128, &tmW, w_bar, kb * 64, 0);
+            for (int j = 0; j < my_tiles; ++j) {
+                const long long tile = blockIdx.x + (long long)j * gridDim.x;
+                if (j + 3 < my_tiles && !(p.debug & 1)) prefetch_l2_bulk(p.x + (tile + 3ll * gridDim.x) * p.stride_n, kRawBytes);
+                const int slot = j & 1;
+                mbar_wait(rempty_bar(slot), (((uint32_t)j >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(rfull_bar(slot), kRawBytes);
+                bulk_load(smem_base + kRawOff + slot * kRawBytes, p.x + tile * p.stride_n, kRawBytes, rfull_bar(slot));
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();              // all lanes loop, one issues (see umma_gemm_kernel)
+        constexpr uint32_t idesc2 = make_idesc(128, BN, 0, 0), idesc1 = make_idesc(128, kC1, 0, 0);
+        mbar_wait(w_bar, 0);
+        const uint64_t db2 = make_smem_desc(smem_base, 16, 1024);
+        const uint64_t db1 = desc32(smem_base + kW1Off);
+        const uint64_t d_ones = desc32(smem_base + kOnesOff);
+        const uint64_t d_bias2 = desc32(smem_base + kBias2Off), d_bias1 = desc32(smem_base + kBias1Off);
+        // first layer of sample j is issued before the second layer of sample j-1: the producers drain its
+        // accumulators while the (longer) second-layer MMAs of sample j-1 run
+        for (int j = 0; j <= my_tiles; ++j) {
+            if (j < my_tiles) {
+                const int g = j & 1;
+                const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+                mbar_wait(c1empty_bar(g), ph ^ 1u);
+                mbar_wait(ifull_bar(g), ph);
+                fence_after_thread_sync();
+                const uint64_t da0 = desc32(smem_base + kS2dOff + g * kS2dBytes);
+                if (leader) {
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        const uint32_t d = tmem_base + kAcc1Col + (uint32_t)((g * 4 + mt) * kC1);
+                        mma_f16_ss(d, d_ones, d_bias1, idesc1, 0u);                                  // D = bias
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)      // tap (bh, bw): the block image shifted by bh*21 + bw rows
+                            mma_f16_ss(d, da0 + (uint64_t)(((mt * 128 + (t >> 1) * kBW + (t & 1)) * 32) >> 4),
+                                       db1 + (uint64_t)((t * kC1 * 32) >> 4), idesc1, 1u);
+                    }
+                    mma_commit(iempty_bar(g));
+                    mma_commit(c1full_bar(g));
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int jj = j - 1, st = jj & 1;    // slab stage == accumulator stage == producer group
+                const uint32_t ph = ((uint32_t)jj >> 1) & 1u;
+                mbar_wait(tempty_bar(st), ph ^ 1u);
+                mbar_wait(full_bar(st), ph);
+                fence_after_thread_sync();
+                const uint64_t da0 = make_smem_desc(smem_base + kSlabOff + st * kStageBytes, 16, 1024);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(st * BN);
+                if (leader) {
+                    mma_f16_ss(d_tmem, d_ones, d_bias2, idesc2, 0u);                                 // D = bias
+#pragma unroll
+                    for (int kb = 0; kb < kTaps; ++kb) {
+                        // tap (kh, kw pair j2): plane kh & 1, shifted by (kh >> 1) grid rows and j2 grid columns
+                        const uint32_t off16 = ((uint32_t)((kb >> 1) & 1) * kPlaneBytes + (uint32_t)((kb >> 2) * kG + (kb & 1)) * 128u) >> 4;
+                        const uint64_t da = da0 + (uint64_t)off16;
+                        const uint64_t db = db2 + (uint64_t)(kb * BN * 8);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, 1u);
+                    }
+                    mma_commit(empty_bar(st));
+                    mma_commit(tfull_bar(st));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < kProdWarp0) {
+        const int quarter = warp & 3;
+        const int sub = (warp - kEpiWarp0) >> 2;
+        const int r = quarter * 32 + lane;
+        const int gy = r / kG, gx = r - gy * kG;
+        const bool ok = r < kG * kG && gy < kO2 && gx < kO2;
+        const long long rel_row = (long long)gy * kO2 + gx;
+        for (int j = 0; j < my_tiles; ++j) {
+            const long long tile = blockIdx.x + (long long)j * gridDim.x;
+            const int acc = j & 1;
+            epilogue_tile<BN, 1, EPI_SIMPLE, kEpiGroups, false>(
+                p.epi, bias2, tmem_base + (uint32_t)(acc * BN), quarter, sub, lane, 0, tfull_bar(acc), ((uint32_t)j >> 1) & 1u,
+                [&](int, bool& valid, long long& grow, long long& base) {
+                    valid = ok;
+                    grow = tile * (kO2 * kO2) + rel_row;
+                    base = grow * BN;
+                });
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    } else {
+        // ---- producers (eight warps, two per TMEM lane quarter).  Iteration j, software-pipelined one sample deep:
+        //   (1) raw frame j+1 -> normalised bf16 image in 4x4-block order (the first layer as a 2x2 convolution over
+        //       blocks: each tap is a row-shifted window of that image, see umma_conv1.cu) -> [tcgen05: 20 MMAs]
+        //   (2) first-layer accumulators of sample j -> LeakyReLU -> bf16 -> slab stage j&1 in the layout the second
+        //       layer's windows read
+        // so the first-layer MMAs of a sample run (behind the previous sample's second layer) while the producers
+        // convert the next frame, and nobody waits for the tensor pipe as long as an iteration is not shorter than it.
+        const int quarter = warp & 3, sub = (warp - kProdWarp0) >> 2;
+        const int tg = threadIdx.x - kProdWarp0 * 32;
+        const float4* s_mean = reinterpret_cast<const float4*>(gen + kTabOff);
+        const float4* s_rstd = reinterpret_cast<const float4*>(gen + kTabOff + kPx * 4);
+        const __nv_bfloat162 slope = __floats2bfloat162_rn(0.01f, 0.01f);
+        const __nv_bfloat162 five = __floats2bfloat162_rn(5.f, 5.f), nfive = __floats2bfloat162_rn(-5.f, -5.f);
+        // where this thread's 4-pixel groups land in the block image (fixed for the whole kernel)
+        uint32_t soff[kItems];
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int g4 = tg + i * kProdThreads, y = g4 / kBW, x4 = g4 - y * kBW;
+            soff[i] = swz32((uint32_t)(((y >> 2) * kBW + x4) * 32 + (y & 3) * 8));
+        }
+        // the two row tiles this warp drains (sub 0: tiles 0 and 3, sub 1: tiles 1 and 2 -- tile 3 is mostly past the
+        // frame) and where this lane's accumulator row goes in the slab: block (by, bx) = output pixel, or none
+        int srow[2]; uint32_t sx[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int mt = sub ? 1 + k : 3 * k;
+            const int r = mt * 128 + quarter * 32 + lane;
+            const int by = r / kBW, bx = r - by * kBW;
+            const bool ok = r < kBRows && by < kO1 && bx < kO1;
+            const uint32_t row = (uint32_t)(by & 1) * kPlaneBytes + (uint32_t)((by >> 1) * kG + (bx >> 1)) * 128u;
+            srow[k] = ok ? (int)row : -1;
+            sx[k] = ((row >> 7) & 7u) ^ ((uint32_t)(bx & 1) * 4u);        // 16-byte chunk c of the pixel goes to chunk c ^ sx
+        }
+        for (int j = -1; j < my_tiles; ++j) {
+            if (j + 1 < my_tiles) {
+                const int b = (j + 1) & 1;
+                const uint32_t ph = ((uint32_t)(j + 1) >> 1) & 1u;
+                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + kRawOff + b * kRawBytes);
+                uint8_t* img = gen + kS2dOff + b * kS2dBytes;
+                mbar_wait(rfull_bar(b), ph);
+                uint32_t px[kItems];                  // all loads first: the raw slot is released early
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    const int g4 = tg + i * kProdThreads;
+                    px[i] = g4 < kPx / 4 ? raw[g4] : 0u;
+                }
+                if (!(p.debug & 4)) loads_landed(bar_base + 176u + 4u * warp, px);   // the slot is refilled as soon as it is released
+                __syncwarp();
+                if (lane == 0 && !(p.debug & 2)) mbar_arrive(rempty_bar(b));
+                mbar_wait(iempty_bar(b), ph ^ 1u);    // the first-layer MMAs of the sample two back are done with this image
+                float4 m = s_mean[tg], r = s_rstd[tg];
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    const int g4 = tg + i * kProdThreads;
+                    const float4 mc = m, rc = r;
+                    if (i + 1 < kItems && g4 + kProdThreads < kPx / 4) {      // next item's statistics: in flight under this item's math
+                        m = s_mean[g4 + kProdThreads]; r = s_rstd[g4 + kProdThreads];
+                    }
+                    if (g4 < kPx / 4) {
+                        float v[4];
+                        u8x4_to_f32(px[i], v);
+                        __nv_bfloat162 lo = __floats2bfloat162_rn((v[0] - mc.x) * rc.x, (v[1] - mc.y) * rc.y);
+                        __nv_bfloat162 hi = __floats2bfloat162_rn((v[2] - mc.z) * rc.z, (v[3] - mc.w) * rc.w);
+                        // clamp after the rounding: 5 is a bf16 value and rounding is monotonic, so the result is the same
+                        lo = __hmin2(__hmax2(lo, nfive), five);
+                        hi = __hmin2(__hmax2(hi, nfive), five);
+                        *reinterpret_cast<uint2*>(img + soff[i]) =
+                            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    }
+                }
+                fence_proxy_async();
+                if (lane == 0 && (p.debug & 2)) mbar_arrive(rempty_bar(b));
+                prod_bar();
+                if (tg == 0) mbar_arrive(ifull_bar(b));
+            }
+            if (j >= 0) {
+                const int b = j & 1;
+                const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+                const long long tile = blockIdx.x + (long long)j * gridDim.x;
+                uint8_t* slab = gen + kSlabOff + b * kStageBytes;
+                // the TMA store of this slab stage's previous contents must have finished reading it (thread 0 issued
+                // it; the barrier above / below orders everyone's writes after this wait)
+                if (p.store_a1 && tg == 0) bulk_wait_read0();
+                if (p.store_a1) prod_bar();
+                mbar_wait(empty_bar(b), ph ^ 1u);     // second-layer MMAs of the sample two back are done with this slab stage
+                mbar_wait(c1full_bar(b), ph);
+                fence_after_thread_sync();
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int mt = sub ? 1 + k : 3 * k;
+                    if (mt * 128 + quarter * 32 >= kBRows) continue;      // (warp-uniform) no block row in this quarter
+                    uint32_t acc[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kAcc1Col + (uint32_t)((b * 4 + mt) * kC1), acc);
+                    tmem_ld_wait();
+                    if (srow[k] < 0) continue;
+                    // accumulator = conv + bias; round to bf16, LeakyReLU on packed pairs (as the stand-alone kernel),
+                    // then the pixel's 64 bytes as four 16-byte chunks of its swizzled 128-byte slab row
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                        h = __hmax2(h, __hmul2(h, slope));
+                        pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint8_t* dst = slab + srow[k];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(dst + (((uint32_t)c ^ sx[k]) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+                fence_before_thread_sync();
+                fence_proxy_async();                  // generic-proxy slab writes -> visible to tcgen05 / TMA
+                prod_bar();
+                if (tg == 0) {
+                    mbar_arrive(c1empty_bar(b));
+                    if (p.store_a1) {
+                        const uint32_t slab_s = smem_base + kSlabOff + b * kStageBytes;
+                        tma_store_5d(&tmA1, slab_s, 0, 0, 0, 0, (int)tile);
+                        tma_store_5d(&tmA1, slab_s + kPlaneBytes, 0, 0, 1, 0, (int)tile);
+                        bulk_commit();
+                    }
+                    mbar_arrive(full_bar(b));
+                }
+            }
+        }
+        if (p.store_a1 && tg == 0) bulk_wait0();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) { fence_after_thread_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+static int g_rnd12_debug = 0;
+extern "C" void cb_rnd_conv12_debug(int v) { g_rnd12_debug = v; }
+extern "C" int cb_rnd_conv12_supported(void) { return cb_device_supports_umma(); }
+
+extern "C" int cb_rnd_conv12_fwd(const uint8_t* x, int64_t stride_n, int n, const float* mean, const float* rstd,
+                                 const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                                 void* a1_out_bf16, void* a2_out_bf16, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CB_REQUIRE(x && mean && rstd && w1_bf16 && b1 && w2_bf16 && b2 && a2_out_bf16, CB_E_ARG, "cb_rnd_conv12_fwd: null pointer");
+    CB_REQUIRE(n > 0, CB_E_ARG, "cb_rnd_conv12_fwd: n = %d", n);
+    CB_REQUIRE(((uintptr_t)x & 15) == 0 && stride_n % 16 == 0, CB_E_ALIGN,
+               "cb_rnd_conv12_fwd: frames must be 16-byte aligned (base %p, stride %lld)", (const void*)x, (long long)stride_n);
+    CB_REQUIRE(cb_device_supports_umma() == 1, CB_E_ARCH, "cb_rnd_conv12_fwd needs an sm_100 device");
+    CUtensorMap tmW, tmA1;
+    {
+        uint64_t dims[2] = {(uint64_t)(16 * kC1), (uint64_t)kC2};
+        uint64_t strides[1] = {(uint64_t)(16 * kC1) * 2};
+        uint32_t box[2] = {64, (uint32_t)kC2};
+        int rc = cb::encode_tmap_bf16(&tmW, w2_bf16, 2, dims, strides, box, 3); if (rc) return rc;
+    }
+    if (a1_out_bf16) {      // [n][20][20][32] seen as [n][10][2][10][64]: one plane of one sample per store
+        uint64_t dims[5] = {64, (uint64_t)kG, 2, (uint64_t)kG, (uint64_t)n};
+        uint64_t strides[4] = {128, (uint64_t)kO1 * 64, (uint64_t)kO1 * 128, (uint64_t)kO1 * kO1 * 64};
+        uint32_t box[5] = {64, (uint32_t)kG, 1, (uint32_t)kG, 1};
+        int rc = cb::encode_tmap_bf16(&tmA1, a1_out_bf16, 5, dims, strides, box, 3); if (rc) return rc;
+    } else {
+        tmA1 = tmW;
+    }
+    Rnd12Params p{};
+    p.x = x; p.stride_n = stride_n; p.n = n; p.mean = mean; p.rstd = rstd;
+    p.w1 = (const __nv_bfloat16*)w1_bf16; p.b1 = b1; p.store_a1 = a1_out_bf16 ? 1 : 0; p.debug = g_rnd12_debug;
+    p.epi.n_total = kC2; p.epi.bias = b2; p.epi.bias_in_acc = 1; p.epi.act = CB_ACT_LRELU;
+    p.epi.out_bf16 = (__nv_bfloat16*)a2_out_bf16;
+    static bool attr = false;
+    if (!attr) {
+        CB_CUDA(cudaFuncSetAttribute(umma_rnd12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        attr = true;
+    }
+    const int grid = n < sm_count() ? n : sm_count();
+    umma_rnd12_kernel<<<grid, kThreads, kSmemBytes, s>>>(tmW, tmA1, p);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}

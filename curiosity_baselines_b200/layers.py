@@ -680,15 +680,17 @@ class Chain:
 
     def forward(self, x, n, in_dtype=L.BF16, strides=None, norm=None, last_f32=True,
                 last_bf16=False, first_out=None):
-        """``first_out``: bf16 output of layer 0 computed elsewhere (fused twin first conv)."""
+        """``first_out``: bf16 output of layer 0 computed elsewhere (fused twin first conv), or a list with the
+        outputs of the first few layers (fused first two convolutions; an entry that is not needed may be None)."""
         acts = []
         cur = x
         last = len(self.layers) - 1
         out_f32 = None
+        lead = [] if first_out is None else (list(first_out) if isinstance(first_out, (list, tuple)) else [first_out])
         for i, layer in enumerate(self.layers):
-            if i == 0 and first_out is not None:
-                acts.append(first_out)
-                cur = first_out
+            if i < len(lead):
+                acts.append(lead[i])
+                cur = lead[i]
                 continue
             kw = dict(in_dtype=in_dtype, strides=strides, norm=norm) if i == 0 else {}
             want_f32 = last_f32 and i == last

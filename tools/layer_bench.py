@@ -76,6 +76,19 @@ if args.only and "c4" in args.only:      # ICM-shaped first conv: 4-channel stac
     st4 = (4 * 7056, 84, 1, 7056)
     cases["conv1c4_fwd"] = (lambda: conv1c4.forward(frames4.data_ptr(), n, in_dtype=L.U8, strides=st4), 2.0 * 256 * 32 * 400 * n)
     cases["conv1c4_wgrad"] = (lambda: conv1c4.wgrad(frames4.data_ptr(), dy1, n, in_dtype=L.U8, strides=st4), 2.0 * 256 * 32 * 400 * n)
+# first two convolutions in one launch (cb_rnd_conv12_fwd), without / with the 20x20x32 activation written out
+conv1.prepare(); conv2.prepare()
+a2o = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
+fl12 = 2.0 * (64 * 32 * 400 + 512 * 64 * 81) * n
+
+
+def fused12(a1_out):
+    L.call("cb_rnd_conv12_fwd", frames.data_ptr(), 7056, n, L.ptr(nm[0]), L.ptr(nm[1]), L.ptr(conv1.w_native),
+           L.ptr(conv1.bias), L.ptr(conv2.w_fwd), L.ptr(conv2.bias), L.ptr(a1_out), L.ptr(a2o), L.stream())
+
+
+cases["fused12_fwd"] = (lambda: fused12(None), fl12)
+cases["fused12_keep_fwd"] = (lambda: fused12(a1), fl12)
 for name, (fn, fl) in cases.items():
     if args.only and args.only not in name:
         continue
