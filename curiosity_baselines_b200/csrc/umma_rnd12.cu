@@ -1,25 +1,32 @@
-// RND trunk, first two convolutions of ONE network in one kernel (rnd.py:55-61 / 40-46):
+// RND trunk, first two convolutions (rnd.py:40-46 / 55-61) without the 20x20x32 activation between them ever
+// leaving the SM:
 //
-//   uint8 newest frame [84x84] --normalise, clamp +-5 (rnd.py:169-170)--> conv 8x8 s4 (1->32) + LeakyReLU
-//                                                                      --> conv 4x4 s2 (32->64) + LeakyReLU  -> a2 [n,9,9,64] bf16
+//   cb_rnd_normalize_s2d   uint8 newest frame [84x84] --normalise, clamp +-5 (rnd.py:169-170)--> bf16 frame in
+//                          4x4-pixel-block order ([21x21 blocks][16 px], 32-byte rows, pre-swizzled), ONCE per
+//                          sample for both networks (target and predictor read the same normalised frame)
+//   cb_rnd_conv12_fwd      block image --conv 8x8 s4 (1->32) + LeakyReLU--> slab in shared memory
+//                                      --conv 4x4 s2 (32->64) + LeakyReLU--> a2 [n,9,9,64] bf16          (one network)
 //
-// The 20x20x32 activation between the two layers (25.6 KB per sample, 3.4 GB per 131 072-sample pass written and
-// read again by the separate kernels) never leaves the SM.  Both layers run on tcgen05:
-//   layer 1  the space-to-depth form of umma_conv1.cu: the normalised frame is written once as [21x21 blocks][16 px]
-//            (32-byte rows) and the 8x8/stride-4 convolution is four K = 16 MMAs per 128-row tile, each reading a
-//            row-shifted window of that image; its accumulators (TMEM) are drained by the producer warps, which apply
-//            LeakyReLU and deposit bf16 pixels in the two-plane, two-pixels-per-128-byte-row swizzled slab that
+// Both layers run on tcgen05:
+//   layer 1  the space-to-depth form of umma_conv1.cu: the 8x8/stride-4 convolution is four K = 16 MMAs per 128-row
+//            tile, each reading a row-shifted window of the block image (which arrives by one bulk copy per sample);
+//            its accumulators (TMEM) are drained by the producer warps, which apply LeakyReLU and deposit bf16 pixels in
+//            the two-plane, two-pixels-per-128-byte-row swizzled slab that
 //   layer 2  the window convolution of umma_window.cuh reads with shifted UMMA descriptors (same taps, same
 //            bias-by-MMA, same epilogue), one sample per 128-row tile.
 // When the caller needs the intermediate activation (predictor in the loss pass: conv2's weight gradient reads it),
 // the slab is also written out by TMA, two plane stores per sample.
-// (A first version computed layer 1 with warp-level mma.sync in the producer warps: HMMA.16816 issues once per ~16
-// cycles per scheduler on this part -- an eighth of the tcgen05 rate -- and the kernel ran at 2.1 ms per 131 072
-// samples, slower than the two separate kernels.)
 //
-// Warp roles (576 threads): 0 = loader (conv2 weights by TMA, raw frames by bulk copy), 1 = TMEM owner + tcgen05
-// issuer for both layers, 2-9 = conv2 epilogue, 10-17 = producers (frame conversion and first-layer drain).  Raw
-// slots, block images, first-layer accumulators and slab stages are all double-buffered on the sample parity.
+// Measured (131 072 samples): 1.53 ms per network (+ 0.54 ms per pass for the normalisation) against 0.78 + 0.98 ms
+// for the separate kernels -- no gain: tcgen05.mma with both operands in shared memory costs ~(M + N) / 4 cycles per
+// K = 16 step here (46 cycles at N = 32, 52 at N = 64, against 16 / 32 for the math), so these skinny layers are bound
+// by the operand fetch from shared memory, not by the HBM round trip the fusion removes.  Earlier versions (layer 1 by
+// mma.sync: 2.1 ms; uint8 conversion inside the kernel with three different producer arrangements: 1.5 ms each) and
+// the ablations are in profiles/r2_fused_conv12_study.txt.  The kernel stays as an option (RND.fuse_conv12).
+//
+// Warp roles (576 threads): 0 = loader (conv2 weights by TMA, block images by bulk copy), 1 = TMEM owner + tcgen05
+// issuer for both layers (and the TMA store of the slab), 2-5 = conv2 epilogue, 6-17 = first-layer drain (three per
+// TMEM lane quarter).  Block images: ring of four; first-layer accumulators and slab stages: double-buffered.
 #include "common.cuh"
 #include "umma_window.cuh"
 
@@ -32,39 +39,36 @@ namespace {
 
 using namespace umma;
 
-constexpr int kH = 84, kPx = kH * kH;                 // 7056 pixels = 1764 groups of four
+constexpr int kH = 84, kPx = kH * kH;                 // 7056 pixels
 constexpr int kBW = 21, kBRows = kBW * kBW;           // 4x4-pixel blocks per frame row / per frame
 constexpr int kO1 = 20, kC1 = 32, kG = 10, kO2 = 9, kC2 = 64;
 constexpr int kTaps = 8;
-constexpr int kEpiGroups = 2;                         // conv2 epilogue warps per TMEM lane quarter
+constexpr int kEpiGroups = 1;                         // conv2 epilogue warps per TMEM lane quarter (two 32-column chunks each)
 constexpr int kProdWarp0 = kEpiWarp0 + 4 * kEpiGroups;
-constexpr int kProdWarps = 8, kProdThreads = kProdWarps * 32;
+constexpr int kProdWarps = 12;                        // three per TMEM lane quarter
 constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;
-constexpr int kItems = (kPx / 4 + kProdThreads - 1) / kProdThreads;   // 4-pixel groups per producer thread (7)
+constexpr int kImgStages = 4;
 
 constexpr uint32_t kW2Bytes = kTaps * kC2 * 128;      // 65536
 constexpr uint32_t kW1Bytes = 4 * kC1 * 32;           // four taps of [32 channels][16 pixels]
 constexpr uint32_t kPlaneBytes = 13312;               // 100 rows of 128 B, rounded up to the 1024-byte swizzle atom
 constexpr uint32_t kStageBytes = 2 * kPlaneBytes;
-constexpr uint32_t kS2dBytes = 14336;                 // 441 block rows of 32 B, rounded
-constexpr uint32_t kRawBytes = kPx, kTabBytes = 2 * kPx * 4;
+constexpr uint32_t kImgBytes = kBRows * 32;           // 14112: one normalised frame in block order
+constexpr uint32_t kS2dBytes = 14336;                 // its shared-memory stage (multiple of the 256-byte swizzle atom)
 constexpr uint32_t kW1Off = kW2Bytes;
 constexpr uint32_t kSlabOff = kW1Off + kW1Bytes;
 constexpr uint32_t kS2dOff = kSlabOff + 2 * kStageBytes;      // shifted windows of the last slab plane / block image read
-constexpr uint32_t kRawOff = kS2dOff + 2 * kS2dBytes;         // on into whatever follows: rows that are never stored
-constexpr uint32_t kTabOff = kRawOff + 2 * kRawBytes;
-constexpr uint32_t kBarOff = (kTabOff + kTabBytes + 1023u) & ~1023u;
+constexpr uint32_t kPadOff = kS2dOff + kImgStages * kS2dBytes;   // on into whatever follows: rows that are never stored
+constexpr uint32_t kBarOff = (kPadOff + 4096u + 1023u) & ~1023u;  // (4 KB of zeros after the last image for its windows)
 constexpr uint32_t kOnesOff = kBarOff + 512u, kBias2Off = kOnesOff + 4096u, kBias1Off = kBias2Off + kC2 * 32u;
 constexpr uint32_t kSmemBytes = kBias1Off + kC1 * 32u + 1024u /*alignment*/;
 static_assert(kSmemBytes <= 227u * 1024u, "shared memory");
-static_assert(kSlabOff % 1024 == 0 && kS2dOff % 1024 == 0 && kRawOff % 16 == 0 && kRawBytes % 16 == 0 && kTabOff % 16 == 0,
-              "alignment");
+static_assert(kSlabOff % 1024 == 0 && kS2dOff % 1024 == 0 && kImgBytes % 16 == 0, "alignment");
 
 struct Rnd12Params {
-    const uint8_t* x; long long stride_n; int n;      // newest frame of sample i at x + i*stride_n (16-byte aligned)
-    const float* mean; const float* rstd;             // per-pixel statistics [7056]
+    const uint8_t* img; int n;                        // normalised block images, kImgBytes per sample (cb_rnd_normalize_s2d)
     const __nv_bfloat16* w1; const float* b1;         // conv1 weights [32][64] in torch's (kh, kw) order, bias [32]
-    int store_a1; int debug;
+    int store_a1;
     GemmParams epi;                                   // conv2 epilogue (bias, activation, out_bf16)
 };
 
@@ -75,12 +79,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory"); }
-// four uint8 pixels -> fp32 without the quarter-rate I2F (PRMT builds 2^23 + x, one FADD removes 2^23)
-__device__ __forceinline__ void u8x4_to_f32(uint32_t px, float (&v)[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u | j)) - 8388608.f;
 }
 __device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
 // SWIZZLE_32B descriptor: rows of 32 B, 8-row atoms of 256 B
@@ -98,27 +96,20 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + kBarOff;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };           // slab stage written            (group -> MMA)
-    auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };    // slab stage consumed           (MMA -> group)
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };           // slab stage written            (drain -> MMA)
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };    // slab stage consumed           (MMA -> drain)
     auto tfull_bar = [&](int a) { return bar_base + 8u * (4 + a); };    // conv2 accumulator ready       (MMA -> epilogue)
     auto tempty_bar = [&](int a) { return bar_base + 8u * (6 + a); };   // conv2 accumulator drained     (epilogue -> MMA)
-    auto rfull_bar = [&](int s) { return bar_base + 8u * (8 + s); };    // raw frame landed              (loader -> group)
-    auto rempty_bar = [&](int s) { return bar_base + 8u * (10 + s); };  // raw frame consumed            (group -> loader)
-    auto ifull_bar = [&](int s) { return bar_base + 8u * (12 + s); };   // block image written           (group -> MMA)
-    auto iempty_bar = [&](int s) { return bar_base + 8u * (14 + s); };  // block image consumed          (MMA -> group)
-    auto c1full_bar = [&](int s) { return bar_base + 8u * (16 + s); };  // conv1 accumulators ready      (MMA -> group)
-    auto c1empty_bar = [&](int s) { return bar_base + 8u * (18 + s); }; // conv1 accumulators drained    (group -> MMA)
-    const uint32_t w_bar = bar_base + 8u * 20;
-    const uint32_t tmem_slot = bar_base + 8u * 21;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + kBarOff + 8u * 21);
+    auto c1full_bar = [&](int s) { return bar_base + 8u * (8 + s); };   // conv1 accumulators ready      (MMA -> drain)
+    auto c1empty_bar = [&](int s) { return bar_base + 8u * (10 + s); }; // conv1 accumulators drained    (drain -> MMA)
+    auto ifull_bar = [&](int s) { return bar_base + 8u * (12 + s); };   // block image landed            (bulk copy -> MMA)
+    auto iempty_bar = [&](int s) { return bar_base + 8u * (12 + kImgStages + s); };  // block image consumed (MMA -> loader)
+    const uint32_t w_bar = bar_base + 8u * (12 + 2 * kImgStages);
+    const uint32_t tmem_slot = bar_base + 8u * (13 + 2 * kImgStages);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + kBarOff + 8u * (13 + 2 * kImgStages));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* bias2 = stage_bias(p.epi, gen + kBarOff + 256u);
-    // per-pixel statistics, resident for the whole kernel
-    {
-        float* tab = reinterpret_cast<float*>(gen + kTabOff);
-        for (int i = threadIdx.x; i < kPx; i += blockDim.x) { tab[i] = __ldg(p.mean + i); tab[kPx + i] = __ldg(p.rstd + i); }
-    }
     // first-layer weights: per tap (bh, bw) a K-major [32 channels][16 = (py, px)] block, SWIZZLE_32B
     for (int i = threadIdx.x; i < 4 * kC1 * 16; i += blockDim.x) {
         const int e = i & 15, n = (i >> 4) & 31, t = i >> 9;
@@ -147,19 +138,20 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // slab padding rows, block-image tails and everything a shifted window may touch start out as zeros
     {
         uint4* z = reinterpret_cast<uint4*>(gen + kSlabOff);
-        for (uint32_t i = threadIdx.x; i < (kTabOff - kSlabOff) / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i < (kBarOff - kSlabOff) / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmW);
         if (p.store_a1) prefetch_tmap(&tmA1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
+            // drain warps arrive one by one (no CTA-wide barrier keeps them in lock-step); a slab stage is free again
+            // when the second-layer MMAs AND (if it is written out) the TMA store have finished reading it
+            mbar_init(full_bar(s), kProdWarps); mbar_init(empty_bar(s), p.store_a1 ? 2 : 1);
             mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * kEpiGroups);
-            mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kProdWarps);
-            mbar_init(ifull_bar(s), 1); mbar_init(iempty_bar(s), 1);
-            mbar_init(c1full_bar(s), 1); mbar_init(c1empty_bar(s), 1);
+            mbar_init(c1full_bar(s), 1); mbar_init(c1empty_bar(s), kProdWarps);
         }
+        for (int s = 0; s < kImgStages; ++s) { mbar_init(ifull_bar(s), 1); mbar_init(iempty_bar(s), 1); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -174,13 +166,13 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) {
             mbar_arrive_expect_tx(w_bar, kW2Bytes);
             for (int kb = 0; kb < kTaps; ++kb) tma_load_2d(smem_base + kb * BN * 128, &tmW, w_bar, kb * 64, 0);
+            int slot = 0; uint32_t ph = 0;
             for (int j = 0; j < my_tiles; ++j) {
                 const long long tile = blockIdx.x + (long long)j * gridDim.x;
-                if (j + 3 < my_tiles && !(p.debug & 1)) prefetch_l2_bulk(p.x + (tile + 3ll * gridDim.x) * p.stride_n, kRawBytes);
-                const int slot = j & 1;
-                mbar_wait(rempty_bar(slot), (((uint32_t)j >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(rfull_bar(slot), kRawBytes);
-                bulk_load(smem_base + kRawOff + slot * kRawBytes, p.x + tile * p.stride_n, kRawBytes, rfull_bar(slot));
+                mbar_wait(iempty_bar(slot), ph ^ 1u);
+                mbar_arrive_expect_tx(ifull_bar(slot), kImgBytes);
+                bulk_load(smem_base + kS2dOff + slot * kS2dBytes, p.img + tile * kImgBytes, kImgBytes, ifull_bar(slot));
+                if (++slot == kImgStages) { slot = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -193,14 +185,15 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const uint64_t d_bias2 = desc32(smem_base + kBias2Off), d_bias1 = desc32(smem_base + kBias1Off);
         // first layer of sample j is issued before the second layer of sample j-1: the producers drain its
         // accumulators while the (longer) second-layer MMAs of sample j-1 run
+        int islot = 0; uint32_t iph = 0;
         for (int j = 0; j <= my_tiles; ++j) {
             if (j < my_tiles) {
                 const int g = j & 1;
                 const uint32_t ph = ((uint32_t)j >> 1) & 1u;
                 mbar_wait(c1empty_bar(g), ph ^ 1u);
-                mbar_wait(ifull_bar(g), ph);
+                mbar_wait(ifull_bar(islot), iph);
                 fence_after_thread_sync();
-                const uint64_t da0 = desc32(smem_base + kS2dOff + g * kS2dBytes);
+                const uint64_t da0 = desc32(smem_base + kS2dOff + islot * kS2dBytes);
                 if (leader) {
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
@@ -211,10 +204,11 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             mma_f16_ss(d, da0 + (uint64_t)(((mt * 128 + (t >> 1) * kBW + (t & 1)) * 32) >> 4),
                                        db1 + (uint64_t)((t * kC1 * 32) >> 4), idesc1, 1u);
                     }
-                    mma_commit(iempty_bar(g));
+                    mma_commit(iempty_bar(islot));
                     mma_commit(c1full_bar(g));
                 }
                 __syncwarp();
+                if (++islot == kImgStages) { islot = 0; iph ^= 1u; }
             }
             if (j >= 1) {
                 const int jj = j - 1, st = jj & 1;    // slab stage == accumulator stage == producer group
@@ -225,6 +219,13 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint64_t da0 = make_smem_desc(smem_base + kSlabOff + st * kStageBytes, 16, 1024);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(st * BN);
                 if (leader) {
+                    if (p.store_a1) {                 // the slab is complete: write the first-layer activation out, plane by plane
+                        const long long tile = blockIdx.x + (long long)jj * gridDim.x;
+                        const uint32_t slab_s = smem_base + kSlabOff + st * kStageBytes;
+                        tma_store_5d(&tmA1, slab_s, 0, 0, 0, 0, (int)tile);
+                        tma_store_5d(&tmA1, slab_s + kPlaneBytes, 0, 0, 1, 0, (int)tile);
+                        bulk_commit();
+                    }
                     mma_f16_ss(d_tmem, d_ones, d_bias2, idesc2, 0u);                                 // D = bias
 #pragma unroll
                     for (int kb = 0; kb < kTaps; ++kb) {
@@ -237,10 +238,16 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     }
                     mma_commit(empty_bar(st));
                     mma_commit(tfull_bar(st));
+                    if (p.store_a1) {                 // (the queued MMAs keep the tensor pipe busy meanwhile)
+                        bulk_wait_read0();
+                        mbar_arrive(empty_bar(st));
+                    }
                 }
                 __syncwarp();
             }
         }
+        if (leader && p.store_a1) bulk_wait0();
+        __syncwarp();
     } else if (warp < kProdWarp0) {
         const int quarter = warp & 3;
         const int sub = (warp - kEpiWarp0) >> 2;
@@ -263,131 +270,60 @@ umma_rnd12_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
     } else {
-        // ---- producers (eight warps, two per TMEM lane quarter).  Iteration j, software-pipelined one sample deep:
-        //   (1) raw frame j+1 -> normalised bf16 image in 4x4-block order (the first layer as a 2x2 convolution over
-        //       blocks: each tap is a row-shifted window of that image, see umma_conv1.cu) -> [tcgen05: 20 MMAs]
-        //   (2) first-layer accumulators of sample j -> LeakyReLU -> bf16 -> slab stage j&1 in the layout the second
-        //       layer's windows read
-        // so the first-layer MMAs of a sample run (behind the previous sample's second layer) while the producers
-        // convert the next frame, and nobody waits for the tensor pipe as long as an iteration is not shorter than it.
+        // ---- first-layer drain (twelve warps, three per TMEM lane quarter, each at its own pace: every hand-over is
+        // an mbarrier with one arrival per warp): accumulators of sample j -> LeakyReLU -> bf16 -> slab stage j&1 in
+        // the layout the second layer's windows read
         const int quarter = warp & 3, sub = (warp - kProdWarp0) >> 2;
-        const int tg = threadIdx.x - kProdWarp0 * 32;
-        const float4* s_mean = reinterpret_cast<const float4*>(gen + kTabOff);
-        const float4* s_rstd = reinterpret_cast<const float4*>(gen + kTabOff + kPx * 4);
         const __nv_bfloat162 slope = __floats2bfloat162_rn(0.01f, 0.01f);
-        const __nv_bfloat162 five = __floats2bfloat162_rn(5.f, 5.f), nfive = __floats2bfloat162_rn(-5.f, -5.f);
-        // where this thread's 4-pixel groups land in the block image (fixed for the whole kernel)
-        uint32_t soff[kItems];
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) {
-            const int g4 = tg + i * kProdThreads, y = g4 / kBW, x4 = g4 - y * kBW;
-            soff[i] = swz32((uint32_t)(((y >> 2) * kBW + x4) * 32 + (y & 3) * 8));
-        }
-        // the two row tiles this warp drains (sub 0: tiles 0 and 3, sub 1: tiles 1 and 2 -- tile 3 is mostly past the
-        // frame) and where this lane's accumulator row goes in the slab: block (by, bx) = output pixel, or none
+        // the row tiles this warp drains: sub-warp s of a quarter takes tile s, sub-warp 0 also tile 3 (only the first
+        // two quarters of it hold block rows of the frame); and where this lane's accumulator row goes in the slab:
+        // block (by, bx) = output pixel, or none
         int srow[2]; uint32_t sx[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int mt = sub ? 1 + k : 3 * k;
+            const int mt = k ? 3 : sub;
             const int r = mt * 128 + quarter * 32 + lane;
             const int by = r / kBW, bx = r - by * kBW;
-            const bool ok = r < kBRows && by < kO1 && bx < kO1;
+            const bool ok = r < kBRows && by < kO1 && bx < kO1 && (k == 0 || sub == 0);
             const uint32_t row = (uint32_t)(by & 1) * kPlaneBytes + (uint32_t)((by >> 1) * kG + (bx >> 1)) * 128u;
             srow[k] = ok ? (int)row : -1;
             sx[k] = ((row >> 7) & 7u) ^ ((uint32_t)(bx & 1) * 4u);        // 16-byte chunk c of the pixel goes to chunk c ^ sx
         }
-        for (int j = -1; j < my_tiles; ++j) {
-            if (j + 1 < my_tiles) {
-                const int b = (j + 1) & 1;
-                const uint32_t ph = ((uint32_t)(j + 1) >> 1) & 1u;
-                const uint32_t* raw = reinterpret_cast<const uint32_t*>(gen + kRawOff + b * kRawBytes);
-                uint8_t* img = gen + kS2dOff + b * kS2dBytes;
-                mbar_wait(rfull_bar(b), ph);
-                uint32_t px[kItems];                  // all loads first: the raw slot is released early
+        const int nblk = (sub == 0 && 3 * 128 + quarter * 32 < kBRows) ? 2 : 1;
+        for (int j = 0; j < my_tiles; ++j) {
+            const int b = j & 1;
+            const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+            uint8_t* slab = gen + kSlabOff + b * kStageBytes;
+            mbar_wait(empty_bar(b), ph ^ 1u);     // second-layer MMAs (and the store) of the sample two back are done with this slab stage
+            mbar_wait(c1full_bar(b), ph);
+            fence_after_thread_sync();
 #pragma unroll
-                for (int i = 0; i < kItems; ++i) {
-                    const int g4 = tg + i * kProdThreads;
-                    px[i] = g4 < kPx / 4 ? raw[g4] : 0u;
-                }
-                if (!(p.debug & 4)) loads_landed(bar_base + 176u + 4u * warp, px);   // the slot is refilled as soon as it is released
-                __syncwarp();
-                if (lane == 0 && !(p.debug & 2)) mbar_arrive(rempty_bar(b));
-                mbar_wait(iempty_bar(b), ph ^ 1u);    // the first-layer MMAs of the sample two back are done with this image
-                float4 m = s_mean[tg], r = s_rstd[tg];
+            for (int k = 0; k < 2; ++k) {
+                if (k >= nblk) continue;          // (warp-uniform)
+                const int mt = k ? 3 : sub;
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kAcc1Col + (uint32_t)((b * 4 + mt) * kC1), acc);
+                tmem_ld_wait();
+                if (srow[k] < 0) continue;
+                // accumulator = conv + bias; round to bf16, LeakyReLU on packed pairs (as the stand-alone kernel),
+                // then the pixel's 64 bytes as four 16-byte chunks of its swizzled 128-byte slab row
+                uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < kItems; ++i) {
-                    const int g4 = tg + i * kProdThreads;
-                    const float4 mc = m, rc = r;
-                    if (i + 1 < kItems && g4 + kProdThreads < kPx / 4) {      // next item's statistics: in flight under this item's math
-                        m = s_mean[g4 + kProdThreads]; r = s_rstd[g4 + kProdThreads];
-                    }
-                    if (g4 < kPx / 4) {
-                        float v[4];
-                        u8x4_to_f32(px[i], v);
-                        __nv_bfloat162 lo = __floats2bfloat162_rn((v[0] - mc.x) * rc.x, (v[1] - mc.y) * rc.y);
-                        __nv_bfloat162 hi = __floats2bfloat162_rn((v[2] - mc.z) * rc.z, (v[3] - mc.w) * rc.w);
-                        // clamp after the rounding: 5 is a bf16 value and rounding is monotonic, so the result is the same
-                        lo = __hmin2(__hmax2(lo, nfive), five);
-                        hi = __hmin2(__hmax2(hi, nfive), five);
-                        *reinterpret_cast<uint2*>(img + soff[i]) =
-                            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                    }
+                for (int e = 0; e < 16; ++e) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+                    h = __hmax2(h, __hmul2(h, slope));
+                    pk[e] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                fence_proxy_async();
-                if (lane == 0 && (p.debug & 2)) mbar_arrive(rempty_bar(b));
-                prod_bar();
-                if (tg == 0) mbar_arrive(ifull_bar(b));
+                uint8_t* dst = slab + srow[k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(dst + (((uint32_t)c ^ sx[k]) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             }
-            if (j >= 0) {
-                const int b = j & 1;
-                const uint32_t ph = ((uint32_t)j >> 1) & 1u;
-                const long long tile = blockIdx.x + (long long)j * gridDim.x;
-                uint8_t* slab = gen + kSlabOff + b * kStageBytes;
-                // the TMA store of this slab stage's previous contents must have finished reading it (thread 0 issued
-                // it; the barrier above / below orders everyone's writes after this wait)
-                if (p.store_a1 && tg == 0) bulk_wait_read0();
-                if (p.store_a1) prod_bar();
-                mbar_wait(empty_bar(b), ph ^ 1u);     // second-layer MMAs of the sample two back are done with this slab stage
-                mbar_wait(c1full_bar(b), ph);
-                fence_after_thread_sync();
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int mt = sub ? 1 + k : 3 * k;
-                    if (mt * 128 + quarter * 32 >= kBRows) continue;      // (warp-uniform) no block row in this quarter
-                    uint32_t acc[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + kAcc1Col + (uint32_t)((b * 4 + mt) * kC1), acc);
-                    tmem_ld_wait();
-                    if (srow[k] < 0) continue;
-                    // accumulator = conv + bias; round to bf16, LeakyReLU on packed pairs (as the stand-alone kernel),
-                    // then the pixel's 64 bytes as four 16-byte chunks of its swizzled 128-byte slab row
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
-                        h = __hmax2(h, __hmul2(h, slope));
-                        pk[e] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    uint8_t* dst = slab + srow[k];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(dst + (((uint32_t)c ^ sx[k]) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                }
-                fence_before_thread_sync();
-                fence_proxy_async();                  // generic-proxy slab writes -> visible to tcgen05 / TMA
-                prod_bar();
-                if (tg == 0) {
-                    mbar_arrive(c1empty_bar(b));
-                    if (p.store_a1) {
-                        const uint32_t slab_s = smem_base + kSlabOff + b * kStageBytes;
-                        tma_store_5d(&tmA1, slab_s, 0, 0, 0, 0, (int)tile);
-                        tma_store_5d(&tmA1, slab_s + kPlaneBytes, 0, 0, 1, 0, (int)tile);
-                        bulk_commit();
-                    }
-                    mbar_arrive(full_bar(b));
-                }
-            }
+            fence_before_thread_sync();
+            fence_proxy_async();                  // generic-proxy slab writes -> visible to tcgen05 / TMA
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(c1empty_bar(b)); mbar_arrive(full_bar(b)); }
         }
-        if (p.store_a1 && tg == 0) bulk_wait0();
     }
     fence_before_thread_sync();
     __syncthreads();
@@ -405,20 +341,68 @@ int sm_count() {
     return n;
 }
 
+
+// uint8 frame -> normalised bf16 block image.  One thread per block row (4x4 pixels): four 4-byte pixel loads
+// (coalesced along the frame row), the per-pixel statistics through L1, one 32-byte store in the address-swizzled
+// order the first layer's UMMA descriptors read after a plain bulk copy into shared memory.
+__global__ void __launch_bounds__(256) rnd_normalize_s2d_kernel(const uint8_t* __restrict__ x, long long stride_n, long long total_rows,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 uint8_t* __restrict__ out) {
+    const __nv_bfloat162 five = __floats2bfloat162_rn(5.f, 5.f), nfive = __floats2bfloat162_rn(-5.f, -5.f);
+    for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total_rows; t += gridDim.x * 256ll) {
+        const long long sidx = t / kBRows;
+        const int row = (int)(t - sidx * kBRows);
+        const int by = row / kBW, bx = row - by * kBW;
+        const int pix0 = (4 * by) * kH + 4 * bx;
+        const uint8_t* src = x + sidx * stride_n + pix0;
+        uint32_t o[8];
+#pragma unroll
+        for (int py = 0; py < 4; ++py) {
+            const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(src + py * kH));
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mean + pix0 + py * kH));
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rstd + pix0 + py * kH));
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (float)((px >> (8 * e)) & 0xffu);
+            __nv_bfloat162 lo = __floats2bfloat162_rn((v[0] - m.x) * r.x, (v[1] - m.y) * r.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn((v[2] - m.z) * r.z, (v[3] - m.w) * r.w);
+            // clamp after the rounding: 5 is a bf16 value and rounding is monotonic, so the result is the same
+            lo = __hmin2(__hmax2(lo, nfive), five);
+            hi = __hmin2(__hmax2(hi, nfive), five);
+            o[2 * py] = *reinterpret_cast<uint32_t*>(&lo); o[2 * py + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + sidx * kImgBytes + (long long)row * 32);
+        const int sw = (row >> 2) & 1;            // SWIZZLE_32B: the two 16-byte halves of rows 4..7 of every 8 swap
+        dst[sw] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[sw ^ 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 }  // namespace
 
-static int g_rnd12_debug = 0;
-extern "C" void cb_rnd_conv12_debug(int v) { g_rnd12_debug = v; }
 extern "C" int cb_rnd_conv12_supported(void) { return cb_device_supports_umma(); }
 
-extern "C" int cb_rnd_conv12_fwd(const uint8_t* x, int64_t stride_n, int n, const float* mean, const float* rstd,
-                                 const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
-                                 void* a1_out_bf16, void* a2_out_bf16, void* stream) {
+extern "C" int cb_rnd_normalize_s2d(const uint8_t* x, int64_t stride_n, int32_t n, const float* mean, const float* rstd,
+                                    void* out_s2d, void* stream) {
+    CB_REQUIRE(x && mean && rstd && out_s2d, CB_E_ARG, "cb_rnd_normalize_s2d: null pointer");
+    CB_REQUIRE(n > 0, CB_E_ARG, "cb_rnd_normalize_s2d: n = %d", n);
+    CB_REQUIRE(((uintptr_t)x & 3) == 0 && stride_n % 4 == 0 && (((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)out_s2d) & 15) == 0,
+               CB_E_ALIGN, "cb_rnd_normalize_s2d: frames must be 4-byte, statistics and output 16-byte aligned");
+    const long long rows = (long long)n * kBRows;
+    long long blocks = (rows + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    rnd_normalize_s2d_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, stride_n, rows, mean, rstd, (uint8_t*)out_s2d);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" int cb_rnd_conv12_fwd(const void* img_s2d, int32_t n, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                                 const float* b2, void* a1_out_bf16, void* a2_out_bf16, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    CB_REQUIRE(x && mean && rstd && w1_bf16 && b1 && w2_bf16 && b2 && a2_out_bf16, CB_E_ARG, "cb_rnd_conv12_fwd: null pointer");
+    CB_REQUIRE(img_s2d && w1_bf16 && b1 && w2_bf16 && b2 && a2_out_bf16, CB_E_ARG, "cb_rnd_conv12_fwd: null pointer");
     CB_REQUIRE(n > 0, CB_E_ARG, "cb_rnd_conv12_fwd: n = %d", n);
-    CB_REQUIRE(((uintptr_t)x & 15) == 0 && stride_n % 16 == 0, CB_E_ALIGN,
-               "cb_rnd_conv12_fwd: frames must be 16-byte aligned (base %p, stride %lld)", (const void*)x, (long long)stride_n);
+    CB_REQUIRE(((uintptr_t)img_s2d & 15) == 0, CB_E_ALIGN, "cb_rnd_conv12_fwd: block images must be 16-byte aligned");
     CB_REQUIRE(cb_device_supports_umma() == 1, CB_E_ARCH, "cb_rnd_conv12_fwd needs an sm_100 device");
     CUtensorMap tmW, tmA1;
     {
@@ -436,8 +420,8 @@ extern "C" int cb_rnd_conv12_fwd(const uint8_t* x, int64_t stride_n, int n, cons
         tmA1 = tmW;
     }
     Rnd12Params p{};
-    p.x = x; p.stride_n = stride_n; p.n = n; p.mean = mean; p.rstd = rstd;
-    p.w1 = (const __nv_bfloat16*)w1_bf16; p.b1 = b1; p.store_a1 = a1_out_bf16 ? 1 : 0; p.debug = g_rnd12_debug;
+    p.img = (const uint8_t*)img_s2d; p.n = n;
+    p.w1 = (const __nv_bfloat16*)w1_bf16; p.b1 = b1; p.store_a1 = a1_out_bf16 ? 1 : 0;
     p.epi.n_total = kC2; p.epi.bias = b2; p.epi.bias_in_acc = 1; p.epi.act = CB_ACT_LRELU;
     p.epi.out_bf16 = (__nv_bfloat16*)a2_out_bf16;
     static bool attr = false;

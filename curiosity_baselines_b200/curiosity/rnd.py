@@ -85,7 +85,9 @@ class RND(nn.Module):
         self._cache = None
         self._wver = 0            # bumped whenever the predictor's master weights change outside torch's tracking
         self.reuse_hits = {"full": 0, "target": 0, "miss": 0}
-        self.fuse_conv12 = True   # first two convolutions in one launch (cb_rnd_conv12_fwd) where the geometry allows
+        # first two convolutions without the HBM round trip between them (cb_rnd_conv12_fwd): parity-tested, but no faster
+        # than the separate kernels (both are bound by the tensor cores' operand fetch, profiles/r2_fused_conv12_study.txt)
+        self.fuse_conv12 = False
         self._fuse_ok = None
 
     # ------------------------------------------------------------------ plumbing
@@ -164,9 +166,11 @@ class RND(nn.Module):
         base = obs.data_ptr() + (Cs - 1) * H * W
         return obs, T, B, base, (Cs * H * W, W, 1, H * W)
 
+    S2D_BYTES = 21 * 21 * 32      # one normalised 84x84 frame in 4x4-pixel-block order (include/curiosity_b200.h)
+
     def _can_fuse12(self, base, strides):
-        """The one-launch conv1+conv2 kernel (cb_rnd_conv12_fwd) covers the reference's 84x84 geometry."""
-        if not self.fuse_conv12 or self.image_hw != (84, 84) or base % 16 or strides[0] % 16:
+        """The conv1+conv2 kernel (cb_rnd_conv12_fwd) covers the reference's 84x84 geometry."""
+        if not self.fuse_conv12 or self.image_hw != (84, 84) or base % 4 or strides[0] % 4:
             return False
         l1, l2 = self._chains[0].layers[:2]
         if type(l1) is not GemmLayer or type(l2) is not GemmLayer:
@@ -175,7 +179,15 @@ class RND(nn.Module):
             self._fuse_ok = bool(L.load().cb_rnd_conv12_supported())
         return self._fuse_ok
 
-    def _conv12(self, chain, base, n, stride_n, keep_a1):
+    def _normalized(self, base, n, stride_n):
+        """Normalised, clamped bf16 copy of the newest frames (rnd.py:169-170) in the block order the first
+        convolution reads: computed once, consumed by target and predictor."""
+        img = torch.empty(n * self.S2D_BYTES, dtype=torch.uint8, device=self._dev)
+        L.call("cb_rnd_normalize_s2d", base, stride_n, n, L.ptr(self._norm[0]), L.ptr(self._norm[1]), L.ptr(img),
+               L.stream())
+        return img
+
+    def _conv12(self, chain, img, n, keep_a1):
         """First two convolutions of one network in one launch; the 20x20x32 activation between them is written
         out only when the backward pass will need it."""
         l1, l2 = chain.layers[0], chain.layers[1]
@@ -183,8 +195,8 @@ class RND(nn.Module):
         dev = l1.w_fwd.device
         a1 = torch.empty(n * 400, 32, dtype=torch.bfloat16, device=dev) if keep_a1 else None
         a2 = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
-        L.call("cb_rnd_conv12_fwd", base, stride_n, n, L.ptr(self._norm[0]), L.ptr(self._norm[1]),
-               L.ptr(l1.w_native), L.ptr(l1.bias), L.ptr(l2.w_fwd), L.ptr(l2.bias), L.ptr(a1), L.ptr(a2), L.stream())
+        L.call("cb_rnd_conv12_fwd", L.ptr(img), n, L.ptr(l1.w_native), L.ptr(l1.bias), L.ptr(l2.w_fwd), L.ptr(l2.bias),
+               L.ptr(a1), L.ptr(a2), L.stream())
         return [a1, a2]
 
     def _forward_nets(self, obs, keep_acts):
@@ -192,8 +204,9 @@ class RND(nn.Module):
         n = T * B
         pred, targ = self._chains
         if self._can_fuse12(base, strides):
-            _, phi = targ.forward(base, n, first_out=self._conv12(targ, base, n, strides[0], False))
-            acts, phi_hat = pred.forward(base, n, first_out=self._conv12(pred, base, n, strides[0], keep_acts))
+            img = self._normalized(base, n, strides[0])
+            _, phi = targ.forward(base, n, first_out=self._conv12(targ, img, n, False))
+            acts, phi_hat = pred.forward(base, n, first_out=self._conv12(pred, img, n, keep_acts))
             return obs, T, B, base, strides, phi, phi_hat, (acts if keep_acts else None)
         # target and predictor read the same normalised frame: one fused first-conv pass for both
         a1_p, _, a1_t = pred.layers[0].forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm,
@@ -207,7 +220,8 @@ class RND(nn.Module):
         obs, T, B, base, strides = self._frame_view(obs)
         if self._can_fuse12(base, strides):
             pred = self._chains[0]
-            return pred.forward(base, T * B, first_out=self._conv12(pred, base, T * B, strides[0], True))
+            img = self._normalized(base, T * B, strides[0])
+            return pred.forward(base, T * B, first_out=self._conv12(pred, img, T * B, True))
         acts, phi_hat = self._chains[0].forward(base, T * B, in_dtype=L.U8, strides=strides, norm=self._norm)
         return acts, phi_hat
 

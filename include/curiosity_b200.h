@@ -188,16 +188,20 @@ int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffl
 int cb_conv1_supported(const cb_conv_desc* d);
 int cb_conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e,
                  const void* w2_native, const float* bias2, void* out2_bf16, void* stream);
-/* RND trunk, first TWO convolutions of one network in one launch (rnd.py:40-46 / 55-61: Conv 8x8 s4 1->32,
- * LeakyReLU, Conv 4x4 s2 32->64, LeakyReLU) over the newest 84x84 uint8 frame of each sample, read in place at
- * x + i*stride_n (16-byte aligned) and normalised with mean / rstd [7056] (rnd.py:169-170).  The 20x20x32
- * activation between the layers stays in shared memory; a1_out_bf16 (NULL to skip) additionally receives it
- * ([n,20,20,32], needed by the second layer's weight gradient).  w1: bf16 [32][64] in torch's (kh, kw) order,
- * w2: bf16 [64][(kh,kw,c) = 512] (the cb_prepare_conv_weight forward layout), a2_out_bf16: [n,9,9,64]. */
+/* RND trunk, first TWO convolutions (rnd.py:40-46 / 55-61: Conv 8x8 s4 1->32, LeakyReLU, Conv 4x4 s2 32->64,
+ * LeakyReLU) with the 20x20x32 activation between them kept in shared memory.
+ *   cb_rnd_normalize_s2d: the newest 84x84 uint8 frame of each sample (read in place at x + i*stride_n) is normalised
+ *     with mean / rstd [7056], clamped to +-5 (rnd.py:169-170) and written as a bf16 image in 4x4-pixel-block order,
+ *     n * 14112 bytes (21 x 21 blocks of 16 bf16) -- once for both networks (target and predictor read the same normalised frame).
+ *   cb_rnd_conv12_fwd: one network over those images.  a1_out_bf16 (NULL to skip) additionally receives the
+ *     intermediate activation ([n,20,20,32], needed by the second layer's weight gradient).  w1: bf16 [32][64] in
+ *     torch's (kh, kw) order, w2: bf16 [64][(kh,kw,c) = 512] (the cb_prepare_conv_weight forward layout),
+ *     a2_out_bf16: [n,9,9,64]. */
 int cb_rnd_conv12_supported(void);
-int cb_rnd_conv12_fwd(const uint8_t* x, int64_t stride_n, int32_t n, const float* mean, const float* rstd,
-                      const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
-                      void* a1_out_bf16, void* a2_out_bf16, void* stream);
+int cb_rnd_normalize_s2d(const uint8_t* x, int64_t stride_n, int32_t n, const float* mean, const float* rstd,
+                         void* out_s2d, void* stream);
+int cb_rnd_conv12_fwd(const void* img_s2d, int32_t n, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                      const float* b2, void* a1_out_bf16, void* a2_out_bf16, void* stream);
 int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
                    const float* norm_rstd, float* dw_native, float* dbias, float beta, void* stream);
 /* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise

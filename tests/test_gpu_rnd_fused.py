@@ -21,6 +21,7 @@ def _model(seed=0):
     g = torch.Generator().manual_seed(seed + 1)
     m._norm[0].copy_((torch.rand(84 * 84, generator=g) * 200 + 20).to(DEV))
     m._norm[1].copy_((torch.rand(84 * 84, generator=g) * 0.05 + 0.005).to(DEV))
+    m.fuse_conv12 = True          # (an option: off by default)
     return m
 
 
@@ -40,8 +41,9 @@ def test_fused_layers_equal_the_separate_kernels(T, B, which):
     assert m._can_fuse12(base, strides)
     a1_ref, _ = chain.layers[0].forward(base, n, in_dtype=L.U8, strides=strides, norm=m._norm)
     a2_ref, _ = chain.layers[1].forward(a1_ref, n)
-    a1, a2 = m._conv12(chain, base, n, strides[0], True)
-    _, a2_only = m._conv12(chain, base, n, strides[0], False)
+    img = m._normalized(base, n, strides[0])
+    a1, a2 = m._conv12(chain, img, n, True)
+    _, a2_only = m._conv12(chain, img, n, False)
     torch.cuda.synchronize()
     assert torch.equal(a2, a2_only)                   # writing a1 out does not change a2
     a1f, r1 = a1.float(), a1_ref.float()
@@ -62,7 +64,7 @@ def test_unaligned_frames_fall_back_to_the_separate_kernels():
     m = _model()
     obs = _frames(2, 3)
     _, _, _, base, strides = m._frame_view(obs)
-    assert not m._can_fuse12(base + 4, strides)
+    assert not m._can_fuse12(base + 2, strides)
     m.fuse_conv12 = False
     assert not m._can_fuse12(base, strides)
 

@@ -82,11 +82,20 @@ a2o = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
 fl12 = 2.0 * (64 * 32 * 400 + 512 * 64 * 81) * n
 
 
+img12 = torch.empty(n * 14112, dtype=torch.uint8, device=dev)
+
+
+def normalize12():
+    L.call("cb_rnd_normalize_s2d", frames.data_ptr(), 7056, n, L.ptr(nm[0]), L.ptr(nm[1]), L.ptr(img12), L.stream())
+
+
 def fused12(a1_out):
-    L.call("cb_rnd_conv12_fwd", frames.data_ptr(), 7056, n, L.ptr(nm[0]), L.ptr(nm[1]), L.ptr(conv1.w_native),
-           L.ptr(conv1.bias), L.ptr(conv2.w_fwd), L.ptr(conv2.bias), L.ptr(a1_out), L.ptr(a2o), L.stream())
+    L.call("cb_rnd_conv12_fwd", L.ptr(img12), n, L.ptr(conv1.w_native), L.ptr(conv1.bias), L.ptr(conv2.w_fwd),
+           L.ptr(conv2.bias), L.ptr(a1_out), L.ptr(a2o), L.stream())
 
 
+normalize12()
+cases["fused12_normalize"] = (normalize12, 0.0)
 cases["fused12_fwd"] = (lambda: fused12(None), fl12)
 cases["fused12_keep_fwd"] = (lambda: fused12(a1), fl12)
 for name, (fn, fl) in cases.items():

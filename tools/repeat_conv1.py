@@ -16,6 +16,7 @@ obs_copy = obs.clone()
 obs, T, B, base, strides = m._frame_view(obs)
 n = T * B
 ch = m._chains[0]
+img = m._normalized(base, n, strides[0])
 ref = None
 bad_sep = {}
 for r in range(reps):
@@ -28,14 +29,11 @@ for r in range(reps):
         if d: bad_sep[r] = d
 print("separate conv1: launches differing from launch 0:", bad_sep)
 print("frames unchanged:", torch.equal(obs, obs_copy))
-dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-L.load().cb_rnd_conv12_debug(dbg)
-print("debug", dbg)
 for keep in (True, False):
     bad = {}
     first = None
     for r in range(reps):
-        a1, a2 = m._conv12(ch, base, n, strides[0], keep)
+        a1, a2 = m._conv12(ch, img, n, keep)
         torch.cuda.synchronize()
         if first is None:
             first = a2
