@@ -785,7 +785,11 @@ def kernel_table(model, T, B, ms_per_step, dev):
                 "frac": frac, "traffic": top["traffic"], "kernel_ms": top["ms"], "share_of_step": top["share_of_step"],
                 "algorithmic_bytes": top["algorithmic_bytes"],
                 "peak_source": f"{src} " + ("HBM copy bandwidth" if top["bound"] == "hbm" else "bf16 burst"),
-                "kernels": rows[:8]}
+                "kernels": rows[:8],
+                "note": "by arithmetic intensity these 32/64-channel layers sit on the HBM side of the roofline; the measured "
+                        "limiter of the window / first-conv kernels is the tensor cores' operand fetch from shared memory "
+                        "(~(M+N)/4 cycles per K=16 tcgen05.mma: 52 at M128 N64, against 32 for the math), see "
+                        "profiles/r2_fused_conv12_study.txt"}
     return roofline
 
 
