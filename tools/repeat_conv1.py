@@ -1,4 +1,6 @@
-"""Repeatability probe: separate first-conv kernel and the fused kernel, many launches on the same frames."""
+"""Repeatability probe (regression check for the raw-frame-slot race): the stand-alone first-conv
+kernel and the fused conv1+conv2 kernel are launched many times on the same frames and every result is compared
+bit for bit with the first one.      python tools/repeat_conv1.py [samples=4000] [launches=20]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
