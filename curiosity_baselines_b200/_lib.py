@@ -62,6 +62,10 @@ _SIGS = {
     "cb_conv1_supported": [C.POINTER(ConvDesc)],
     "cb_conv1_fwd": [C.POINTER(ConvDesc), _P, _P, C.POINTER(Epilogue), _P, _P, _P, _P],
     "cb_rnd_conv12_supported": [],
+    "cb_bn_moments": [_P, _L, _I, _P, _P, _P],
+    "cb_bn_apply": [_P, _L, _I, _P, _P, _P, _P, _P],
+    "cb_bn_bwd_moments": [_P, _L, _I, _P, _P, _P, _P, _P],
+    "cb_bn_bwd_apply": [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P],
     "cb_rnd_normalize_s2d": [_P, _L, _I, _P, _P, _P, _P],
     "cb_rnd_conv12_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P],
     "cb_conv1_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],

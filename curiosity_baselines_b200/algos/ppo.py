@@ -98,7 +98,8 @@ class PPO:
         if (self.twin_conv1 and self.curiosity_type in ("icm", "disagreement") and curiosity_inputs is not None
                 and curiosity_inputs[0] is observation):
             twin = cm.twin_first_conv()
-            if twin is not None and cm.dedup_shifted_observations and cm.shifted(curiosity_inputs[0], curiosity_inputs[1]):
+            if (twin is not None and cm.dedup_shifted_observations and not getattr(cm, "_batch_stats", False)
+                    and cm.shifted(curiosity_inputs[0], curiosity_inputs[1])):
                 twin_steps = T + 1          # next_obs = obs shifted by one step: the curiosity encoder wants all T+1 steps
         s = m._run_forward(observation, _onehot(prev_action, A), init_rnn_state, save=True, twin=twin, twin_steps=twin_steps)
         if s["twin_out"] is not None:

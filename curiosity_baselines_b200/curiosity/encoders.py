@@ -7,58 +7,71 @@ from torch import nn
 
 from .. import _lib as L
 from .. import layers as LY
-from ..layers import Chain, DenseConvLayer, conv_layer, linear_layer
+from ..layers import BatchNormLayer, Chain, DenseConvLayer, conv_layer, linear_layer
 
 
 class BurdaHead(nn.Module):
-    """encoders.py:68-119 (batch_norm=False): conv8s4-32, conv4s2-64, conv3s1-64, Linear(3136->out)."""
+    """encoders.py:68-119: conv8s4-32, conv4s2-64, conv3s1-64, each followed by LeakyReLU (and BatchNorm2d when
+    ``batch_norm``), Linear(3136->out).  The Sequential indices -- hence the ``state_dict`` keys -- are the
+    reference's in both variants."""
 
     def __init__(self, image_shape, output_size=512, conv_output_size=3136, batch_norm=False):
         super().__init__()
-        if batch_norm:
-            raise NotImplementedError("batch_norm=True is outside the hot-path scope (reference default is False)")
         c, h, w = image_shape
         self.image_shape = image_shape
         self.output_size = output_size
         self.conv_output_size = conv_output_size
-        self.model = nn.Sequential(
-            nn.Conv2d(c, 32, kernel_size=(8, 8), stride=(4, 4)), nn.LeakyReLU(),
-            nn.Conv2d(32, 64, kernel_size=(4, 4), stride=(2, 2)), nn.LeakyReLU(),
-            nn.Conv2d(64, 64, kernel_size=(3, 3), stride=(1, 1)), nn.LeakyReLU(),
-            nn.Flatten(), nn.Linear(conv_output_size, output_size))
+        self.batch_norm = bool(batch_norm)
+        seq = []
+        for cin, cout, k, s in ((c, 32, 8, 4), (32, 64, 4, 2), (64, 64, 3, 1)):
+            seq += [nn.Conv2d(cin, cout, kernel_size=(k, k), stride=(s, s)), nn.LeakyReLU()]
+            if batch_norm:
+                seq.append(nn.BatchNorm2d(cout))
+        seq += [nn.Flatten(), nn.Linear(conv_output_size, output_size)]
+        self.model = nn.Sequential(*seq)
 
     def build_chain(self, trainable=True, last_act="none"):
         c, h, w = self.image_shape
         m = self.model
-        l1 = conv_layer(m[0], (h, w, c), "lrelu", trainable)
-        l2 = conv_layer(m[2], (l1.out_h, l1.out_w, 32), "lrelu", trainable)
-        l3 = conv_layer(m[4], (l2.out_h, l2.out_w, 64), "lrelu", trainable)
-        assert l3.out_h == l3.out_w and l3.out_h * l3.out_w * 64 == self.conv_output_size
-        fc = linear_layer(m[7], last_act, spatial=(l3.out_h, 64), trainable=trainable)
-        return Chain([l1, l2, l3, fc]), None
+        step = 3 if self.batch_norm else 2
+        layers, shape = [], (h, w, c)
+        for i in range(3):
+            lay = conv_layer(m[step * i], shape, "lrelu", trainable)
+            layers.append(lay)
+            shape = (lay.out_h, lay.out_w, lay.out_c)
+            if self.batch_norm:
+                layers.append(BatchNormLayer(m[step * i + 2], shape, trainable))
+        assert shape[0] == shape[1] and shape[0] * shape[1] * 64 == self.conv_output_size
+        fc = linear_layer(m[3 * step + 1], last_act, spatial=(shape[0], 64), trainable=trainable)
+        return Chain(layers + [fc]), None
 
 
 class UniverseHead(nn.Module):
-    """encoders.py:7-35: five conv3x3 s2 p1 -> 32 + ELU; features are the CHW flatten (288)."""
+    """encoders.py:7-35: five conv3x3 s2 p1 -> 32 + ELU (+ BatchNorm2d when ``batch_norm``); features are the CHW
+    flatten (288)."""
 
     def __init__(self, image_shape, batch_norm=False):
         super().__init__()
-        if batch_norm:
-            raise NotImplementedError("batch_norm=True is outside the hot-path scope")
         c, h, w = image_shape
         self.image_shape = image_shape
+        self.batch_norm = bool(batch_norm)
         seq = []
         for layer in range(5):
             seq += [nn.Conv2d(c if layer == 0 else 32, 32, kernel_size=(3, 3), stride=(2, 2), padding=(1, 1)), nn.ELU()]
+            if batch_norm:
+                seq.append(nn.BatchNorm2d(32))
         self.model = nn.Sequential(*seq)
 
     def build_chain(self, trainable=True, last_act=None):
         c, h, w = self.image_shape
+        step = 3 if self.batch_norm else 2
         layers, shape = [], (h, w, c)
         for i in range(5):
-            lay = conv_layer(self.model[2 * i], shape, "elu", trainable)
+            lay = conv_layer(self.model[step * i], shape, "elu", trainable)
             layers.append(lay)
             shape = (lay.out_h, lay.out_w, 32)
+            if self.batch_norm:
+                layers.append(BatchNormLayer(self.model[step * i + 2], shape, trainable))
         hw = shape[0] * shape[1]
         # our activations are NHWC; the reference flattens CHW.  perm[j] = NHWC index of CHW feature j
         j = torch.arange(32 * hw)
@@ -70,9 +83,10 @@ class MazeHead(nn.Module):
     """encoders.py:37-66: conv3 s1 p1 -> 16, ReLU, conv3 s2 p2 -> 16, ReLU, Linear(256->256), ReLU."""
 
     def __init__(self, image_shape, output_size=256, conv_output_size=256, batch_norm=False):
-        super().__init__()
+        super().__init__()                # (the reference's MazeHead accepts batch_norm and ignores it, encoders.py:41-58)
         c, h, w = image_shape
         self.image_shape = image_shape
+        self.batch_norm = False
         self.output_size = output_size
         self.conv_output_size = conv_output_size
         self.model = nn.Sequential(

@@ -18,7 +18,6 @@ from .. import dist
 from ..layers import linear_layer, narrow_head, NarrowHead, pad_side, ACT
 from .encoders import make_encoder, frame_input
 
-ENC_LAST_ACT = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}
 
 
 class ResBlock(nn.Module):
@@ -241,11 +240,23 @@ class _IcmBase(nn.Module):
         self.inverse_model = nn.Sequential(nn.Linear(self.feature_size * 2, self.feature_size), nn.ReLU(),
                                            nn.Linear(self.feature_size, action_size))
         self._exec = None
+        # BatchNorm2d in the encoder (`-batch_norm`): every encoder pass is its own batch in the reference (statistics
+        # of that pass, running statistics updated by each, icm.py:114-117), so neither merging the obs / next_obs
+        # passes (de-duplication) nor serving the loss pass from the bonus pass's features (reuse) would be exact
+        self._batch_stats = bool(getattr(self.encoder, "batch_norm", False))
         # opt-in exact reuse of a batch's forward pass between compute_bonus and compute_loss (see _cached_forward)
         self.reuse_features = self.default_reuse_features
         self._cache = None
         self._wver = 0
         self.reuse_hits = {"full": 0, "miss": 0}
+
+    @property
+    def reuse_features(self):
+        return self._reuse_features and not self._batch_stats
+
+    @reuse_features.setter
+    def reuse_features(self, on):
+        self._reuse_features = bool(on)
 
     # ------------------------------------------------------------------ executors
     def _forward_models(self):
@@ -317,7 +328,7 @@ class _IcmBase(nn.Module):
         T, B = observations.shape[:2]
         n = T * B
         shp = observations.shape[2:]
-        if self.dedup_shifted_observations and self.shifted(observations, next_observations):
+        if self.dedup_shifted_observations and not self._batch_stats and self.shifted(observations, next_observations):
             n1 = (T + 1) * B
             allf = torch.as_strided(observations, (T + 1, B) + tuple(shp), observations.stride(),
                                     observations.storage_offset())
@@ -468,7 +479,7 @@ class _IcmBase(nn.Module):
                 ex["inv2"].wgrad(h, dlog_b, n)
                 dh = ex["inv2"].dgrad(dlog_b, n, x_saved=h, x_act="relu")
         ex["inv0"].wgrad(cat, dh, n)
-        dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ENC_LAST_ACT[self.feature_encoding])
+        dcat = ex["inv0"].dgrad(dh, n, x_saved=cat, x_act=ex["chain"].last_act)
         if enc2 is None:            # one encoder pass over the T+1 distinct steps: d phi[t] = d phi1[t] + d phi2[t-1]
             n1 = enc1["n1"]
             dall = torch.zeros(n1, F, dtype=torch.bfloat16, device=dev)

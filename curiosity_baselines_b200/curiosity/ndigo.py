@@ -41,9 +41,9 @@ class _EncoderFn(torch.autograd.Function):
         # gradient w.r.t. the last layer's pre-activation output
         dy = dphi.reshape(-1, last.out_c)
         y = enc["acts"][-1].float()
-        if m._enc_last_act == "relu":
+        if chain.last_act == "relu":
             dy = dy * (y > 0)
-        elif m._enc_last_act == "elu":
+        elif chain.last_act == "elu":
             dy = dy * torch.where(y > 0, torch.ones_like(y), y + 1)
         saved = [p.grad for p in ctx.params]
         for p in ctx.params:
@@ -331,7 +331,6 @@ class NDIGO(nn.Module):
         self.action_size, self.horizon = action_size, horizon
         self.feature_encoding, self.obs_stats, self.num_predictors = feature_encoding, obs_stats, num_predictors
         self.encoder, self.feature_size = make_encoder(feature_encoding, image_shape, batch_norm)
-        self._enc_last_act = {"idf": "elu", "idf_burda": "none", "idf_maze": "relu"}[feature_encoding]
         self.gru_size = gru_size
         self.gru = nn.GRU(self.feature_size + action_size, gru_size)
         self.gru_states = None

@@ -613,6 +613,114 @@ def narrow_head(module, act="none"):
     return NarrowHead(module, act) if _engine != L.ENGINE_SIMT else linear_layer(module, act)
 
 
+class BatchNormLayer:
+    """nn.BatchNorm2d between two layers of an encoder ``Chain`` (rlpyt/models/curiosity/encoders.py:23-25, 87-96):
+    torch's arithmetic on bf16 NHWC activations.  Training mode (``module.training``): statistics of THIS batch over
+    all rows of a channel, running statistics updated as torch does (momentum, unbiased variance,
+    ``num_batches_tracked``); evaluation mode: the running statistics.
+
+    It follows the Chain protocol of ``GemmLayer``: ``forward`` -> (bf16, fp32), ``wgrad`` leaves dgamma / dbeta in the
+    holder's ``.grad``, ``dgrad`` returns the gradient w.r.t. the PRE-activation output of the layer in front (the
+    activation's derivative is folded into the same pass, as the conv dgrad epilogues do).  What the backward pass
+    needs from the forward pass (mean, 1/sqrt(var+eps)) travels as attributes of the INPUT activation tensor, so an
+    encoder that is run twice before its backward passes (ICM: obs and next_obs) keeps the two apart."""
+
+    def __init__(self, module, shape, trainable=True):
+        self.module = module
+        self.in_h, self.in_w, self.in_c = shape
+        self.out_h, self.out_w, self.out_c = shape
+        self.k, self.stride, self.pad = 1, 1, 0
+        self.act = ACT["none"]
+        self.trainable = trainable
+        self._version = None
+        if self.in_c % 8 or 256 % (self.in_c // 8):
+            raise L.CuriosityLibError(f"BatchNorm2d over {self.in_c} channels is not supported (8 * a power of two)")
+
+    def prepare(self, force=False):
+        pass
+
+    def _rows(self, n):
+        return n * self.in_h * self.in_w
+
+    def forward(self, x, n, out_bf16=True, out_f32=False, **kw):
+        m, C, rows = self.module, self.in_c, self._rows(n)
+        dev = x.device
+        st = L.stream()
+        if m.training or m.running_mean is None:
+            s = torch.zeros(2, C, dtype=torch.float64, device=dev)
+            L.call("cb_bn_moments", L.ptr(x), rows, C, L.ptr(s[0]), L.ptr(s[1]), st)
+            mean = s[0] / rows
+            var = (s[1] / rows - mean * mean).clamp_min_(0.0)          # biased, as torch normalises with
+            if m.training and m.track_running_stats and m.running_mean is not None:
+                with torch.no_grad():
+                    m.num_batches_tracked += 1
+                    mom = m.momentum if m.momentum is not None else 1.0 / float(m.num_batches_tracked)
+                    m.running_mean.mul_(1 - mom).add_((mom * mean).to(m.running_mean.dtype))
+                    m.running_var.mul_(1 - mom).add_((mom * var * (rows / max(rows - 1, 1))).to(m.running_var.dtype))
+            batch_stats = True
+        else:
+            mean, var = m.running_mean.double(), m.running_var.double()
+            batch_stats = False
+        invstd = (var + m.eps).rsqrt()
+        gamma = m.weight.detach().double() if m.weight is not None else torch.ones(C, dtype=torch.float64, device=dev)
+        beta = m.bias.detach().double() if m.bias is not None else torch.zeros(C, dtype=torch.float64, device=dev)
+        scale = (gamma * invstd).float()
+        shift = (beta - mean * gamma * invstd).float()
+        yb = torch.empty(rows, C, dtype=torch.bfloat16, device=dev) if out_bf16 else None
+        yf = torch.empty(rows, C, dtype=torch.float32, device=dev) if out_f32 else None
+        L.call("cb_bn_apply", L.ptr(x), rows, C, L.ptr(scale), L.ptr(shift), L.ptr(yb), L.ptr(yf), st)
+        x._bn_saved = (mean.float(), invstd.float(), batch_stats)
+        x._bn_sums = None
+        return yb, yf
+
+    def _sums(self, x, dy, n):
+        if getattr(x, "_bn_sums", None) is None:
+            C, rows = self.in_c, self._rows(n)
+            mean, invstd, _ = x._bn_saved
+            s = torch.zeros(2, C, dtype=torch.float64, device=dy.device)
+            L.call("cb_bn_bwd_moments", L.ptr(dy), L.ptr(x), rows, C, L.ptr(mean), L.ptr(invstd), L.ptr(s[0]), L.ptr(s[1]),
+                   L.stream())
+            x._bn_sums = s
+        return x._bn_sums
+
+    def wgrad(self, x, dy, n, accumulate=False, final=True, **kw):
+        m = self.module
+        if not self.trainable or m.weight is None:
+            return
+        s = self._sums(x, dy, n)
+        for p, g in ((m.weight, s[1]), (m.bias, s[0])):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            if accumulate:
+                p.grad.add_(g.to(p.grad.dtype))
+            else:
+                p.grad.copy_(g)
+        if final:
+            dist.grads_ready((m.weight.grad, m.bias.grad))
+
+    def dgrad(self, dy, n, x_saved=None, x_act="none", dx_add=None):
+        assert dx_add is None
+        m, C, rows = self.module, self.in_c, self._rows(n)
+        x = x_saved
+        mean, invstd, batch_stats = x._bn_saved
+        mean, invstd = mean.double(), invstd.double()
+        gamma = m.weight.detach().double() if m.weight is not None else torch.ones(C, dtype=torch.float64, device=dy.device)
+        a = gamma * invstd
+        if batch_stats:      # dx = gamma*invstd * (dz - mean(dz) - xhat * mean(dz*xhat)), xhat = (x - mean)*invstd
+            s = self._sums(x, dy, n)
+            m_dz, m_dzx = s[0] / rows, s[1] / rows
+            b = -a * invstd * m_dzx
+            c = -a * m_dz - b * mean
+        else:
+            b = torch.zeros_like(a)
+            c = torch.zeros_like(a)
+        dx = torch.empty(rows, C, dtype=torch.bfloat16, device=dy.device)
+        af, bf, cf = a.float(), b.float(), c.float()         # (named: the pointers must outlive the argument list)
+        L.call("cb_bn_bwd_apply", L.ptr(dy), L.ptr(x), rows, C, L.ptr(af), L.ptr(bf), L.ptr(cf), ACT[x_act], L.ptr(dx),
+               L.stream())
+        return dx
+
+
 class ParamPair:
     """A (weight, bias) pair of an ``nn.LSTM`` / ``nn.GRU`` holder presented like a ``Linear`` to ``GemmLayer``."""
 
@@ -677,6 +785,12 @@ class Chain:
 
     def __init__(self, layers):
         self.layers = layers
+
+    @property
+    def last_act(self):
+        """Name of the activation the chain's output has been through (whoever computes the gradient w.r.t. that output
+        folds its derivative in): 'none' when the chain ends in a Linear without activation or a BatchNorm2d."""
+        return self.ACT_NAME[self.layers[-1].act]
 
     def forward(self, x, n, in_dtype=L.BF16, strides=None, norm=None, last_f32=True,
                 last_bf16=False, first_out=None):

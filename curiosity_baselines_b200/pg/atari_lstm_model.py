@@ -28,12 +28,10 @@ from .. import layers as LY
 from ..layers import linear_layer, pad_side
 from ..curiosity.encoders import BurdaHead, UniverseHead, MazeHead, frame_input
 from ..curiosity.icm import ICM, Disagreement
-from ..curiosity.icm import ENC_LAST_ACT as _CUR_LAST_ACT
 from ..curiosity.rnd import RND
 from ..curiosity.ndigo import NDIGO
 
 RnnState = namedtuple("RnnState", ["h", "c"])
-ENC_LAST_ACT = dict(_CUR_LAST_ACT, none="relu")          # Conv2dHeadModel applies its nonlinearity at the end
 
 
 class _Holder(nn.Module):
@@ -362,7 +360,7 @@ class AtariLstmModel(nn.Module):
         # ---- weight gradients as single GEMMs over all T*B rows
         ex["hh"].wgrad(h_all[:T].reshape(n, H), dg, n)
         ex["ih"].wgrad(s["feat"], dg, n, side=s["side"])
-        dfeat = ex["ih"].dgrad(dg, n, x_saved=s["feat"], x_act=ENC_LAST_ACT[self.feature_encoding])
+        dfeat = ex["ih"].dgrad(dg, n, x_saved=s["feat"], x_act=ex["chain"].last_act)
         if ex["inv_perm"] is not None:
             dfeat = dfeat.index_select(1, ex["inv_perm"])
         last = ex["chain"].layers[-1]

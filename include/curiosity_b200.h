@@ -188,6 +188,21 @@ int cb_conv_dgrad_s2(const cb_conv_desc* d, const void* dy, const void* w_shuffl
 int cb_conv1_supported(const cb_conv_desc* d);
 int cb_conv1_fwd(const cb_conv_desc* d, const void* x, const void* w_native, const cb_epilogue* e,
                  const void* w2_native, const float* bias2, void* out2_bf16, void* stream);
+/* BatchNorm2d of the curiosity encoders (rlpyt/models/curiosity/encoders.py:23-25, 87-96, `-batch_norm`) on bf16 NHWC
+ * activations seen as [rows, c] (rows = N*H*W, c = 8 * a power of two <= 256), torch's training-mode arithmetic as
+ * HBM-bound passes; the per-channel scalars in between are the caller's (c-element tensors).
+ *   cb_bn_moments      sum[c] += sum_r x, sumsq[c] += sum_r x^2              (double; caller zeroes)
+ *   cb_bn_apply        out = x * scale[c] + shift[c]                         (bf16 and / or fp32 output)
+ *   cb_bn_bwd_moments  sum_dz[c] += sum_r dz, sum_dz_xhat[c] += sum_r dz * (x - mean[c]) * invstd[c]
+ *   cb_bn_bwd_apply    dx = (dz*coef_dz[c] + x*coef_x[c] + coef_1[c]) * act'(x), x being the OUTPUT of activation
+ *                      x_act in front of the normalisation (CB_ACT_*) */
+int cb_bn_moments(const void* x_bf16, int64_t rows, int32_t c, double* sum, double* sumsq, void* stream);
+int cb_bn_apply(const void* x_bf16, int64_t rows, int32_t c, const float* scale, const float* shift,
+                void* out_bf16, float* out_f32, void* stream);
+int cb_bn_bwd_moments(const void* dz_bf16, const void* x_bf16, int64_t rows, int32_t c, const float* mean,
+                      const float* invstd, double* sum_dz, double* sum_dz_xhat, void* stream);
+int cb_bn_bwd_apply(const void* dz_bf16, const void* x_bf16, int64_t rows, int32_t c, const float* coef_dz,
+                    const float* coef_x, const float* coef_1, int32_t x_act, void* dx_bf16, void* stream);
 /* RND trunk, first TWO convolutions (rnd.py:40-46 / 55-61: Conv 8x8 s4 1->32, LeakyReLU, Conv 4x4 s2 32->64,
  * LeakyReLU) with the 20x20x32 activation between them kept in shared memory.
  *   cb_rnd_normalize_s2d: the newest 84x84 uint8 frame of each sample (read in place at x + i*stride_n) is normalised

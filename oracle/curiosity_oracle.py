@@ -99,25 +99,44 @@ def _sub(p, prefix):
 
 
 # --------------------------------------------------------------------------- encoders
-def burda_head(x, p):
-    """encoders.py:68-119 (batch_norm=False).  x: [N,C,84,84] float -> [N,512].
+def _batch_norm(h, p, idx, training=True):
+    """nn.BatchNorm2d(C) as the encoders place it (encoders.py:23-25, 87-96; eps 1e-5, affine): statistics of this
+    batch in training mode (what agent.train_mode() selects for optimize_agent), the running ones otherwise.  The
+    running statistics themselves are not updated here (functional restatement; the tests check that update
+    against torch.nn.BatchNorm2d directly)."""
+    w, b = p[f"model.{idx}.weight"], p[f"model.{idx}.bias"]
+    if training:
+        return F.batch_norm(h, None, None, w, b, training=True, eps=1e-5)
+    return F.batch_norm(h, p[f"model.{idx}.running_mean"], p[f"model.{idx}.running_var"], w, b, training=False, eps=1e-5)
 
-    conv(C->32,k8,s4) lrelu conv(32->64,k4,s2) lrelu conv(64->64,k3,s1) lrelu
-    flatten(CHW order) linear(3136->512); no activation after the linear.
-    """
-    h = F.leaky_relu(_conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=4))
-    h = F.leaky_relu(_conv2d(h, p["model.2.weight"], p["model.2.bias"], stride=2))
-    h = F.leaky_relu(_conv2d(h, p["model.4.weight"], p["model.4.bias"], stride=1))
+
+def burda_head(x, p, bn_training=True):
+    """encoders.py:68-119.  x: [N,C,84,84] float -> [N,512].
+
+    conv(C->32,k8,s4) lrelu [bn] conv(32->64,k4,s2) lrelu [bn] conv(64->64,k3,s1) lrelu [bn]
+    flatten(CHW order) linear(3136->512); no activation after the linear.  With ``batch_norm`` the Sequential
+    indices are conv 0/3/6, BatchNorm2d 2/5/8, Linear 10 (recognised by the keys present)."""
+    bn = "model.2.running_mean" in p
+    step = 3 if bn else 2
+    h = x
+    for i, stride in enumerate((4, 2, 1)):
+        h = F.leaky_relu(_conv2d(h, p[f"model.{step * i}.weight"], p[f"model.{step * i}.bias"], stride=stride))
+        if bn:
+            h = _batch_norm(h, p, step * i + 2, bn_training)
     h = h.reshape(h.shape[0], -1)
-    return _linear(h, p["model.7.weight"], p["model.7.bias"])
+    return _linear(h, p[f"model.{3 * step + 1}.weight"], p[f"model.{3 * step + 1}.bias"])
 
 
-def universe_head(x, p):
-    """encoders.py:7-35.  5x [conv 3x3 s2 p1 -> 32, ELU]; flatten -> [N,288]."""
+def universe_head(x, p, bn_training=True):
+    """encoders.py:7-35.  5x [conv 3x3 s2 p1 -> 32, ELU, [BatchNorm2d]]; flatten -> [N,288]."""
+    bn = "model.2.running_mean" in p
+    step = 3 if bn else 2
     h = x
     for layer in range(5):
-        h = F.elu(_conv2d(h, p[f"model.{2 * layer}.weight"], p[f"model.{2 * layer}.bias"],
+        h = F.elu(_conv2d(h, p[f"model.{step * layer}.weight"], p[f"model.{step * layer}.bias"],
                            stride=2, padding=1))
+        if bn:
+            h = _batch_norm(h, p, step * layer + 2, bn_training)
     return h.reshape(h.shape[0], -1)
 
 
