@@ -21,7 +21,14 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refshim.available(), reaso
 FIELDS = ("loss", "pi_loss", "value_loss", "entropy_loss", "inv_loss", "forward_loss", "entropy", "perplexity")
 
 
+_REF_INIT = {}
+
+
 def _params(kind, A, seed):
+    if kind == "icm_bn":       # `-batch_norm`: the reference's own (seeded) initialisation, captured from its model once
+        if kind not in _REF_INIT:
+            raise RuntimeError("the reference pass must run first")
+        return {k: v.clone() for k, v in _REF_INIT[kind].items()}
     if kind in ("icm", "disagreement"):
         pol = R.make_policy_params(A, seed)
         shapes = R.icm_shapes(A, "idf_burda") if kind == "icm" else R.disagreement_shapes(A, "idf_burda")
@@ -50,6 +57,12 @@ def _one_iteration(kind, ck, A, T, B, seed, cuda_idx):
     agent, algo = refshim.make_agent_and_algo(ck, A, T, B, cuda_idx=cuda_idx,
                                               image_shape=(3, 5, 5) if kind == "ndigo" else (4, 84, 84),
                                               ppo_kwargs=dict(epochs=2, minibatches=1, gae_lambda=0.95, learning_rate=1e-4))
+    if kind == "icm_bn" and kind not in _REF_INIT:
+        torch.manual_seed(seed)
+        for mod in agent.model.modules():
+            if hasattr(mod, "reset_parameters"):
+                mod.reset_parameters()
+        _REF_INIT[kind] = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
     agent.model.load_state_dict(_params(kind, A, seed))
     before = {k: v.detach().cpu().clone() for k, v in agent.model.state_dict().items()}
     s = _samples(A, T, B, seed, kind)
@@ -62,15 +75,15 @@ def _one_iteration(kind, ck, A, T, B, seed, cuda_idx):
 
 
 @pytest.mark.parametrize("kind,native_algo", [("icm", False), ("disagreement", False), ("rnd", False), ("ndigo", False),
-                                              ("icm", True), ("rnd", True), ("ndigo", True)])
+                                              ("icm", True), ("rnd", True), ("ndigo", True), ("icm_bn", False)])
 def test_reference_optimize_agent_through_install(kind, native_algo):
     """native_algo: ``install(policy=True, algo=True)`` -- the runner-level call ``algo.optimize_agent(itr, samples)`` on
     host ``Samples`` lands on the fused iteration (algos.ppo.rlpyt_optimize_agent) instead of the reference's loop."""
     import curiosity_baselines_b200.integration as cbi
     refshim.import_reference()
     A, T, B, seed = (5 if kind == "ndigo" else 4), 16, 8, 55
-    ck = dict(curiosity_alg=kind, feature_encoding="idf_burda", batch_norm=False, prediction_beta=1.0,
-              forward_loss_wt=0.2, device="cpu")
+    ck = dict(curiosity_alg=kind.split("_")[0], feature_encoding="idf_burda", batch_norm=kind.endswith("_bn"),
+              prediction_beta=1.0, forward_loss_wt=0.2, device="cpu")
     if kind == "rnd":          # launch.py's kwargs for RND (drop_probability 0: the mask rand > 0 keeps every sample)
         ck = dict(curiosity_alg="rnd", feature_encoding="none", prediction_beta=1.0, drop_probability=0.0, gamma=0.99,
                   device="cpu")
