@@ -845,6 +845,14 @@ def run_workload(kind, ctx, args, T, B, steps, warmup, headline):
         rec["cuda_graph"] = {"ms_per_step": gms, "value": n_global / (gms * 1e-3), "unit": "samples/s",
                              "loss": float(gloss), "note": "trainer.GraphedStep: the whole step captured once, replayed per step"}
         w.graphed = None
+    # ---- RND with the first two convolutions as one kernel (cb_rnd_conv12_fwd; off by default because it is no faster)
+    if headline and kind == "rnd" and getattr(w.model, "fuse_conv12", None) is False:
+        w.model.fuse_conv12 = True
+        fms, _ = timed(ctx, w.step, 2, max(3, steps // 2))
+        w.model.fuse_conv12 = False
+        rec["with_fused_conv12"] = {"ms_per_step": fms, "value": n_global / (fms * 1e-3), "unit": "samples/s",
+                                    "note": "conv1 -> conv2 with the activation kept in shared memory: at parity, not faster "
+                                            "(tcgen05 operand fetch bounds these layers), profiles/r2_fused_conv12_study.txt"}
     # ---- the same iteration with exact feature reuse between bonus and loss (NOT the headline value)
     if not args.no_reuse and w.set_reuse(True):
         h0 = w.reuse_hits()
@@ -999,7 +1007,7 @@ def main():
         "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head.get("e2e"),
         "roofline": head.get("roofline") or head["step_roofline"], "step_roofline": head["step_roofline"],
         "cpu_baseline": head.get("cpu_baseline"), "with_feature_reuse": head.get("with_feature_reuse"),
-        "with_obs_dedup": head.get("with_obs_dedup"), "cuda_graph": head.get("cuda_graph"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
+        "with_obs_dedup": head.get("with_obs_dedup"), "with_fused_conv12": head.get("with_fused_conv12"), "cuda_graph": head.get("cuda_graph"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
         {"per_gpu": h2d_gbs, "aggregate": h2d_gbs * ctx.world, "note": "1 GiB pinned copies, all ranks at once"},
         "configs": [dict(finish(k, r), name=k) for k, r in others],
     }
