@@ -75,7 +75,7 @@ def _one_iteration(kind, ck, A, T, B, seed, cuda_idx):
 
 
 @pytest.mark.parametrize("kind,native_algo", [("icm", False), ("disagreement", False), ("rnd", False), ("ndigo", False),
-                                              ("icm", True), ("rnd", True), ("ndigo", True), ("icm_bn", False)])
+                                              ("icm", True), ("rnd", True), ("ndigo", True), ("icm_bn", False), ("icm_bn", True)])
 def test_reference_optimize_agent_through_install(kind, native_algo):
     """native_algo: ``install(policy=True, algo=True)`` -- the runner-level call ``algo.optimize_agent(itr, samples)`` on
     host ``Samples`` lands on the fused iteration (algos.ppo.rlpyt_optimize_agent) instead of the reference's loop."""
