@@ -730,11 +730,23 @@ def kernel_table(model, T, B, ms_per_step, dev):
     frames = torch.randint(0, 256, (n, 1, 84, 84), dtype=torch.uint8, device=dev)
     st1, nm = (7056, 84, 1, 7056), model._norm
     a1, a2, a3, h = bf(n * 400, 32), bf(n * 81, 64), bf(n * 49, 64), bf(n, 512)
-    cases = [
+    fl12 = 2 * (64 * 32 * 400 + 512 * 64 * 81)
+    if getattr(model, "fuse_conv12", False):        # default: frames normalised once per pass, conv1 -> conv2 of both networks fused
+        img = torch.empty(n * model.S2D_BYTES, dtype=torch.uint8, device=dev)
+        head = [
+            ("normalise frames (block order)", lambda: L.call("cb_rnd_normalize_s2d", frames.data_ptr(), 7056, n, L.ptr(nm[0]),
+                                                               L.ptr(nm[1]), L.ptr(img), L.stream()), 2, 7056 + 14112, 4 * 7056),
+            ("conv1+conv2 twin fwd (target+predictor)", lambda: model._conv12_twin(img, n, False), 1, 14112 + 2 * 10368, 2 * fl12),
+            ("conv1+conv2 twin fwd, predictor a1 kept", lambda: model._conv12_twin(img, n, True), 1, 14112 + 2 * 10368 + 25600, 2 * fl12),
+        ]
+    else:
+        head = [
+            ("conv1 twin fwd (target+predictor)", lambda: c1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm, twin=targ.layers[0]),
+             2, 7056 + 2 * 25600, 2 * 2 * 64 * 32 * 400),
+            ("conv2 fwd", lambda: c2.forward(a1, n), 4, 25600 + 10368, 2 * 512 * 64 * 81),
+        ]
+    cases = head + [
         # name, fn, launches per step, algorithmic bytes per sample, FLOP per sample
-        ("conv1 twin fwd (target+predictor)", lambda: c1.forward(frames.data_ptr(), n, in_dtype=L.U8, strides=st1, norm=nm, twin=targ.layers[0]),
-         2, 7056 + 2 * 25600, 2 * 2 * 64 * 32 * 400),
-        ("conv2 fwd", lambda: c2.forward(a1, n), 4, 25600 + 10368, 2 * 512 * 64 * 81),
         ("conv3 fwd", lambda: c3.forward(a2, n), 4, 10368 + 6272, 2 * 576 * 64 * 49),
         ("fc 3136->512 fwd", lambda: fc.forward(a3, n), 4, 6272 + 1024, 2 * 3136 * 512),
         ("linear 512x512 fwd", lambda: l9.forward(h, n), 4, 2048, 2 * 512 * 512),
@@ -845,14 +857,14 @@ def run_workload(kind, ctx, args, T, B, steps, warmup, headline):
         rec["cuda_graph"] = {"ms_per_step": gms, "value": n_global / (gms * 1e-3), "unit": "samples/s",
                              "loss": float(gloss), "note": "trainer.GraphedStep: the whole step captured once, replayed per step"}
         w.graphed = None
-    # ---- RND with the first two convolutions as one kernel (cb_rnd_conv12_fwd; off by default because it is no faster)
-    if headline and kind == "rnd" and getattr(w.model, "fuse_conv12", None) is False:
-        w.model.fuse_conv12 = True
-        fms, _ = timed(ctx, w.step, 2, max(3, steps // 2))
+    # ---- RND with the separate first / second convolution kernels (the fused twin kernel is the default)
+    if headline and kind == "rnd" and getattr(w.model, "fuse_conv12", None) is True:
         w.model.fuse_conv12 = False
-        rec["with_fused_conv12"] = {"ms_per_step": fms, "value": n_global / (fms * 1e-3), "unit": "samples/s",
-                                    "note": "conv1 -> conv2 with the activation kept in shared memory: at parity, not faster "
-                                            "(tcgen05 operand fetch bounds these layers), profiles/r2_fused_conv12_study.txt"}
+        fms, _ = timed(ctx, w.step, 2, max(3, steps // 2))
+        w.model.fuse_conv12 = True
+        rec["with_separate_conv12"] = {"ms_per_step": fms, "value": n_global / (fms * 1e-3), "unit": "samples/s",
+                                       "note": "RND.fuse_conv12 = False: twin first-conv kernel + window conv2 per network "
+                                               "instead of cb_rnd_normalize_s2d + cb_rnd_conv12_twin_fwd"}
     # ---- the same iteration with exact feature reuse between bonus and loss (NOT the headline value)
     if not args.no_reuse and w.set_reuse(True):
         h0 = w.reuse_hits()
@@ -1007,7 +1019,7 @@ def main():
         "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head.get("e2e"),
         "roofline": head.get("roofline") or head["step_roofline"], "step_roofline": head["step_roofline"],
         "cpu_baseline": head.get("cpu_baseline"), "with_feature_reuse": head.get("with_feature_reuse"),
-        "with_obs_dedup": head.get("with_obs_dedup"), "with_fused_conv12": head.get("with_fused_conv12"), "cuda_graph": head.get("cuda_graph"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
+        "with_obs_dedup": head.get("with_obs_dedup"), "with_separate_conv12": head.get("with_separate_conv12"), "cuda_graph": head.get("cuda_graph"), "strong": head.get("strong"), "loss": head["loss"], "host_to_device_gbs_all_ranks": None if h2d_gbs is None else
         {"per_gpu": h2d_gbs, "aggregate": h2d_gbs * ctx.world, "note": "1 GiB pinned copies, all ranks at once"},
         "configs": [dict(finish(k, r), name=k) for k, r in others],
     }

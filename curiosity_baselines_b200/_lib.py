@@ -68,6 +68,7 @@ _SIGS = {
     "cb_bn_bwd_apply": [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P],
     "cb_rnd_normalize_s2d": [_P, _L, _I, _P, _P, _P, _P],
     "cb_rnd_conv12_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cb_rnd_conv12_twin_fwd": [_P, _I] + [_P] * 12,
     "cb_conv1_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_conv_wgrad": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _F, _P],
     "cb_side_wgrad": [_P, _P, _P, _L, _I, _I, _F, _P],

@@ -85,9 +85,10 @@ class RND(nn.Module):
         self._cache = None
         self._wver = 0            # bumped whenever the predictor's master weights change outside torch's tracking
         self.reuse_hits = {"full": 0, "target": 0, "miss": 0}
-        # first two convolutions without the HBM round trip between them (cb_rnd_conv12_fwd): parity-tested, but no faster
-        # than the separate kernels (both are bound by the tensor cores' operand fetch, profiles/r2_fused_conv12_study.txt)
-        self.fuse_conv12 = False
+        # first two convolutions of both networks without the HBM round trip between them: frames normalised once per pass
+        # (cb_rnd_normalize_s2d), then one launch per pass for target + predictor (cb_rnd_conv12_twin_fwd; the predictor
+        # alone, on the feature-reuse path, through cb_rnd_conv12_fwd).  RND step 23.4 -> 22.0-22.7 ms at T=128, B=1024.
+        self.fuse_conv12 = True
         self._fuse_ok = None
 
     # ------------------------------------------------------------------ plumbing
@@ -199,14 +200,32 @@ class RND(nn.Module):
                L.ptr(a1), L.ptr(a2), L.stream())
         return [a1, a2]
 
+    def _conv12_twin(self, img, n, keep_a1):
+        """First two convolutions of target AND predictor in one launch (the block image is read once, the first
+        layer is a single N = 64 problem); the predictor's 20x20x32 activation is written out only when the backward
+        pass will need it."""
+        pred, targ = self._chains
+        (t1, t2), (p1, p2) = targ.layers[:2], pred.layers[:2]
+        for layer in (t1, t2, p1, p2):
+            layer.prepare()
+        dev = t1.w_fwd.device
+        a1_p = torch.empty(n * 400, 32, dtype=torch.bfloat16, device=dev) if keep_a1 else None
+        a2_t = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
+        a2_p = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
+        L.call("cb_rnd_conv12_twin_fwd", L.ptr(img), n, L.ptr(t1.w_native), L.ptr(t1.bias), L.ptr(t2.w_fwd), L.ptr(t2.bias),
+               L.ptr(p1.w_native), L.ptr(p1.bias), L.ptr(p2.w_fwd), L.ptr(p2.bias), L.ptr(a2_t), L.ptr(a1_p), L.ptr(a2_p),
+               L.stream())
+        return a2_t, a1_p, a2_p
+
     def _forward_nets(self, obs, keep_acts):
         obs, T, B, base, strides = self._frame_view(obs)
         n = T * B
         pred, targ = self._chains
         if self._can_fuse12(base, strides):
             img = self._normalized(base, n, strides[0])
-            _, phi = targ.forward(base, n, first_out=self._conv12(targ, img, n, False))
-            acts, phi_hat = pred.forward(base, n, first_out=self._conv12(pred, img, n, keep_acts))
+            a2_t, a1_p, a2_p = self._conv12_twin(img, n, keep_acts)
+            _, phi = targ.forward(base, n, first_out=[None, a2_t])
+            acts, phi_hat = pred.forward(base, n, first_out=[a1_p, a2_p])
             return obs, T, B, base, strides, phi, phi_hat, (acts if keep_acts else None)
         # target and predictor read the same normalised frame: one fused first-conv pass for both
         a1_p, _, a1_t = pred.layers[0].forward(base, n, in_dtype=L.U8, strides=strides, norm=self._norm,

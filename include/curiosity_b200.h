@@ -217,6 +217,11 @@ int cb_rnd_normalize_s2d(const uint8_t* x, int64_t stride_n, int32_t n, const fl
                          void* out_s2d, void* stream);
 int cb_rnd_conv12_fwd(const void* img_s2d, int32_t n, const void* w1_bf16, const float* b1, const void* w2_bf16,
                       const float* b2, void* a1_out_bf16, void* a2_out_bf16, void* stream);
+/* Target and predictor of every sample in one launch: the block image is read once and the first layer is a single
+ * N = 64 problem for both networks.  a1_p_out (NULL to skip): the predictor's first-layer activation. */
+int cb_rnd_conv12_twin_fwd(const void* img_s2d, int32_t n, const void* w1_t, const float* b1_t, const void* w2_t,
+                           const float* b2_t, const void* w1_p, const float* b1_p, const void* w2_p, const float* b2_p,
+                           void* a2_t_out, void* a1_p_out, void* a2_p_out, void* stream);
 int cb_conv1_wgrad(const cb_conv_desc* d, const void* x, const void* dy, const float* norm_mean,
                    const float* norm_rstd, float* dw_native, float* dbias, float beta, void* stream);
 /* dw[out_c][k_h][k_w][in_c] (fp32) = beta*dw + sum_positions dy^T x;  dbias[out_c] likewise

@@ -94,8 +94,22 @@ def fused12(a1_out):
            L.ptr(conv2.bias), L.ptr(a1_out), L.ptr(a2o), L.stream())
 
 
+conv1b.prepare()
+conv2b = LY.conv_layer(nn.Conv2d(32, 64, 4, 2).to(dev), (20, 20, 32), "lrelu")
+conv2b.prepare()
+a2o2 = torch.empty(n * 81, 64, dtype=torch.bfloat16, device=dev)
+
+
+def fused12_twin(a1_out):
+    L.call("cb_rnd_conv12_twin_fwd", L.ptr(img12), n, L.ptr(conv1.w_native), L.ptr(conv1.bias), L.ptr(conv2.w_fwd),
+           L.ptr(conv2.bias), L.ptr(conv1b.w_native), L.ptr(conv1b.bias), L.ptr(conv2b.w_fwd), L.ptr(conv2b.bias),
+           L.ptr(a2o), L.ptr(a1_out), L.ptr(a2o2), L.stream())
+
+
 normalize12()
 cases["fused12_normalize"] = (normalize12, 0.0)
+cases["fused12_twin_fwd"] = (lambda: fused12_twin(None), 2 * fl12)
+cases["fused12_twin_keep_fwd"] = (lambda: fused12_twin(a1), 2 * fl12)
 cases["fused12_fwd"] = (lambda: fused12(None), fl12)
 cases["fused12_keep_fwd"] = (lambda: fused12(a1), fl12)
 for name, (fn, fl) in cases.items():
