@@ -18,12 +18,15 @@
 // When the caller needs the intermediate activation (predictor in the loss pass: conv2's weight gradient reads it),
 // the slab is also written out by TMA, two plane stores per sample.
 //
-// Measured (131 072 samples): 1.53 ms per network (+ 0.54 ms per pass for the normalisation) against 0.78 + 0.98 ms
-// for the separate kernels -- no gain: tcgen05.mma with both operands in shared memory costs ~(M + N) / 4 cycles per
-// K = 16 step here (46 cycles at N = 32, 52 at N = 64, against 16 / 32 for the math), so these skinny layers are bound
-// by the operand fetch from shared memory, not by the HBM round trip the fusion removes.  Earlier versions (layer 1 by
-// mma.sync: 2.1 ms; uint8 conversion inside the kernel with three different producer arrangements: 1.5 ms each) and
-// the ablations are in profiles/r2_fused_conv12_study.txt.  The kernel stays as an option (RND.fuse_conv12).
+// Measured (131 072 samples): the one-network kernel takes 1.45-1.55 ms (+ 0.54 ms per pass for the normalisation)
+// against 0.78 + 0.98 ms for the separate kernels -- no gain: tcgen05.mma with both operands in shared memory costs
+// ~(M + N) / 4 cycles per K = 16 step here (46 cycles at N = 32, 52 at N = 64, against 16 / 32 for the math), so these
+// skinny layers are bound by the operand fetch from shared memory, not by the HBM round trip the fusion removes.  The
+// TWIN kernel further down shares that fetch between target and predictor (one image, first layer as one N = 64
+// problem): 2.5 ms for both networks against 3.5 ms, and is what RND runs; this one serves the predictor-only
+// (feature reuse) path with identical numerics.  Earlier versions (layer 1 by mma.sync: 2.1 ms; uint8 conversion inside
+// the kernel with three different producer arrangements: 1.5 ms each) and the ablations are in
+// profiles/r2_fused_conv12_study.txt.
 //
 // Warp roles (576 threads): 0 = loader (conv2 weights by TMA, block images by bulk copy), 1 = TMEM owner + tcgen05
 // issuer for both layers (and the TMA store of the slab), 2-5 = conv2 epilogue, 6-17 = first-layer drain (three per
