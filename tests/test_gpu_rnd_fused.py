@@ -146,8 +146,9 @@ def test_first_conv_kernels_are_repeatable():
         a1_p, _, a1_t = pred.layers[0].forward(base, n, in_dtype=L.U8, strides=strides, norm=m._norm, twin=targ.layers[0])
         img = m._normalized(base, n, strides[0])
         _, a2 = m._conv12(pred, img, n, False)
+        tw = m._conv12_twin(img, n, True)
         torch.cuda.synchronize()
         if first is None:
-            first = (a1_p, a1_t, a2)
+            first = (a1_p, a1_t, a2) + tuple(tw)
         else:
-            assert torch.equal(a1_p, first[0]) and torch.equal(a1_t, first[1]) and torch.equal(a2, first[2])
+            assert all(torch.equal(a, b) for a, b in zip((a1_p, a1_t, a2) + tuple(tw), first))
